@@ -1,0 +1,209 @@
+/*
+ * rlx_b200.h — C-ABI of the B200-native (sm_100a) RL-X hot path.
+ *
+ * The reference (nico-bohlinger/RL-X) is pure Python and has no FFI of its own; its hot path is the body of
+ * PPO.train() (rl_x/algorithms/ppo/pytorch/ppo.py:97-393) and SAC.train() (rl_x/algorithms/sac/pytorch/sac.py:89-348).
+ * Each entry point below replaces a block of that Python; the block is cited as `ref:`.  The Python plugin
+ * (rl_x_b200/algorithms/ppo/b200/ppo.py) binds these with ctypes — see INTEGRATION.md for the stub a maintainer
+ * would add to the reference itself.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch / C++ types.  All device pointers are raw CUDA device addresses
+ *     (tensor.data_ptr()), row-major contiguous unless a leading dimension is given.
+ *   - every device entry point is stream-ordered on `stream` (a cudaStream_t passed as void*; NULL = default stream),
+ *     never allocates or frees memory, never synchronises the device.  Scratch is caller-provided
+ *     (`*_workspace_bytes` queries).
+ *   - return value: 0 = OK, negative = error (RLX_ERR_*); rlx_last_error_string() describes the last error of the
+ *     calling thread.  Nothing throws across the boundary.
+ *   - fp32 everywhere (the reference's parity path: bf16 autocast off, ppo.py:60-70); indices are int64 like
+ *     np.arange(B) (ppo.py:273).
+ */
+#ifndef RLX_B200_H
+#define RLX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLX_OK 0
+#define RLX_ERR_INVALID_ARG (-1)
+#define RLX_ERR_CUDA (-2)
+#define RLX_ERR_WORKSPACE (-3)
+#define RLX_ERR_UNSUPPORTED (-4)
+
+/* ------------------------------------------------------------------------------------------------ library -- */
+int rlx_version(void);                        /* ABI version, currently 1 */
+const char* rlx_last_error_string(void);      /* thread-local, never NULL */
+uint64_t rlx_launch_count(void);              /* kernels launched by this library since load / last reset */
+void rlx_reset_launch_count(void);
+/* GEMM engine used by the MLP entry points: 0 = fp32 SIMT (FFMA), 1 = tcgen05 3xTF32 (tensor cores, TMEM accumulators).
+ * Returns the engine actually in effect (a request for 1 falls back to 0 with an error string if the shape is unsupported). */
+int rlx_set_gemm_engine(int engine);
+int rlx_get_gemm_engine(void);
+
+/* ------------------------------------------------------------------------------- numpy-compatible host RNG -- */
+/* ref: self.rng = np.random.default_rng(self.seed)  (ppo.py:72; sac.py replay_buffer.py:8) — Generator(PCG64(SeedSequence(seed))).
+ * state[0..1] = 128-bit LCG state (hi, lo); state[2..3] = increment (hi, lo); state[4] = has_uint32; state[5] = buffered uinteger. */
+typedef struct rlx_pcg64 { uint64_t s[6]; } rlx_pcg64;
+int rlx_pcg64_seed(uint64_t seed, rlx_pcg64* st);
+uint64_t rlx_pcg64_next64(rlx_pcg64* st);
+uint32_t rlx_pcg64_next32(rlx_pcg64* st);
+/* ref: self.rng.shuffle(batch_indices)  (ppo.py:276) — in place, bit-exact with numpy.random.Generator.shuffle on a 1-D int64 array. HOST memory. */
+int rlx_pcg64_shuffle_i64(rlx_pcg64* st, int64_t* a, int64_t n);
+/* ref: self.rng.integers(high, size=n)  (sac/pytorch/replay_buffer.py:33-34) — int64 output, low = 0. HOST memory. */
+int rlx_pcg64_integers_i64(rlx_pcg64* st, int64_t high, int64_t* out, int64_t n);
+
+/* ------------------------------------------------------------------------------------- PPO network layout -- */
+/* Policy: obs -> hidden -> hidden -> act (tanh, tanh, linear) + logstd(act)   ref: policy.py:34-52
+ * Critic: obs -> hidden -> hidden -> 1   (tanh, tanh, linear)                 ref: critic.py:23-41
+ * All parameters live in ONE flat fp32 buffer; gradients and both Adam moments use the same layout.
+ * Segment order (nn.Linear weights are [out, in] row-major exactly as in the reference state_dict):
+ *   0 W1p[H,obs] 1 W1c[H,obs] 2 b1p[H] 3 b1c[H] 4 W2p[H,H] 5 W2c[H,H] 6 b2p[H] 7 b2c[H]
+ *   8 W3p[A,H]   9 W3c[1,H]  10 b3p[A] 11 b3c[1] 12 logstd[A]
+ * (policy and critic first layers are adjacent so that layer 1 runs as one [2H, obs] GEMM on the shared input.) */
+#define RLX_PPO_NSEG 13
+typedef struct rlx_ppo_dims { int32_t obs_dim, act_dim, hidden; } rlx_ppo_dims;
+int64_t rlx_ppo_param_count(const rlx_ppo_dims* d);
+/* offsets[RLX_PPO_NSEG+1]: start of each segment, last entry = total count.  is_critic[RLX_PPO_NSEG]: 0 policy / 1 critic. */
+int rlx_ppo_param_layout(const rlx_ppo_dims* d, int64_t* offsets, int32_t* is_critic);
+
+/* ------------------------------------------------------------------------------------------ rollout (acting) -- */
+/* ref: policy.get_action_logprob(state) + critic.get_value(state)  (ppo.py:207-209; policy.py:61-73; critic.py:44-46)
+ *   mean = MLP_p(obs); a = mean + exp(logstd) * noise; logp = sum_a Normal(mean, std).log_prob(a); value = MLP_c(obs)
+ *   env_action = low + 0.5 * (clip(a,-1,1) + 1) * (high - low)   if clip_rescale else a
+ * obs [n, obs_dim]; noise [n, act] standard-normal draws supplied by the caller, or NULL: a counter-based Philox4x32-10
+ * stream keyed by (rng_seed, rng_offset, row) is used (rng_offset must advance by 1 per call).
+ * deterministic != 0 reproduces get_deterministic_action (policy.py:85-93): a = mean, no noise, logp not written.
+ * Outputs (any may be NULL): action [n, act] (unclipped sample, what ppo.py:233 stores), env_action [n, act],
+ * logp [n], value [n].  workspace: rlx_ppo_forward_workspace_bytes(d, n). */
+typedef struct rlx_ppo_forward_args {
+  rlx_ppo_dims dims;
+  int64_t n;
+  const float* params;
+  const float* obs;
+  const float* noise;
+  uint64_t rng_seed, rng_offset;
+  const float* act_low;   /* [act] device */
+  const float* act_high;  /* [act] device */
+  int32_t clip_rescale;
+  int32_t deterministic;
+  float* action;
+  float* env_action;
+  float* logp;
+  float* value;
+  void* workspace;
+  size_t workspace_bytes;
+} rlx_ppo_forward_args;
+size_t rlx_ppo_forward_workspace_bytes(const rlx_ppo_dims* d, int64_t n);
+int rlx_ppo_forward_f32(const rlx_ppo_forward_args* a, void* stream);
+
+/* ref: critic.get_value(x) alone  (ppo.py:253-254 next_values; critic.py:44-46).  obs [n, obs_dim] -> value [n]. */
+int rlx_critic_forward_f32(const rlx_ppo_dims* d, const float* params, const float* obs, int64_t n, float* value,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ref: the per-step buffer writes  batch.rewards[step] = reward; batch.terminations[step] = terminated;
+ * state = next_state  (ppo.py:231-245) plus the running `dones_this_rollout += done.sum()` (ppo.py:227) kept on device.
+ * reward [n] f32; terminated/truncated [n] uint8 (torch.bool); next_obs [n, obs] may be NULL.
+ * Writes rewards_row [n], terminations_row [n] (0/1 float), next_obs_dst [n, obs] (copy), done_count[0] += #done. */
+int rlx_rollout_store_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* next_obs,
+                          int64_t n, int64_t obs_dim, float* rewards_row, float* terminations_row, float* next_obs_dst,
+                          int64_t* done_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------ GAE -- */
+/* ref: calculate_gae_advantages_and_returns  (ppo.py:110-118)
+ *   delta = r + gamma * nv * (1 - term) - v;  A[t] = delta[t] + gamma*lambda*(1-term[t]) * A[t+1];  R = A + v
+ * All arrays time-major [T, N].  Two ways to supply next values:
+ *   next_values != NULL : full [T, N] tensor as in the reference (ppo.py:253-254)
+ *   next_values == NULL : TORCH-interface shortcut, nv[t] = values[t+1] for t < T-1 and nv[T-1] = last_value[N]
+ *                         (valid because next_states[t] is states[t+1], ppo.py:224-232,244).
+ * gamma / gae_lambda are the Python floats (doubles) of the config: TorchScript multiplies them in double before the
+ * cast to fp32.  Bit-exact with the reference's fp32 arithmetic (same operation order, no FMA contraction). */
+int rlx_gae_f32(const float* rewards, const float* terminations, const float* values, const float* next_values,
+                const float* last_value, int64_t T, int64_t N, double gamma, double gae_lambda, float* advantages,
+                float* returns, void* stream);
+
+/* -------------------------------------------------------------------------------- minibatch gather + stats -- */
+/* ref: batch_states[minibatch_indices], batch_actions[...], batch_log_probs[...], batch_advantages[...], batch_returns[...]
+ * (ppo.py:277-284).  idx [count] int64 indices into the flattened (T*N) batch.  Gathers rows into contiguous
+ * minibatch-ordered buffers; with count = B and idx = the epoch permutation, minibatch k is the slice [k*mb, (k+1)*mb). */
+int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64_t obs_dim, int64_t act_dim, const float* states,
+                             const float* actions, const float* log_probs, const float* advantages, const float* returns,
+                             float* out_states, float* out_actions, float* out_log_probs, float* out_advantages,
+                             float* out_returns, void* stream);
+
+/* ref: minibatch_advantages.mean(), .std() (unbiased)  (ppo.py:133-134), for `num_mb` consecutive minibatches of size mb
+ * (last one may be short) over gathered advantages adv [count].  stats [num_mb, 2] = (mean, unbiased std). */
+int rlx_advantage_stats_f32(const float* adv, int64_t count, int64_t mb, float* stats, void* stream);
+
+/* ------------------------------------------------------------------------------- PPO minibatch update step -- */
+/* Device-resident optimiser state: one struct per (policy, critic) pair.  ref: optim.Adam(lr, betas=(0.9,0.999), eps=1e-8)
+ * x2 (ppo.py:82-84), clip_grad_norm_ x2 (ppo.py:146,162). */
+typedef struct rlx_ppo_hparams {
+  float clip_range;      /* ppo.py:46 */
+  float entropy_coef;    /* ppo.py:47 */
+  float critic_coef;     /* ppo.py:48 */
+  float max_grad_norm;   /* ppo.py:49 */
+  float adam_beta1, adam_beta2, adam_eps;
+  float reserved;
+} rlx_ppo_hparams;
+
+/* Per-minibatch metric record written by the update (ref: ppo.py:285-294 .item() calls, kept on device instead). */
+#define RLX_PPO_NMETRIC 8
+/* 0 pg_loss 1 critic_loss 2 entropy_loss 3 approx_kl 4 clip_fraction 5 policy_grad_norm 6 critic_grad_norm 7 count */
+
+typedef struct rlx_ppo_minibatch_args {
+  rlx_ppo_dims dims;
+  int64_t m;                 /* rows in this minibatch (this rank's share) */
+  int64_t m_global;          /* divisor of the mean reductions (= m on one GPU; global minibatch size when sharded) */
+  const float* states;       /* [m, obs]  gathered */
+  const float* actions;      /* [m, act] */
+  const float* log_probs;    /* [m]  old log-probs */
+  const float* advantages;   /* [m]  raw advantages */
+  const float* returns;      /* [m] */
+  const float* adv_stats;    /* [2] device: mean, unbiased std of the (global) minibatch advantages */
+  float* params;             /* flat parameters (updated in place by the optimiser step) */
+  float* grads;              /* flat gradient out [P] */
+  float* exp_avg;            /* Adam m [P] */
+  float* exp_avg_sq;         /* Adam v [P] */
+  const float* lr;           /* [1] device: current learning rate (LinearLR runs on the host, ppo.py:302-304) */
+  int64_t* step_count;       /* [1] device: Adam step counter, incremented by the optimiser kernel */
+  rlx_ppo_hparams hp;
+  float* metrics;            /* [RLX_PPO_NMETRIC] device, overwritten */
+  void* workspace;
+  size_t workspace_bytes;
+} rlx_ppo_minibatch_args;
+size_t rlx_ppo_minibatch_workspace_bytes(const rlx_ppo_dims* d, int64_t m);
+
+/* ref: policy_loss_fn forward+backward (ppo.py:121-144) and critic_loss_fn forward+backward (ppo.py:153-160):
+ * writes the flat gradient of (pg_loss - c_ent*entropy) wrt policy params and of c_v*mean(0.5 (v-R)^2) wrt critic
+ * params (sums over the m local rows divided by m_global), and metrics[0..4].  Does NOT touch params. */
+int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, void* stream);
+
+/* ref: clip_grad_norm_(policy) + Adam.step(); clip_grad_norm_(critic) + Adam.step()  (ppo.py:146-148,162-164;
+ * torch/nn/utils/clip_grad.py; torch/optim/adam.py single-tensor path).  Reads grads (already all-reduced when
+ * sharded), writes params/exp_avg/exp_avg_sq, increments step_count, writes metrics[5..6] (pre-clip norms). */
+int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void* stream);
+
+/* fwdbwd + clip/Adam for `num_mb` consecutive minibatches of gathered data (one epoch or part of it), all launched
+ * from C with no host round trip.  states etc. point at the first row; minibatch k covers rows [k*mb, min((k+1)*mb, count)).
+ * adv_stats [num_mb,2]; metrics [num_mb, RLX_PPO_NMETRIC].  Single-GPU only (no collective between the two halves). */
+int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int64_t count, int64_t mb, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- SAC path -- */
+/* ref: ReplayBuffer.sample gathers  (sac/pytorch/replay_buffer.py:32-40):  rows states[idx1, idx2] etc. from the device ring.
+ * ring arrays are [capacity_per_env, nr_envs, dim]; idx_t/idx_e [n] int64. */
+int rlx_replay_sample_gather_f32(const int64_t* idx_t, const int64_t* idx_e, int64_t n, int64_t nr_envs, int64_t obs_dim,
+                                 int64_t act_dim, const float* states, const float* next_states, const float* actions,
+                                 const float* rewards, const float* terminations, float* out_states, float* out_next_states,
+                                 float* out_actions, float* out_rewards, float* out_terminations, void* stream);
+
+/* ref: Polyak update loop  (sac/pytorch/sac.py:238-242):  target = (1-tau)*target + tau*online over a flat buffer. */
+int rlx_polyak_f32(float* target, const float* online, int64_t n, float tau, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLX_B200_H */

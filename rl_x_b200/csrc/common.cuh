@@ -1,0 +1,101 @@
+// Shared helpers for the rlx_b200 C-ABI library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <atomic>
+
+#include "../../include/rlx_b200.h"
+
+namespace rlx {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+extern int g_gemm_engine;
+
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define RLX_CHECK_ARG(cond, msg)                                  \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      rlx::set_error("%s: invalid argument: %s", __func__, msg);  \
+      return RLX_ERR_INVALID_ARG;                                 \
+    }                                                             \
+  } while (0)
+
+#define RLX_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      rlx::set_error("%s: CUDA error %s at %s:%d", __func__, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return RLX_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+// Every kernel launch in the library goes through this so that rlx_launch_count() is an honest count.
+#define RLX_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+  do {                                                                \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
+    rlx::count_launch();                                              \
+    RLX_CHECK_CUDA(cudaPeekAtLastError());                            \
+  } while (0)
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count();
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32); result valid in all threads. `sh` holds >= 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) {
+    r = warp_sum(r);
+    if (lane == 0) sh[32] = r;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ------------------------------------------------------------------ PPO flat parameter layout (see rlx_b200.h)
+struct PpoLayout {
+  int64_t off[RLX_PPO_NSEG + 1];
+  int obs, act, H;
+  __host__ __device__ int64_t total() const { return off[RLX_PPO_NSEG]; }
+};
+enum Seg { W1P = 0, W1C, B1P, B1C, W2P, W2C, B2P, B2C, W3P, W3C, B3P, B3C, LOGSTD };
+
+inline PpoLayout make_layout(const rlx_ppo_dims& d) {
+  PpoLayout L;
+  const int64_t H = d.hidden, O = d.obs_dim, A = d.act_dim;
+  const int64_t sz[RLX_PPO_NSEG] = {H * O, H * O, H, H, H * H, H * H, H, H, A * H, H, A, 1, A};
+  int64_t o = 0;
+  for (int i = 0; i < RLX_PPO_NSEG; ++i) {
+    L.off[i] = o;
+    o += sz[i];
+  }
+  L.off[RLX_PPO_NSEG] = o;
+  L.obs = d.obs_dim;
+  L.act = d.act_dim;
+  L.H = d.hidden;
+  return L;
+}
+inline bool seg_is_critic(int s) { return s == W1C || s == B1C || s == W2C || s == B2C || s == W3C || s == B3C; }
+
+inline bool dims_ok(const rlx_ppo_dims& d) {
+  return d.obs_dim > 0 && d.act_dim > 0 && d.hidden > 0 && d.act_dim <= 64 && d.hidden <= 4096 && d.obs_dim <= 65536;
+}
+
+}  // namespace rlx

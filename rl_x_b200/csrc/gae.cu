@@ -1,0 +1,109 @@
+// GAE backward scan (ref: calculate_gae_advantages_and_returns, rl_x/algorithms/ppo/pytorch/ppo.py:110-118).
+//
+// HBM-bound: 20-24 algorithmic bytes per (t, env).  The recurrence is serial in t but independent per env, and the
+// loads do not depend on the recurrence, so a CTA owns a strip of 32 envs and
+//   phase 1: all 256 threads stream the [TT x 32] tiles of rewards / terminations / values (/ next_values) into
+//            shared memory (fully coalesced 128-byte rows, every load independent => deep memory-level parallelism),
+//   phase 2: one warp (lane = env) runs the bit-exact sequential recurrence out of shared memory,
+//   phase 3: all threads stream advantages / returns back out, coalesced.
+// Tiles of TT time steps are processed from the end of the rollout backwards; the carry (last advantage, next value)
+// stays in the scanning warp's registers.  Arithmetic follows the reference's fp32 evaluation order with explicit
+// __fmul_rn/__fadd_rn so that no FMA contraction changes a bit.
+#include "common.cuh"
+
+namespace rlx {
+
+constexpr int GAE_ENVS = 32;   // envs per CTA (one 128-byte row segment)
+constexpr int GAE_TT = 128;    // time steps per shared-memory tile
+
+struct GaeP {
+  const float* r;
+  const float* term;
+  const float* v;
+  const float* nv;      // [T, N] or null
+  const float* last_v;  // [N] (used when nv == null)
+  float* adv;
+  float* ret;
+  long long T, N;
+  float gamma_f;        // (float)gamma
+  float gl_f;           // (float)(gamma * lambda), product taken in double as TorchScript does
+};
+
+__global__ void __launch_bounds__(256) gae_kernel(const GaeP p) {
+  extern __shared__ __align__(16) float gae_smem[];
+  float (*s_r)[GAE_ENVS] = reinterpret_cast<float (*)[GAE_ENVS]>(gae_smem);
+  float (*s_t)[GAE_ENVS] = s_r + GAE_TT;
+  float (*s_v)[GAE_ENVS] = s_t + GAE_TT;
+  float (*s_x)[GAE_ENVS] = s_v + GAE_TT;  // next_values in, advantages out
+  const long long n0 = (long long)blockIdx.x * GAE_ENVS;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long n = n0 + lane;
+  const bool valid = n < p.N;
+  const bool has_nv = p.nv != nullptr;
+
+  float last = 0.f;                                         // lastgaelam
+  float vnext = (valid && !has_nv) ? p.last_v[n] : 0.f;     // value of the state after step t (shortcut mode)
+
+  for (long long t_hi = p.T; t_hi > 0; t_hi -= GAE_TT) {
+    const long long t_lo = (t_hi > GAE_TT) ? t_hi - GAE_TT : 0;
+    const int nt = (int)(t_hi - t_lo);
+    // phase 1: coalesced tile loads (row = time step, 32 consecutive envs)
+    for (int tt = wrp; tt < nt; tt += nw) {
+      const long long g = (t_lo + tt) * p.N + n;
+      s_r[tt][lane] = valid ? p.r[g] : 0.f;
+      s_t[tt][lane] = valid ? p.term[g] : 0.f;
+      s_v[tt][lane] = valid ? p.v[g] : 0.f;
+      if (has_nv) s_x[tt][lane] = valid ? p.nv[g] : 0.f;
+    }
+    __syncthreads();
+    // phase 2: sequential recurrence, one warp, lane = env
+    if (wrp == 0) {
+#pragma unroll 4
+      for (int tt = nt - 1; tt >= 0; --tt) {
+        const float r = s_r[tt][lane], tm = s_t[tt][lane], v = s_v[tt][lane];
+        const float nv = has_nv ? s_x[tt][lane] : vnext;
+        const float nonterm = __fsub_rn(1.f, tm);
+        // delta = rewards + gamma * next_values * (1 - terminations) - values
+        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma_f, nv), nonterm)), v);
+        // lastgaelam = delta + gamma * gae_lambda * (1 - terminations) * lastgaelam
+        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gl_f, nonterm), last));
+        s_x[tt][lane] = last;
+        vnext = v;
+      }
+    }
+    __syncthreads();
+    // phase 3: coalesced stores; returns = advantages + values
+    for (int tt = wrp; tt < nt; tt += nw) {
+      if (valid) {
+        const long long g = (t_lo + tt) * p.N + n;
+        const float a = s_x[tt][lane];
+        p.adv[g] = a;
+        p.ret[g] = __fadd_rn(a, s_v[tt][lane]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace rlx
+
+extern "C" int rlx_gae_f32(const float* rewards, const float* terminations, const float* values, const float* next_values,
+                           const float* last_value, int64_t T, int64_t N, double gamma, double gae_lambda, float* advantages,
+                           float* returns, void* stream) {
+  using namespace rlx;
+  RLX_CHECK_ARG(T >= 0 && N >= 0, "T, N must be non-negative");
+  if (T == 0 || N == 0) return RLX_OK;
+  RLX_CHECK_ARG(rewards && terminations && values && advantages && returns, "null tensor");
+  RLX_CHECK_ARG(next_values || last_value, "either next_values or last_value is required");
+  GaeP p{rewards, terminations, values, next_values, last_value, advantages, returns, T, N, (float)gamma,
+         (float)(gamma * gae_lambda)};
+  const unsigned grid = (unsigned)ceil_div(N, GAE_ENVS);
+  constexpr size_t smem = 4ull * GAE_TT * GAE_ENVS * sizeof(float);  // 64 KB
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  RLX_LAUNCH(gae_kernel, grid, 256, smem, stream, p);
+  return RLX_OK;
+}

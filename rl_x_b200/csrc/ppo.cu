@@ -1,0 +1,378 @@
+// PPO MLP pair: forward (rollout / eval / bootstrap values) and the minibatch forward+backward+optimiser step.
+//
+// Network (ref: policy.py:45-52, critic.py:29-35): two independent 3-layer tanh MLPs on the same input.  They are
+// evaluated as ONE pipeline over a fused activation layout [rows, 2H] = [policy half | critic half]:
+//   layer 1   one GEMM  [rows, obs] x [2H, obs]^T          (shared A operand)
+//   layer 2   one batched GEMM (batch = 2 nets) [rows, H] x [H, H]^T on the two halves
+//   layer 3   skinny head kernels (ppo_head.cuh) fused with sampling / loss
+// Backward mirrors it: head -> (dW3 | dZ2) -> batched dW2 (split over rows) -> batched dH1*tanh' -> dW1 (split over rows),
+// no dX for layer 1.  Bias gradients fall out of the dW GEMMs as row sums of the dZ operand.
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "ppo_head.cuh"
+#include "ppo_optim.cuh"
+
+namespace rlx {
+
+// tcgen05 engine hooks (gemm_tc.cu). Return RLX_ERR_UNSUPPORTED when the shape is not covered.
+int tc_supported(const rlx_ppo_dims& d);
+int tc_mlp_hidden_forward(const rlx_ppo_dims& d, const float* params, const float* X, long long rows, float* H1, float* H2,
+                          void* tc_ws, size_t tc_ws_bytes, cudaStream_t stream);
+size_t tc_workspace_bytes(const rlx_ppo_dims& d, long long rows, bool train);
+
+struct Splits {
+  int splits, kchunk;
+};
+// choose a split-K factor for a [M' x N'] output reduced over `rows`, aiming at ~2 CTAs per SM
+static Splits choose_splits(long long rows, int out_m, int out_n, int batch) {
+  const long long tiles = ceil_div(out_m, GBM) * ceil_div(out_n, GBN) * batch;
+  const long long target = (long long)sm_count() * 2;
+  long long s = std::max<long long>(1, target / std::max<long long>(tiles, 1));
+  s = std::min<long long>(s, std::max<long long>(1, rows / 256));  // at least 256 rows per split
+  long long kchunk = ceil_div(ceil_div(rows, s), 8) * 8;
+  kchunk = std::max<long long>(kchunk, 8);
+  s = ceil_div(rows, kchunk);
+  return Splits{(int)s, (int)kchunk};
+}
+
+struct FwdPlan {
+  size_t off_H1, off_H2, total;
+};
+static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
+  FwdPlan P;
+  size_t o = 0;
+  const size_t act_bytes = align_up((size_t)n * 2 * d.hidden * sizeof(float), 256);
+  P.off_H1 = o; o += act_bytes;
+  P.off_H2 = o; o += act_bytes;
+  P.total = o;
+  return P;
+}
+
+constexpr int kHeadWgradRows = 256;
+
+struct TrainPlan {
+  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_rs2, off_part3, off_norm, total;
+  Splits s1, s2;
+  int head_blocks, wgrad_chunks, norm_blocks;
+};
+static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 8), (long long)sm_count() * 4); }
+
+static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
+  TrainPlan P;
+  const long long H = d.hidden, O = d.obs_dim, A = d.act_dim;
+  P.s1 = choose_splits(m, (int)(2 * H), (int)O, 1);
+  P.s2 = choose_splits(m, (int)H, (int)H, 2);
+  P.head_blocks = head_grid(m);
+  P.wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
+  P.norm_blocks = 64;
+  size_t o = 0;
+  auto take = [&](size_t& off, size_t nfloats) {
+    off = o;
+    o += align_up(nfloats * sizeof(float), 256);
+  };
+  take(P.off_H1, (size_t)m * 2 * H);
+  take(P.off_H2, (size_t)m * 2 * H);
+  take(P.off_dZ2, (size_t)m * 2 * H);
+  take(P.off_dZ1, (size_t)m * 2 * H);
+  take(P.off_dhead, (size_t)m * (A + 1));
+  take(P.off_headpart, (size_t)P.head_blocks * (2 * A + 5));
+  take(P.off_part1, (size_t)P.s1.splits * 2 * H * O);
+  take(P.off_rs1, (size_t)P.s1.splits * 2 * H);
+  take(P.off_part2, (size_t)P.s2.splits * 2 * H * H);
+  take(P.off_rs2, (size_t)P.s2.splits * 2 * H);
+  take(P.off_part3, (size_t)P.wgrad_chunks * (A + 1) * H);
+  take(P.off_norm, (size_t)P.norm_blocks * 2);
+  P.total = o;
+  return P;
+}
+
+template <typename T>
+static T* ws_ptr(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+
+static size_t head_smem_bytes(const rlx_ppo_dims& d, bool train) {
+  size_t s = ((size_t)d.act_dim * d.hidden + d.hidden) * sizeof(float);
+  if (train) s += (size_t)8 * (2 * d.act_dim + 5) * sizeof(float);
+  return s;
+}
+
+// hidden layers: H1 = tanh(X W1cat^T + b1cat), H2 = tanh(H1 (blockdiag W2)^T + b2cat)
+static int mlp_hidden_forward_simt(const PpoLayout& L, const float* params, const float* X, long long rows, float* H1, float* H2,
+                                   cudaStream_t stream) {
+  const int H = L.H;
+  GemmP g{};
+  g.A = X; g.B = params + L.off[W1P]; g.C = H1; g.bias = params + L.off[B1P];
+  g.M = (int)rows; g.N = 2 * H; g.K = L.obs;
+  g.lda = L.obs; g.ldb = L.obs; g.ldc = 2 * H;
+  g.splits = 1; g.kchunk = (int)(ceil_div(L.obs, 8) * 8);
+  int rc = launch_sgemm<true, true, EPI_BIAS_TANH>(g, 1, stream);
+  if (rc) return rc;
+  GemmP g2{};
+  g2.A = H1; g2.B = params + L.off[W2P]; g2.C = H2; g2.bias = params + L.off[B2P];
+  g2.M = (int)rows; g2.N = H; g2.K = H;
+  g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
+  g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
+  g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
+  return launch_sgemm<true, true, EPI_BIAS_TANH>(g2, 2, stream);
+}
+
+static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const float* params, const float* X, long long rows, float* H1,
+                              float* H2, cudaStream_t stream) {
+  if (g_gemm_engine == 1 && tc_supported(d)) {
+    int rc = tc_mlp_hidden_forward(d, params, X, rows, H1, H2, nullptr, 0, stream);
+    if (rc != RLX_ERR_UNSUPPORTED) return rc;
+  }
+  return mlp_hidden_forward_simt(L, params, X, rows, H1, H2, stream);
+}
+
+#define RLX_DISPATCH_NCH(H, KERNEL, grid, block, smem, stream, arg)                                              \
+  do {                                                                                                            \
+    const int _nch = (int)ceil_div((H), 32);                                                                      \
+    if (_nch <= 2) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<2>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 4) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<4>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 8) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<8>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 16) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<16>, grid, block, smem, stream, arg); } \
+    else { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<32>, grid, block, smem, stream, arg); } \
+  } while (0)
+
+static bool head_dims_ok(const rlx_ppo_dims& d) {
+  return dims_ok(d) && d.hidden <= 1024 && head_smem_bytes(d, true) <= 200 * 1024;
+}
+
+static void fill_head_common(HeadP& h, const PpoLayout& L, const float* params, const float* H2, long long rows) {
+  h.M = (int)rows; h.H = L.H; h.act = L.act;
+  h.H2 = H2;
+  h.W3p = params + L.off[W3P]; h.W3c = params + L.off[W3C];
+  h.b3p = params + L.off[B3P]; h.b3c = params + L.off[B3C];
+  h.logstd = params + L.off[LOGSTD];
+}
+
+}  // namespace rlx
+
+using namespace rlx;
+
+// ------------------------------------------------------------------------------------------------ forward API
+extern "C" size_t rlx_ppo_forward_workspace_bytes(const rlx_ppo_dims* d, int64_t n) {
+  if (d == nullptr || !head_dims_ok(*d) || n < 0) return 0;
+  return plan_forward(*d, n).total;
+}
+
+extern "C" int rlx_ppo_forward_f32(const rlx_ppo_forward_args* a, void* stream) {
+  RLX_CHECK_ARG(a != nullptr, "args is null");
+  RLX_CHECK_ARG(head_dims_ok(a->dims), "unsupported dims (act <= 64, hidden <= 1024)");
+  RLX_CHECK_ARG(a->n >= 0 && a->n < (1LL << 31), "bad row count");
+  if (a->n == 0) return RLX_OK;
+  RLX_CHECK_ARG(a->params && a->obs, "params / obs is null");
+  RLX_CHECK_ARG(!a->env_action || !a->clip_rescale || (a->act_low && a->act_high), "action bounds required for clip_rescale");
+  const FwdPlan P = plan_forward(a->dims, a->n);
+  if (a->workspace == nullptr || a->workspace_bytes < P.total) {
+    set_error("rlx_ppo_forward_f32: workspace too small (%zu < %zu)", a->workspace_bytes, P.total);
+    return RLX_ERR_WORKSPACE;
+  }
+  const PpoLayout L = make_layout(a->dims);
+  float* H1 = ws_ptr<float>(a->workspace, P.off_H1);
+  float* H2 = ws_ptr<float>(a->workspace, P.off_H2);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = mlp_hidden_forward(a->dims, L, a->params, a->obs, a->n, H1, H2, st);
+  if (rc) return rc;
+  HeadP h{};
+  fill_head_common(h, L, a->params, H2, a->n);
+  h.noise = a->noise; h.seed = a->rng_seed; h.offset = a->rng_offset;
+  h.act_low = a->act_low; h.act_high = a->act_high;
+  h.clip_rescale = a->clip_rescale; h.deterministic = a->deterministic;
+  h.action = a->action; h.env_action = a->env_action; h.logp_out = a->logp; h.value_out = a->value;
+  const size_t smem = head_smem_bytes(a->dims, false);
+  const int grid = head_grid(a->n);
+  RLX_DISPATCH_NCH(L.H, ppo_head_rollout_kernel, grid, 256, smem, st, h);
+  return RLX_OK;
+}
+
+extern "C" int rlx_critic_forward_f32(const rlx_ppo_dims* d, const float* params, const float* obs, int64_t n, float* value,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  RLX_CHECK_ARG(d != nullptr, "dims is null");
+  rlx_ppo_forward_args a{};
+  a.dims = *d; a.n = n; a.params = params; a.obs = obs; a.deterministic = 1; a.value = value;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+  return rlx_ppo_forward_f32(&a, stream);
+}
+
+// ---------------------------------------------------------------------------------------- minibatch update API
+extern "C" size_t rlx_ppo_minibatch_workspace_bytes(const rlx_ppo_dims* d, int64_t m) {
+  if (d == nullptr || !head_dims_ok(*d) || m < 0) return 0;
+  return plan_train(*d, std::max<int64_t>(m, 1)).total;
+}
+
+static int check_mb_args(const rlx_ppo_minibatch_args* a, bool need_data) {
+  RLX_CHECK_ARG(a != nullptr, "args is null");
+  RLX_CHECK_ARG(head_dims_ok(a->dims), "unsupported dims (act <= 64, hidden <= 1024)");
+  RLX_CHECK_ARG(a->m >= 0 && a->m < (1LL << 31) && a->m_global >= 1, "bad minibatch size");
+  RLX_CHECK_ARG(a->params && a->grads, "params / grads is null");
+  if (need_data && a->m > 0) {
+    RLX_CHECK_ARG(a->states && a->actions && a->log_probs && a->advantages && a->returns && a->adv_stats, "null minibatch tensor");
+  }
+  const TrainPlan P = plan_train(a->dims, std::max<int64_t>(a->m, 1));
+  if (a->workspace == nullptr || a->workspace_bytes < P.total) {
+    set_error("rlx_ppo_minibatch: workspace too small (%zu < %zu)", a->workspace_bytes, P.total);
+    return RLX_ERR_WORKSPACE;
+  }
+  return RLX_OK;
+}
+
+extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, void* stream) {
+  int rc = check_mb_args(a, true);
+  if (rc) return rc;
+  const rlx_ppo_dims& d = a->dims;
+  const PpoLayout L = make_layout(d);
+  const long long m = a->m;
+  const int H = L.H, O = L.obs, A = L.act;
+  const TrainPlan P = plan_train(d, std::max<long long>(m, 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  void* ws = a->workspace;
+  float* H1 = ws_ptr<float>(ws, P.off_H1);
+  float* H2 = ws_ptr<float>(ws, P.off_H2);
+  float* dZ2 = ws_ptr<float>(ws, P.off_dZ2);
+  float* dZ1 = ws_ptr<float>(ws, P.off_dZ1);
+  float* dhead = ws_ptr<float>(ws, P.off_dhead);
+  float* headpart = ws_ptr<float>(ws, P.off_headpart);
+  float* part1 = ws_ptr<float>(ws, P.off_part1);
+  float* rs1 = ws_ptr<float>(ws, P.off_rs1);
+  float* part2 = ws_ptr<float>(ws, P.off_part2);
+  float* rs2 = ws_ptr<float>(ws, P.off_rs2);
+  float* part3 = ws_ptr<float>(ws, P.off_part3);
+  const float inv_mg = 1.f / (float)a->m_global;
+
+  int head_blocks = 0, wgrad_chunks = 0, s1 = 0, s2 = 0;
+  if (m > 0) {
+    // ---- forward hidden layers
+    rc = mlp_hidden_forward(d, L, a->params, a->states, m, H1, H2, st);
+    if (rc) return rc;
+    // ---- head: loss + dZ2 + dhead + block partials
+    HeadP h{};
+    fill_head_common(h, L, a->params, H2, m);
+    h.actions = a->actions; h.logp_old = a->log_probs; h.adv = a->advantages; h.ret = a->returns; h.adv_stats = a->adv_stats;
+    h.inv_mg = inv_mg; h.clip_range = a->hp.clip_range; h.critic_coef = a->hp.critic_coef;
+    h.dZ2 = dZ2; h.dhead = dhead; h.block_partials = headpart;
+    head_blocks = P.head_blocks;
+    const size_t smem = head_smem_bytes(d, true);
+    RLX_DISPATCH_NCH(H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
+    // ---- dW3 (thread per column, chunked over rows)
+    HeadWgradP w{(int)m, H, A, kHeadWgradRows, H2, dhead, part3};
+    wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
+    dim3 wg((unsigned)wgrad_chunks, (unsigned)ceil_div(2 * H, 256));
+    const size_t wsmem = (size_t)kHeadWgradRows * (A + 1) * sizeof(float);
+    if (A <= 8) {
+      RLX_LAUNCH(ppo_head_wgrad_kernel<8>, wg, 256, wsmem, st, w);
+    } else if (A <= 32) {
+      RLX_LAUNCH(ppo_head_wgrad_kernel<32>, wg, 256, wsmem, st, w);
+    } else {
+      RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+      RLX_LAUNCH(ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
+    }
+    // ---- dW2 | db2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]
+    const Splits S2 = choose_splits(m, H, H, 2);
+    s2 = S2.splits;
+    GemmP g{};
+    g.A = dZ2; g.B = H1; g.C = part2; g.rowsum = rs2;
+    g.M = H; g.N = H; g.K = (int)m;
+    g.lda = 2 * H; g.ldb = 2 * H; g.ldc = H;
+    g.sA = H; g.sB = H; g.sC = (long long)H * H; g.sRowsum = H;
+    g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H; g.sSplitRowsum = 2LL * H;
+    rc = launch_sgemm<false, false, EPI_NONE>(g, 2, st);
+    if (rc) return rc;
+    // ---- dZ1 = (dZ2 @ W2) * (1 - H1^2)   per net
+    GemmP gd{};
+    gd.A = dZ2; gd.B = a->params + L.off[W2P]; gd.C = dZ1; gd.aux = H1;
+    gd.M = (int)m; gd.N = H; gd.K = H;
+    gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
+    gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
+    gd.splits = 1; gd.kchunk = (int)(ceil_div(H, 8) * 8);
+    rc = launch_sgemm<true, false, EPI_DTANH>(gd, 2, st);
+    if (rc) return rc;
+    // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i]
+    const Splits S1 = choose_splits(m, 2 * H, O, 1);
+    s1 = S1.splits;
+    GemmP g1{};
+    g1.A = dZ1; g1.B = a->states; g1.C = part1; g1.rowsum = rs1;
+    g1.M = 2 * H; g1.N = O; g1.K = (int)m;
+    g1.lda = 2 * H; g1.ldb = O; g1.ldc = O;
+    g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O; g1.sSplitRowsum = 2LL * H;
+    rc = launch_sgemm<false, false, EPI_NONE>(g1, 1, st);
+    if (rc) return rc;
+  }
+  // ---- assemble the flat gradient (m == 0: a rank that owns no row of this minibatch contributes zeros)
+  GradReduceP r{};
+  r.g[0] = GradGroup{L.off[W1P], 2LL * H * O, part1, s1, 2LL * H * O};
+  r.g[1] = GradGroup{L.off[B1P], 2LL * H, rs1, s1, 2LL * H};
+  r.g[2] = GradGroup{L.off[W2P], 2LL * H * H, part2, s2, 2LL * H * H};
+  r.g[3] = GradGroup{L.off[B2P], 2LL * H, rs2, s2, 2LL * H};
+  r.g[4] = GradGroup{L.off[W3P], (long long)(A + 1) * H, part3, wgrad_chunks, (long long)(A + 1) * H};
+  r.g[5] = GradGroup{L.off[B3P], 2LL * A + 1, headpart, head_blocks, 2LL * A + 5};
+  r.total = L.total();
+  r.logstd_off = L.off[LOGSTD];
+  r.act = A;
+  r.entropy_grad = -a->hp.entropy_coef * (float)m * inv_mg;
+  r.grads = a->grads;
+  r.head_partials = headpart; r.nblk = head_blocks; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
+  r.logstd = a->params + L.off[LOGSTD];
+  r.metrics = a->metrics; r.m_local = (float)m;
+  RLX_LAUNCH(ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
+  return RLX_OK;
+}
+
+extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void* stream) {
+  int rc = check_mb_args(a, false);
+  if (rc) return rc;
+  RLX_CHECK_ARG(a->exp_avg && a->exp_avg_sq && a->lr && a->step_count, "optimizer state is null");
+  const PpoLayout L = make_layout(a->dims);
+  const TrainPlan P = plan_train(a->dims, std::max<int64_t>(a->m, 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamP p{};
+  p.total = L.total();
+  for (int i = 0; i <= RLX_PPO_NSEG; ++i) p.seg_off[i] = L.off[i];
+  p.critic_mask = 0;
+  for (int i = 0; i < RLX_PPO_NSEG; ++i)
+    if (seg_is_critic(i)) p.critic_mask |= (1u << i);
+  p.params = a->params; p.grads = a->grads; p.m = a->exp_avg; p.v = a->exp_avg_sq;
+  p.lr = a->lr; p.step_count = (long long*)a->step_count;
+  p.max_norm = a->hp.max_grad_norm; p.beta1 = a->hp.adam_beta1; p.beta2 = a->hp.adam_beta2; p.eps = a->hp.adam_eps;
+  p.norm_partials = ws_ptr<float>(a->workspace, P.off_norm);
+  p.nblk_norm = P.norm_blocks;
+  p.metrics = a->metrics;
+  RLX_LAUNCH(ppo_grad_sumsq_kernel, (unsigned)P.norm_blocks, 256, 0, st, p);
+  RLX_LAUNCH(ppo_clip_adam_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, p);
+  return RLX_OK;
+}
+
+extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int64_t count, int64_t mb, void* stream) {
+  RLX_CHECK_ARG(first != nullptr && count >= 0 && mb > 0, "bad arguments");
+  const int64_t nmb = ceil_div(count, mb);
+  const int O = first->dims.obs_dim, A = first->dims.act_dim;
+  for (int64_t k = 0; k < nmb; ++k) {
+    rlx_ppo_minibatch_args a = *first;
+    const int64_t r0 = k * mb;
+    a.m = std::min<int64_t>(mb, count - r0);
+    a.m_global = a.m;
+    a.states = first->states + r0 * O;
+    a.actions = first->actions + r0 * A;
+    a.log_probs = first->log_probs + r0;
+    a.advantages = first->advantages + r0;
+    a.returns = first->returns + r0;
+    a.adv_stats = first->adv_stats + 2 * k;
+    a.metrics = first->metrics ? first->metrics + RLX_PPO_NMETRIC * k : nullptr;
+    int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
+    if (rc) return rc;
+    rc = rlx_gradnorm_clip_adam_f32(&a, stream);
+    if (rc) return rc;
+  }
+  return RLX_OK;
+}
+
+extern "C" int rlx_set_gemm_engine(int engine) {
+  if (engine != 0 && engine != 1) {
+    set_error("rlx_set_gemm_engine: unknown engine %d", engine);
+    return g_gemm_engine;
+  }
+  g_gemm_engine = engine;
+  return g_gemm_engine;
+}
