@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the PPO hot path (BASELINE.json metric: env-steps/sec, PPO update included).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--epochs E] [--engine auto|simt|tcgen05]
+
+One "step" = one full PPO iteration of BASELINE config 2 per GPU: 128 rollout steps of 4096 synthetic Box(376)/Box(17)
+envs (policy+critic forward, sampling, buffer writes), bootstrap values + GAE, then nr_epochs x (B / minibatch) shuffled
+minibatch updates (gather, forward, loss, backward, two clip+Adam) — the body of the reference's `while` loop
+(rl_x/algorithms/ppo/pytorch/ppo.py:195-393), driven through the plugin class PPO._train_iteration().
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel class (the MLP GEMMs): achieved fp32-equivalent TFLOP/s from CUDA events recorded around every
+                launch of the class inside a second, instrumented timed region, vs the measured bf16 tensor peak
+  roofline_hbm  the HBM-bound kernels named by north_star (minibatch gather, GAE) against the measured copy bandwidth
+  kernel_ms     per-kernel-class device milliseconds per step from the same instrumented region
+  cpu_baseline  the CPU oracle (oracle/ppo_oracle.py, torch fp32 on all host cores) on a bounded sample of the same workload
+  e2e           same metric through PPO.train()'s loop with a NUMPY-interface env: observations/rewards in pinned HOST memory,
+                H2D every step, actions D2H every step, metrics D2H every iteration
+`--impl reference` times the CPU oracle alone (the reference's algorithm restated with the same torch primitives; the
+reference itself is Python and does not travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+C2 = dict(nr_envs=4096, nr_steps=128, obs_dim=376, act_dim=17, hidden=256, minibatch_size=32768, nr_epochs=10)
+FLOP_PER_SAMPLE_TRAIN = 1_584_128  # fwd 656 384 + bwd 927 744 per sample per epoch
+FLOP_PER_SAMPLE_ROLLOUT = 656_384
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ---------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            if not (t0 <= ts <= t1 + 0.15):
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); power.append(float(parts[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------------------------------------- GPU arm
+def build_model(args, rank, world, interface):
+    from rl_x_b200.runner.runner import Runner
+    argv = [f"--environment.nr_envs={args.envs}", f"--environment.obs_dim={C2['obs_dim']}", f"--environment.act_dim={C2['act_dim']}",
+            f"--environment.seed={1 + rank}", f"--environment.data_interface={interface}", "--environment.horizon=1000",
+            f"--environment.stream={'ring' if interface == 'numpy' else 'fresh'}",
+            f"--algorithm.nr_steps={C2['nr_steps']}", f"--algorithm.nr_epochs={args.epochs}",
+            f"--algorithm.minibatch_size={args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
+            f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15"]
+    r = Runner(argv=argv)
+    train_env, eval_env = r._create_train_and_eval_env(r._config)
+    r._config.environment.seed = 1  # identical policy init / permutation stream on every rank; env streams differ via the env seed above
+    model = r._model_class(r._config, train_env, eval_env, "/tmp/rlx_bench", None)
+    return model
+
+
+def timed_iterations(model, steps, dist):
+    """Exactly `steps` iterations between two CUDA events, barrier + synchronize on both sides."""
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        model._train_iteration()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1) / 1e3, t0, t1
+
+
+def cpu_baseline_sample(args, threads, minibatches=8, rollout_steps=8):
+    """CPU oracle on a bounded sample of config 2, composed into seconds per full iteration (see `sample` in the result)."""
+    from oracle import ppo_oracle as O
+    torch.set_num_threads(threads)
+    N, T, E, mb = args.envs, C2["nr_steps"], args.epochs, args.minibatch
+    env = O.SyntheticVecEnv(N, C2["obs_dim"], C2["act_dim"], seed=1)
+    pol, cri = O.init_params(C2["obs_dim"], C2["act_dim"], C2["hidden"], seed=1)
+    L = O.Learner(pol, cri)
+    gen = torch.Generator().manual_seed(1)
+    state = env.reset()
+    t = time.perf_counter()
+    batch, state = O.rollout(L, env, state, rollout_steps, gen)
+    t_act = (time.perf_counter() - t) / rollout_steps
+    t = time.perf_counter()
+    adv, ret = O.advantages_and_returns(L, batch, 0.99, 0.95)
+    t_adv = (time.perf_counter() - t) / rollout_steps
+    batch["advantages"], batch["returns"] = adv, ret
+    flat = O.flatten({k: v for k, v in batch.items() if k != "next_states"})
+    B = flat["states"].shape[0]
+    rng = np.random.default_rng(1)
+    idx = np.arange(B)
+    rng.shuffle(idx)
+    reps = max(1, (minibatches * mb + B - 1) // B)
+    pool = np.concatenate([np.random.default_rng(i).permutation(B) for i in range(reps)])
+    t = time.perf_counter()
+    for i in range(minibatches):
+        sel = torch.as_tensor(pool[i * mb:(i + 1) * mb] if mb <= len(pool) else np.resize(pool, mb))
+        L.minibatch_step(flat["states"][sel], flat["actions"][sel], flat["log_probs"][sel], flat["advantages"][sel], flat["returns"][sel])
+    t_mb = (time.perf_counter() - t) / minibatches
+    nmb = -(-(N * T) // mb)
+    t_iter = T * t_act + T * t_adv + E * nmb * t_mb
+    sample = (f"{rollout_steps} rollout steps + next-value/GAE over {rollout_steps} steps at {N} envs, {minibatches} minibatch updates of {mb} rows; "
+              f"composed as T*t_step + T*t_adv + E*{nmb}*t_minibatch (t_step={t_act * 1e3:.1f} ms, t_adv={t_adv * 1e3:.1f} ms, t_minibatch={t_mb * 1e3:.1f} ms)")
+    return N * T / t_iter, t_iter, sample
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, t_iter, sample = cpu_baseline_sample(args, threads, minibatches=4, rollout_steps=4)
+        if i >= args.warmup:
+            per_step.append(t_iter)
+    t = float(np.mean(per_step))
+    value = args.envs * C2["nr_steps"] / t
+    line = {"impl": "reference", "metric": "env-steps/sec (PPO update incl.)", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": f"PPO synthetic Box(obs={C2['obs_dim']}, act={C2['act_dim']}) ~Humanoid, num_envs={args.envs}/GPU, horizon={C2['nr_steps']}, "
+                        f"hidden={C2['hidden']}, nr_epochs={args.epochs}, minibatch={args.minibatch}/GPU (BASELINE.json configs[1])",
+            "num_envs_global": args.envs * world, "minibatch_size_global": args.minibatch * world, "nr_epochs": args.epochs,
+            "parallelism": f"dp{world} (env-sharded, reference-exact global permutation, 1 all-reduce per minibatch)" if world > 1 else "single GPU",
+            "l2_policy": "per-step working set (rollout buffer 0.83 GB + gathered copy 0.83 GB + activations) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--epochs", type=int, default=C2["nr_epochs"])
+    ap.add_argument("--envs", type=int, default=C2["nr_envs"], help="envs per GPU")
+    ap.add_argument("--minibatch", type=int, default=C2["minibatch_size"], help="minibatch rows per GPU")
+    ap.add_argument("--engine", default="auto")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rl_x_b200 import _native as nt
+    lib = nt.load()
+
+    model = build_model(args, rank, world, "torch")
+    model._begin_training()
+    for _ in range(args.warmup):
+        model._train_iteration()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.rlx_reset_launch_count()
+    seconds, t0, t1 = timed_iterations(model, args.steps, dist)
+    launches = int(lib.rlx_launch_count())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if dist is not None:
+        tt = torch.tensor([seconds], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        seconds = float(tt.item())
+    steps_per_iter = args.envs * world * C2["nr_steps"]
+    value = steps_per_iter * args.steps / seconds
+
+    # instrumented second region: CUDA events around every launch, per kernel class
+    nt.timing_begin()
+    for _ in range(2):
+        model._train_iteration()
+    classes = nt.timing_end()
+    kernel_ms = {k: round(v["ms"] / 2, 4) for k, v in classes.items() if v["launches"]}
+    engine = "tcgen05-3xTF32" if lib.rlx_get_gemm_engine() == 1 and getattr(model.kernels, "tc_active", False) else "simt-fp32"
+    peaks = measured_peaks()
+    gemm = {k: classes[k] for k in ("gemm_fwd", "gemm_dx", "gemm_dw")}
+    gflops, gms = sum(v["flops"] for v in gemm.values()), sum(v["ms"] for v in gemm.values())
+    achieved_tf = gflops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+    total_ms = sum(v["ms"] for v in classes.values())
+    roofline = {"bound": "tensor", "kernel": f"MLP GEMMs ({engine}): gemm_fwd + gemm_dx + gemm_dw", "achieved": achieved_tf, "peak": peaks["tflops"],
+                "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                "share_of_step": gms / total_ms if total_ms else None,
+                "note": "fp32-equivalent algorithmic FLOPs (2*M*N*K) of the exact-fp32 path against the dense bf16 tensor peak"}
+    hbm = {}
+    for name in ("gather", "gae", "clip_adam", "head_train"):
+        c = classes[name]
+        if c["launches"]:
+            gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+            hbm[name] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "bytes_per_launch": c["bytes"] / c["launches"], "us_per_launch": c["ms"] * 1e3 / c["launches"]}
+
+    line = {"metric": "env-steps/sec (PPO update incl.)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "roofline_hbm": hbm, "kernel_ms": kernel_ms, "gemm_engine": engine,
+            "train_tflops_per_step": FLOP_PER_SAMPLE_TRAIN * args.envs * C2["nr_steps"] * args.epochs / 1e12}
+
+    # end-to-end through the host-buffer path (NUMPY-interface env: pinned host observations, H2D/D2H every step)
+    if not args.no_e2e:
+        del model
+        torch.cuda.empty_cache()
+        m2 = build_model(args, rank, world, "numpy")
+        m2._begin_training()
+        for _ in range(max(1, args.warmup - 1)):
+            m2._train_iteration()
+        s2, _, _ = timed_iterations(m2, args.steps, dist)
+        if dist is not None:
+            tt = torch.tensor([s2], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            s2 = float(tt.item())
+        T, N = C2["nr_steps"], args.envs
+        h2d = T * N * (C2["obs_dim"] * 4 + 4 + 2) + args.epochs * N * T * 8 + 4
+        d2h = T * N * C2["act_dim"] * 4 + m2.metrics_host.numel() * 4 + 16
+        line["e2e"] = {"value": steps_per_iter * args.steps / s2, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "ms_per_step": s2 / args.steps * 1e3,
+                       "path": "PPO._train_iteration() with a NUMPY-interface env: obs/reward/done from pinned host buffers every env step, actions read back every env step"}
+        del m2
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, t_iter, sample = cpu_baseline_sample(args, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample, "s_per_step": t_iter}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,13 @@ int rlx_version(void);                        /* ABI version, currently 1 */
 const char* rlx_last_error_string(void);      /* thread-local, never NULL */
 uint64_t rlx_launch_count(void);              /* kernels launched by this library since load / last reset */
 void rlx_reset_launch_count(void);
+/* Optional per-kernel-class device timing (CUDA events recorded around every launch on the launching stream).
+ * rlx_timing_begin() enables it and clears the records; rlx_timing_end() synchronises the device, disables it and fills four
+ * arrays of RLX_NKCLASS entries: summed duration (ms), launch count, summed ALGORITHMIC flops and bytes of each class. */
+#define RLX_NKCLASS 13
+int rlx_timing_begin(void);
+int rlx_timing_end(double* ms, uint64_t* launches, double* flops, double* bytes);
+const char* rlx_kernel_class_name(int cls);
 /* GEMM engine used by the MLP entry points: 0 = fp32 SIMT (FFMA), 1 = tcgen05 3xTF32 (tensor cores, TMEM accumulators).
  * Returns the engine actually in effect (a request for 1 falls back to 0 with an error string if the shape is unsupported). */
 int rlx_set_gemm_engine(int engine);

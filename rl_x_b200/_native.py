@@ -87,6 +87,9 @@ _SIGNATURES = {
     "rlx_last_error_string": (C.c_char_p, []),
     "rlx_launch_count": (C.c_uint64, []),
     "rlx_reset_launch_count": (None, []),
+    "rlx_timing_begin": (C.c_int, []),
+    "rlx_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rlx_kernel_class_name": (C.c_char_p, [C.c_int]),
     "rlx_set_gemm_engine": (C.c_int, [C.c_int]),
     "rlx_get_gemm_engine": (C.c_int, []),
     "rlx_pcg64_seed": (C.c_int, [C.c_uint64, C.POINTER(Pcg64)]),
@@ -162,6 +165,22 @@ def last_error():
 def check(rc, what=""):
     if rc != 0:
         raise RuntimeError(f"rl_x_b200 native call failed ({what}, code {rc}): {last_error()}")
+
+
+RLX_NKCLASS = 13
+
+
+def timing_begin():
+    check(load().rlx_timing_begin(), "rlx_timing_begin")
+
+
+def timing_end():
+    """{class name: dict(ms, launches, flops, bytes)} of everything launched since timing_begin()."""
+    lib = load()
+    ms, fl, by = (C.c_double * RLX_NKCLASS)(), (C.c_double * RLX_NKCLASS)(), (C.c_double * RLX_NKCLASS)()
+    n = (C.c_uint64 * RLX_NKCLASS)()
+    check(lib.rlx_timing_end(ms, n, fl, by), "rlx_timing_end")
+    return {lib.rlx_kernel_class_name(i).decode(): dict(ms=ms[i], launches=int(n[i]), flops=fl[i], bytes=by[i]) for i in range(RLX_NKCLASS)}
 
 
 def ptr(t):

@@ -1,0 +1,675 @@
+"""PPO with the reference's plugin surface (rl_x/algorithms/ppo/pytorch/ppo.py), executed by hand-written sm_100a kernels.
+
+Same constructor / train / test / save / load / general_properties contract and the same metric names as the reference
+class `PPO` (ppo.py:22-486).  What differs is where the work happens:
+
+  reference (ppo.py)                                   this build
+  ---------------------------------------------------  -------------------------------------------------------------
+  acting: 2 compiled modules + ~10 kernels + .item()   1 native call per step (3 kernels) + 1 store kernel, no host sync
+          per step (:203-246)
+  next_values: critic over all next_states (:253-254)  TORCH envs: one critic pass over the last next_state
+  GAE: TorchScript loop over T (:110-118)              1 kernel, bit-exact
+  shuffle: numpy Generator.shuffle on host (:276)      same PCG64 stream restated in C (bit-exact), overlapped with GPU work
+  6 index-gathers + 7 .item() per minibatch (:283-294) 1 gather per epoch; whole epoch launched from C; 1 metrics D2H/iteration
+  autograd + clip_grad_norm_ + Adam (:121-166)         fused GEMM / loss / clip+Adam kernels on one flat parameter buffer
+  single device                                        env-sharded data parallel, one NCCL all-reduce per minibatch
+
+There is no CPU path: a missing CUDA device or native library raises.
+"""
+import logging
+import os
+import time
+from collections import deque
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from rl_x_b200 import _native as nt
+from rl_x_b200.algorithms.ppo.b200.batch import Batch
+from rl_x_b200.algorithms.ppo.b200.general_properties import GeneralProperties
+from rl_x_b200.algorithms.ppo.b200.kernels import PpoKernels, make_hparams
+from rl_x_b200.algorithms.ppo.b200 import sharding
+from rl_x_b200.environments.types import DataInterfaceType, same_member
+
+rlx_logger = logging.getLogger("rl_x")
+
+
+def init_reference_parameters(obs_dim, act_dim, hidden, std_dev, seed):
+    """Initial weights bit-identical to the reference for the same seed: torch.manual_seed(seed) (ppo.py:73), then the
+    policy's three nn.Linear layers (constructor init followed by orthogonal_/constant_, policy.py:45-58) and the critic's
+    (critic.py:29-41), created on the CPU in that order.  Returns {reference state_dict key: tensor}."""
+    torch.manual_seed(seed)
+
+    def layer(i, o, std):
+        lin = nn.Linear(i, o)
+        nn.init.orthogonal_(lin.weight, std)
+        nn.init.constant_(lin.bias, 0.0)
+        return lin
+
+    out = {}
+    pol = [layer(obs_dim, hidden, np.sqrt(2)), layer(hidden, hidden, np.sqrt(2)), layer(hidden, act_dim, 0.01)]
+    for idx, lin in zip((0, 2, 4), pol):
+        out[f"policy_mean.{idx}.weight"], out[f"policy_mean.{idx}.bias"] = lin.weight.detach().clone(), lin.bias.detach().clone()
+    out["policy_logstd"] = torch.full((1, act_dim), np.log(std_dev).item())
+    cri = [layer(obs_dim, hidden, np.sqrt(2)), layer(hidden, hidden, np.sqrt(2)), layer(hidden, 1, 1.0)]
+    for idx, lin in zip((0, 2, 4), cri):
+        out[f"critic.{idx}.weight"], out[f"critic.{idx}.bias"] = lin.weight.detach().clone(), lin.bias.detach().clone()
+    return out
+
+
+class FlatParameters:
+    """One flat fp32 device buffer for policy + critic (layout: include/rlx_b200.h), with named views that carry the
+    reference's state_dict keys so checkpoints interoperate (ppo.py:426-451)."""
+
+    def __init__(self, kernels, device):
+        self.k = kernels
+        self.flat = torch.zeros(kernels.param_count, dtype=torch.float32, device=device)
+        self.shapes = nt.segment_shapes(kernels.obs_dim, kernels.act_dim, kernels.hidden)
+
+    def view(self, flat, seg):
+        i = nt.SEGMENT_NAMES.index(seg)
+        return flat[self.k.offsets[i]:self.k.offsets[i + 1]].view(self.shapes[seg])
+
+    def load_named(self, named, flat=None):
+        flat = self.flat if flat is None else flat
+        for keys in (nt.POLICY_KEYS, nt.CRITIC_KEYS):
+            for key, seg in keys.items():
+                src = named[key] if key in named else named["_orig_mod." + key]  # torch.compile'd reference modules prefix keys
+                self.view(flat, seg).copy_(torch.as_tensor(src, dtype=torch.float32).reshape(self.shapes[seg]))
+
+    def state_dicts(self, flat=None):
+        flat = self.flat if flat is None else flat
+        pol = {key: self.view(flat, seg).detach().cpu().clone() for key, seg in nt.POLICY_KEYS.items()}
+        cri = {key: self.view(flat, seg).detach().cpu().clone() for key, seg in nt.CRITIC_KEYS.items()}
+        return pol, cri
+
+
+class PPO:
+    def __init__(self, config, train_env, eval_env, run_path, writer):
+        self.config = config
+        self.train_env = train_env
+        self.eval_env = eval_env
+        self.writer = writer
+
+        self.save_model = config.runner.save_model
+        self.save_path = os.path.join(run_path, "models")
+        self.track_console = config.runner.track_console
+        self.track_tb = config.runner.track_tb
+        self.track_wandb = config.runner.track_wandb
+        self.seed = config.environment.seed
+        self.total_timesteps = config.algorithm.total_timesteps
+        self.nr_envs = config.environment.nr_envs
+        self.learning_rate = config.algorithm.learning_rate
+        self.anneal_learning_rate = config.algorithm.anneal_learning_rate
+        self.nr_steps = config.algorithm.nr_steps
+        self.nr_epochs = config.algorithm.nr_epochs
+        self.minibatch_size = config.algorithm.minibatch_size
+        self.gamma = config.algorithm.gamma
+        self.gae_lambda = config.algorithm.gae_lambda
+        self.clip_range = config.algorithm.clip_range
+        self.entropy_coef = config.algorithm.entropy_coef
+        self.critic_coef = config.algorithm.critic_coef
+        self.max_grad_norm = config.algorithm.max_grad_norm
+        self.std_dev = config.algorithm.std_dev
+        self.action_clipping_and_rescaling = config.algorithm.action_clipping_and_rescaling
+        self.nr_hidden_units = config.algorithm.nr_hidden_units
+        self.evaluation_frequency = config.algorithm.evaluation_frequency
+        self.evaluation_episodes = config.algorithm.evaluation_episodes
+
+        # ---- data-parallel topology: one process per GPU, envs sharded over ranks (SURVEY §8 e)
+        import torch.distributed as dist
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world_size = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.global_nr_envs = self.nr_envs * self.world_size
+        self.batch_size = self.global_nr_envs * self.nr_steps          # global batch (ppo.py:54)
+        self.local_batch_size = self.nr_envs * self.nr_steps
+        self.nr_minibatches = self.batch_size // self.minibatch_size   # ppo.py:55
+        self.exact_global_permutation = bool(config.algorithm.get("exact_global_permutation", True))
+
+        if self.evaluation_frequency % (self.nr_steps * self.nr_envs) != 0 and self.evaluation_frequency != -1:
+            raise ValueError("Evaluation frequency must be a multiple of the number of steps and environments.")
+        if config.algorithm.get("bf16_mixed_precision_training", False):
+            raise ValueError("rl_x_b200 PPO implements the reference's fp32 path; set algorithm.bf16_mixed_precision_training=False.")
+        if config.algorithm.device != "gpu" or not torch.cuda.is_available():
+            raise RuntimeError("rl_x_b200 PPO needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        rlx_logger.info(f"Using device: {self.device}")
+
+        self.rng = nt.Pcg64Generator(self.seed)  # np.random.default_rng(self.seed), ppo.py:72
+
+        self.os_shape = self.train_env.single_observation_space.shape
+        self.as_shape = self.train_env.single_action_space.shape
+        if len(self.os_shape) != 1 or len(self.as_shape) != 1:
+            raise ValueError("rl_x_b200 PPO supports flat observations and flat continuous actions only.")
+        obs_dim, act_dim = int(self.os_shape[0]), int(self.as_shape[0])
+        for attr in ("policy_observation_indices", "critic_observation_indices"):
+            ind = getattr(self.train_env, attr, None)
+            if ind is not None and not np.array_equal(np.asarray(ind), np.arange(obs_dim)):
+                raise ValueError(f"rl_x_b200 PPO does not implement a non-identity {attr} (policy.py:14, critic.py:10).")
+
+        self.kernels = PpoKernels(obs_dim, act_dim, self.nr_hidden_units)
+        engine = config.algorithm.get("gemm_engine", "auto")
+        lib = self.kernels.lib
+        lib.rlx_set_gemm_engine({"simt": 0, "tcgen05": 1, "auto": 1}[engine])
+        self.params = FlatParameters(self.kernels, self.device)
+        self.params.load_named(init_reference_parameters(obs_dim, act_dim, self.nr_hidden_units, self.std_dev, self.seed))
+        P = self.kernels.param_count
+        self.exp_avg = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(P, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(P + nt.RLX_PPO_NMETRIC, dtype=torch.float32, device=self.device)  # metrics ride in the tail (one all-reduce)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.lr_dev = torch.full((1,), float(self.learning_rate), dtype=torch.float32, device=self.device)
+        self.lr_iteration = 0
+        self.hp = make_hparams(self.clip_range, self.entropy_coef, self.critic_coef, self.max_grad_norm)
+
+        low = np.asarray(torch.as_tensor(self.train_env.single_action_space.low).cpu(), dtype=np.float32).reshape(-1)
+        high = np.asarray(torch.as_tensor(self.train_env.single_action_space.high).cpu(), dtype=np.float32).reshape(-1)
+        self.env_as_low = torch.from_numpy(np.broadcast_to(low, (act_dim,)).copy()).to(self.device)
+        self.env_as_high = torch.from_numpy(np.broadcast_to(high, (act_dim,)).copy()).to(self.device)
+
+        self.is_torch_data_interface = same_member(self.train_env.general_properties.data_interface_type, DataInterfaceType.TORCH)
+        self.rollout_noise = config.algorithm.get("rollout_noise", "philox")
+        self.noise_seed = (int(self.seed) * 0x9E3779B1 + 0x7F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF
+        self.noise_offset = 0
+
+        if self.save_model:
+            os.makedirs(self.save_path)
+            self.best_mean_return = -np.inf
+        self._alloc_done = False
+
+    # ------------------------------------------------------------------------------------------------ buffers
+    def _allocate(self):
+        if self._alloc_done:
+            return
+        dev, T, N = self.device, self.nr_steps, self.nr_envs
+        obs, act = self.kernels.obs_dim, self.kernels.act_dim
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        self.batch = Batch(
+            states=z(T + 1, N, obs),
+            next_states=None if self.is_torch_data_interface else z(T, N, obs),
+            actions=z(T, N, act), rewards=z(T, N), values=z(T, N), terminations=z(T, N), log_probs=z(T, N),
+            advantages=z(T, N), returns=z(T, N),
+        )
+        self.env_action = z(N, act)
+        self.last_value = z(N)
+        self.next_values = None if self.is_torch_data_interface else z(T, N)
+        self.done_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        Bl = self.local_batch_size
+        self.g_states, self.g_actions = z(Bl, obs), z(Bl, act)
+        self.g_log_probs, self.g_advantages, self.g_returns = z(Bl), z(Bl), z(Bl)
+        self.perm_dev = torch.zeros(Bl, dtype=torch.int64, device=dev)
+        self.perm_host = torch.zeros(self.nr_epochs, Bl, dtype=torch.int64).pin_memory()
+        self.nmb_epoch = -(-self.batch_size // self.minibatch_size)  # ceil: a short last minibatch is processed (ppo.py:277-279)
+        self.adv_stats = z(self.nmb_epoch, 2)
+        self.metrics_dev = z(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC)
+        self.metrics_host = torch.zeros(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC).pin_memory()
+        self.ev_dev = z(4)
+        self.fwd_ws = self.kernels.forward_workspace(max(N, 1) if self.is_torch_data_interface else T * N, dev)
+        mb_rows = min(self.minibatch_size, self.batch_size)
+        if self.world_size > 1:
+            mb_rows = min(mb_rows, Bl)  # a rank can own at most all of its rows in one minibatch
+        self.train_ws = self.kernels.minibatch_workspace(mb_rows, dev)
+        self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        if not self.is_torch_data_interface:
+            self.h_action = torch.zeros(N, act).pin_memory()
+            self.h_obs = torch.zeros(N, obs).pin_memory()
+            self.h_final = torch.zeros(N, obs).pin_memory()
+            self.h_reward = torch.zeros(N).pin_memory()
+            self.h_term = torch.zeros(N, dtype=torch.bool).pin_memory()
+            self.h_trunc = torch.zeros(N, dtype=torch.bool).pin_memory()
+            self.d_reward = z(N)
+            self.d_term = torch.zeros(N, dtype=torch.bool, device=dev)
+            self.d_trunc = torch.zeros(N, dtype=torch.bool, device=dev)
+            self.d_obs = z(N, obs)
+        self.noise_buf = z(N, act) if self.rollout_noise == "torch" else None
+        self._alloc_done = True
+
+    # ------------------------------------------------------------------------------------------------- acting
+    def _policy_step(self, state, step):
+        """ref: policy.get_action_logprob + critic.get_value + buffer writes of action/value/log_prob (ppo.py:207-209,233,238,243)."""
+        b = self.batch
+        noise = self._draw_noise(step)
+        self.kernels.forward(self.params.flat, state, self.fwd_ws, noise=noise, rng_seed=self.noise_seed, rng_offset=self.noise_offset,
+                             act_low=self.env_as_low, act_high=self.env_as_high, clip_rescale=self.action_clipping_and_rescaling,
+                             action=b.actions[step], env_action=self.env_action, logp=b.log_probs[step], value=b.values[step])
+        self.noise_offset += 1
+
+    def _draw_noise(self, step):
+        """Standard-normal draws for Normal.sample() (policy.py:66).  None = in-kernel Philox stream; `rollout_noise=torch`
+        injects torch.randn draws; tests override this hook to teacher-force the reference's samples."""
+        if self.noise_buf is not None:
+            return self.noise_buf.normal_()
+        return None
+
+    def _to_device_obs(self, obs_np, dst):
+        self.h_obs.copy_(torch.from_numpy(np.ascontiguousarray(obs_np, dtype=np.float32)))
+        dst.copy_(self.h_obs, non_blocking=True)
+
+    def _collect_rollout(self, state_is_in_slot0):
+        """ref: the acting loop, ppo.py:203-246."""
+        b, env, T = self.batch, self.train_env, self.nr_steps
+        step_info_collection = {}
+        saving_returns = []
+        dones_host = 0
+        self.done_count.zero_()
+        for step in range(T):
+            state = b.states[step]
+            self._policy_step(state, step)
+            if self.is_torch_data_interface:
+                next_state, reward, terminated, truncated, info = env.step(self.env_action)
+                if reward.dtype != torch.float32:
+                    reward = reward.float()
+                terminated = terminated if terminated.dtype == torch.bool else terminated.bool()
+                truncated = truncated if truncated.dtype == torch.bool else truncated.bool()
+                self.kernels.rollout_store(reward.contiguous(), terminated.contiguous(), truncated.contiguous(), next_state.contiguous(),
+                                           b.rewards[step], b.terminations[step], b.states[step + 1], self.done_count)
+            else:
+                self.h_action.copy_(self.env_action, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                next_state, reward, terminated, truncated, info = env.step(self.h_action.numpy())
+                done = np.logical_or(terminated, truncated)
+                self._to_device_obs(next_state, b.states[step + 1])
+                self.h_reward.copy_(torch.from_numpy(np.asarray(reward, dtype=np.float32)))
+                self.h_term.copy_(torch.from_numpy(np.asarray(terminated, dtype=bool)))
+                self.h_trunc.copy_(torch.from_numpy(np.asarray(truncated, dtype=bool)))
+                self.d_reward.copy_(self.h_reward, non_blocking=True)
+                self.d_term.copy_(self.h_term, non_blocking=True)
+                self.d_trunc.copy_(self.h_trunc, non_blocking=True)
+                # next_states[step] = next_state with final observations patched in for finished episodes (ppo.py:217-223)
+                self.kernels.rollout_store(self.d_reward, self.d_term, self.d_trunc, b.states[step + 1], b.rewards[step],
+                                           b.terminations[step], b.next_states[step], None)
+                if done.any():
+                    idx = np.nonzero(done)[0]
+                    finals = np.stack([np.asarray(env.get_final_observation_at_index(info, int(i)), dtype=np.float32) for i in idx])
+                    b.next_states[step][torch.from_numpy(idx).to(self.device)] = torch.from_numpy(finals).to(self.device)
+                    for i in idx:
+                        saving_returns.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
+                    dones_host += len(idx)
+                torch.cuda.current_stream().synchronize()  # pinned staging buffers are reused next step
+            for key, info_value in env.get_logging_info_dict(info).items():
+                step_info_collection.setdefault(key, []).extend(info_value)
+        return step_info_collection, saving_returns, dones_host
+
+    # ------------------------------------------------------------------------------------ advantages / returns
+    def _compute_advantages(self):
+        """ref: ppo.py:253-258."""
+        b, k = self.batch, self.kernels
+        if self.is_torch_data_interface:
+            k.critic_forward(self.params.flat, b.states[self.nr_steps], self.last_value, self.fwd_ws)
+            k.gae(b.rewards, b.terminations, b.values, self.gamma, self.gae_lambda, b.advantages, b.returns, last_value=self.last_value)
+        else:
+            k.critic_forward(self.params.flat, b.next_states.view(-1, k.obs_dim), self.next_values.view(-1), self.fwd_ws)
+            k.gae(b.rewards, b.terminations, b.values, self.gamma, self.gae_lambda, b.advantages, b.returns, next_values=self.next_values)
+
+    # ---------------------------------------------------------------------------------------------- optimising
+    def _first_minibatch_args(self, metrics_row0):
+        return self.kernels.minibatch_args(
+            m=0, m_global=1, states=self.g_states, actions=self.g_actions, log_probs=self.g_log_probs, advantages=self.g_advantages,
+            returns=self.g_returns, adv_stats=self.adv_stats, params=self.params.flat, grads=self.grads, exp_avg=self.exp_avg,
+            exp_avg_sq=self.exp_avg_sq, lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=metrics_row0, workspace=self.train_ws)
+
+    def _optimize(self):
+        """ref: ppo.py:265-294 (epochs x shuffled minibatches)."""
+        b, k = self.batch, self.kernels
+        T, N, obs, act = self.nr_steps, self.nr_envs, k.obs_dim, k.act_dim
+        flat_states = b.states[:T].view(T * N, obs)
+        flat_actions = b.actions.view(T * N, act)
+        lp, adv, ret = b.log_probs.view(-1), b.advantages.view(-1), b.returns.view(-1)
+        batch_indices = np.arange(self.batch_size)  # int64, re-created every iteration (ppo.py:273)
+        mbs = self.minibatch_size
+        for epoch in range(self.nr_epochs):
+            self.rng.shuffle(batch_indices)
+            row0 = epoch * self.nmb_epoch
+            if self.world_size == 1:
+                self.perm_host[epoch].copy_(torch.from_numpy(batch_indices))
+                self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
+                k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
+                         self.g_advantages, self.g_returns)
+                k.advantage_stats(self.g_advantages, self.batch_size, mbs, self.adv_stats)
+                k.update_epoch(self._first_minibatch_args(self.metrics_dev[row0]), self.batch_size, mbs)
+            else:
+                self._optimize_epoch_sharded(batch_indices, epoch, flat_states, flat_actions, lp, adv, ret)
+
+    def _optimize_epoch_sharded(self, batch_indices, epoch, flat_states, flat_actions, lp, adv, ret):
+        """Reference-exact data parallelism: every rank walks the same global permutation, computes the gradient SUM over the
+        rows it owns, one all-reduce(sum) per minibatch makes the full-minibatch gradient (divided by the global minibatch
+        size inside the kernels), then every rank applies the identical clip+Adam step (SURVEY §8 e)."""
+        k, dist = self.kernels, self.dist
+        mbs, row0 = self.minibatch_size, epoch * self.nmb_epoch
+        local_idx, counts = sharding.local_rows_of_permutation(batch_indices, mbs, self.global_nr_envs, self.nr_envs, self.rank)
+        self.perm_host[epoch][:local_idx.shape[0]].copy_(torch.from_numpy(local_idx))
+        self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
+        k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
+                 self.g_advantages, self.g_returns, count=local_idx.shape[0])
+        offsets = np.concatenate([[0], np.cumsum(counts)])
+        global_counts = sharding.global_minibatch_sizes(self.batch_size, mbs)
+        # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
+        seg = torch.from_numpy(np.repeat(np.arange(len(counts)), counts)).to(self.device)
+        gc = torch.from_numpy(global_counts.astype(np.float32)).to(self.device)
+        sums = torch.zeros(len(counts), dtype=torch.float32, device=self.device).index_add_(0, seg, self.g_advantages[:offsets[-1]])
+        dist.all_reduce(sums)
+        mean = sums / gc
+        dev2 = (self.g_advantages[:offsets[-1]] - mean[seg]) ** 2
+        ssq = torch.zeros(len(counts), dtype=torch.float32, device=self.device).index_add_(0, seg, dev2)
+        dist.all_reduce(ssq)
+        self.adv_stats[:, 0] = mean
+        self.adv_stats[:, 1] = torch.sqrt(ssq / (gc - 1.0))
+        P = k.param_count
+        for i in range(len(counts)):
+            a = self.kernels.minibatch_args(
+                m=int(counts[i]), m_global=int(global_counts[i]), states=self.g_states[offsets[i]:], actions=self.g_actions[offsets[i]:],
+                log_probs=self.g_log_probs[offsets[i]:], advantages=self.g_advantages[offsets[i]:], returns=self.g_returns[offsets[i]:],
+                adv_stats=self.adv_stats[i], params=self.params.flat, grads=self.grads, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
+                lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=self.grads[P:], workspace=self.train_ws)
+            k.fwdbwd(a)
+            dist.all_reduce(self.grads)          # gradient + metric sums, 1.32 MB over NVLink
+            k.clip_adam(a)                       # writes the two grad norms into grads[P+5..P+6]
+            self.metrics_dev[row0 + i].copy_(self.grads[P:])
+
+    def _explained_variance(self):
+        """ref: ppo.py:298-300, computed on the device instead of on the host."""
+        b = self.batch
+        y_true, y_pred = b.returns.view(-1), b.values.view(-1)
+        if self.world_size == 1:
+            var_y = torch.var(y_true, unbiased=False)
+            ev = 1.0 - torch.var(y_true - y_pred, unbiased=False) / var_y
+            return var_y, ev
+        n = torch.tensor([float(self.batch_size)], device=self.device)
+        s = torch.stack([y_true.sum(), (y_true - y_pred).sum()])
+        self.dist.all_reduce(s)
+        m = s / n
+        q = torch.stack([((y_true - m[0]) ** 2).sum(), ((y_true - y_pred - m[1]) ** 2).sum()])
+        self.dist.all_reduce(q)
+        return q[0] / n[0], 1.0 - q[1] / q[0]
+
+    def _set_learning_rate(self, lr):
+        self.lr_host[0] = lr
+        self.lr_dev.copy_(self.lr_host, non_blocking=True)
+
+    def current_learning_rate(self):
+        if not self.anneal_learning_rate:
+            return self.learning_rate
+        total_iters = int(self.total_timesteps // self.batch_size)  # LinearLR(1 -> 0, total_iters), ppo.py:87-88
+        return self.learning_rate * (1.0 - min(self.lr_iteration, total_iters) / max(total_iters, 1))
+
+    # ---------------------------------------------------------------------------------------------------- train
+    def train(self):
+        self._begin_training()
+        while self.global_step < self.total_timesteps:
+            self._train_iteration()
+
+    def _begin_training(self):
+        """Everything PPO.train() does before its while loop (ppo.py:169-193)."""
+        self._allocate()
+        b, k = self.batch, self.kernels
+        self.set_train_mode()
+        self.saving_return_buffer = deque(maxlen=100 * self.nr_envs)
+        state, _ = self.train_env.reset()
+        if self.is_torch_data_interface:
+            k.rollout_store(None, None, None, state.float().contiguous(), None, None, b.states[0], None)
+        else:
+            self._to_device_obs(state, b.states[0])
+        self.global_step = 0
+        self.nr_updates = 0
+        self.nr_episodes = 0
+        self.prev_saving_end_time = None
+        self.logging_time_prev = None
+        self.iteration_times = []
+
+    def _train_iteration(self):
+        """One pass of the reference's while-loop body (ppo.py:195-393): acting, advantages, optimising, eval, save, log."""
+        b, k = self.batch, self.kernels
+        start_time = time.time()
+        time_metrics = {}
+        steps_metrics = {}
+        if self.logging_time_prev:
+            time_metrics["time/logging_time_prev"] = self.logging_time_prev
+
+        # Acting
+        if self.global_step > 0:  # the observation after the last step of the previous rollout is the first state of this one
+            k.rollout_store(None, None, None, b.states[self.nr_steps], None, None, b.states[0], None)
+        step_info_collection, saving_returns, dones_host = self._collect_rollout(True)
+        self.saving_return_buffer.extend(saving_returns)
+        self.global_step += self.nr_steps * self.global_nr_envs
+        global_step = self.global_step
+        acting_end_time = time.time()
+        time_metrics["time/acting_time"] = acting_end_time - start_time
+
+        # Calculating advantages and returns
+        self._compute_advantages()
+        calc_adv_return_end_time = time.time()
+        time_metrics["time/calc_adv_and_return_time"] = calc_adv_return_end_time - acting_end_time
+
+        # Optimizing
+        self._set_learning_rate(self.current_learning_rate())
+        self._optimize()
+        var_y, ev = self._explained_variance()
+        ev_pair = torch.stack([var_y, ev])
+        lr_used = self.current_learning_rate()
+        if self.anneal_learning_rate:
+            self.lr_iteration += 1  # policy_scheduler.step(); critic_scheduler.step()  (ppo.py:302-304)
+
+        # the only device->host transfers of the iteration: per-minibatch metric records, explained variance, done count
+        self.metrics_host.copy_(self.metrics_dev, non_blocking=True)
+        ev_host = ev_pair.cpu()
+        dones_this_rollout = dones_host if not self.is_torch_data_interface else int(self.done_count.item())
+        if self.dist:
+            t = torch.tensor([dones_this_rollout], device=self.device)
+            self.dist.all_reduce(t)
+            dones_this_rollout = int(t.item())
+        self.nr_episodes += dones_this_rollout
+        m = self.metrics_host.numpy()
+        optimization_metrics = {
+            "loss/policy_gradient_loss": m[:, 0].mean(),
+            "loss/critic_loss": m[:, 1].mean(),
+            "loss/entropy_loss": m[:, 2].mean(),
+            "policy_ratio/clip_fraction": m[:, 4].mean(),
+            "gradients/policy_grad_norm": m[:, 5].mean(),
+            "gradients/critic_grad_norm": m[:, 6].mean(),
+        }
+        # the reference logs get_last_lr() AFTER scheduler.step() (ppo.py:302-307)
+        optimization_metrics["lr/learning_rate"] = self.current_learning_rate()
+        optimization_metrics["v_value/explained_variance"] = np.nan if float(ev_host[0]) == 0 else float(ev_host[1])
+        optimization_metrics["policy_ratio/approx_kl"] = m[-self.nmb_epoch:, 3].mean()  # last epoch only (approx_kl_divs reset at ppo.py:275)
+        optimization_metrics["policy/std_dev"] = float(np.mean(np.exp(self.params.view(self.params.flat, "logstd").cpu().numpy())))
+        self.nr_updates += self.nr_epochs * self.nr_minibatches
+
+        optimizing_end_time = time.time()
+        time_metrics["time/optimizing_time"] = optimizing_end_time - calc_adv_return_end_time
+
+        # Evaluating
+        evaluation_metrics = {}
+        if global_step % self.evaluation_frequency == 0 and self.evaluation_frequency != -1:
+            evaluation_metrics = self._evaluate()
+        evaluating_end_time = time.time()
+        time_metrics["time/evaluating_time"] = evaluating_end_time - optimizing_end_time
+
+        # Saving (only when episodes finished this update, ppo.py:353-357)
+        if self.save_model and dones_this_rollout > 0 and len(self.saving_return_buffer) > 0 and self.rank == 0:
+            mean_return = np.mean(self.saving_return_buffer)
+            if mean_return > self.best_mean_return:
+                self.best_mean_return = mean_return
+                self.save()
+
+        saving_end_time = time.time()
+        if self.prev_saving_end_time:
+            time_metrics["time/sps"] = int((self.nr_steps * self.global_nr_envs) / (saving_end_time - self.prev_saving_end_time))
+            self.iteration_times.append(saving_end_time - self.prev_saving_end_time)
+        self.prev_saving_end_time = saving_end_time
+        time_metrics["time/saving_time"] = saving_end_time - evaluating_end_time
+
+        # Logging
+        self.start_logging(global_step)
+        steps_metrics["steps/nr_env_steps"] = global_step
+        steps_metrics["steps/nr_updates"] = self.nr_updates
+        steps_metrics["steps/nr_episodes"] = self.nr_episodes
+
+        rollout_info_metrics = {}
+        env_info_metrics = {}
+        for info_name, values in step_info_collection.items():
+            metric_group = "rollout" if info_name in ["episode_return", "episode_length"] else "env_info"
+            metric_dict = rollout_info_metrics if metric_group == "rollout" else env_info_metrics
+            mean_value = np.mean(values)
+            if mean_value == mean_value:
+                metric_dict[f"{metric_group}/{info_name}"] = mean_value
+        evaluation_metrics = {key: np.mean(value) for key, value in evaluation_metrics.items()}
+        combined_metrics = {**rollout_info_metrics, **evaluation_metrics, **env_info_metrics, **steps_metrics, **time_metrics, **optimization_metrics}
+        for key, value in combined_metrics.items():
+            self.log(f"{key}", value, global_step)
+        self.end_logging()
+        logging_end_time = time.time()
+        self.logging_time_prev = logging_end_time - saving_end_time
+
+    # ------------------------------------------------------------------------------------------ eval / test
+    def _deterministic_action(self, state):
+        """ref: policy.get_deterministic_action (policy.py:85-93)."""
+        self.kernels.forward(self.params.flat, state, self._eval_ws(state.shape[0]), act_low=self.env_as_low, act_high=self.env_as_high,
+                             clip_rescale=self.action_clipping_and_rescaling, deterministic=True, env_action=self._eval_action(state.shape[0]))
+        return self._eval_action(state.shape[0])
+
+    def _eval_ws(self, n):
+        if getattr(self, "_eval_ws_buf", None) is None or self._eval_ws_n < n:
+            self._eval_ws_buf, self._eval_ws_n = self.kernels.forward_workspace(n, self.device), n
+            self._eval_action_buf = torch.zeros(n, self.kernels.act_dim, dtype=torch.float32, device=self.device)
+        return self._eval_ws_buf
+
+    def _eval_action(self, n):
+        return self._eval_action_buf[:n]
+
+    def _obs_to_device(self, state):
+        if torch.is_tensor(state):
+            return state.to(self.device, torch.float32).contiguous()
+        return torch.tensor(np.asarray(state), dtype=torch.float32).to(self.device)
+
+    def _evaluate(self):
+        """ref: ppo.py:319-345."""
+        self.set_eval_mode()
+        eval_state, _ = self.eval_env.reset()
+        eval_nr_episodes = 0
+        evaluation_metrics = {"eval/episode_return": [], "eval/episode_length": []}
+        while True:
+            action = self._deterministic_action(self._obs_to_device(eval_state))
+            if not self.is_torch_data_interface:
+                action = action.cpu().numpy()
+            eval_state, eval_reward, eval_terminated, eval_truncated, eval_info = self.eval_env.step(action)
+            eval_done = eval_terminated | eval_truncated
+            for i, single_done in enumerate(eval_done):
+                if single_done:
+                    eval_nr_episodes += 1
+                    evaluation_metrics["eval/episode_return"].append(self.eval_env.get_final_info_value_at_index(eval_info, "episode_return", i))
+                    evaluation_metrics["eval/episode_length"].append(self.eval_env.get_final_info_value_at_index(eval_info, "episode_length", i))
+                    if eval_nr_episodes == self.evaluation_episodes:
+                        break
+            if eval_nr_episodes == self.evaluation_episodes:
+                break
+        self.set_train_mode()
+        return evaluation_metrics
+
+    def test(self, episodes):
+        """ref: ppo.py:454-472."""
+        self.set_eval_mode()
+        for i in range(episodes):
+            done = False
+            episode_return = 0
+            state, _ = self.eval_env.reset()
+            while not done:
+                processed_action = self._deterministic_action(self._obs_to_device(state))
+                if not self.is_torch_data_interface:
+                    processed_action = processed_action.cpu().numpy()
+                state, reward, terminated, truncated, info = self.eval_env.step(processed_action)
+                done = terminated | truncated
+                done = bool(done.any()) if hasattr(done, "any") else bool(done)
+                episode_return += reward
+            rlx_logger.info(f"Episode {i + 1} - Return: {episode_return}")
+
+    # --------------------------------------------------------------------------------------------- logging
+    def log(self, name, value, step):
+        if self.rank != 0:
+            return
+        if self.track_wandb:
+            self.wandb_log_cache[name] = value
+        if self.track_tb:
+            self.writer.add_scalar(name, value, step)
+        if self.track_console:
+            self.log_console(name, value)
+
+    def log_console(self, name, value):
+        value = np.format_float_positional(value, trim="-")
+        rlx_logger.info(f"│ {name.ljust(30)}│ {str(value).ljust(14)[:14]} │")
+
+    def start_logging(self, step):
+        if self.rank != 0:
+            return
+        if self.track_wandb:
+            self.wandb_log_cache = {"global_step": int(step)}
+        if self.track_console:
+            rlx_logger.info("┌" + "─" * 31 + "┬" + "─" * 16 + "┐")
+        else:
+            rlx_logger.info(f"Step: {step}")
+
+    def end_logging(self, wandb_commit=True):
+        if self.rank != 0:
+            return
+        if self.track_wandb:
+            import wandb
+            wandb.log(self.wandb_log_cache, commit=wandb_commit)
+        if self.track_console:
+            rlx_logger.info("└" + "─" * 31 + "┴" + "─" * 16 + "┘")
+
+    # ------------------------------------------------------------------------------------- checkpointing
+    def _adam_state_dict(self, keys):
+        """torch.optim.Adam.state_dict() layout of the reference checkpoints (ppo.py:426-436)."""
+        state = {}
+        for i, (key, seg) in enumerate(keys.items()):
+            state[i] = {"step": torch.tensor(float(self.adam_step.item())),
+                        "exp_avg": self.params.view(self.exp_avg, seg).detach().cpu().clone(),
+                        "exp_avg_sq": self.params.view(self.exp_avg_sq, seg).detach().cpu().clone()}
+        group = {"lr": self.current_learning_rate(), "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(keys)))}
+        return {"state": state, "param_groups": [group]}
+
+    def save(self):
+        file_path = self.save_path + "/best.model"
+        pol, cri = self.params.state_dicts()
+        torch.save({
+            "config_algorithm": self.config.algorithm,
+            "policy_state_dict": pol,
+            "critic_state_dict": cri,
+            "policy_optimizer_state_dict": self._adam_state_dict(nt.POLICY_KEYS),
+            "critic_optimizer_state_dict": self._adam_state_dict(nt.CRITIC_KEYS),
+        }, file_path)
+        if self.track_wandb:
+            import wandb
+            wandb.save(file_path, base_path=os.path.dirname(file_path))
+
+    def load(config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
+        checkpoint = torch.load(config.runner.load_model, weights_only=False)
+        loaded_algorithm_config = checkpoint["config_algorithm"]
+        for key, value in loaded_algorithm_config.items():
+            if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device", "bf16_mixed_precision_training", "compile_mode"):
+                config.algorithm[key] = value
+        model = PPO(config, train_env, eval_env, run_path, writer)
+        named = {**checkpoint["policy_state_dict"], **checkpoint["critic_state_dict"]}
+        model.params.load_named(named)
+        step = 0.0
+        for opt_key, keys in (("policy_optimizer_state_dict", nt.POLICY_KEYS), ("critic_optimizer_state_dict", nt.CRITIC_KEYS)):
+            st = checkpoint[opt_key]["state"]
+            for i, (key, seg) in enumerate(keys.items()):
+                if i in st:
+                    model.params.view(model.exp_avg, seg).copy_(st[i]["exp_avg"].reshape(model.params.shapes[seg]))
+                    model.params.view(model.exp_avg_sq, seg).copy_(st[i]["exp_avg_sq"].reshape(model.params.shapes[seg]))
+                    step = max(step, float(st[i]["step"]))
+        model.adam_step.fill_(int(step))
+        return model
+
+    def set_train_mode(self):
+        self.training = True
+
+    def set_eval_mode(self):
+        self.training = False
+
+    def general_properties():
+        return GeneralProperties

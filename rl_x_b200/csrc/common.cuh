@@ -34,13 +34,26 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
     }                                                                                             \
   } while (0)
 
+// Kernel classes for the optional event-timing facility (rlx_timing_begin / rlx_timing_end).
+enum KClass { KC_GEMM_FWD = 0, KC_GEMM_DX, KC_GEMM_DW, KC_HEAD_ROLLOUT, KC_HEAD_TRAIN, KC_HEAD_WGRAD, KC_GRAD_REDUCE, KC_CLIP_ADAM,
+              KC_GATHER, KC_ADV_STATS, KC_GAE, KC_STORE, KC_OTHER, KC_COUNT };
+static_assert(KC_COUNT == RLX_NKCLASS, "kernel class count out of sync with rlx_b200.h");
+extern bool g_timing;
+void timing_before(int cls, double flops, double bytes, cudaStream_t stream);
+void timing_after(cudaStream_t stream);
+
 // Every kernel launch in the library goes through this so that rlx_launch_count() is an honest count.
-#define RLX_LAUNCH(kernel, grid, block, smem, stream, ...)            \
-  do {                                                                \
-    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
-    rlx::count_launch();                                              \
-    RLX_CHECK_CUDA(cudaPeekAtLastError());                            \
+// cls/flops/bytes: kernel class and ALGORITHMIC work of this launch (only consumed when timing is enabled).
+#define RLX_LAUNCH_C(cls, flops, bytes, kernel, grid, block, smem, stream, ...)              \
+  do {                                                                                       \
+    if (rlx::g_timing) rlx::timing_before((cls), (double)(flops), (double)(bytes), (cudaStream_t)(stream)); \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                \
+    if (rlx::g_timing) rlx::timing_after((cudaStream_t)(stream));                            \
+    rlx::count_launch();                                                                     \
+    RLX_CHECK_CUDA(cudaPeekAtLastError());                                                   \
   } while (0)
+#define RLX_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  RLX_LAUNCH_C(rlx::KC_OTHER, 0, 0, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

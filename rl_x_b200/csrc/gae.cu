@@ -104,6 +104,6 @@ extern "C" int rlx_gae_f32(const float* rewards, const float* terminations, cons
     RLX_CHECK_CUDA(cudaFuncSetAttribute(gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  RLX_LAUNCH(gae_kernel, grid, 256, smem, stream, p);
+  RLX_LAUNCH_C(KC_GAE, 0, (next_values ? 24.0 : 20.0) * (double)T * (double)N, gae_kernel, grid, 256, smem, stream, p);
   return RLX_OK;
 }

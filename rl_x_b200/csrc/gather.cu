@@ -33,12 +33,14 @@ __global__ void __launch_bounds__(256) rollout_store_kernel(const float* __restr
     }
   }
   int dones = 0;
-  for (long long i = tid; i < n; i += stride) {
-    const bool te = terminated[i] != 0;
-    const bool tr = truncated != nullptr && truncated[i] != 0;
-    if (rewards_row) rewards_row[i] = reward[i];
-    if (term_row) term_row[i] = te ? 1.f : 0.f;
-    dones += (te || tr) ? 1 : 0;
+  if (terminated != nullptr) {
+    for (long long i = tid; i < n; i += stride) {
+      const bool te = terminated[i] != 0;
+      const bool tr = truncated != nullptr && truncated[i] != 0;
+      if (rewards_row && reward) rewards_row[i] = reward[i];
+      if (term_row) term_row[i] = te ? 1.f : 0.f;
+      dones += (te || tr) ? 1 : 0;
+    }
   }
   if (done_count != nullptr) {
     // warp-aggregated count, one atomic per warp that saw a done
@@ -158,11 +160,12 @@ extern "C" int rlx_rollout_store_f32(const float* reward, const uint8_t* termina
                                      int64_t* done_count, void* stream) {
   RLX_CHECK_ARG(n >= 0 && obs_dim >= 0, "negative size");
   if (n == 0) return RLX_OK;
-  RLX_CHECK_ARG(reward && terminated, "reward / terminated must not be null");
+  RLX_CHECK_ARG((reward && terminated) || (next_obs && next_obs_dst), "nothing to store");
+  RLX_CHECK_ARG(!rewards_row || reward, "rewards_row given without reward");
   const int vec = (next_obs && next_obs_dst && aligned16(next_obs) && aligned16(next_obs_dst) && ((n * obs_dim) % 4 == 0)) ? 1 : 0;
   const long long work = (next_obs && next_obs_dst) ? (vec ? n * obs_dim / 4 : n * obs_dim) : n;
   const unsigned grid = (unsigned)std::min<long long>(ceil_div(std::max<long long>(work, n), 256), (long long)sm_count() * 8);
-  RLX_LAUNCH(rollout_store_kernel, grid, 256, 0, stream, reward, terminated, truncated, next_obs, (long long)n, (long long)obs_dim,
+  RLX_LAUNCH_C(KC_STORE, 0, ((next_obs && next_obs_dst) ? 8.0 * n * obs_dim : 0.0) + 10.0 * n, rollout_store_kernel, grid, 256, 0, stream, reward, terminated, truncated, next_obs, (long long)n, (long long)obs_dim,
              rewards_row, terminations_row, next_obs_dst, (long long*)done_count, vec);
   return RLX_OK;
 }
@@ -185,7 +188,7 @@ extern "C" int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64
   // 8 warps per CTA, grid sized to a multiple of the SM count (persistent-style grid-stride loop over rows)
   const long long want = ceil_div(count, 8);
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)sm_count() * 16);
-  RLX_LAUNCH(gather_minibatch_kernel, grid, 256, 0, stream, p);
+  RLX_LAUNCH_C(KC_GATHER, 0, (double)count * (8.0 + 8.0 * (obs_dim + act_dim + 3)), gather_minibatch_kernel, grid, 256, 0, stream, p);
   return RLX_OK;
 }
 
@@ -194,7 +197,7 @@ extern "C" int rlx_advantage_stats_f32(const float* adv, int64_t count, int64_t 
   if (count == 0) return RLX_OK;
   RLX_CHECK_ARG(adv && stats, "null pointer");
   const unsigned grid = (unsigned)ceil_div(count, mb);
-  RLX_LAUNCH(advantage_stats_kernel, grid, 512, 0, stream, adv, (long long)count, (long long)mb, stats);
+  RLX_LAUNCH_C(KC_ADV_STATS, 0, 4.0 * count, advantage_stats_kernel, grid, 512, 0, stream, adv, (long long)count, (long long)mb, stats);
   return RLX_OK;
 }
 

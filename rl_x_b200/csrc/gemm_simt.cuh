@@ -199,13 +199,15 @@ inline bool gemm_vec_ok(const GemmP& p) {
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
-int launch_sgemm(const GemmP& p, int batch, cudaStream_t stream) {
+int launch_sgemm(const GemmP& p, int batch, cudaStream_t stream, int kclass = KC_OTHER) {
   if (p.M <= 0 || p.N <= 0) return RLX_OK;
   dim3 grid((unsigned)ceil_div(p.N, GBN), (unsigned)ceil_div(p.M, GBM), (unsigned)(batch * p.splits));
+  const double flops = 2.0 * p.M * p.N * (double)p.K * batch;
+  const double bytes = 4.0 * batch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * p.splits);
   if (gemm_vec_ok(p)) {
-    RLX_LAUNCH((sgemm_kernel<A_KMAJ, B_KMAJ, EPI, true>), grid, 256, 0, stream, p);
+    RLX_LAUNCH_C(kclass, flops, bytes, (sgemm_kernel<A_KMAJ, B_KMAJ, EPI, true>), grid, 256, 0, stream, p);
   } else {
-    RLX_LAUNCH((sgemm_kernel<A_KMAJ, B_KMAJ, EPI, false>), grid, 256, 0, stream, p);
+    RLX_LAUNCH_C(kclass, flops, bytes, (sgemm_kernel<A_KMAJ, B_KMAJ, EPI, false>), grid, 256, 0, stream, p);
   }
   return RLX_OK;
 }

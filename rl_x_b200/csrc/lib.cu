@@ -1,5 +1,6 @@
 // Library-level state: error strings, launch counter, engine selection, device properties.
 #include "common.cuh"
+#include <vector>
 
 namespace rlx {
 
@@ -13,6 +14,29 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// ------------------------------------------------------------------------------------------- event timing
+bool g_timing = false;
+namespace {
+struct TimingRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+std::vector<TimingRec> g_recs;
+std::vector<cudaEvent_t> g_event_pool;
+size_t g_event_next = 0;
+cudaEvent_t take_event() {
+  if (g_event_next == g_event_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_event_pool.push_back(e);
+  }
+  return g_event_pool[g_event_next++];
+}
+}  // namespace
+void timing_before(int cls, double flops, double bytes, cudaStream_t stream) {
+  TimingRec r{cls, flops, bytes, take_event(), take_event()};
+  cudaEventRecord(r.e0, stream);
+  g_recs.push_back(r);
+}
+void timing_after(cudaStream_t stream) { cudaEventRecord(g_recs.back().e1, stream); }
 
 int sm_count() {
   static int n = 0;
@@ -48,4 +72,39 @@ extern "C" int rlx_ppo_param_layout(const rlx_ppo_dims* d, int64_t* offsets, int
   if (is_critic)
     for (int i = 0; i < RLX_PPO_NSEG; ++i) is_critic[i] = rlx::seg_is_critic(i) ? 1 : 0;
   return RLX_OK;
+}
+
+extern "C" int rlx_timing_begin(void) {
+  rlx::g_recs.clear();
+  rlx::g_event_next = 0;
+  rlx::g_timing = true;
+  return RLX_OK;
+}
+
+extern "C" int rlx_timing_end(double* ms, uint64_t* launches, double* flops, double* bytes) {
+  rlx::g_timing = false;
+  RLX_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < RLX_NKCLASS; ++i) {
+    if (ms) ms[i] = 0;
+    if (launches) launches[i] = 0;
+    if (flops) flops[i] = 0;
+    if (bytes) bytes[i] = 0;
+  }
+  for (const auto& r : rlx::g_recs) {
+    float t = 0.f;
+    RLX_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (ms) ms[r.cls] += t;
+    if (launches) launches[r.cls] += 1;
+    if (flops) flops[r.cls] += r.flops;
+    if (bytes) bytes[r.cls] += r.bytes;
+  }
+  rlx::g_recs.clear();
+  rlx::g_event_next = 0;
+  return RLX_OK;
+}
+
+extern "C" const char* rlx_kernel_class_name(int cls) {
+  static const char* names[RLX_NKCLASS] = {"gemm_fwd", "gemm_dx", "gemm_dw", "head_rollout", "head_train", "head_wgrad", "grad_reduce",
+                                           "clip_adam", "gather", "adv_stats", "gae", "rollout_store", "other"};
+  return (cls >= 0 && cls < RLX_NKCLASS) ? names[cls] : "?";
 }

@@ -106,7 +106,7 @@ static int mlp_hidden_forward_simt(const PpoLayout& L, const float* params, cons
   g.M = (int)rows; g.N = 2 * H; g.K = L.obs;
   g.lda = L.obs; g.ldb = L.obs; g.ldc = 2 * H;
   g.splits = 1; g.kchunk = (int)(ceil_div(L.obs, 8) * 8);
-  int rc = launch_sgemm<true, true, EPI_BIAS_TANH>(g, 1, stream);
+  int rc = launch_sgemm<true, true, EPI_BIAS_TANH>(g, 1, stream, KC_GEMM_FWD);
   if (rc) return rc;
   GemmP g2{};
   g2.A = H1; g2.B = params + L.off[W2P]; g2.C = H2; g2.bias = params + L.off[B2P];
@@ -114,7 +114,7 @@ static int mlp_hidden_forward_simt(const PpoLayout& L, const float* params, cons
   g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
   g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
   g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
-  return launch_sgemm<true, true, EPI_BIAS_TANH>(g2, 2, stream);
+  return launch_sgemm<true, true, EPI_BIAS_TANH>(g2, 2, stream, KC_GEMM_FWD);
 }
 
 static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const float* params, const float* X, long long rows, float* H1,
@@ -126,14 +126,14 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   return mlp_hidden_forward_simt(L, params, X, rows, H1, H2, stream);
 }
 
-#define RLX_DISPATCH_NCH(H, KERNEL, grid, block, smem, stream, arg)                                              \
+#define RLX_DISPATCH_NCH(CLS, FLOPS, BYTES, H, KERNEL, grid, block, smem, stream, arg)                                              \
   do {                                                                                                            \
     const int _nch = (int)ceil_div((H), 32);                                                                      \
-    if (_nch <= 2) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<2>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 4) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<4>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 8) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<8>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 16) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<16>, grid, block, smem, stream, arg); } \
-    else { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH(KERNEL<32>, grid, block, smem, stream, arg); } \
+    if (_nch <= 2) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<2>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 4) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<4>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 8) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<8>, grid, block, smem, stream, arg); } \
+    else if (_nch <= 16) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<16>, grid, block, smem, stream, arg); } \
+    else { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<32>, grid, block, smem, stream, arg); } \
   } while (0)
 
 static bool head_dims_ok(const rlx_ppo_dims& d) {
@@ -184,7 +184,7 @@ extern "C" int rlx_ppo_forward_f32(const rlx_ppo_forward_args* a, void* stream) 
   h.action = a->action; h.env_action = a->env_action; h.logp_out = a->logp; h.value_out = a->value;
   const size_t smem = head_smem_bytes(a->dims, false);
   const int grid = head_grid(a->n);
-  RLX_DISPATCH_NCH(L.H, ppo_head_rollout_kernel, grid, 256, smem, st, h);
+  RLX_DISPATCH_NCH(KC_HEAD_ROLLOUT, 2.0 * a->n * L.H * (L.act + 1), 4.0 * a->n * (2.0 * L.H + 3.0 * L.act + 2), L.H, ppo_head_rollout_kernel, grid, 256, smem, st, h);
   return RLX_OK;
 }
 
@@ -255,19 +255,19 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     h.dZ2 = dZ2; h.dhead = dhead; h.block_partials = headpart;
     head_blocks = P.head_blocks;
     const size_t smem = head_smem_bytes(d, true);
-    RLX_DISPATCH_NCH(H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
+    RLX_DISPATCH_NCH(KC_HEAD_TRAIN, 4.0 * m * H * (A + 1), 4.0 * m * (4.0 * H + 2.0 * A + 5), H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
     // ---- dW3 (thread per column, chunked over rows)
     HeadWgradP w{(int)m, H, A, kHeadWgradRows, H2, dhead, part3};
     wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
     dim3 wg((unsigned)wgrad_chunks, (unsigned)ceil_div(2 * H, 256));
     const size_t wsmem = (size_t)kHeadWgradRows * (A + 1) * sizeof(float);
     if (A <= 8) {
-      RLX_LAUNCH(ppo_head_wgrad_kernel<8>, wg, 256, wsmem, st, w);
+      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<8>, wg, 256, wsmem, st, w);
     } else if (A <= 32) {
-      RLX_LAUNCH(ppo_head_wgrad_kernel<32>, wg, 256, wsmem, st, w);
+      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<32>, wg, 256, wsmem, st, w);
     } else {
       RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      RLX_LAUNCH(ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
+      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
     }
     // ---- dW2 | db2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]
     const Splits S2 = choose_splits(m, H, H, 2);
@@ -278,7 +278,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     g.lda = 2 * H; g.ldb = 2 * H; g.ldc = H;
     g.sA = H; g.sB = H; g.sC = (long long)H * H; g.sRowsum = H;
     g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H; g.sSplitRowsum = 2LL * H;
-    rc = launch_sgemm<false, false, EPI_NONE>(g, 2, st);
+    rc = launch_sgemm<false, false, EPI_NONE>(g, 2, st, KC_GEMM_DW);
     if (rc) return rc;
     // ---- dZ1 = (dZ2 @ W2) * (1 - H1^2)   per net
     GemmP gd{};
@@ -287,7 +287,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
     gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
     gd.splits = 1; gd.kchunk = (int)(ceil_div(H, 8) * 8);
-    rc = launch_sgemm<true, false, EPI_DTANH>(gd, 2, st);
+    rc = launch_sgemm<true, false, EPI_DTANH>(gd, 2, st, KC_GEMM_DX);
     if (rc) return rc;
     // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i]
     const Splits S1 = choose_splits(m, 2 * H, O, 1);
@@ -297,7 +297,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     g1.M = 2 * H; g1.N = O; g1.K = (int)m;
     g1.lda = 2 * H; g1.ldb = O; g1.ldc = O;
     g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O; g1.sSplitRowsum = 2LL * H;
-    rc = launch_sgemm<false, false, EPI_NONE>(g1, 1, st);
+    rc = launch_sgemm<false, false, EPI_NONE>(g1, 1, st, KC_GEMM_DW);
     if (rc) return rc;
   }
   // ---- assemble the flat gradient (m == 0: a rank that owns no row of this minibatch contributes zeros)
@@ -316,7 +316,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   r.head_partials = headpart; r.nblk = head_blocks; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
-  RLX_LAUNCH(ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
+  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * (H + 1) + (double)wgrad_chunks * (A + 1) * H + L.total()), ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
   return RLX_OK;
 }
 
@@ -339,8 +339,8 @@ extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void*
   p.norm_partials = ws_ptr<float>(a->workspace, P.off_norm);
   p.nblk_norm = P.norm_blocks;
   p.metrics = a->metrics;
-  RLX_LAUNCH(ppo_grad_sumsq_kernel, (unsigned)P.norm_blocks, 256, 0, st, p);
-  RLX_LAUNCH(ppo_clip_adam_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, p);
+  RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 4.0 * L.total(), ppo_grad_sumsq_kernel, (unsigned)P.norm_blocks, 256, 0, st, p);
+  RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 28.0 * L.total(), ppo_clip_adam_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, p);
   return RLX_OK;
 }
 

@@ -1,0 +1,73 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+class Golden:
+    """Golden vectors captured from the executed reference (tests/golden/make_golden_ppo.py)."""
+
+    def __init__(self, tag):
+        self.z = np.load(os.path.join(GOLDEN_DIR, f"ppo_{tag}.npz"))
+        m = self.z["meta"]
+        self.N, self.T, self.obs, self.act, self.hidden, self.mb, self.epochs, self.iterations, self.seed = (int(x) for x in m)
+        f = self.z["meta_f"]
+        (self.gamma, self.gae_lambda, self.clip_range, self.entropy_coef, self.critic_coef, self.max_grad_norm, self.lr,
+         self.std_dev, self.act_low, self.act_high) = (float(x) for x in f[:10])
+        self.anneal = bool(f[10])
+        self.B = self.N * self.T
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    def params(self, prefix):
+        """(policy dict, critic dict) of numpy arrays under e.g. 'init' or 'iter0'."""
+        pol = {k.split("/", 2)[2]: self.z[k] for k in self.z.files if k.startswith(f"{prefix}/policy/")}
+        cri = {k.split("/", 2)[2]: self.z[k] for k in self.z.files if k.startswith(f"{prefix}/critic/")}
+        return pol, cri
+
+    def perms(self, iteration):
+        return [self.z[f"perm/{iteration * self.epochs + e}"] for e in range(self.epochs)]
+
+    def lr_at(self, iteration):
+        # LinearLR(start 1 -> end 0 over total_iters = iterations), stepped once per iteration (ppo.py:87-88,302-304)
+        if not self.anneal:
+            return self.lr
+        return self.lr * (1.0 - iteration / self.iterations)
+
+
+@pytest.fixture(scope="session", params=["small", "humanoid"])
+def golden(request):
+    return Golden(request.param)
+
+
+@pytest.fixture(scope="session")
+def golden_small():
+    return Golden("small")
+
+
+@pytest.fixture(scope="session")
+def golden_humanoid():
+    return Golden("humanoid")

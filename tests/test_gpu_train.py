@@ -1,0 +1,196 @@
+"""End-to-end GPU tests of the plugin class: PPO.train() through the reference-shaped API, replaying the environment
+stream and action noise of the executed reference (golden fixtures) and comparing the resulting weights and logged metrics."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class _Space:
+    def __init__(self, shape, low=None, high=None):
+        self.shape, self.low, self.high = shape, low, high
+
+
+def _props(interface):
+    from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
+
+    class P:
+        observation_space_type = ObservationSpaceType.FLAT_VALUES
+        action_space_type = ActionSpaceType.CONTINUOUS
+        data_interface_type = getattr(DataInterfaceType, interface)
+    return P
+
+
+class ReplayEnv:
+    """Feeds back the exact observation / reward / termination stream the reference saw (captured in the golden file)."""
+
+    def __init__(self, g, interface="TORCH"):
+        self.g, self.numpy = g, interface == "NUMPY"
+        self.general_properties = _props(interface)
+        self.single_observation_space = _Space((g.obs,))
+        self.single_action_space = _Space((g.act,), np.full(g.act, g.act_low, np.float32), np.full(g.act, g.act_high, np.float32))
+        self.t = 0
+        self.actions = []
+
+    def _o(self, x, dtype=None):
+        if self.numpy:
+            return np.asarray(x)
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+        return t
+
+    def reset(self):
+        return self._o(self.g["iter0/states"][0]), {}
+
+    def step(self, action):
+        g = self.g
+        self.actions.append(torch.as_tensor(action).detach().cpu().clone())
+        it, s = divmod(self.t, g.T)
+        self.t += 1
+        nxt = g[f"iter{it}/next_states"][s]
+        rew = g[f"iter{it}/rewards"][s]
+        term = g[f"iter{it}/terminations"][s] > 0.5
+        trunc = np.full(g.N, self.t % 11 == 0)
+        self._last_next = nxt
+        return self._o(nxt), self._o(rew), self._o(term), self._o(trunc), {}
+
+    def get_logging_info_dict(self, info):
+        return {}
+
+    def get_final_observation_at_index(self, info, i):
+        return self._last_next[i]  # the replayed stream already holds what the reference stored as next_states
+
+    def get_final_info_value_at_index(self, info, key, i):
+        return 0.0
+
+    def close(self):
+        pass
+
+
+def _config(g, **algo):
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.ppo.b200.default_config import get_config
+    a = get_config("ppo.b200")
+    a.nr_steps, a.minibatch_size, a.nr_epochs, a.nr_hidden_units = g.T, g.mb, g.epochs, g.hidden
+    a.total_timesteps = g.N * g.T * g.iterations
+    a.std_dev, a.entropy_coef, a.anneal_learning_rate = g.std_dev, g.entropy_coef, g.anneal
+    a.learning_rate, a.clip_range, a.critic_coef, a.max_grad_norm = g.lr, g.clip_range, g.critic_coef, g.max_grad_norm
+    a.gamma, a.gae_lambda = g.gamma, g.gae_lambda
+    for k, v in algo.items():
+        a[k] = v
+    return ConfigDict(algorithm=a, environment=ConfigDict(seed=g.seed, nr_envs=g.N),
+                      runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+
+
+def _reference_noise(g):
+    """eps such that mean + std * eps reproduces the reference's stored actions, from the weights the reference acted with."""
+    out = []
+    for it in range(g.iterations):
+        pol, _ = g.params("init" if it == 0 else f"iter{it - 1}")
+        pol = {k: torch.from_numpy(v) for k, v in pol.items()}
+        states = torch.from_numpy(g[f"iter{it}/states"]).reshape(-1, g.obs)
+        with torch.no_grad():
+            mean = O.policy_mean(pol, states)
+        eps = (torch.from_numpy(g[f"iter{it}/actions"]).reshape(-1, g.act) - mean) / torch.exp(pol["policy_logstd"])
+        out.append(eps.reshape(g.T, g.N, g.act))
+    return torch.cat(out).to(DEV).contiguous()
+
+
+@pytest.mark.parametrize("interface", ["TORCH", "NUMPY"])
+def test_train_reproduces_reference_run(golden, interface):
+    from rl_x_b200.algorithms.ppo.b200.ppo import PPO
+    g = golden
+    env = ReplayEnv(g, interface)
+    model = PPO(_config(g), env, env, "/tmp/rlx_test_run", None)
+    eps = _reference_noise(g)
+    calls = {"n": 0}
+
+    def draw(step):
+        i = calls["n"]
+        calls["n"] += 1
+        return eps[i]
+
+    model._draw_noise = draw
+    logged = []
+    model.log = lambda name, value, step: logged.append((name, float(value), int(step)))
+    snaps = []
+    orig = model.start_logging
+
+    def start_logging(step):
+        b = model.batch
+        snaps.append(dict(adv=b.advantages.cpu().numpy().copy(), ret=b.returns.cpu().numpy().copy(), val=b.values.cpu().numpy().copy(),
+                          lp=b.log_probs.cpu().numpy().copy(), sd=model.params.state_dicts()))
+        orig(step)
+
+    model.start_logging = start_logging
+    model.train()
+    assert calls["n"] == g.T * g.iterations and len(snaps) == g.iterations
+    # the env received the clipped / rescaled actions the reference sent
+    np.testing.assert_allclose(torch.stack(env.actions).numpy(), g["env_actions"], rtol=1e-4, atol=5e-6)
+    for it, s in enumerate(snaps):
+        np.testing.assert_allclose(s["val"], g[f"iter{it}/values"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(s["lp"], g[f"iter{it}/log_probs"], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(s["adv"], g[f"iter{it}/advantages"], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(s["ret"], g[f"iter{it}/returns"], rtol=1e-4, atol=2e-5)
+        pol_ref, cri_ref = g.params(f"iter{it}")
+        pol, cri = s["sd"]
+        for name, v in {**pol_ref, **cri_ref}.items():
+            ours = (pol if name in pol else cri)[name].numpy()
+            rel = float(np.linalg.norm(ours - v) / np.linalg.norm(v))
+            assert rel <= 2e-5, (it, name, rel)
+    names = {n for n, _, _ in logged}
+    for n in ["loss/policy_gradient_loss", "loss/critic_loss", "loss/entropy_loss", "policy_ratio/clip_fraction", "policy_ratio/approx_kl",
+              "gradients/policy_grad_norm", "gradients/critic_grad_norm", "lr/learning_rate", "v_value/explained_variance", "policy/std_dev",
+              "steps/nr_env_steps", "steps/nr_updates", "steps/nr_episodes", "time/acting_time", "time/calc_adv_and_return_time",
+              "time/optimizing_time", "time/evaluating_time", "time/saving_time"]:
+        assert n in names, n
+    for n in ["loss/critic_loss", "loss/entropy_loss", "gradients/policy_grad_norm", "gradients/critic_grad_norm", "lr/learning_rate",
+              "v_value/explained_variance", "policy/std_dev", "steps/nr_env_steps", "steps/nr_updates", "steps/nr_episodes"]:
+        ours = [v for m, v, _ in logged if m == n]
+        ref = g[f"metric/{n}"]
+        np.testing.assert_allclose(ours, ref, rtol=2e-4, atol=1e-6, err_msg=n)
+    ours = [v for m, v, _ in logged if m == "loss/policy_gradient_loss"]
+    np.testing.assert_allclose(ours, g["metric/loss/policy_gradient_loss"], rtol=0, atol=2e-5)
+
+
+def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch):
+    from rl_x_b200.runner.runner import Runner
+    from rl_x_b200 import _native as nt
+    monkeypatch.chdir(tmp_path)
+    argv = ["--environment.nr_envs=64", "--environment.obs_dim=24", "--environment.act_dim=5", "--algorithm.nr_steps=16",
+            "--algorithm.minibatch_size=256", "--algorithm.nr_epochs=2", "--algorithm.nr_hidden_units=64", "--algorithm.total_timesteps=3072",
+            "--runner.save_model=True", "--runner.run_name=t1", "--environment.termination_probability=0.05"]
+    nt.load().rlx_reset_launch_count()
+    r = Runner(argv=argv)
+    r.run()
+    assert not getattr(r, "failed", False)
+    assert nt.load().rlx_launch_count() > 100
+    model = r.model
+    assert len(model.iteration_times) == 2
+    # like the reference, "save best" needs episode returns from the env (ppo.py:353-357); the synthetic stream has none
+    model.save()
+    ckpt = tmp_path / "runs" / "placeholder" / "placeholder" / "t1" / "models" / "best.model"
+    assert ckpt.exists()
+    ck = torch.load(ckpt, weights_only=False)
+    assert set(ck) == {"config_algorithm", "policy_state_dict", "critic_state_dict", "policy_optimizer_state_dict", "critic_optimizer_state_dict"}
+    assert set(ck["policy_state_dict"]) == set(O.POLICY_KEYS) and set(ck["critic_state_dict"]) == set(O.CRITIC_KEYS)
+    # the checkpoint drives plain torch modules shaped like the reference's (policy.py:45-52)
+    pol = {k: v for k, v in ck["policy_state_dict"].items()}
+    x = torch.randn(7, 24)
+    mean = O.policy_mean(pol, x)
+    assert mean.shape == (7, 5) and torch.isfinite(mean).all()
+    # and loads back into the plugin, continuing with identical weights / moments
+    r2 = Runner(argv=argv[:-3] + ["--runner.load_model=" + str(ckpt), "--runner.run_name=t2", "--runner.mode=test", "--runner.nr_test_episodes=1",
+                                  "--environment.horizon=5"])
+    m2, env, _ = r2._build_model(str(tmp_path / "x"), None)
+    p1, c1 = ck["policy_state_dict"], ck["critic_state_dict"]
+    p2, c2 = m2.params.state_dicts()
+    for k in p1:
+        assert torch.equal(p1[k], p2[k])
+    for k in c1:
+        assert torch.equal(c1[k], c2[k])
+    assert int(m2.adam_step.item()) == int(float(ck["policy_optimizer_state_dict"]["state"][0]["step"]))
+    m2.test(1)

@@ -1,0 +1,238 @@
+"""CPU-side tests: C-ABI surface, numpy-exact host RNG, reference-identical initialisation, config/runner plumbing,
+shard index arithmetic (incl. a world_size-2 gloo run).  No CUDA compute is invoked here."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rl_x_b200 import _native as nt
+    import ctypes
+    lib = nt.load()
+    header = open(os.path.join(ROOT, "include", "rlx_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rlx_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    raw = ctypes.CDLL(nt.library_path())
+    for name in sorted(declared):
+        assert hasattr(raw, name), f"{name} declared in include/rlx_b200.h but not exported"
+    assert declared == set(nt.exported_symbols()), declared ^ set(nt.exported_symbols())
+    assert lib.rlx_version() == 1
+    assert isinstance(nt.last_error(), str)
+
+
+def test_param_layout_matches_reference_shapes():
+    from rl_x_b200 import _native as nt
+    off, crit = nt.ppo_layout(376, 17, 256)
+    assert off[-1] == 329251  # 166 690 + 162 561
+    shapes = nt.segment_shapes(376, 17, 256)
+    for i, name in enumerate(nt.SEGMENT_NAMES):
+        assert off[i + 1] - off[i] == int(np.prod(shapes[name]))
+    assert sum(off[i + 1] - off[i] for i in range(13) if crit[i]) == 162561
+
+
+@pytest.mark.parametrize("seed", [0, 1, 3, 12345, 2**40 + 17])
+def test_pcg64_stream_is_numpy_exact(seed):
+    from rl_x_b200 import _native as nt
+    g, r = nt.Pcg64Generator(seed), np.random.default_rng(seed)
+    st = r.bit_generator.state["state"]
+    assert (g.state.s[0] << 64 | g.state.s[1], g.state.s[2] << 64 | g.state.s[3]) == (st["state"], st["inc"])
+    for n in [0, 1, 2, 3, 10, 1000, 65536]:
+        a, b = np.arange(n), np.arange(n)
+        for _ in range(2):  # in-place re-shuffle continues the stream, like the epochs of ppo.py:274-276
+            g.shuffle(a)
+            r.shuffle(b)
+            assert np.array_equal(a, b)
+    for high in [1, 2, 4, 977, 10**6, 2**32 - 1, 2**32, 2**32 + 5, 2**40]:
+        assert np.array_equal(g.integers(high, 1001), r.integers(high, size=1001))
+    assert g.next_uint64() == int(r.bit_generator.random_raw())
+
+
+def test_pcg64_matches_golden_permutations(golden):
+    from rl_x_b200 import _native as nt
+    g = nt.Pcg64Generator(golden.seed)
+    k = 0
+    for it in range(golden.iterations):
+        idx = np.arange(golden.B)
+        for _ in range(golden.epochs):
+            g.shuffle(idx)
+            assert np.array_equal(idx, golden[f"perm/{k}"])
+            k += 1
+
+
+def test_pcg64_rejects_bad_arrays():
+    from rl_x_b200 import _native as nt
+    g = nt.Pcg64Generator(1)
+    with pytest.raises(TypeError):
+        g.shuffle(np.arange(10, dtype=np.int32))
+    with pytest.raises(RuntimeError):
+        g.integers(0, 5)
+
+
+def test_initial_parameters_identical_to_reference(golden):
+    from rl_x_b200.algorithms.ppo.b200.ppo import init_reference_parameters
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)  # the fixture was generated single-threaded; LAPACK's QR rounds differently per thread count / CPU
+    try:
+        named = init_reference_parameters(golden.obs, golden.act, golden.hidden, golden.std_dev, golden.seed)
+    finally:
+        torch.set_num_threads(nthreads)
+    pol, cri = golden.params("init")
+    for k, v in {**pol, **cri}.items():
+        # same RNG stream and same call order; the QR inside orthogonal_ is LAPACK and differs by an ulp with the thread count
+        np.testing.assert_allclose(named[k].numpy(), v, rtol=1e-5, atol=1e-5, err_msg=k)
+
+
+def test_config_overrides_and_runner_show_config():
+    from rl_x_b200.runner.runner import Runner
+    r = Runner(argv=["--runner.mode=show_config", "--algorithm.nr_steps=128", "--environment.nr_envs=64",
+                     "--algorithm.anneal_learning_rate=True", "--algorithm.learning_rate=1e-3"])
+    c = r._config
+    assert c.algorithm.nr_steps == 128 and c.environment.nr_envs == 64 and c.algorithm.anneal_learning_rate is True
+    assert c.algorithm.learning_rate == 1e-3 and c.algorithm.name == "ppo.b200" and c.environment.name == "synthetic.box"
+    assert sorted(r._explicitly_set) == ["algorithm.anneal_learning_rate", "algorithm.learning_rate", "algorithm.nr_steps", "environment.nr_envs"]
+    with pytest.raises(KeyError):
+        Runner(argv=["--algorithm.no_such_key=1"])
+    with pytest.raises(ModuleNotFoundError):
+        Runner(argv=["--algorithm.name=does.not.exist"])
+
+
+def test_default_config_keys_cover_reference_keys():
+    from rl_x_b200.algorithms.ppo.b200.default_config import get_config
+    ref_keys = ["name", "device", "compile_mode", "bf16_mixed_precision_training", "total_timesteps", "learning_rate", "anneal_learning_rate",
+                "nr_steps", "nr_epochs", "minibatch_size", "gamma", "gae_lambda", "clip_range", "entropy_coef", "critic_coef", "max_grad_norm",
+                "std_dev", "action_clipping_and_rescaling", "nr_hidden_units", "evaluation_frequency", "evaluation_episodes"]
+    c = get_config("ppo.b200")
+    for k in ref_keys:  # rl_x/algorithms/ppo/pytorch/default_config.py:4-30
+        assert k in c, k
+    assert (c.nr_steps, c.nr_epochs, c.minibatch_size, c.gamma, c.gae_lambda, c.clip_range) == (2048, 10, 64, 0.99, 0.95, 0.2)
+
+
+def test_ppo_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from rl_x_b200.runner.runner import Runner
+    r = Runner(argv=["--environment.nr_envs=8", "--algorithm.nr_steps=4", "--algorithm.minibatch_size=8"])
+    from rl_x_b200.algorithms.ppo.b200.ppo import PPO
+    train_env, eval_env = r._create_train_and_eval_env(r._config)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PPO(r._config, train_env, eval_env, "/tmp/x", None)
+
+
+def test_synthetic_env_contract():
+    from rl_x_b200.runner.runner import Runner
+    r = Runner(argv=["--environment.nr_envs=8", "--environment.device=cpu", "--algorithm.device=cpu", "--environment.horizon=3"])
+    env, eval_env = r._create_train_and_eval_env(r._config)
+    assert env is eval_env
+    obs, info = env.reset()
+    assert obs.shape == (8, 376) and info == {}
+    for t in range(1, 4):
+        o, rew, term, trunc, info = env.step(torch.zeros(8, 17))
+        assert o.shape == (8, 376) and rew.shape == (8,) and term.dtype == torch.bool and trunc.dtype == torch.bool
+        assert bool(trunc.all()) == (t % 3 == 0)
+    assert env.get_logging_info_dict(info) == {}
+    assert env.single_action_space.low.shape == (17,) and env.general_properties.data_interface_type.name == "TORCH"
+
+
+# ------------------------------------------------------------------------------------------------------- sharding
+def test_local_rows_partition_the_permutation():
+    from rl_x_b200.algorithms.ppo.b200 import sharding
+    T, Ng, W, mb = 7, 12, 4, 10
+    Nl = Ng // W
+    perm = np.random.default_rng(0).permutation(T * Ng)
+    gsizes = sharding.global_minibatch_sizes(T * Ng, mb)
+    assert gsizes.sum() == T * Ng and gsizes[-1] == (T * Ng) % mb
+    total = np.zeros(len(gsizes), dtype=np.int64)
+    seen = []
+    for rank in range(W):
+        idx, counts = sharding.local_rows_of_permutation(perm, mb, Ng, Nl, rank)
+        assert idx.shape[0] == T * Nl and sorted(idx.tolist()) == list(range(T * Nl))
+        total += counts
+        # map local rows back to global flat indices and check order within each minibatch
+        t, e = np.divmod(idx, Nl)
+        glob = t * Ng + e + rank * Nl
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for k in range(len(counts)):
+            mine = [p for p in perm[k * mb:(k + 1) * mb] if (p % Ng) // Nl == rank]
+            assert glob[off[k]:off[k + 1]].tolist() == mine
+        seen.extend(glob.tolist())
+    assert np.array_equal(total, gsizes) and sorted(seen) == list(range(T * Ng))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import ppo_oracle as O
+    from rl_x_b200.algorithms.ppo.b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    T, Ng, obs, act, H, mb = 6, 8, 5, 2, 16, 16
+    Nl = Ng // world
+    g = torch.Generator().manual_seed(0)
+    states = torch.randn(T, Ng, obs, generator=g)
+    actions = torch.randn(T, Ng, act, generator=g)
+    logp = torch.randn(T, Ng, generator=g) * 0.1 - 2.0
+    adv = torch.randn(T, Ng, generator=g)
+    ret = torch.randn(T, Ng, generator=g)
+    pol, cri = O.init_params(obs, act, H, seed=5)
+    perm = np.random.default_rng(3).permutation(T * Ng)
+    full = O.Learner(pol, cri)
+    flat = lambda x: x.reshape((-1,) + x.shape[2:])
+    idx0 = torch.as_tensor(perm[:mb])
+    gp_full, gc_full, m_full = full.grads(flat(states)[idx0], flat(actions)[idx0], flat(logp)[idx0], flat(adv)[idx0], flat(ret)[idx0])
+
+    # sharded: this rank's rows of minibatch 0, global advantage statistics, gradient SUM / global size
+    sl = sharding.shard_env_slice(Ng, world, rank)
+    loc = lambda x: x[:, sl].reshape((-1,) + x.shape[2:])
+    lidx, counts = sharding.local_rows_of_permutation(perm, mb, Ng, Nl, rank)
+    rows = torch.as_tensor(lidx[:counts[0]])
+    a_loc = loc(adv)[rows]
+    s = torch.stack([a_loc.sum(), torch.tensor(float(len(rows)))])
+    dist.all_reduce(s)
+    mean = s[0] / s[1]
+    ssq = ((a_loc - mean) ** 2).sum()
+    dist.all_reduce(ssq)
+    std = torch.sqrt(ssq / (s[1] - 1))
+    L = O.Learner(pol, cri)
+    new_logp, _ = O.get_logprob_entropy(L.pol, loc(states)[rows], loc(actions)[rows])
+    ratio = (new_logp - loc(logp)[rows]).exp()
+    A = (a_loc - mean) / (std + 1e-8)
+    pg = torch.maximum(-A * ratio, -A * torch.clamp(ratio, 0.8, 1.2)).sum() / mb
+    closs = 0.5 * (0.5 * (O.critic_value(L.cri, loc(states)[rows]).reshape(-1) - loc(ret)[rows]) ** 2).sum() / mb
+    (pg + closs).backward()
+    err = 0.0
+    for k in O.POLICY_KEYS:
+        gsum = L.pol[k].grad.clone()
+        dist.all_reduce(gsum)
+        err = max(err, float((gsum - gp_full[k]).abs().max()))
+    for k in O.CRITIC_KEYS:
+        gsum = L.cri[k].grad.clone()
+        dist.all_reduce(gsum)
+        err = max(err, float((gsum - gc_full[k]).abs().max()))
+    dist.destroy_process_group()
+    q.put((rank, err))
+
+
+def test_sharded_gradient_equals_single_process_gloo_world2():
+    """The data-parallel recipe (global permutation, owner-computes rows, global advantage statistics, gradient sums
+    divided by the global minibatch size, all-reduce(sum)) reproduces the unsharded minibatch gradient."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in results:
+        assert err < 5e-7, (rank, err)
