@@ -151,6 +151,17 @@ def run(tag, N, T, obs_dim, act_dim, hidden, mb, epochs, iterations, seed, act_l
     out = {}
     out.update(sd_to_np("init/policy", model.policy.state_dict()))
     out.update(sd_to_np("init/critic", model.critic.state_dict()))
+    # next_values is a local of train() (ppo.py:253-254): capture the critic output of the one call that sees the 3-D next_states
+    next_values_log = []
+    orig_get_value = model.critic.get_value
+
+    def get_value(x):
+        out = orig_get_value(x)
+        if x.dim() == 3:
+            next_values_log.append(out.detach().squeeze(-1).numpy().copy())
+        return out
+
+    model.critic.get_value = get_value
     spy = RngSpy(model.rng)
     model.rng = spy
     metrics = []
@@ -178,6 +189,9 @@ def run(tag, N, T, obs_dim, act_dim, hidden, mb, epochs, iterations, seed, act_l
     for it, snap in enumerate(per_iter):
         for k, v in snap.items():
             out[f"iter{it}/{k}"] = v
+    assert len(next_values_log) == iterations
+    for it, nv in enumerate(next_values_log):
+        out[f"iter{it}/next_values"] = nv
     for i, p in enumerate(spy.perms):
         out[f"perm/{i}"] = p.astype(np.int64)
     out["env_actions"] = torch.stack(env.received_actions).numpy()

@@ -66,9 +66,7 @@ def test_gae_bit_exact_vs_reference_golden(golden):
     g = golden
     k = _kern(g.obs, g.act, g.hidden)
     for it in range(g.iterations):
-        pol, cri = g.params("init" if it == 0 else f"iter{it - 1}")
-        with torch.no_grad():
-            nv = O.critic_value(_t(cri), torch.from_numpy(g[f"iter{it}/next_states"])).squeeze(-1)
+        nv = torch.from_numpy(g[f"iter{it}/next_values"])  # the critic output the reference fed into its GAE (ppo.py:253-254)
         adv, ret = torch.empty(g.T, g.N, device=DEV), torch.empty(g.T, g.N, device=DEV)
         k.gae(torch.from_numpy(g[f"iter{it}/rewards"]).to(DEV), torch.from_numpy(g[f"iter{it}/terminations"]).to(DEV),
               torch.from_numpy(g[f"iter{it}/values"]).to(DEV), g.gamma, g.gae_lambda, adv, ret, next_values=nv.to(DEV))
