@@ -123,6 +123,42 @@ def timed_iterations(model, steps, dist):
     return e0.elapsed_time(e1) / 1e3, t0, t1
 
 
+def available_cores():
+    """Host cores this process may actually use: scheduler affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def calibrate_threads(limit):
+    """torch's intra-op thread count that makes the oracle's minibatch update fastest on this host (more threads than the
+    box can schedule makes it much slower); the baseline is reported at its best setting."""
+    from oracle import ppo_oracle as O
+    cands = sorted({c for c in (4, 8, 16, 32, 48, 64, 96, 128, limit) if c <= limit})
+    pol, cri = O.init_params(C2["obs_dim"], C2["act_dim"], C2["hidden"], seed=1)
+    g = torch.Generator().manual_seed(0)
+    m = 8192
+    mbatch = (torch.randn(m, C2["obs_dim"], generator=g), torch.randn(m, C2["act_dim"], generator=g), -20 + torch.randn(m, generator=g),
+              torch.randn(m, generator=g), torch.randn(m, generator=g))
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        L = O.Learner(pol, cri)
+        L.minibatch_step(*mbatch)
+        t = time.perf_counter()
+        for _ in range(2):
+            L.minibatch_step(*mbatch)
+        t = time.perf_counter() - t
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def cpu_baseline_sample(args, threads, minibatches=8, rollout_steps=8):
     """CPU oracle on a bounded sample of config 2, composed into seconds per full iteration (see `sample` in the result)."""
     from oracle import ppo_oracle as O
@@ -162,7 +198,7 @@ def cpu_baseline_sample(args, threads, minibatches=8, rollout_steps=8):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = calibrate_threads(available_cores())
     per_step = []
     sample = ""
     for i in range(args.warmup + args.steps):
@@ -286,9 +322,9 @@ def main():
                        "path": "PPO._train_iteration() with a NUMPY-interface env: obs/reward/done from pinned host buffers every env step, actions read back every env step"}
         del m2
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        threads = calibrate_threads(available_cores())
         v, t_iter, sample = cpu_baseline_sample(args, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample, "s_per_step": t_iter}
+        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "host_cores_available": available_cores(), "kind": "port", "sample": sample, "s_per_step": t_iter}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
