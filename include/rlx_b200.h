@@ -51,6 +51,12 @@ const char* rlx_kernel_class_name(int cls);
 int rlx_set_gemm_engine(int engine);
 int rlx_get_gemm_engine(void);
 
+/* Test hook: one plain fp32 GEMM through either engine.  layout 0: C[M,N] = A[M,K] B[N,K]^T; 1: C = A[M,K] B[K,N];
+ * 2: C = A[K,M]^T B[K,N].  epilogue 0 none, 1 tanh(x + bias[n]) (layout 0), 2 x * (1 - aux[m,n]^2) (layout 1). */
+int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                       const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, const float* aux, int64_t ldaux,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------- numpy-compatible host RNG -- */
 /* ref: self.rng = np.random.default_rng(self.seed)  (ppo.py:72; sac.py replay_buffer.py:8) — Generator(PCG64(SeedSequence(seed))).
  * state[0..1] = 128-bit LCG state (hi, lo); state[2..3] = increment (hi, lo); state[4] = has_uint32; state[5] = buffered uinteger. */
@@ -135,11 +141,13 @@ int rlx_gae_f32(const float* rewards, const float* terminations, const float* va
 /* -------------------------------------------------------------------------------- minibatch gather + stats -- */
 /* ref: batch_states[minibatch_indices], batch_actions[...], batch_log_probs[...], batch_advantages[...], batch_returns[...]
  * (ppo.py:277-284).  idx [count] int64 indices into the flattened (T*N) batch.  Gathers rows into contiguous
- * minibatch-ordered buffers; with count = B and idx = the epoch permutation, minibatch k is the slice [k*mb, (k+1)*mb). */
+ * minibatch-ordered buffers; with count = B and idx = the epoch permutation, minibatch k is the slice [k*mb, (k+1)*mb).
+ * out_states_ld: row pitch of out_states in floats (0 = obs_dim).  When it is larger than obs_dim the pad columns are written too:
+ * out_states[:, obs_dim] = 1.0 (a constant-one feature used by the dW1 GEMM to emit the bias gradient), the rest 0. */
 int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64_t obs_dim, int64_t act_dim, const float* states,
                              const float* actions, const float* log_probs, const float* advantages, const float* returns,
                              float* out_states, float* out_actions, float* out_log_probs, float* out_advantages,
-                             float* out_returns, void* stream);
+                             float* out_returns, int64_t out_states_ld, void* stream);
 
 /* ref: minibatch_advantages.mean(), .std() (unbiased)  (ppo.py:133-134), for `num_mb` consecutive minibatches of size mb
  * (last one may be short) over gathered advantages adv [count].  stats [num_mb, 2] = (mean, unbiased std). */
@@ -181,6 +189,10 @@ typedef struct rlx_ppo_minibatch_args {
   float* metrics;            /* [RLX_PPO_NMETRIC] device, overwritten */
   void* workspace;
   size_t workspace_bytes;
+  int64_t states_ld;         /* row pitch of `states` in floats; 0 = obs_dim (contiguous) */
+  int32_t states_ones_col;   /* != 0: states[:, obs_dim] == 1.0 in every row (written by rlx_gather_minibatch_f32 when out_states_ld > obs):
+                                lets the tensor-core dW1 GEMM produce the layer-1 bias gradient as one extra output column */
+  int32_t reserved2;
 } rlx_ppo_minibatch_args;
 size_t rlx_ppo_minibatch_workspace_bytes(const rlx_ppo_dims* d, int64_t m);
 

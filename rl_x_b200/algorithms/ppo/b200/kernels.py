@@ -89,7 +89,7 @@ class PpoKernels:
 
     # ------------------------------------------------------------------------------------------------- gather
     def gather(self, idx, states, actions, log_probs, advantages, returns, out_states, out_actions, out_log_probs,
-               out_advantages, out_returns, count=None):
+               out_advantages, out_returns, count=None, out_states_ld=0):
         if not (idx.is_cuda and idx.dtype == torch.int64 and idx.is_contiguous()):
             raise TypeError("idx: expected a contiguous int64 CUDA tensor")
         count = idx.shape[0] if count is None else int(count)
@@ -97,7 +97,7 @@ class PpoKernels:
                                                    _f32(actions, "actions"), _f32(log_probs, "log_probs"), _f32(advantages, "advantages"),
                                                    _f32(returns, "returns"), _f32(out_states, "out_states"), _f32(out_actions, "out_actions"),
                                                    _f32(out_log_probs, "out_log_probs"), _f32(out_advantages, "out_advantages"),
-                                                   _f32(out_returns, "out_returns"), _stream()), "rlx_gather_minibatch_f32")
+                                                   _f32(out_returns, "out_returns"), int(out_states_ld), _stream()), "rlx_gather_minibatch_f32")
 
     def advantage_stats(self, adv, count, mb, stats):
         nt.check(self.lib.rlx_advantage_stats_f32(_f32(adv, "adv"), int(count), int(mb), _f32(stats, "stats"), _stream()),
@@ -105,7 +105,7 @@ class PpoKernels:
 
     # ------------------------------------------------------------------------------------------------- update
     def minibatch_args(self, *, m, m_global, states, actions, log_probs, advantages, returns, adv_stats, params, grads, exp_avg,
-                       exp_avg_sq, lr, step_count, hp, metrics, workspace):
+                       exp_avg_sq, lr, step_count, hp, metrics, workspace, states_ld=0, states_ones_col=False):
         a = nt.PpoMinibatchArgs()
         a.dims = self.dims
         a.m, a.m_global = int(m), int(m_global)
@@ -119,7 +119,17 @@ class PpoKernels:
         a.hp = hp
         a.metrics = _f32(metrics, "metrics")
         a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
+        a.states_ld, a.states_ones_col = int(states_ld), int(bool(states_ones_col))
         return a
+
+    def debug_gemm(self, engine, layout, epilogue, A, B, C, M, N, K, bias=None, aux=None):
+        nt.check(self.lib.rlx_debug_gemm_f32(int(engine), int(layout), int(epilogue), M, N, K, _f32(A, "A"), A.stride(0), _f32(B, "B"), B.stride(0),
+                                             _f32(C, "C"), C.stride(0), _f32(bias, "bias"), _f32(aux, "aux"), aux.stride(0) if aux is not None else 0,
+                                             _stream()), "rlx_debug_gemm_f32")
+
+    def states_pitch(self):
+        """Row pitch (floats) of the gathered-states buffer: obs_dim plus a constant-one column, rounded up to 16 bytes."""
+        return (self.obs_dim + 1 + 3) // 4 * 4
 
     def fwdbwd(self, args):
         nt.check(self.lib.rlx_ppo_minibatch_fwdbwd_f32(C.byref(args), _stream()), "rlx_ppo_minibatch_fwdbwd_f32")

@@ -197,7 +197,9 @@ class PPO:
         self.next_values = None if self.is_torch_data_interface else z(T, N)
         self.done_count = torch.zeros(1, dtype=torch.int64, device=dev)
         Bl = self.local_batch_size
-        self.g_states, self.g_actions = z(Bl, obs), z(Bl, act)
+        # gathered states carry a constant-one column (pitch rounded to 16 B): the tensor-core dW1 GEMM emits db1 from it
+        self.ldx = self.kernels.states_pitch()
+        self.g_states, self.g_actions = z(Bl, self.ldx), z(Bl, act)
         self.g_log_probs, self.g_advantages, self.g_returns = z(Bl), z(Bl), z(Bl)
         self.perm_dev = torch.zeros(Bl, dtype=torch.int64, device=dev)
         self.perm_host = torch.zeros(self.nr_epochs, Bl, dtype=torch.int64).pin_memory()
@@ -308,7 +310,8 @@ class PPO:
         return self.kernels.minibatch_args(
             m=0, m_global=1, states=self.g_states, actions=self.g_actions, log_probs=self.g_log_probs, advantages=self.g_advantages,
             returns=self.g_returns, adv_stats=self.adv_stats, params=self.params.flat, grads=self.grads, exp_avg=self.exp_avg,
-            exp_avg_sq=self.exp_avg_sq, lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=metrics_row0, workspace=self.train_ws)
+            exp_avg_sq=self.exp_avg_sq, lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=metrics_row0, workspace=self.train_ws,
+            states_ld=self.ldx, states_ones_col=True)
 
     def _optimize(self):
         """ref: ppo.py:265-294 (epochs x shuffled minibatches)."""
@@ -326,7 +329,7 @@ class PPO:
                 self.perm_host[epoch].copy_(torch.from_numpy(batch_indices))
                 self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
                 k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
-                         self.g_advantages, self.g_returns)
+                         self.g_advantages, self.g_returns, out_states_ld=self.ldx)
                 k.advantage_stats(self.g_advantages, self.batch_size, mbs, self.adv_stats)
                 k.update_epoch(self._first_minibatch_args(self.metrics_dev[row0]), self.batch_size, mbs)
             else:
@@ -342,7 +345,7 @@ class PPO:
         self.perm_host[epoch][:local_idx.shape[0]].copy_(torch.from_numpy(local_idx))
         self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
         k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
-                 self.g_advantages, self.g_returns, count=local_idx.shape[0])
+                 self.g_advantages, self.g_returns, count=local_idx.shape[0], out_states_ld=self.ldx)
         offsets = np.concatenate([[0], np.cumsum(counts)])
         global_counts = sharding.global_minibatch_sizes(self.batch_size, mbs)
         # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
@@ -362,7 +365,8 @@ class PPO:
                 m=int(counts[i]), m_global=int(global_counts[i]), states=self.g_states[offsets[i]:], actions=self.g_actions[offsets[i]:],
                 log_probs=self.g_log_probs[offsets[i]:], advantages=self.g_advantages[offsets[i]:], returns=self.g_returns[offsets[i]:],
                 adv_stats=self.adv_stats[i], params=self.params.flat, grads=self.grads, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq,
-                lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=self.grads[P:], workspace=self.train_ws)
+                lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=self.grads[P:], workspace=self.train_ws,
+                states_ld=self.ldx, states_ones_col=True)
             k.fwdbwd(a)
             dist.all_reduce(self.grads)          # gradient + metric sums, 1.32 MB over NVLink
             k.clip_adam(a)                       # writes the two grad norms into grads[P+5..P+6]

@@ -60,6 +60,7 @@ struct GatherP {
   const float *states, *actions, *logp, *adv, *ret;
   float *o_states, *o_actions, *o_logp, *o_adv, *o_ret;
   int vec_obs;
+  long long o_ld;  // row pitch of o_states
 };
 
 __global__ void __launch_bounds__(256) gather_minibatch_kernel(const GatherP p) {
@@ -71,14 +72,15 @@ __global__ void __launch_bounds__(256) gather_minibatch_kernel(const GatherP p) 
     if (p.o_states) {
       if (p.vec_obs) {
         const float4* s = reinterpret_cast<const float4*>(p.states + src * p.obs);
-        float4* d = reinterpret_cast<float4*>(p.o_states + r * p.obs);
+        float4* d = reinterpret_cast<float4*>(p.o_states + r * p.o_ld);
         const int nv = p.obs >> 2;
         for (int i = lane; i < nv; i += 32) st_stream4(d + i, ld_stream4(s + i));
       } else {
         const float* s = p.states + src * p.obs;
-        float* d = p.o_states + r * p.obs;
+        float* d = p.o_states + r * p.o_ld;
         for (int i = lane; i < p.obs; i += 32) d[i] = s[i];
       }
+      if (p.o_ld > p.obs && lane < (int)(p.o_ld - p.obs)) p.o_states[r * p.o_ld + p.obs + lane] = (lane == 0) ? 1.f : 0.f;
     }
     if (p.o_actions) {
       const float* s = p.actions + src * p.act;
@@ -173,7 +175,7 @@ extern "C" int rlx_rollout_store_f32(const float* reward, const uint8_t* termina
 extern "C" int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64_t obs_dim, int64_t act_dim, const float* states,
                                         const float* actions, const float* log_probs, const float* advantages, const float* returns,
                                         float* out_states, float* out_actions, float* out_log_probs, float* out_advantages,
-                                        float* out_returns, void* stream) {
+                                        float* out_returns, int64_t out_states_ld, void* stream) {
   RLX_CHECK_ARG(count >= 0 && obs_dim > 0 && act_dim > 0, "bad sizes");
   if (count == 0) return RLX_OK;
   RLX_CHECK_ARG(idx != nullptr, "idx is null");
@@ -183,8 +185,10 @@ extern "C" int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64
   RLX_CHECK_ARG(!out_advantages || advantages, "advantages is null");
   RLX_CHECK_ARG(!out_returns || returns, "returns is null");
   GatherP p{(const long long*)idx, count, (int)obs_dim, (int)act_dim, states, actions, log_probs, advantages, returns,
-            out_states, out_actions, out_log_probs, out_advantages, out_returns, 0};
-  p.vec_obs = (obs_dim % 4 == 0 && aligned16(states) && aligned16(out_states)) ? 1 : 0;
+            out_states, out_actions, out_log_probs, out_advantages, out_returns, 0, 0};
+  p.o_ld = out_states_ld > 0 ? out_states_ld : obs_dim;
+  RLX_CHECK_ARG(p.o_ld >= obs_dim && p.o_ld - obs_dim <= 32, "out_states_ld must be in [obs_dim, obs_dim + 32]");
+  p.vec_obs = (obs_dim % 4 == 0 && p.o_ld % 4 == 0 && aligned16(states) && aligned16(out_states)) ? 1 : 0;
   // 8 warps per CTA, grid sized to a multiple of the SM count (persistent-style grid-stride loop over rows)
   const long long want = ceil_div(count, 8);
   const unsigned grid = (unsigned)std::min<long long>(want, (long long)sm_count() * 16);

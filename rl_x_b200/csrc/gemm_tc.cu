@@ -1,10 +1,508 @@
-// tcgen05 (5th-gen tensor core) 3xTF32 GEMM engine — placeholder until the engine lands; the SIMT engine is used.
+// tcgen05 (5th-generation tensor core) GEMM engine with fp32-equivalent accuracy: 3xTF32 split.
+//
+//   C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ),  A, B, C fp32 in global memory, accumulation in fp32 in TMEM.
+//
+// Each fp32 operand x is used as  x = hi + lo  with hi = tf32(x) (the tensor core reads the top 19 bits of the fp32 word)
+// and lo = x - hi (exact in fp32); three MMAs per k-slice accumulate  hi*hi + hi*lo + lo*hi  (the lo*lo term is below fp32
+// resolution).  That is the accuracy class of an fp32 FMA loop (single-pass TF32 misses the 1e-5 loss-parity bar,
+// 3xTF32 does not) at one third of the TF32 tensor rate.
+//
+// Structure (one persistent CTA per SM, 320 threads, static tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of raw fp32 A and B into a shared-memory ring
+//   warps 2-5   splitter: read the raw tiles, write the lo tiles (same swizzled layout) next to them, fence.proxy.async
+//   warp 1      MMA issuer: ONE thread issues tcgen05.mma.cta_group::1.kind::tf32 (3 per k-slice of 8), tcgen05.commit frees the
+//               ring slot / publishes the accumulator
+//   warps 6-9   epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (double-buffered: the next tile's MMAs overlap),
+//               bias+tanh / tanh' / plain, 128-bit global stores
+// Operand layouts: K-major (row = m or n, 32 consecutive k = one 128-byte swizzle row) or MN-major (row = k, 32 consecutive
+// m/n per 128-byte row; used by the weight-gradient GEMMs whose reduction runs over the minibatch rows).  Out-of-bounds parts
+// of a box are zero-filled by TMA, so M / N / K tails need no special code in the main loop.
+#include <cuda.h>
+
 #include "common.cuh"
+#include "gemm_simt.cuh"
 
 namespace rlx {
-int tc_supported(const rlx_ppo_dims&) { return 0; }
-int tc_mlp_hidden_forward(const rlx_ppo_dims&, const float*, const float*, long long, float*, float*, void*, size_t, cudaStream_t) {
+namespace tc {
+
+constexpr int BM = 128;        // UMMA M (cta_group::1)
+constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;      // tf32: 32 bytes of K per instruction
+constexpr int NUM_THREADS = 320;
+constexpr int SPLIT_WARP0 = 2, EPI_WARP0 = 6;
+
+enum TcEpi { TC_EPI_NONE = 0, TC_EPI_BIAS_TANH = 1, TC_EPI_DTANH = 2 };
+
+struct TcParams {
+  int M, N, K;               // per-z output is [M, N]; K = full reduction extent
+  int batch, splits, kchunk; // z = batch * splits; kchunk multiple of BK
+  int tiles_m, tiles_n;
+  // TMA coordinate offsets per batch index (elements)
+  int a_mn_off, a_k_off, b_mn_off, b_k_off;
+  float* C;
+  long long ldc, c_batch_off, c_split_off;
+  int n_main;                // columns >= n_main are not stored to C; column == n_main goes to extra_col (bias-gradient trick)
+  float* extra_col;          // [z][M] or null
+  long long extra_batch_off, extra_split_off;
+  const float* bias;         // TC_EPI_BIAS_TANH
+  long long bias_batch_off;
+  const float* aux;          // TC_EPI_DTANH: activation values, same indexing as C
+  long long ldaux, aux_batch_off;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem)),
+               "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4   [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6); a/b format TF32 = 2 @ [7,10) / [10,13);
+// a_major @ 15, b_major @ 16 (0 = K-major, 1 = MN-major); N >> 3 @ [17,23); M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 4;                   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 4;                   // 16 / 32 KB
+  static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw + lo
+  static constexpr int STAGES = (BN == 256) ? 2 : 3;
+  static constexpr int TMEM_COLS = 2 * BN;                      // double-buffered accumulator
+  static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + BN * 4 /*bias*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024 /*alignment slack*/;
+};
+
+template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                 const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+  using C_ = Cfg<BN>;
+  constexpr int STAGES = C_::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* aux = smem + STAGES * C_::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]  TMA landed
+  uint64_t* split_bar = full_bar + STAGES;                          // [STAGES]  lo tiles written
+  uint64_t* empty_bar = split_bar + STAGES;                         // [STAGES]  MMAs of the slot retired
+  uint64_t* tmem_full_bar = empty_bar + STAGES;                     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_smem = reinterpret_cast<float*>(aux + 1024);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&split_bar[s], 4);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full_bar[a], 1);
+        mbar_init(&tmem_empty_bar[a], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, C_::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_per_z = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_per_z * p.batch * p.splits;
+
+  auto tile_coords = [&](int tile, int& zb, int& zs, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int z = tile / tiles_per_z, r = tile % tiles_per_z;
+    zb = z / p.splits;
+    zs = z % p.splits;
+    m0 = (r / p.tiles_n) * BM;
+    n0 = (r % p.tiles_n) * BN;
+    kbeg = zs * p.kchunk;
+    const int kend = min(p.K, kbeg + p.kchunk);
+    nkb = (kend - kbeg + BK - 1) / BK;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int zb, zs, m0, n0, kbeg, nkb;
+        tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * C_::STAGE_BYTES;
+          uint8_t* sa = st;
+          uint8_t* sb = st + C_::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], C_::A_BYTES + C_::B_BYTES);
+          const int k0 = kbeg + kb * BK;
+          if (A_KMAJ) {
+            tma_load_2d(&tmap_a, &full_bar[s], sa, p.a_k_off * zb + k0, p.a_mn_off * zb + m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 32; ++j)
+              tma_load_2d(&tmap_a, &full_bar[s], sa + j * (BK * 128), p.a_mn_off * zb + m0 + 32 * j, p.a_k_off * zb + k0);
+          }
+          if (B_KMAJ) {
+            tma_load_2d(&tmap_b, &full_bar[s], sb, p.b_k_off * zb + k0, p.b_mn_off * zb + n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 32; ++j)
+              tma_load_2d(&tmap_b, &full_bar[s], sb + j * (BK * 128), p.b_mn_off * zb + n0 + 32 * j, p.b_k_off * zb + k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, !A_KMAJ, !B_KMAJ);
+      // K-major: LBO unused (1), SBO = 8 rows * 128 B.  MN-major: LBO = stride between 32-wide MN atoms, SBO = 8 k-rows * 128 B.
+      constexpr uint32_t A_LBO = A_KMAJ ? 16u : (uint32_t)(BK * 128), B_LBO = B_KMAJ ? 16u : (uint32_t)(BK * 128);
+      constexpr uint32_t A_KSTEP = A_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128), B_KSTEP = B_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128);
+      int s = 0, acc = 0;
+      uint32_t ph = 0, acc_ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int zb, zs, m0, n0, kbeg, nkb;
+        tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          mbar_wait(&split_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
+          const uint32_t sb = sa + C_::A_BYTES;
+          const uint32_t sa_lo = sb + C_::B_BYTES;
+          const uint32_t sb_lo = sa_lo + C_::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+            const uint64_t da = make_smem_desc(sa + kk * A_KSTEP, A_LBO, 1024);
+            const uint64_t db = make_smem_desc(sb + kk * B_KSTEP, B_LBO, 1024);
+            const uint64_t da_lo = make_smem_desc(sa_lo + kk * A_KSTEP, A_LBO, 1024);
+            const uint64_t db_lo = make_smem_desc(sb_lo + kk * B_KSTEP, B_LBO, 1024);
+            umma_tf32(d_tmem, da_lo, db, idesc, (kb | kk) != 0 ? 1u : 0u);  // lo * hi
+            umma_tf32(d_tmem, da, db_lo, idesc, 1u);                        // hi * lo
+            umma_tf32(d_tmem, da, db, idesc, 1u);                           // hi * hi
+          }
+          umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
+    // ===================================================== splitter: lo = x - tf32_trunc(x)
+    const int t = threadIdx.x - SPLIT_WARP0 * 32;  // 0..127
+    constexpr int NV = (C_::A_BYTES + C_::B_BYTES) / 16;  // float4 chunks per stage (raw A and raw B are contiguous)
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int zb, zs, m0, n0, kbeg, nkb;
+      tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
+        const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C_::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + s * C_::STAGE_BYTES + C_::A_BYTES + C_::B_BYTES);
+#pragma unroll 8
+        for (int i = t; i < NV; i += 128) {
+          const uint4 v = raw[i];
+          float4 o;
+          o.x = __uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u);
+          o.y = __uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u);
+          o.z = __uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u);
+          o.w = __uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u);
+          lo[i] = o;
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue: TMEM -> registers -> global
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - EPI_WARP0 * 32;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int zb, zs, m0, n0, kbeg, nkb;
+      tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
+      if (EPI == TC_EPI_BIAS_TANH) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done with bias_smem
+        const float* bias = p.bias + p.bias_batch_off * zb;
+        for (int i = et; i < BN; i += 128) bias_smem[i] = (n0 + i < p.N) ? bias[n0 + i] : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* crow = p.C + p.c_batch_off * zb + p.c_split_off * zs + (long long)row * p.ldc;
+      const float* arow = (EPI == TC_EPI_DTANH) ? (p.aux + p.aux_batch_off * zb + (long long)row * p.ldaux) : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < p.N) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = __uint_as_float(r[j4 * 4 + j]);
+              const int n = nb + j4 * 4 + j;
+              if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bias_smem[c * 32 + j4 * 4 + j]);
+              if (EPI == TC_EPI_DTANH) {
+                const float h = (n < p.N) ? arow[n] : 0.f;
+                x = x * (1.f - h * h);
+              }
+              v[j] = x;
+            }
+            const int n = nb + j4 * 4;
+            if (n + 3 < p.n_main) {
+              *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (n + j < p.n_main) crow[n + j] = v[j];
+                else if (n + j == p.n_main && p.extra_col != nullptr && n + j < p.N)
+                  p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = v[j];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_cols (<= 32), box_rows], SWIZZLE_128B.
+static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("tcgen05 engine: cuTensorMapEncodeTiled is unavailable");
+    return RLX_ERR_UNSUPPORTED;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tcgen05 engine: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows);
+    return RLX_ERR_CUDA;
+  }
+  return RLX_OK;
+}
+
+struct TcOperand {
+  const float* base;
+  long long rows, cols, ld;  // global tensor as allocated: [rows, cols], pitch ld
+};
+
+template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI>
+static int launch_cfg(const TcOperand& A, const TcOperand& B, TcParams p, int kclass, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A.base, A.rows, A.cols, A.ld, 32, A_KMAJ ? BM : BK);
+  if (rc) return rc;
+  rc = make_tmap(&tb, B.base, B.rows, B.cols, B.ld, 32, B_KMAJ ? BN : BK);
+  if (rc) return rc;
+  p.tiles_m = (int)ceil_div(p.M, BM);
+  p.tiles_n = (int)ceil_div(p.N, BN);
+  const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch * p.splits;
+  if (tiles <= 0) return RLX_OK;
+  auto kern = tc_gemm_kernel<BN, A_KMAJ, B_KMAJ, EPI>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    attr_done = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(tiles, sm_count());
+  const double flops = 2.0 * p.M * p.N * (double)p.K * p.batch;
+  const double bytes = 4.0 * p.batch * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N * p.splits);
+  RLX_LAUNCH_C(kclass, flops, bytes, kern, grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream, ta, tb, p);
+  return RLX_OK;
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------ engine entry points
+using namespace tc;
+
+int tc_supported(const rlx_ppo_dims& d) {
+  return (d.hidden % 128 == 0) && d.hidden >= 128 && d.hidden <= 1024 && (d.obs_dim % 4 == 0) && d.obs_dim >= 32;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Generic front end over the SIMT engine's GemmP (same meaning of every field).  Supported: all strides multiples of 4 floats,
+// 16-byte aligned bases, batch strides that are pure row or column offsets of the operand tensors.
+int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
+            float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream) {
+  if (g.M <= 0 || g.N <= 0) return RLX_OK;
+  if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || g.lda % 4 || g.ldb % 4 || g.ldc % 4) return RLX_ERR_UNSUPPORTED;
+  if (g.splits > 1 && g.kchunk % BK) return RLX_ERR_UNSUPPORTED;
+  TcParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.batch = batch; p.splits = g.splits;
+  p.kchunk = (g.splits > 1) ? g.kchunk : (int)(ceil_div(g.K, BK) * BK);
+  // batch offsets -> TMA coordinates
+  auto split_off = [](long long off, int ld, bool kmaj, int& mn_off, int& k_off) {
+    const long long r = off / ld, c = off % ld;
+    if (kmaj) { mn_off = (int)r; k_off = (int)c; } else { k_off = (int)r; mn_off = (int)c; }
+  };
+  split_off(g.sA, g.lda, a_kmaj, p.a_mn_off, p.a_k_off);
+  split_off(g.sB, g.ldb, b_kmaj, p.b_mn_off, p.b_k_off);
+  p.C = g.C; p.ldc = g.ldc; p.c_batch_off = g.sC; p.c_split_off = g.sSplitC;
+  p.n_main = n_main > 0 ? n_main : g.N;
+  p.extra_col = extra_col; p.extra_batch_off = extra_batch_off; p.extra_split_off = extra_split_off;
+  p.bias = g.bias; p.bias_batch_off = g.sBias;
+  p.aux = g.aux; p.ldaux = g.ldaux; p.aux_batch_off = g.sAux;
+  // global tensors: K-major [mn_rows, k_cols]; MN-major [k_rows, mn_cols]
+  TcOperand A{g.A, a_rows, a_kmaj ? (long long)(p.a_k_off * (batch - 1) + g.K) : (long long)(p.a_mn_off * (batch - 1) + g.M), g.lda};
+  TcOperand B{g.B, b_rows, b_kmaj ? (long long)(p.b_k_off * (batch - 1) + g.K) : (long long)(p.b_mn_off * (batch - 1) + g.N), g.ldb};
+  const long long tiles256 = ceil_div(g.M, BM) * ceil_div(g.N, 256) * batch * g.splits;
+  const bool use256 = (g.N % 256 == 0 || g.N > 256 + 128) && tiles256 >= sm_count() / 2;
+#define RLX_TC_DISPATCH(BN_)                                                                                                   \
+  do {                                                                                                                        \
+    if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg<BN_, true, true, TC_EPI_BIAS_TANH>(A, B, p, kclass, stream); \
+    if (a_kmaj && b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, true, true, TC_EPI_NONE>(A, B, p, kclass, stream);       \
+    if (a_kmaj && !b_kmaj && epi == TC_EPI_DTANH) return launch_cfg<BN_, true, false, TC_EPI_DTANH>(A, B, p, kclass, stream);   \
+    if (a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, true, false, TC_EPI_NONE>(A, B, p, kclass, stream);     \
+    if (!a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, false, false, TC_EPI_NONE>(A, B, p, kclass, stream);   \
+  } while (0)
+  if (use256) {
+    RLX_TC_DISPATCH(256);
+  } else {
+    RLX_TC_DISPATCH(128);
+  }
+#undef RLX_TC_DISPATCH
   return RLX_ERR_UNSUPPORTED;
 }
-size_t tc_workspace_bytes(const rlx_ppo_dims&, long long, bool) { return 0; }
+
 }  // namespace rlx

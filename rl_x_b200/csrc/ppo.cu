@@ -14,23 +14,39 @@
 
 namespace rlx {
 
-// tcgen05 engine hooks (gemm_tc.cu). Return RLX_ERR_UNSUPPORTED when the shape is not covered.
+// tcgen05 engine hooks (gemm_tc.cu). tc_gemm returns RLX_ERR_UNSUPPORTED when a shape / alignment is not covered.
 int tc_supported(const rlx_ppo_dims& d);
-int tc_mlp_hidden_forward(const rlx_ppo_dims& d, const float* params, const float* X, long long rows, float* H1, float* H2,
-                          void* tc_ws, size_t tc_ws_bytes, cudaStream_t stream);
-size_t tc_workspace_bytes(const rlx_ppo_dims& d, long long rows, bool train);
+int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
+            float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream);
+enum { TC_NONE = 0, TC_BIAS_TANH = 1, TC_DTANH = 2 };
+
+static bool use_tc(const rlx_ppo_dims& d) { return g_gemm_engine == 1 && tc_supported(d); }
+
+// One GEMM through the selected engine (tcgen05 when it covers the shape, fp32 SIMT otherwise).
+// a_rows / b_rows: number of rows of the operand tensors as laid out in memory (TMA needs the true extents for zero fill).
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+static int run_gemm(bool tc, const GemmP& g, int batch, cudaStream_t st, int kclass, long long a_rows, long long b_rows) {
+  if (tc && g.rowsum == nullptr) {
+    const int epi = (EPI == EPI_BIAS_TANH) ? TC_BIAS_TANH : (EPI == EPI_DTANH) ? TC_DTANH : TC_NONE;
+    const int rc = tc_gemm(g, A_KMAJ, B_KMAJ, epi, batch, kclass, a_rows, b_rows, 0, nullptr, 0, 0, st);
+    if (rc != RLX_ERR_UNSUPPORTED) return rc;
+  }
+  return launch_sgemm<A_KMAJ, B_KMAJ, EPI>(g, batch, st, kclass);
+}
 
 struct Splits {
   int splits, kchunk;
 };
-// choose a split-K factor for a [M' x N'] output reduced over `rows`, aiming at ~2 CTAs per SM
-static Splits choose_splits(long long rows, int out_m, int out_n, int batch) {
+// choose a split-K factor for a [M' x N'] output reduced over `rows`: ~2 CTAs per SM for the SIMT engine, one persistent
+// CTA per SM for the tcgen05 engine (k-chunks are multiples of 32 there: one 128-byte swizzle row of fp32)
+static Splits choose_splits(long long rows, int out_m, int out_n, int batch, bool tc) {
   const long long tiles = ceil_div(out_m, GBM) * ceil_div(out_n, GBN) * batch;
-  const long long target = (long long)sm_count() * 2;
+  const long long target = (long long)sm_count() * (tc ? 1 : 2);
+  const long long gran = tc ? 32 : 8;
   long long s = std::max<long long>(1, target / std::max<long long>(tiles, 1));
   s = std::min<long long>(s, std::max<long long>(1, rows / 256));  // at least 256 rows per split
-  long long kchunk = ceil_div(ceil_div(rows, s), 8) * 8;
-  kchunk = std::max<long long>(kchunk, 8);
+  long long kchunk = ceil_div(ceil_div(rows, s), gran) * gran;
+  kchunk = std::max<long long>(kchunk, gran);
   s = ceil_div(rows, kchunk);
   return Splits{(int)s, (int)kchunk};
 }
@@ -51,18 +67,19 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
 constexpr int kHeadWgradRows = 256;
 
 struct TrainPlan {
-  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_rs2, off_part3, off_norm, total;
-  Splits s1, s2;
-  int head_blocks, wgrad_chunks, norm_blocks;
+  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, total;
+  int max_s1, max_s2;
+  int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
 static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 8), (long long)sm_count() * 4); }
 
 static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   TrainPlan P;
   const long long H = d.hidden, O = d.obs_dim, A = d.act_dim;
-  P.s1 = choose_splits(m, (int)(2 * H), (int)O, 1);
-  P.s2 = choose_splits(m, (int)H, (int)H, 2);
+  P.max_s1 = std::max(choose_splits(m, (int)(2 * H), (int)O, 1, false).splits, choose_splits(m, (int)(2 * H), (int)O + 1, 1, true).splits);
+  P.max_s2 = std::max(choose_splits(m, (int)H, (int)H, 2, false).splits, choose_splits(m, (int)H, (int)H, 2, true).splits);
   P.head_blocks = head_grid(m);
+  P.head_npart = (int)(2 * A + 5 + 2 * H);
   P.wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
   P.norm_blocks = 64;
   size_t o = 0;
@@ -75,11 +92,10 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   take(P.off_dZ2, (size_t)m * 2 * H);
   take(P.off_dZ1, (size_t)m * 2 * H);
   take(P.off_dhead, (size_t)m * (A + 1));
-  take(P.off_headpart, (size_t)P.head_blocks * (2 * A + 5));
-  take(P.off_part1, (size_t)P.s1.splits * 2 * H * O);
-  take(P.off_rs1, (size_t)P.s1.splits * 2 * H);
-  take(P.off_part2, (size_t)P.s2.splits * 2 * H * H);
-  take(P.off_rs2, (size_t)P.s2.splits * 2 * H);
+  take(P.off_headpart, (size_t)P.head_blocks * P.head_npart);
+  take(P.off_part1, (size_t)P.max_s1 * 2 * H * O);
+  take(P.off_rs1, (size_t)P.max_s1 * 2 * H);
+  take(P.off_part2, (size_t)P.max_s2 * 2 * H * H);
   take(P.off_part3, (size_t)P.wgrad_chunks * (A + 1) * H);
   take(P.off_norm, (size_t)P.norm_blocks * 2);
   P.total = o;
@@ -93,20 +109,21 @@ static T* ws_ptr(void* ws, size_t off) {
 
 static size_t head_smem_bytes(const rlx_ppo_dims& d, bool train) {
   size_t s = ((size_t)d.act_dim * d.hidden + d.hidden) * sizeof(float);
-  if (train) s += (size_t)8 * (2 * d.act_dim + 5) * sizeof(float);
+  if (train) s += (size_t)8 * (2 * d.act_dim + 5 + 2 * d.hidden) * sizeof(float);
   return s;
 }
 
-// hidden layers: H1 = tanh(X W1cat^T + b1cat), H2 = tanh(H1 (blockdiag W2)^T + b2cat)
-static int mlp_hidden_forward_simt(const PpoLayout& L, const float* params, const float* X, long long rows, float* H1, float* H2,
-                                   cudaStream_t stream) {
+// hidden layers: H1 = tanh(X W1cat^T + b1cat), H2 = tanh(H1 (blockdiag W2)^T + b2cat).  ldx = row pitch of X.
+static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const float* params, const float* X, long long ldx, long long rows,
+                              float* H1, float* H2, cudaStream_t stream) {
   const int H = L.H;
+  const bool tc = use_tc(d);
   GemmP g{};
   g.A = X; g.B = params + L.off[W1P]; g.C = H1; g.bias = params + L.off[B1P];
   g.M = (int)rows; g.N = 2 * H; g.K = L.obs;
-  g.lda = L.obs; g.ldb = L.obs; g.ldc = 2 * H;
+  g.lda = (int)ldx; g.ldb = L.obs; g.ldc = 2 * H;
   g.splits = 1; g.kchunk = (int)(ceil_div(L.obs, 8) * 8);
-  int rc = launch_sgemm<true, true, EPI_BIAS_TANH>(g, 1, stream, KC_GEMM_FWD);
+  int rc = run_gemm<true, true, EPI_BIAS_TANH>(tc, g, 1, stream, KC_GEMM_FWD, rows, 2 * H);
   if (rc) return rc;
   GemmP g2{};
   g2.A = H1; g2.B = params + L.off[W2P]; g2.C = H2; g2.bias = params + L.off[B2P];
@@ -114,16 +131,7 @@ static int mlp_hidden_forward_simt(const PpoLayout& L, const float* params, cons
   g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
   g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
   g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
-  return launch_sgemm<true, true, EPI_BIAS_TANH>(g2, 2, stream, KC_GEMM_FWD);
-}
-
-static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const float* params, const float* X, long long rows, float* H1,
-                              float* H2, cudaStream_t stream) {
-  if (g_gemm_engine == 1 && tc_supported(d)) {
-    int rc = tc_mlp_hidden_forward(d, params, X, rows, H1, H2, nullptr, 0, stream);
-    if (rc != RLX_ERR_UNSUPPORTED) return rc;
-  }
-  return mlp_hidden_forward_simt(L, params, X, rows, H1, H2, stream);
+  return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, 2 * H);
 }
 
 #define RLX_DISPATCH_NCH(CLS, FLOPS, BYTES, H, KERNEL, grid, block, smem, stream, arg)                                              \
@@ -174,7 +182,7 @@ extern "C" int rlx_ppo_forward_f32(const rlx_ppo_forward_args* a, void* stream) 
   float* H1 = ws_ptr<float>(a->workspace, P.off_H1);
   float* H2 = ws_ptr<float>(a->workspace, P.off_H2);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = mlp_hidden_forward(a->dims, L, a->params, a->obs, a->n, H1, H2, st);
+  int rc = mlp_hidden_forward(a->dims, L, a->params, a->obs, a->dims.obs_dim, a->n, H1, H2, st);
   if (rc) return rc;
   HeadP h{};
   fill_head_common(h, L, a->params, H2, a->n);
@@ -226,6 +234,10 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   const PpoLayout L = make_layout(d);
   const long long m = a->m;
   const int H = L.H, O = L.obs, A = L.act;
+  const long long ldx = a->states_ld > 0 ? a->states_ld : O;
+  RLX_CHECK_ARG(ldx >= O, "states_ld smaller than obs_dim");
+  RLX_CHECK_ARG(!a->states_ones_col || ldx > O, "states_ones_col needs states_ld > obs_dim");
+  const bool tc = use_tc(d);
   const TrainPlan P = plan_train(d, std::max<long long>(m, 1));
   cudaStream_t st = (cudaStream_t)stream;
   void* ws = a->workspace;
@@ -238,16 +250,16 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   float* part1 = ws_ptr<float>(ws, P.off_part1);
   float* rs1 = ws_ptr<float>(ws, P.off_rs1);
   float* part2 = ws_ptr<float>(ws, P.off_part2);
-  float* rs2 = ws_ptr<float>(ws, P.off_rs2);
   float* part3 = ws_ptr<float>(ws, P.off_part3);
   const float inv_mg = 1.f / (float)a->m_global;
+  const int npart = P.head_npart;
 
   int head_blocks = 0, wgrad_chunks = 0, s1 = 0, s2 = 0;
   if (m > 0) {
     // ---- forward hidden layers
-    rc = mlp_hidden_forward(d, L, a->params, a->states, m, H1, H2, st);
+    rc = mlp_hidden_forward(d, L, a->params, a->states, ldx, m, H1, H2, st);
     if (rc) return rc;
-    // ---- head: loss + dZ2 + dhead + block partials
+    // ---- head: loss + dZ2 + dhead + block partials (incl. db2 = column sums of dZ2)
     HeadP h{};
     fill_head_common(h, L, a->params, H2, m);
     h.actions = a->actions; h.logp_old = a->log_probs; h.adv = a->advantages; h.ret = a->returns; h.adv_stats = a->adv_stats;
@@ -269,16 +281,16 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
       RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
       RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
     }
-    // ---- dW2 | db2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]
-    const Splits S2 = choose_splits(m, H, H, 2);
+    // ---- dW2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]   (db2 comes from the head kernel)
+    const Splits S2 = choose_splits(m, H, H, 2, tc);
     s2 = S2.splits;
     GemmP g{};
-    g.A = dZ2; g.B = H1; g.C = part2; g.rowsum = rs2;
+    g.A = dZ2; g.B = H1; g.C = part2;
     g.M = H; g.N = H; g.K = (int)m;
     g.lda = 2 * H; g.ldb = 2 * H; g.ldc = H;
-    g.sA = H; g.sB = H; g.sC = (long long)H * H; g.sRowsum = H;
-    g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H; g.sSplitRowsum = 2LL * H;
-    rc = launch_sgemm<false, false, EPI_NONE>(g, 2, st, KC_GEMM_DW);
+    g.sA = H; g.sB = H; g.sC = (long long)H * H;
+    g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H;
+    rc = run_gemm<false, false, EPI_NONE>(tc, g, 2, st, KC_GEMM_DW, m, m);
     if (rc) return rc;
     // ---- dZ1 = (dZ2 @ W2) * (1 - H1^2)   per net
     GemmP gd{};
@@ -287,36 +299,55 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
     gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
     gd.splits = 1; gd.kchunk = (int)(ceil_div(H, 8) * 8);
-    rc = launch_sgemm<true, false, EPI_DTANH>(gd, 2, st, KC_GEMM_DX);
+    rc = run_gemm<true, false, EPI_DTANH>(tc, gd, 2, st, KC_GEMM_DX, m, 2 * H);
     if (rc) return rc;
-    // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i]
-    const Splits S1 = choose_splits(m, 2 * H, O, 1);
-    s1 = S1.splits;
+    // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i];  db1[o] = sum_rows dZ1[r, o]
     GemmP g1{};
-    g1.A = dZ1; g1.B = a->states; g1.C = part1; g1.rowsum = rs1;
+    g1.A = dZ1; g1.B = a->states; g1.C = part1;
     g1.M = 2 * H; g1.N = O; g1.K = (int)m;
-    g1.lda = 2 * H; g1.ldb = O; g1.ldc = O;
-    g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O; g1.sSplitRowsum = 2LL * H;
-    rc = launch_sgemm<false, false, EPI_NONE>(g1, 1, st, KC_GEMM_DW);
-    if (rc) return rc;
+    g1.lda = 2 * H; g1.ldb = (int)ldx; g1.ldc = O;
+    bool done = false;
+    if (tc && a->states_ones_col) {
+      // tensor-core path: the constant-one column of X makes db1 the (O+1)-th output column of the same GEMM
+      const Splits S1 = choose_splits(m, 2 * H, O + 1, 1, true);
+      g1.N = O + 1;
+      g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O;
+      rc = tc_gemm(g1, false, false, TC_NONE, 1, KC_GEMM_DW, m, m, O, rs1, 0, 2LL * H, st);
+      if (rc == RLX_OK) {
+        done = true;
+        s1 = S1.splits;
+      } else if (rc != RLX_ERR_UNSUPPORTED) {
+        return rc;
+      }
+      g1.N = O;
+    }
+    if (!done) {
+      const Splits S1 = choose_splits(m, 2 * H, O, 1, false);
+      s1 = S1.splits;
+      g1.rowsum = rs1;
+      g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O; g1.sSplitRowsum = 2LL * H;
+      rc = launch_sgemm<false, false, EPI_NONE>(g1, 1, st, KC_GEMM_DW);
+      if (rc) return rc;
+    }
   }
   // ---- assemble the flat gradient (m == 0: a rank that owns no row of this minibatch contributes zeros)
   GradReduceP r{};
   r.g[0] = GradGroup{L.off[W1P], 2LL * H * O, part1, s1, 2LL * H * O};
   r.g[1] = GradGroup{L.off[B1P], 2LL * H, rs1, s1, 2LL * H};
   r.g[2] = GradGroup{L.off[W2P], 2LL * H * H, part2, s2, 2LL * H * H};
-  r.g[3] = GradGroup{L.off[B2P], 2LL * H, rs2, s2, 2LL * H};
+  r.g[3] = GradGroup{L.off[B2P], 2LL * H, headpart + (2 * A + 5), head_blocks, (long long)npart};
   r.g[4] = GradGroup{L.off[W3P], (long long)(A + 1) * H, part3, wgrad_chunks, (long long)(A + 1) * H};
-  r.g[5] = GradGroup{L.off[B3P], 2LL * A + 1, headpart, head_blocks, 2LL * A + 5};
+  r.g[5] = GradGroup{L.off[B3P], 2LL * A + 1, headpart, head_blocks, (long long)npart};
   r.total = L.total();
   r.logstd_off = L.off[LOGSTD];
   r.act = A;
   r.entropy_grad = -a->hp.entropy_coef * (float)m * inv_mg;
   r.grads = a->grads;
-  r.head_partials = headpart; r.nblk = head_blocks; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
+  r.head_partials = headpart; r.nblk = head_blocks; r.npart = npart; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
-  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * (H + 1) + (double)wgrad_chunks * (A + 1) * H + L.total()), ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
+  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * H + (double)wgrad_chunks * (A + 1) * H + L.total()),
+               ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
   return RLX_OK;
 }
 
@@ -347,7 +378,8 @@ extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void*
 extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int64_t count, int64_t mb, void* stream) {
   RLX_CHECK_ARG(first != nullptr && count >= 0 && mb > 0, "bad arguments");
   const int64_t nmb = ceil_div(count, mb);
-  const int O = first->dims.obs_dim, A = first->dims.act_dim;
+  const int A = first->dims.act_dim;
+  const int64_t O = first->states_ld > 0 ? first->states_ld : first->dims.obs_dim;  // row pitch of the gathered states
   for (int64_t k = 0; k < nmb; ++k) {
     rlx_ppo_minibatch_args a = *first;
     const int64_t r0 = k * mb;
@@ -366,6 +398,33 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
     if (rc) return rc;
   }
   return RLX_OK;
+}
+
+// Test hook: one plain GEMM through either engine (single batch, no split): layout 0 = A k-major, B k-major (C = A B^T);
+// 1 = A k-major, B n-major (C = A B); 2 = A m-major, B n-major (C = A^T B, A is [K, M]).  epilogue 0 none, 1 bias+tanh, 2 tanh'.
+extern "C" int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                                  const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, const float* aux, int64_t ldaux,
+                                  void* stream) {
+  RLX_CHECK_ARG(A && B && C && M > 0 && N > 0 && K > 0, "bad arguments");
+  RLX_CHECK_ARG((epilogue == 0) || (epilogue == 1 && layout == 0 && bias) || (epilogue == 2 && layout == 1 && aux), "unsupported epilogue/layout");
+  GemmP g{};
+  g.A = A; g.B = B; g.C = C; g.bias = bias; g.aux = aux;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.lda = (int)lda; g.ldb = (int)ldb; g.ldc = (int)ldc; g.ldaux = (int)ldaux;
+  g.splits = 1; g.kchunk = (int)(ceil_div(K, 8) * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool a_k = layout != 2, b_k = layout == 0;
+  const long long a_rows = a_k ? M : K, b_rows = b_k ? N : K;
+  if (engine == 1) {
+    const int rc = tc_gemm(g, a_k, b_k, epilogue, 1, KC_OTHER, a_rows, b_rows, 0, nullptr, 0, 0, st);
+    if (rc == RLX_ERR_UNSUPPORTED) set_error("rlx_debug_gemm_f32: shape/alignment not supported by the tcgen05 engine");
+    return rc;
+  }
+  if (layout == 0 && epilogue == 1) return launch_sgemm<true, true, EPI_BIAS_TANH>(g, 1, st);
+  if (layout == 0) return launch_sgemm<true, true, EPI_NONE>(g, 1, st);
+  if (layout == 1 && epilogue == 2) return launch_sgemm<true, false, EPI_DTANH>(g, 1, st);
+  if (layout == 1) return launch_sgemm<true, false, EPI_NONE>(g, 1, st);
+  return launch_sgemm<false, false, EPI_NONE>(g, 1, st);
 }
 
 extern "C" int rlx_set_gemm_engine(int engine) {

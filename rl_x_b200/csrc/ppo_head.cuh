@@ -65,7 +65,7 @@ struct HeadP {
   float clip_range, critic_coef;
   float* dZ2;              // [M, 2H]
   float* dhead;            // [M, act+1]   (dmean | dv)
-  float* block_partials;   // [gridDim.x, 2*act+5]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac)
+  float* block_partials;   // [gridDim.x, 2*act+5+2H]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac | db2p[H] | db2c[H])
 };
 
 // Loads the row's H2 slices and returns the act means (lane a holds mean a; a+32 in mean_hi) and the value (all lanes).
@@ -163,10 +163,13 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
   extern __shared__ float smem[];
   float* sW3p = smem;
   float* sW3c = smem + p.act * p.H;
-  float* sred = sW3c + p.H;  // [nw][2*act+5]
+  float* sred = sW3c + p.H;  // [nw][2*act+5+2H]
   head_stage_weights(p, sW3p, sW3c);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int npart = 2 * p.act + 5;
+  const int npart = 2 * p.act + 5 + 2 * p.H;
+  float acc_db2p[NCH], acc_db2c[NCH];  // column sums of dZ2 = layer-2 bias gradients (lane owns columns lane + 32c)
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) acc_db2p[c] = acc_db2c[c] = 0.f;
 
   const float adv_mean = p.adv_stats[0];
   const float adv_den = p.adv_stats[1] + 1e-8f;  // ppo.py:134
@@ -245,8 +248,12 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     for (int c = 0; c < NCH; ++c) {
       const int j = lane + 32 * c;
       if (j < p.H) {
-        out[j] = dz[c] * (1.f - hp[c] * hp[c]);
-        out[p.H + j] = dv * sW3c[j] * (1.f - hc[c] * hc[c]);
+        const float zp = dz[c] * (1.f - hp[c] * hp[c]);
+        const float zc = dv * sW3c[j] * (1.f - hc[c] * hc[c]);
+        out[j] = zp;
+        out[p.H + j] = zc;
+        acc_db2p[c] += zp;
+        acc_db2c[c] += zc;
       }
     }
   }
@@ -267,6 +274,14 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     my[2 * p.act + 2] = acc_vl;
     my[2 * p.act + 3] = acc_kl;
     my[2 * p.act + 4] = acc_cf;
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = lane + 32 * c;
+    if (j < p.H) {
+      my[2 * p.act + 5 + j] = acc_db2p[c];
+      my[2 * p.act + 5 + p.H + j] = acc_db2c[c];
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < npart; i += blockDim.x) {

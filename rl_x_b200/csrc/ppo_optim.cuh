@@ -23,8 +23,8 @@ struct GradReduceP {
   float entropy_grad;          // -entropy_coef * m / m_global, added to every logstd gradient
   float* grads;
   // metrics
-  const float* head_partials;  // [nblk, 2*act+5]
-  int nblk;
+  const float* head_partials;  // [nblk, npart]
+  int nblk, npart;
   float inv_mg;
   float critic_coef;
   const float* logstd;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
   }
   if (blockIdx.x == 0 && p.metrics != nullptr) {
     // metric sums of this minibatch (ref: ppo.py:126-141,157): warp 0 reduces the head block partials in fixed order
-    const int npart = 2 * p.act + 5;
+    const int npart = p.npart;
     if (threadIdx.x < 4) {
       float s = 0.f;
       for (int b = 0; b < p.nblk; ++b) s += p.head_partials[(long long)b * npart + 2 * p.act + 1 + threadIdx.x];

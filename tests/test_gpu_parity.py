@@ -16,6 +16,16 @@ from oracle import ppo_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["simt", "tcgen05"])
+def gemm_engine(request):
+    """Every test runs once per GEMM engine (shapes the tcgen05 engine does not cover fall back to the SIMT engine)."""
+    from rl_x_b200 import _native as nt
+    lib = nt.load()
+    lib.rlx_set_gemm_engine(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    lib.rlx_set_gemm_engine(0)
+
 DEV = "cuda"
 
 
@@ -217,6 +227,11 @@ def _run_fwdbwd(k, fp, mbatch, hp, m_global=None):
     m = mbatch["states"].shape[0]
     P = k.param_count
     d = {n: v.to(DEV).contiguous() for n, v in mbatch.items()}
+    ldx = k.states_pitch()  # padded pitch + constant-one column, as the plugin's gather produces it
+    xs = torch.zeros(m, ldx, device=DEV)
+    xs[:, :k.obs_dim] = d["states"]
+    xs[:, k.obs_dim] = 1.0
+    d["states"] = xs
     stats = torch.empty(1, 2, device=DEV)
     k.advantage_stats(d["advantages"], m, m, stats)
     grads, metrics = torch.zeros(P, device=DEV), torch.zeros(8, device=DEV)
@@ -226,7 +241,7 @@ def _run_fwdbwd(k, fp, mbatch, hp, m_global=None):
     args = k.minibatch_args(m=m, m_global=m_global or m, states=d["states"], actions=d["actions"], log_probs=d["log_probs"],
                             advantages=d["advantages"], returns=d["returns"], adv_stats=stats, params=fp.flat, grads=grads,
                             exp_avg=st["exp_avg"], exp_avg_sq=st["exp_avg_sq"], lr=st["lr"], step_count=st["step"], hp=hp,
-                            metrics=metrics, workspace=ws)
+                            metrics=metrics, workspace=ws, states_ld=ldx, states_ones_col=True)
     k.fwdbwd(args)
     return args, grads, metrics, st, (d, stats, ws)
 
@@ -324,18 +339,20 @@ def test_update_epochs_vs_reference_golden(golden):
         lr.fill_(g.lr_at(it))
         src = [torch.from_numpy(g[f"iter{it}/{n}"]).reshape((B,) + g[f"iter{it}/{n}"].shape[2:]).to(DEV).contiguous()
                for n in ["states", "actions", "log_probs", "advantages", "returns"]]
-        dst = [torch.empty_like(s) for s in src]
+        ldx = k.states_pitch()
+        dst = [torch.empty(B, ldx, device=DEV)] + [torch.empty_like(s) for s in src[1:]]
         metrics = torch.zeros(g.epochs * nmb, 8, device=DEV)
         stats = torch.empty(nmb, 2, device=DEV)
         idx = np.arange(B)
         for e in range(g.epochs):
             rng.shuffle(idx)
             assert np.array_equal(idx, g.perms(it)[e])
-            k.gather(torch.from_numpy(idx).to(DEV), *src, *dst)
+            k.gather(torch.from_numpy(idx).to(DEV), *src, *dst, out_states_ld=ldx)
+            assert torch.equal(dst[0][:, g.obs], torch.ones(B, device=DEV)) and torch.equal(dst[0][:, :g.obs], src[0][torch.from_numpy(idx).to(DEV)])
             k.advantage_stats(dst[3], B, g.mb, stats)
             args = k.minibatch_args(m=0, m_global=1, states=dst[0], actions=dst[1], log_probs=dst[2], advantages=dst[3], returns=dst[4],
                                     adv_stats=stats, params=fp.flat, grads=grads, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, lr=lr,
-                                    step_count=step, hp=hp, metrics=metrics[e * nmb], workspace=ws)
+                                    step_count=step, hp=hp, metrics=metrics[e * nmb], workspace=ws, states_ld=ldx, states_ones_col=True)
             k.update_epoch(args, B, g.mb)
         torch.cuda.synchronize()
         pol_ref, cri_ref = g.params(f"iter{it}")

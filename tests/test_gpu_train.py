@@ -7,6 +7,16 @@ import torch
 from oracle import ppo_oracle as O
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["simt", "tcgen05"])
+def gemm_engine(request):
+    """Every test runs once per GEMM engine (shapes the tcgen05 engine does not cover fall back to the SIMT engine)."""
+    from rl_x_b200 import _native as nt
+    lib = nt.load()
+    lib.rlx_set_gemm_engine(1 if request.param == "tcgen05" else 0)
+    yield request.param
+    lib.rlx_set_gemm_engine(0)
 DEV = "cuda"
 
 
@@ -70,7 +80,7 @@ class ReplayEnv:
         pass
 
 
-def _config(g, **algo):
+def _config(g, engine="simt", **algo):
     from rl_x_b200.config_dict import ConfigDict
     from rl_x_b200.algorithms.ppo.b200.default_config import get_config
     a = get_config("ppo.b200")
@@ -79,6 +89,7 @@ def _config(g, **algo):
     a.std_dev, a.entropy_coef, a.anneal_learning_rate = g.std_dev, g.entropy_coef, g.anneal
     a.learning_rate, a.clip_range, a.critic_coef, a.max_grad_norm = g.lr, g.clip_range, g.critic_coef, g.max_grad_norm
     a.gamma, a.gae_lambda = g.gamma, g.gae_lambda
+    a.gemm_engine = engine
     for k, v in algo.items():
         a[k] = v
     return ConfigDict(algorithm=a, environment=ConfigDict(seed=g.seed, nr_envs=g.N),
@@ -100,11 +111,11 @@ def _reference_noise(g):
 
 
 @pytest.mark.parametrize("interface", ["TORCH", "NUMPY"])
-def test_train_reproduces_reference_run(golden, interface):
+def test_train_reproduces_reference_run(golden, interface, gemm_engine):
     from rl_x_b200.algorithms.ppo.b200.ppo import PPO
     g = golden
     env = ReplayEnv(g, interface)
-    model = PPO(_config(g), env, env, "/tmp/rlx_test_run", None)
+    model = PPO(_config(g, engine=gemm_engine), env, env, "/tmp/rlx_test_run", None)
     eps = _reference_noise(g)
     calls = {"n": 0}
 
@@ -156,12 +167,13 @@ def test_train_reproduces_reference_run(golden, interface):
     np.testing.assert_allclose(ours, g["metric/loss/policy_gradient_loss"], rtol=0, atol=2e-5)
 
 
-def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch):
+def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch, gemm_engine):
     from rl_x_b200.runner.runner import Runner
     from rl_x_b200 import _native as nt
     monkeypatch.chdir(tmp_path)
     argv = ["--environment.nr_envs=64", "--environment.obs_dim=24", "--environment.act_dim=5", "--algorithm.nr_steps=16",
             "--algorithm.minibatch_size=256", "--algorithm.nr_epochs=2", "--algorithm.nr_hidden_units=64", "--algorithm.total_timesteps=3072",
+            f"--algorithm.gemm_engine={gemm_engine}",
             "--runner.save_model=True", "--runner.run_name=t1", "--environment.termination_probability=0.05"]
     nt.load().rlx_reset_launch_count()
     r = Runner(argv=argv)
