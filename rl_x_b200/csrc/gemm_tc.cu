@@ -125,13 +125,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4   [16,30) leading byte offset >> 4   [32,46) stride byte offset >> 4   [46,48) version = 1
 //   [61,64) layout type = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   K-major operands use SWIZZLE_128B (type 2: 16-byte chunks XOR row%8, 8-row groups of 1024 B).  MN-major 32-bit operands
+//   must use SWIZZLE_128B_BASE32B (type 1: 32-byte chunks XOR row%4, 4-row groups of 512 B) — the only MN-major layout the
+//   tensor core accepts for tf32 (cutlass sm100_common.inl:92); TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6); a/b format TF32 = 2 @ [7,10) / [10,13);
@@ -141,13 +144,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+// TMEM: every output tile owns TWO fp32 accumulators of BN columns: `main` collects hi*hi, `corr` collects hi*lo + lo*hi.
+// The tensor core adds into an accumulator with round-toward-zero (measured: error grows by ~0.3 ulp per MMA, profiles/
+// tc_accuracy_probe.py), so the tiny correction terms must not touch the main accumulator; the epilogue adds the two in fp32 RN.
+// BN = 256 -> one tile in flight (512 columns); BN = 128 -> double-buffered (2 x 256 columns: next tile's MMAs overlap the epilogue).
 template <int BN>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;                   // 16 KB
   static constexpr int B_BYTES = BN * BK * 4;                   // 16 / 32 KB
   static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);   // raw + lo
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
-  static constexpr int TMEM_COLS = 2 * BN;                      // double-buffered accumulator
+  static constexpr int ACC_STAGES = (BN == 256) ? 1 : 2;
+  static constexpr int TMEM_COLS = ACC_STAGES * 2 * BN;         // 512
   static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + BN * 4 /*bias*/;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024 /*alignment slack*/;
 };
@@ -157,15 +165,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
   using C_ = Cfg<BN>;
   constexpr int STAGES = C_::STAGES;
+  constexpr int ACC_STAGES = C_::ACC_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* aux = smem + STAGES * C_::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]  TMA landed
   uint64_t* split_bar = full_bar + STAGES;                          // [STAGES]  lo tiles written
   uint64_t* empty_bar = split_bar + STAGES;                         // [STAGES]  MMAs of the slot retired
-  uint64_t* tmem_full_bar = empty_bar + STAGES;                     // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;                     // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;                     // [ACC_STAGES]
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;            // [ACC_STAGES]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
   float* bias_smem = reinterpret_cast<float*>(aux + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         mbar_init(&split_bar[s], 4);
         mbar_init(&empty_bar[s], 1);
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < ACC_STAGES; ++a) {
         mbar_init(&tmem_full_bar[a], 1);
         mbar_init(&tmem_empty_bar[a], 4);
       }
@@ -248,6 +257,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       constexpr uint32_t idesc = make_idesc(BN, !A_KMAJ, !B_KMAJ);
       // K-major: LBO unused (1), SBO = 8 rows * 128 B.  MN-major: LBO = stride between 32-wide MN atoms, SBO = 8 k-rows * 128 B.
       constexpr uint32_t A_LBO = A_KMAJ ? 16u : (uint32_t)(BK * 128), B_LBO = B_KMAJ ? 16u : (uint32_t)(BK * 128);
+      constexpr uint32_t A_SBO = A_KMAJ ? 1024u : 512u, B_SBO = B_KMAJ ? 1024u : 512u;
+      constexpr uint32_t A_LT = A_KMAJ ? 2u : 1u, B_LT = B_KMAJ ? 2u : 1u;
       constexpr uint32_t A_KSTEP = A_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128), B_KSTEP = B_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128);
       int s = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0;
@@ -256,7 +267,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN);
+        const uint32_t d_corr = d_main + (uint32_t)BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full_bar[s], ph);
           mbar_wait(&split_bar[s], ph);
@@ -267,19 +279,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           const uint32_t sb_lo = sa_lo + C_::A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * A_KSTEP, A_LBO, 1024);
-            const uint64_t db = make_smem_desc(sb + kk * B_KSTEP, B_LBO, 1024);
-            const uint64_t da_lo = make_smem_desc(sa_lo + kk * A_KSTEP, A_LBO, 1024);
-            const uint64_t db_lo = make_smem_desc(sb_lo + kk * B_KSTEP, B_LBO, 1024);
-            umma_tf32(d_tmem, da_lo, db, idesc, (kb | kk) != 0 ? 1u : 0u);  // lo * hi
-            umma_tf32(d_tmem, da, db_lo, idesc, 1u);                        // hi * lo
-            umma_tf32(d_tmem, da, db, idesc, 1u);                           // hi * hi
+            const uint64_t da = make_smem_desc(sa + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
+            const uint64_t db = make_smem_desc(sb + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+            const uint64_t da_lo = make_smem_desc(sa_lo + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
+            const uint64_t db_lo = make_smem_desc(sb_lo + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+            const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
+            umma_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
+            umma_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
+            umma_tf32(d_main, da, db, idesc, accum);     // hi * hi
           }
           umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
-        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        umma_commit(&tmem_full_bar[acc]);  // accumulators complete
+        if (++acc == ACC_STAGES) { acc = 0; acc_ph ^= 1; }
       }
     }
   } else if (warp >= SPLIT_WARP0 && warp < EPI_WARP0) {
@@ -334,8 +347,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       const float* arow = (EPI == TC_EPI_DTANH) ? (p.aux + p.aux_batch_off * zb + (long long)row * p.ldaux) : nullptr;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        uint32_t r[32], rc[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
+        tmem_ld_32x32b_x32(taddr, r);
+        tmem_ld_32x32b_x32(taddr + BN, rc);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
         if (row_ok && nb < p.N) {
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float x = __uint_as_float(r[j4 * 4 + j]);
+              float x = __uint_as_float(r[j4 * 4 + j]) + __uint_as_float(rc[j4 * 4 + j]);
               const int n = nb + j4 * 4 + j;
               if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bias_smem[c * 32 + j4 * 4 + j]);
               if (EPI == TC_EPI_DTANH) {
@@ -370,7 +385,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      if (++acc == ACC_STAGES) { acc = 0; acc_ph ^= 1; }
     }
   }
 
@@ -401,7 +416,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 row-major tensor [rows, cols] with row pitch ld (elements); box = [box_cols (<= 32), box_rows], SWIZZLE_128B.
-static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+static int make_tmap(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows, bool kmaj) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("tcgen05 engine: cuTensorMapEncodeTiled is unavailable");
@@ -412,7 +427,8 @@ static int make_tmap(CUtensorMap* map, const float* base, long long rows, long l
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  kmaj ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tcgen05 engine: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r, rows, cols, ld, box_cols, box_rows);
     return RLX_ERR_CUDA;
@@ -428,9 +444,9 @@ struct TcOperand {
 template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI>
 static int launch_cfg(const TcOperand& A, const TcOperand& B, TcParams p, int kclass, cudaStream_t stream) {
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, A.base, A.rows, A.cols, A.ld, 32, A_KMAJ ? BM : BK);
+  int rc = make_tmap(&ta, A.base, A.rows, A.cols, A.ld, 32, A_KMAJ ? BM : BK, A_KMAJ);
   if (rc) return rc;
-  rc = make_tmap(&tb, B.base, B.rows, B.cols, B.ld, 32, B_KMAJ ? BN : BK);
+  rc = make_tmap(&tb, B.base, B.rows, B.cols, B.ld, 32, B_KMAJ ? BN : BK, B_KMAJ);
   if (rc) return rc;
   p.tiles_m = (int)ceil_div(p.M, BM);
   p.tiles_n = (int)ceil_div(p.N, BN);
