@@ -277,7 +277,8 @@ def main():
         model._train_iteration()
     classes = nt.timing_end()
     kernel_ms = {k: round(v["ms"] / 2, 4) for k, v in classes.items() if v["launches"]}
-    engine = "tcgen05-3xTF32" if lib.rlx_get_gemm_engine() == 1 and getattr(model.kernels, "tc_active", False) else "simt-fp32"
+    tc_shape_ok = C2["hidden"] % 128 == 0 and C2["obs_dim"] % 4 == 0
+    engine = "tcgen05-3xTF32" if lib.rlx_get_gemm_engine() == 1 and tc_shape_ok else "simt-fp32"
     peaks = measured_peaks()
     gemm = {k: classes[k] for k in ("gemm_fwd", "gemm_dx", "gemm_dw")}
     gflops, gms = sum(v["flops"] for v in gemm.values()), sum(v["ms"] for v in gemm.values())

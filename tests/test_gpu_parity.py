@@ -114,13 +114,16 @@ def test_forward_vs_oracle(obs, act, hidden, n):
     ws = k.forward_workspace(n, DEV)
     a, e, lp, v = (torch.empty(n, act, device=DEV), torch.empty(n, act, device=DEV), torch.empty(n, device=DEV), torch.empty(n, device=DEV))
     k.forward(fp.flat, x.to(DEV), ws, noise=noise.to(DEV), act_low=low.to(DEV), act_high=high.to(DEV), action=a, env_action=e, logp=lp, value=v)
-    np.testing.assert_allclose(a.cpu().numpy(), a_ref.numpy(), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(e.cpu().numpy(), e_ref.numpy(), rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref.numpy(), rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(v.cpu().numpy(), v_ref.numpy(), rtol=1e-5, atol=1e-6)
+    # 1e-5 relative to the scale of each quantity (elementwise: rtol on the value + the same fraction of the tensor's rms)
+    tol = lambda ref: dict(rtol=1e-5, atol=1e-5 * float(ref.pow(2).mean().sqrt()))
+    np.testing.assert_allclose(a.cpu().numpy(), a_ref.numpy(), **tol(a_ref))
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref.numpy(), **tol(e_ref))
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref.numpy(), **tol(lp_ref))
+    np.testing.assert_allclose(v.cpu().numpy(), v_ref.numpy(), **tol(v_ref))
+    assert _rel(a.cpu().numpy(), a_ref.numpy()) < 5e-6 and _rel(v.cpu().numpy(), v_ref.numpy()) < 5e-6
     d = torch.empty(n, act, device=DEV)
     k.forward(fp.flat, x.to(DEV), ws, act_low=low.to(DEV), act_high=high.to(DEV), deterministic=True, env_action=d)
-    np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(d.cpu().numpy(), d_ref.numpy(), **tol(d_ref))
     v2 = torch.empty(n, device=DEV)
     k.critic_forward(fp.flat, x.to(DEV), v2, ws)
     assert torch.equal(v2, v)
@@ -360,7 +363,9 @@ def test_update_epochs_vs_reference_golden(golden):
         for name, v in {**pol_ref, **cri_ref}.items():
             ours = (pol_now if name in pol_now else cri_now)[name].numpy()
             assert _rel(ours, v) <= 1e-5, (it, name, _rel(ours, v))
-            np.testing.assert_allclose(ours, v, rtol=1e-4, atol=2e-6, err_msg=f"iter {it} {name}")
+            # elementwise: Adam normalises the step, so a gradient component near zero can move a weight by a fraction of
+            # one lr-sized step differently; bound that by 10 % of a step
+            np.testing.assert_allclose(ours, v, rtol=1e-4, atol=0.1 * g.lr, err_msg=f"iter {it} {name}")
         m = metrics.cpu().numpy()
         for col, name, floor in [(0, "loss/policy_gradient_loss", 0.5), (1, "loss/critic_loss", 0.0), (2, "loss/entropy_loss", 0.0),
                                  (4, "policy_ratio/clip_fraction", 1.0), (5, "gradients/policy_grad_norm", 0.0),
