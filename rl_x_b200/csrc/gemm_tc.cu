@@ -156,7 +156,7 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
   static constexpr int ACC_STAGES = (BN == 256) ? 1 : 2;
   static constexpr int TMEM_COLS = ACC_STAGES * 2 * BN;         // 512
-  static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + BN * 4 /*bias*/;
+  static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + 4 * 32 * 33 * 4 /*epilogue transpose staging, one [32][33] tile per warp*/;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024 /*alignment slack*/;
 };
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   uint64_t* tmem_full_bar = empty_bar + STAGES;                     // [ACC_STAGES]
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;            // [ACC_STAGES]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
-  float* bias_smem = reinterpret_cast<float*>(aux + 1024);
+  float* stage_smem = reinterpret_cast<float*>(aux + 1024);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -325,26 +325,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       }
     }
   } else {
-    // ===================================================== epilogue: TMEM -> registers -> global
+    // ===================================================== epilogue: TMEM -> registers -> smem transpose -> coalesced global
+    // tcgen05.ld hands each thread 32 consecutive columns of ONE accumulator row.  Writing that straight out would touch 32
+    // different 128-byte lines per instruction, so the 32x32 chunk is transposed through a padded shared-memory tile: afterwards
+    // lane = column, and every global load (aux) / store (C) of a warp is one fully coalesced 128-byte row segment.
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - EPI_WARP0 * 32;
+    float* tile = stage_smem + (warp - EPI_WARP0) * (32 * 33);
     int acc = 0;
     uint32_t acc_ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile_i = blockIdx.x; tile_i < num_tiles; tile_i += gridDim.x) {
       int zb, zs, m0, n0, kbeg, nkb;
-      tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
-      if (EPI == TC_EPI_BIAS_TANH) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done with bias_smem
-        const float* bias = p.bias + p.bias_batch_off * zb;
-        for (int i = et; i < BN; i += 128) bias_smem[i] = (n0 + i < p.N) ? bias[n0 + i] : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
+      tile_coords(tile_i, zb, zs, m0, n0, kbeg, nkb);
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      float* crow = p.C + p.c_batch_off * zb + p.c_split_off * zs + (long long)row * p.ldc;
-      const float* arow = (EPI == TC_EPI_DTANH) ? (p.aux + p.aux_batch_off * zb + (long long)row * p.ldaux) : nullptr;
+      const int row0 = m0 + q * 32;
+      float* cbase = p.C + p.c_batch_off * zb + p.c_split_off * zs;
+      const float* abase = (EPI == TC_EPI_DTANH) ? (p.aux + p.aux_batch_off * zb) : nullptr;
+      const float* bias = (EPI == TC_EPI_BIAS_TANH) ? (p.bias + p.bias_batch_off * zb) : nullptr;
+      const int rows_valid = min(32, p.M - row0);  // warp-uniform
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32], rc[32];
@@ -353,33 +351,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         tmem_ld_32x32b_x32(taddr + BN, rc);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
-        if (row_ok && nb < p.N) {
+        if (rows_valid > 0 && nb < p.N) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float x = __uint_as_float(r[j4 * 4 + j]) + __uint_as_float(rc[j4 * 4 + j]);
-              const int n = nb + j4 * 4 + j;
-              if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bias_smem[c * 32 + j4 * 4 + j]);
-              if (EPI == TC_EPI_DTANH) {
-                const float h = (n < p.N) ? arow[n] : 0.f;
-                x = x * (1.f - h * h);
-              }
-              v[j] = x;
+          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);  // main + correction (fp32 RN)
+          __syncwarp();
+          const int n = nb + lane;
+          const bool n_ok = n < p.N;
+          float bv = 0.f;
+          if (EPI == TC_EPI_BIAS_TANH && n_ok) bv = bias[n];
+#pragma unroll 4
+          for (int rr = 0; rr < rows_valid; ++rr) {
+            float x = tile[rr * 33 + lane];
+            const long long row = row0 + rr;
+            if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bv);
+            if (EPI == TC_EPI_DTANH) {
+              const float h = n_ok ? abase[row * p.ldaux + n] : 0.f;
+              x = x * (1.f - h * h);
             }
-            const int n = nb + j4 * 4;
-            if (n + 3 < p.n_main) {
-              *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (n + j < p.n_main) crow[n + j] = v[j];
-                else if (n + j == p.n_main && p.extra_col != nullptr && n + j < p.N)
-                  p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = v[j];
-              }
-            }
+            if (n < p.n_main) cbase[row * p.ldc + n] = x;
+            else if (n == p.n_main && n_ok && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = x;
           }
+          __syncwarp();
         }
       }
       tc_fence_before();

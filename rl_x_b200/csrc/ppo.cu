@@ -67,7 +67,7 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
   return P;
 }
 
-constexpr int kHeadWgradRows = 256;
+constexpr int kHeadWgradRows = 128;
 
 struct TrainPlan {
   size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, total;
@@ -94,7 +94,7 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   take(P.off_H2, (size_t)m * 2 * H);
   take(P.off_dZ2, (size_t)m * 2 * H);
   take(P.off_dZ1, (size_t)m * 2 * H);
-  take(P.off_dhead, (size_t)m * (A + 1));
+  take(P.off_dhead, (size_t)m * (ceil_div(A + 1, 4) * 4));
   take(P.off_headpart, (size_t)P.head_blocks * P.head_npart);
   take(P.off_part1, (size_t)P.max_s1 * 2 * H * O);
   take(P.off_rs1, (size_t)P.max_s1 * 2 * H);
@@ -270,19 +270,59 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     h.dZ2 = dZ2; h.dhead = dhead; h.block_partials = headpart;
     head_blocks = P.head_blocks;
     const size_t smem = head_smem_bytes(d, true);
-    RLX_DISPATCH_NCH(KC_HEAD_TRAIN, 4.0 * m * H * (A + 1), 4.0 * m * (4.0 * H + 2.0 * A + 5), H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
-    // ---- dW3 (thread per column, chunked over rows)
-    HeadWgradP w{(int)m, H, A, kHeadWgradRows, H2, dhead, part3};
-    wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
-    dim3 wg((unsigned)wgrad_chunks, (unsigned)ceil_div(2 * H, 256));
-    const size_t wsmem = (size_t)kHeadWgradRows * (A + 1) * sizeof(float);
-    if (A <= 8) {
-      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<8>, wg, 256, wsmem, st, w);
-    } else if (A <= 32) {
-      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<32>, wg, 256, wsmem, st, w);
+    const int dh_ld = (int)(ceil_div(A + 1, 4) * 4);
+    const bool fast_head = (A <= 31) && (H % 2 == 0) && (H <= 1024);
+    const double head_flops = 4.0 * m * H * (A + 1), head_bytes = 4.0 * m * (4.0 * H + 2.0 * A + 5);
+    if (fast_head) {
+      HeadTrain2Extra ex{dh_ld};
+      const int nch = (int)ceil_div(H, 32);
+#define RLX_HEAD2(NCH_, AM_)                                                                                                     \
+  do {                                                                                                                           \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train2_kernel<NCH_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train2_kernel<NCH_, AM_>), head_blocks, 256, smem, st, h, ex);  \
+  } while (0)
+#define RLX_HEAD2_ACT(NCH_)                         \
+  do {                                              \
+    if (A <= 8) RLX_HEAD2(NCH_, 8);                 \
+    else if (A <= 16) RLX_HEAD2(NCH_, 16);          \
+    else if (A <= 24) RLX_HEAD2(NCH_, 24);          \
+    else RLX_HEAD2(NCH_, 31);                       \
+  } while (0)
+      if (nch <= 2) RLX_HEAD2_ACT(2);
+      else if (nch <= 4) RLX_HEAD2_ACT(4);
+      else if (nch <= 8) RLX_HEAD2_ACT(8);
+      else if (nch <= 16) RLX_HEAD2_ACT(16);
+      else RLX_HEAD2_ACT(32);
+#undef RLX_HEAD2_ACT
+#undef RLX_HEAD2
+      // ---- dW3: register-tiled, H/2 threads per CTA, 128 rows per CTA
+      HeadWgrad2P w{(int)m, H, A, dh_ld, kHeadWgradRows, H2, dhead, part3};
+      wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
+      const unsigned wthreads = (unsigned)(ceil_div(H / 2, 32) * 32);
+      const size_t wsmem = (size_t)kHeadWgradRows * dh_ld * sizeof(float);
+      const double wflops = 2.0 * m * H * (A + 1), wbytes = 4.0 * m * (2.0 * H + A + 1);
+      if (A + 1 <= 4) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<4>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 8) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<8>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 12) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<12>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 16) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<16>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 20) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<20>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 24) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<24>, wgrad_chunks, wthreads, wsmem, st, w);
+      else RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<32>, wgrad_chunks, wthreads, wsmem, st, w);
     } else {
-      RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
+      RLX_DISPATCH_NCH(KC_HEAD_TRAIN, head_flops, head_bytes, H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
+      // ---- dW3 (thread per column, chunked over rows)
+      HeadWgradP w{(int)m, H, A, kHeadWgradRows, H2, dhead, part3};
+      wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
+      dim3 wg((unsigned)wgrad_chunks, (unsigned)ceil_div(2 * H, 256));
+      const size_t wsmem = (size_t)kHeadWgradRows * (A + 1) * sizeof(float);
+      if (A <= 8) {
+        RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<8>, wg, 256, wsmem, st, w);
+      } else if (A <= 32) {
+        RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<32>, wg, 256, wsmem, st, w);
+      } else {
+        RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+        RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
+      }
     }
     // ---- dW2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]   (db2 comes from the head kernel)
     const Splits S2 = choose_splits(m, H, H, 2, tc);

@@ -291,6 +291,289 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
   }
 }
 
+// ------------------------------------------------------------------------------------- train head, fast variant
+// Same math as ppo_head_train_kernel, restructured for throughput (act <= 31, i.e. act+1 outputs fit one warp):
+//   * two rows per warp iteration: every W3 element fetched from shared memory feeds two FMAs (the kernel is LDS-bound otherwise)
+//   * the act+1 dot products are reduced with a halving butterfly (31 shuffles instead of 5 per output); it leaves output a in
+//     lane a, which is exactly the ownership the loss code wants
+//   * everything is unrolled at compile time (ACT_MAX) so the independent chains overlap
+// dhead is written with a 16-byte-aligned pitch dh_ld = round_up(act+1, 4) for the vectorised weight-gradient kernel below.
+template <int NV>
+__device__ __forceinline__ void butterfly_step(float (&v)[32], int lane) {
+  constexpr int HALF = NV / 2;
+  const bool up = (lane & HALF) != 0;
+#pragma unroll
+  for (int j = 0; j < HALF; ++j) {
+    const float a = v[j], b = v[j + HALF];
+    const float send = up ? a : b, keep = up ? b : a;
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+  }
+}
+// v[i] (i < 32) summed over the warp; on return lane l holds the total of index l in v[0].
+__device__ __forceinline__ float butterfly_reduce32(float (&v)[32], int lane) {
+  butterfly_step<32>(v, lane);
+  butterfly_step<16>(v, lane);
+  butterfly_step<8>(v, lane);
+  butterfly_step<4>(v, lane);
+  butterfly_step<2>(v, lane);
+  return v[0];
+}
+
+struct HeadTrain2Extra {
+  int dh_ld;  // pitch of dhead rows
+};
+
+template <int NCH, int ACT_MAX>
+__global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, const HeadTrain2Extra ex) {
+  extern __shared__ float smem[];
+  float* sW3p = smem;
+  float* sW3c = smem + p.act * p.H;
+  float* sred = sW3c + p.H;
+  head_stage_weights(p, sW3p, sW3c);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int npart = 2 * p.act + 5 + 2 * p.H;
+  const int act = p.act, H = p.H;
+  const float adv_mean = p.adv_stats[0];
+  const float adv_den = p.adv_stats[1] + 1e-8f;
+  const float clip_lo = 1.f - p.clip_range, clip_hi = 1.f + p.clip_range;
+  // per-lane constants of the component this lane owns
+  const bool own = lane < act;
+  const float my_b3 = own ? p.b3p[lane] : ((lane == act) ? p.b3c[0] : 0.f);
+  const float my_sd = own ? expf(p.logstd[lane]) : 1.f;
+  const float my_var = my_sd * my_sd;
+  const float my_logsd = logf(my_sd);
+
+  float acc_db2p[NCH], acc_db2c[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) acc_db2p[c] = acc_db2c[c] = 0.f;
+  float acc_db3 = 0.f, acc_dls = 0.f;  // lane a: db3p[a] / dlogstd[a]; lane act: db3c
+  float acc_pg = 0.f, acc_vl = 0.f, acc_kl = 0.f, acc_cf = 0.f;
+
+  const long long npairs = ((long long)p.M + 1) / 2;
+  for (long long pr = (long long)blockIdx.x * nw + wib; pr < npairs; pr += (long long)gridDim.x * nw) {
+    const long long row0 = 2 * pr;
+    const bool has1 = row0 + 1 < p.M;
+    float hp[2][NCH], hc[2][NCH];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float* __restrict__ h = p.H2 + (row0 + ((r == 1 && !has1) ? 0 : r)) * (2LL * H);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int j = lane + 32 * c;
+        hp[r][c] = (j < H) ? h[j] : 0.f;
+        hc[r][c] = (j < H) ? h[H + j] : 0.f;
+      }
+    }
+    // ---- act+1 partial dot products per row, W3 fetched once for both rows
+    float v0[32], v1[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) v0[a] = v1[a] = 0.f;
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < act) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int j = lane + 32 * c;
+          const float w = (j < H) ? sW3p[a * H + j] : 0.f;
+          s0 = fmaf(hp[0][c], w, s0);
+          s1 = fmaf(hp[1][c], w, s1);
+        }
+        v0[a] = s0;
+        v1[a] = s1;
+      }
+    }
+    {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int j = lane + 32 * c;
+        const float w = (j < H) ? sW3c[j] : 0.f;
+        s0 = fmaf(hc[0][c], w, s0);
+        s1 = fmaf(hc[1][c], w, s1);
+      }
+      // the value head rides in slot `act` (act <= 31)
+#pragma unroll
+      for (int a = 0; a < 32; ++a)
+        if (a == act) { v0[a] = s0; v1[a] = s1; }
+    }
+    const float out0 = butterfly_reduce32(v0, lane) + my_b3;  // lane a < act: mean_a; lane act: value
+    const float out1 = butterfly_reduce32(v1, lane) + my_b3;
+
+    float dmean[2], dvv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long row = row0 + r;
+      const bool valid = (r == 0) || has1;  // warp-uniform
+      const float out = r ? out1 : out0;
+      const float value = __shfl_sync(0xffffffffu, out, act);
+      float lp = 0.f, dmu = 0.f, zz = 0.f;
+      if (own && valid) {
+        const float d = p.actions[row * act + lane] - out;
+        lp = -(d * d) / (2.f * my_var) - my_logsd - kLogSqrt2Pi;
+        dmu = d / my_var;
+        zz = d * d / my_var;
+      }
+      const float logp_new = warp_sum(lp);
+      float dm = 0.f, dv = 0.f;
+      if (valid) {
+        const float logratio = logp_new - p.logp_old[row];
+        const float ratio = expf(logratio);
+        const float A = (p.adv[row] - adv_mean) / adv_den;
+        const float pg1 = -A * ratio;
+        const float pg2 = -A * fminf(fmaxf(ratio, clip_lo), clip_hi);
+        const float w1 = (pg1 > pg2) ? 1.f : ((pg1 == pg2) ? 0.5f : 0.f);
+        const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
+        const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
+        const float verr = value - p.ret[row];
+        dv = p.critic_coef * verr * p.inv_mg;
+        acc_pg += fmaxf(pg1, pg2);
+        acc_vl += 0.5f * verr * verr;
+        acc_kl += (ratio - 1.f) - logratio;
+        acc_cf += (fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f;
+        dm = dlogp * dmu;
+        if (own) {
+          acc_db3 += dm;
+          acc_dls += dlogp * (zz - 1.f);
+          p.dhead[row * ex.dh_ld + lane] = dm;
+        } else if (lane == act) {
+          acc_db3 += dv;
+          p.dhead[row * ex.dh_ld + act] = dv;
+        } else if (lane < ex.dh_ld) {
+          p.dhead[row * ex.dh_ld + lane] = 0.f;
+        }
+      }
+      dmean[r] = dm;
+      dvv[r] = dv;
+    }
+    // ---- dZ2 = (dhead @ W3) * (1 - H2^2) for both rows, W3 fetched once
+    float dz0[NCH], dz1[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) dz0[c] = dz1[c] = 0.f;
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < act) {
+        const float g0 = __shfl_sync(0xffffffffu, dmean[0], a);
+        const float g1 = __shfl_sync(0xffffffffu, dmean[1], a);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int j = lane + 32 * c;
+          const float w = (j < H) ? sW3p[a * H + j] : 0.f;
+          dz0[c] = fmaf(g0, w, dz0[c]);
+          dz1[c] = fmaf(g1, w, dz1[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !has1) break;
+      float* __restrict__ out = p.dZ2 + (row0 + r) * (2LL * H);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int j = lane + 32 * c;
+        if (j < H) {
+          const float hpv = hp[r][c], hcv = hc[r][c];
+          const float zp = (r ? dz1[c] : dz0[c]) * (1.f - hpv * hpv);
+          const float zc = dvv[r] * sW3c[j] * (1.f - hcv * hcv);
+          out[j] = zp;
+          out[H + j] = zc;
+          acc_db2p[c] += zp;
+          acc_db2c[c] += zc;
+        }
+      }
+    }
+  }
+
+  // ---- block reduction (fixed order => deterministic); partial layout as in ppo_head_train_kernel
+  float* my = sred + wib * npart;
+  if (own) {
+    my[lane] = acc_db3;
+    my[act + 1 + lane] = acc_dls;
+  } else if (lane == act) {
+    my[act] = acc_db3;
+  }
+  if (lane == 0) {
+    my[2 * act + 1] = acc_pg;
+    my[2 * act + 2] = acc_vl;
+    my[2 * act + 3] = acc_kl;
+    my[2 * act + 4] = acc_cf;
+  }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int j = lane + 32 * c;
+    if (j < H) {
+      my[2 * act + 5 + j] = acc_db2p[c];
+      my[2 * act + 5 + H + j] = acc_db2c[c];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npart; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sred[w * npart + i];
+    p.block_partials[(long long)blockIdx.x * npart + i] = s;
+  }
+}
+
+// ------------------------------------------------------- weight gradient of the head, fast variant (register tiled)
+// dW3 = dhead^T [act+1, M] . H2 [M, 2H].  Thread t owns policy columns {2t, 2t+1} and critic columns {H+2t, H+2t+1}
+// (64-bit coalesced loads); the act+1 gradient scalars of a row are broadcast from shared memory as float4.
+// part[chunk][(act+1)*H]: rows 0..act-1 = dW3p, row act = dW3c.
+struct HeadWgrad2P {
+  int M, H, act, dh_ld, rows_per_chunk;
+  const float* H2;
+  const float* dhead;  // [M, dh_ld]
+  float* part;
+};
+
+template <int ACT_MAX>  // multiple of 4, >= act + 1
+__global__ void __launch_bounds__(512) ppo_head_wgrad2_kernel(const HeadWgrad2P p) {
+  extern __shared__ __align__(16) float sd[];  // [rows_per_chunk][dh_ld]
+  const int chunk = blockIdx.x;
+  const long long r0 = (long long)chunk * p.rows_per_chunk;
+  const int nrows = (int)min((long long)p.rows_per_chunk, (long long)p.M - r0);
+  for (int i = threadIdx.x; i < nrows * p.dh_ld; i += blockDim.x) sd[i] = p.dhead[r0 * p.dh_ld + i];
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (2 * t >= p.H) return;
+  float accp[ACT_MAX][2], accc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < ACT_MAX; ++a) accp[a][0] = accp[a][1] = 0.f;
+  const float* __restrict__ base = p.H2 + r0 * (2LL * p.H) + 2 * t;
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r) {
+    const float2 hpv = *reinterpret_cast<const float2*>(base + (long long)r * 2 * p.H);
+    const float2 hcv = *reinterpret_cast<const float2*>(base + (long long)r * 2 * p.H + p.H);
+    const float4* dr = reinterpret_cast<const float4*>(sd + r * p.dh_ld);
+    float d[ACT_MAX];
+#pragma unroll
+    for (int q = 0; q < ACT_MAX / 4; ++q) {
+      if (4 * q < p.dh_ld) {
+        const float4 v = dr[q];
+        d[4 * q] = v.x; d[4 * q + 1] = v.y; d[4 * q + 2] = v.z; d[4 * q + 3] = v.w;
+      } else {
+        d[4 * q] = d[4 * q + 1] = d[4 * q + 2] = d[4 * q + 3] = 0.f;
+      }
+    }
+    float dv = 0.f;
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < p.act) {
+        accp[a][0] = fmaf(d[a], hpv.x, accp[a][0]);
+        accp[a][1] = fmaf(d[a], hpv.y, accp[a][1]);
+      } else if (a == p.act) {
+        dv = d[a];
+      }
+    }
+    accc[0] = fmaf(dv, hcv.x, accc[0]);
+    accc[1] = fmaf(dv, hcv.y, accc[1]);
+  }
+  float* out = p.part + (long long)chunk * (p.act + 1) * p.H + 2 * t;
+#pragma unroll
+  for (int a = 0; a < ACT_MAX; ++a)
+    if (a < p.act) *reinterpret_cast<float2*>(out + (long long)a * p.H) = make_float2(accp[a][0], accp[a][1]);
+  *reinterpret_cast<float2*>(out + (long long)p.act * p.H) = make_float2(accc[0], accc[1]);
+}
+
 // ------------------------------------------------------------------ weight gradient of the head (thread per column)
 // part[chunk][(act+1)*H]: rows 0..act-1 = dW3p, row act = dW3c, summed over the chunk's rows.
 struct HeadWgradP {

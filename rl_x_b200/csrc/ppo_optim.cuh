@@ -41,7 +41,15 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
       const GradGroup& g = p.g[gi];
       if (i >= g.off && i < g.off + g.len) {
         const float* __restrict__ q = g.src + (i - g.off);
-        for (int sp = 0; sp < g.nsplit; ++sp) s += q[(long long)sp * g.stride];
+        int sp = 0;
+        for (; sp + 8 <= g.nsplit; sp += 8) {  // 8 independent loads in flight, summed in a fixed order
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = q[(long long)(sp + u) * g.stride];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) s += v[u];
+        }
+        for (; sp < g.nsplit; ++sp) s += q[(long long)sp * g.stride];
       }
     }
     if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
