@@ -359,17 +359,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           const bool n_ok = n < p.N;
           float bv = 0.f;
           if (EPI == TC_EPI_BIAS_TANH && n_ok) bv = bias[n];
-#pragma unroll 4
-          for (int rr = 0; rr < rows_valid; ++rr) {
-            float x = tile[rr * 33 + lane];
-            const long long row = row0 + rr;
-            if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bv);
-            if (EPI == TC_EPI_DTANH) {
-              const float h = n_ok ? abase[row * p.ldaux + n] : 0.f;
-              x = x * (1.f - h * h);
+          // fully unrolled: 32 independent load -> math -> store chains per lane (rows_valid is warp-uniform)
+          float hv[32];
+          if (EPI == TC_EPI_DTANH) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            if (rr < rows_valid) {
+              float x = tile[rr * 33 + lane];
+              const long long row = row0 + rr;
+              if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bv);
+              if (EPI == TC_EPI_DTANH) x = x * (1.f - hv[rr] * hv[rr]);
+              if (n < p.n_main) cbase[row * p.ldc + n] = x;
+              else if (n == p.n_main && n_ok && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = x;
             }
-            if (n < p.n_main) cbase[row * p.ldc + n] = x;
-            else if (n == p.n_main && n_ok && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = x;
           }
           __syncwarp();
         }
