@@ -359,22 +359,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           const bool n_ok = n < p.N;
           float bv = 0.f;
           if (EPI == TC_EPI_BIAS_TANH && n_ok) bv = bias[n];
-          // fully unrolled: 32 independent load -> math -> store chains per lane (rows_valid is warp-uniform)
-          float hv[32];
+          // Math is unconditional and fully unrolled (32 independent chains per lane: a branch per row would serialise the
+          // ~40-instruction tanhf sequences); only the global accesses are predicated.  Rows >= rows_valid hold zeros.
+          float x[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) x[rr] = tile[rr * 33 + lane];
           if (EPI == TC_EPI_DTANH) {
+            float hv[32];
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
-          }
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            if (rr < rows_valid) {
-              float x = tile[rr * 33 + lane];
-              const long long row = row0 + rr;
-              if (EPI == TC_EPI_BIAS_TANH) x = tanhf(x + bv);
-              if (EPI == TC_EPI_DTANH) x = x * (1.f - hv[rr] * hv[rr]);
-              if (n < p.n_main) cbase[row * p.ldc + n] = x;
-              else if (n == p.n_main && n_ok && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + row] = x;
-            }
+            for (int rr = 0; rr < 32; ++rr) x[rr] = x[rr] * (1.f - hv[rr] * hv[rr]);
+          }
+          if (EPI == TC_EPI_BIAS_TANH) {
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) x[rr] = tanhf(x[rr] + bv);
+          }
+          if (n < p.n_main) {
+            float* cp = cbase + (long long)row0 * p.ldc + n;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < rows_valid) cp[(long long)rr * p.ldc] = x[rr];
+          } else if (n == p.n_main && n_ok && p.extra_col != nullptr) {
+            float* ep = p.extra_col + p.extra_batch_off * zb + p.extra_split_off * zs + row0;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < rows_valid) ep[rr] = x[rr];
           }
           __syncwarp();
         }

@@ -67,14 +67,14 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
   return P;
 }
 
-constexpr int kHeadWgradRows = 128;
+constexpr int kHeadWgradRows = 64;
 
 struct TrainPlan {
   size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, total;
   int max_s1, max_s2;
   int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
-static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 8), (long long)sm_count() * 4); }
+static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 16), (long long)sm_count() * 2); }
 
 static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   TrainPlan P;
@@ -275,7 +275,27 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     const double head_flops = 4.0 * m * H * (A + 1), head_bytes = 4.0 * m * (4.0 * H + 2.0 * A + 5);
     if (fast_head) {
       HeadTrain2Extra ex{dh_ld};
-      const int nch = (int)ceil_div(H, 32);
+      const bool vec_head = (H == 128 || H == 256 || H == 512);
+      if (vec_head) {
+#define RLX_HEAD3(H_, AM_)                                                                                                       \
+  do {                                                                                                                           \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train3_kernel<H_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train3_kernel<H_, AM_>), head_blocks, 256, smem, st, h, ex);    \
+  } while (0)
+#define RLX_HEAD3_ACT(H_)                      \
+  do {                                         \
+    if (A <= 8) RLX_HEAD3(H_, 8);              \
+    else if (A <= 16) RLX_HEAD3(H_, 16);       \
+    else if (A <= 24) RLX_HEAD3(H_, 24);       \
+    else RLX_HEAD3(H_, 31);                    \
+  } while (0)
+        if (H == 128) RLX_HEAD3_ACT(128);
+        else if (H == 256) RLX_HEAD3_ACT(256);
+        else RLX_HEAD3_ACT(512);
+#undef RLX_HEAD3_ACT
+#undef RLX_HEAD3
+      } else {
+        const int nch = (int)ceil_div(H, 32);
 #define RLX_HEAD2(NCH_, AM_)                                                                                                     \
   do {                                                                                                                           \
     RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train2_kernel<NCH_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -288,26 +308,27 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     else if (A <= 24) RLX_HEAD2(NCH_, 24);          \
     else RLX_HEAD2(NCH_, 31);                       \
   } while (0)
-      if (nch <= 2) RLX_HEAD2_ACT(2);
-      else if (nch <= 4) RLX_HEAD2_ACT(4);
-      else if (nch <= 8) RLX_HEAD2_ACT(8);
-      else if (nch <= 16) RLX_HEAD2_ACT(16);
-      else RLX_HEAD2_ACT(32);
+        if (nch <= 2) RLX_HEAD2_ACT(2);
+        else if (nch <= 4) RLX_HEAD2_ACT(4);
+        else if (nch <= 8) RLX_HEAD2_ACT(8);
+        else if (nch <= 16) RLX_HEAD2_ACT(16);
+        else RLX_HEAD2_ACT(32);
 #undef RLX_HEAD2_ACT
 #undef RLX_HEAD2
-      // ---- dW3: register-tiled, H/2 threads per CTA, 128 rows per CTA
+      }
+      // ---- dW3: one thread per (policy, critic) column pair, 64 rows per CTA
       HeadWgrad2P w{(int)m, H, A, dh_ld, kHeadWgradRows, H2, dhead, part3};
       wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
-      const unsigned wthreads = (unsigned)(ceil_div(H / 2, 32) * 32);
+      const unsigned wthreads = (unsigned)(ceil_div(H, 32) * 32);
       const size_t wsmem = (size_t)kHeadWgradRows * dh_ld * sizeof(float);
       const double wflops = 2.0 * m * H * (A + 1), wbytes = 4.0 * m * (2.0 * H + A + 1);
-      if (A + 1 <= 4) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<4>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 8) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<8>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 12) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<12>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 16) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<16>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 20) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<20>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 24) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<24>, wgrad_chunks, wthreads, wsmem, st, w);
-      else RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad2_kernel<32>, wgrad_chunks, wthreads, wsmem, st, w);
+      if (A + 1 <= 4) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<4>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 8) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<8>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 12) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<12>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 16) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<16>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 20) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<20>, wgrad_chunks, wthreads, wsmem, st, w);
+      else if (A + 1 <= 24) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<24>, wgrad_chunks, wthreads, wsmem, st, w);
+      else RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<32>, wgrad_chunks, wthreads, wsmem, st, w);
     } else {
       RLX_DISPATCH_NCH(KC_HEAD_TRAIN, head_flops, head_bytes, H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
       // ---- dW3 (thread per column, chunked over rows)
@@ -389,8 +410,13 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   r.head_partials = headpart; r.nblk = head_blocks; r.npart = npart; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
+  const int flat_blocks = (int)ceil_div(L.total(), 256);
+  long long tall = 0;
+  for (int gi = 0; gi < kNumGroups; ++gi)
+    if (r.g[gi].nsplit > kTallSplit) tall += r.g[gi].len;
+  const int tall_blocks = (int)ceil_div(tall, 8);  // 8 warps per CTA, one element per warp
   RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * H + (double)wgrad_chunks * (A + 1) * H + L.total()),
-               ppo_grad_reduce_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, r);
+               ppo_grad_reduce_kernel, (unsigned)(flat_blocks + tall_blocks), 256, 0, st, r, flat_blocks);
   return RLX_OK;
 }
 

@@ -574,6 +574,257 @@ __global__ void __launch_bounds__(512) ppo_head_wgrad2_kernel(const HeadWgrad2P 
   *reinterpret_cast<float2*>(out + (long long)p.act * p.H) = make_float2(accc[0], accc[1]);
 }
 
+// ------------------------------------------------------------ train head, vectorised variant (H multiple of 128)
+// Lane l owns the 4-column groups {g*128 + 4l .. +3}: H2 / dZ2 rows move as coalesced 128-bit accesses and every W3 fetch is
+// one conflict-free LDS.128 that feeds 8 FMAs (2 rows x 4 columns).  ~1.3k warp instructions per row pair (the scalar variant
+// above needs ~7k: it is issue-bound, profiles/r01_tc_minibatch_ncu_details_v1.txt).
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float s) {
+  s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); return fmaf(a.w, b.w, s);
+}
+__device__ __forceinline__ void axpy4(float g, const float4& w, float4& d) {
+  d.x = fmaf(g, w.x, d.x); d.y = fmaf(g, w.y, d.y); d.z = fmaf(g, w.z, d.z); d.w = fmaf(g, w.w, d.w);
+}
+
+template <int H_, int ACT_MAX>
+__global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, const HeadTrain2Extra ex) {
+  constexpr int NG = H_ / 128;
+  constexpr int H4 = H_ / 4;
+  extern __shared__ __align__(16) float smem[];
+  float* sW3p = smem;
+  float* sW3c = smem + p.act * H_;
+  float* sred = sW3c + H_;
+  head_stage_weights(p, sW3p, sW3c);
+  const float4* sW3p4 = reinterpret_cast<const float4*>(sW3p);
+  const float4* sW3c4 = reinterpret_cast<const float4*>(sW3c);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int act = p.act;
+  const int npart = 2 * act + 5 + 2 * H_;
+  const float adv_mean = p.adv_stats[0];
+  const float adv_den = p.adv_stats[1] + 1e-8f;
+  const float clip_lo = 1.f - p.clip_range, clip_hi = 1.f + p.clip_range;
+  const bool own = lane < act;
+  const float my_b3 = own ? p.b3p[lane] : ((lane == act) ? p.b3c[0] : 0.f);
+  const float my_sd = own ? expf(p.logstd[lane]) : 1.f;
+  const float my_var = my_sd * my_sd;
+  const float my_logsd = logf(my_sd);
+
+  float4 acc_db2p[NG], acc_db2c[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) acc_db2p[g] = acc_db2c[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float acc_db3 = 0.f, acc_dls = 0.f, acc_pg = 0.f, acc_vl = 0.f, acc_kl = 0.f, acc_cf = 0.f;
+
+  const long long npairs = ((long long)p.M + 1) / 2;
+  for (long long pr = (long long)blockIdx.x * nw + wib; pr < npairs; pr += (long long)gridDim.x * nw) {
+    const long long row0 = 2 * pr;
+    const bool has1 = row0 + 1 < p.M;
+    float4 hp[2][NG], hc[2][NG];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float4* __restrict__ h = reinterpret_cast<const float4*>(p.H2 + (row0 + ((r == 1 && !has1) ? 0 : r)) * (2LL * H_));
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        hp[r][g] = h[g * 32 + lane];
+        hc[r][g] = h[H4 + g * 32 + lane];
+      }
+    }
+    float v0[32], v1[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) v0[a] = v1[a] = 0.f;
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < act) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float4 w = sW3p4[a * H4 + g * 32 + lane];
+          s0 = dot4(hp[0][g], w, s0);
+          s1 = dot4(hp[1][g], w, s1);
+        }
+        v0[a] = s0;
+        v1[a] = s1;
+      }
+    }
+    {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 w = sW3c4[g * 32 + lane];
+        s0 = dot4(hc[0][g], w, s0);
+        s1 = dot4(hc[1][g], w, s1);
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a)
+        if (a == act) { v0[a] = s0; v1[a] = s1; }
+    }
+    const float out0 = butterfly_reduce32(v0, lane) + my_b3;  // lane a < act: mean_a; lane act: value
+    const float out1 = butterfly_reduce32(v1, lane) + my_b3;
+
+    float dmean[2], dvv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const long long row = row0 + r;
+      const bool valid = (r == 0) || has1;  // warp-uniform
+      const float out = r ? out1 : out0;
+      const float value = __shfl_sync(0xffffffffu, out, act);
+      float lp = 0.f, dmu = 0.f, zz = 0.f;
+      if (own && valid) {
+        const float d = p.actions[row * act + lane] - out;
+        lp = -(d * d) / (2.f * my_var) - my_logsd - kLogSqrt2Pi;
+        dmu = d / my_var;
+        zz = d * d / my_var;
+      }
+      const float logp_new = warp_sum(lp);
+      float dm = 0.f, dv = 0.f;
+      if (valid) {
+        const float logratio = logp_new - p.logp_old[row];
+        const float ratio = expf(logratio);
+        const float A = (p.adv[row] - adv_mean) / adv_den;
+        const float pg1 = -A * ratio;
+        const float pg2 = -A * fminf(fmaxf(ratio, clip_lo), clip_hi);
+        const float w1 = (pg1 > pg2) ? 1.f : ((pg1 == pg2) ? 0.5f : 0.f);
+        const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
+        const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
+        const float verr = value - p.ret[row];
+        dv = p.critic_coef * verr * p.inv_mg;
+        acc_pg += fmaxf(pg1, pg2);
+        acc_vl += 0.5f * verr * verr;
+        acc_kl += (ratio - 1.f) - logratio;
+        acc_cf += (fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f;
+        dm = dlogp * dmu;
+        if (own) {
+          acc_db3 += dm;
+          acc_dls += dlogp * (zz - 1.f);
+          p.dhead[row * ex.dh_ld + lane] = dm;
+        } else if (lane == act) {
+          acc_db3 += dv;
+          p.dhead[row * ex.dh_ld + act] = dv;
+        } else if (lane < ex.dh_ld) {
+          p.dhead[row * ex.dh_ld + lane] = 0.f;
+        }
+      }
+      dmean[r] = dm;
+      dvv[r] = dv;
+    }
+    // ---- dZ2 = (dhead @ W3) * (1 - H2^2)
+    float4 dz0[NG], dz1[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) dz0[g] = dz1[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < act) {
+        const float g0 = __shfl_sync(0xffffffffu, dmean[0], a);
+        const float g1 = __shfl_sync(0xffffffffu, dmean[1], a);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const float4 w = sW3p4[a * H4 + g * 32 + lane];
+          axpy4(g0, w, dz0[g]);
+          axpy4(g1, w, dz1[g]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !has1) break;
+      float4* __restrict__ out = reinterpret_cast<float4*>(p.dZ2 + (row0 + r) * (2LL * H_));
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 a4 = hp[r][g], c4 = hc[r][g], d4 = r ? dz1[g] : dz0[g], wc = sW3c4[g * 32 + lane];
+        float4 zp, zc;
+        zp.x = d4.x * (1.f - a4.x * a4.x); zp.y = d4.y * (1.f - a4.y * a4.y); zp.z = d4.z * (1.f - a4.z * a4.z); zp.w = d4.w * (1.f - a4.w * a4.w);
+        zc.x = dvv[r] * wc.x * (1.f - c4.x * c4.x); zc.y = dvv[r] * wc.y * (1.f - c4.y * c4.y);
+        zc.z = dvv[r] * wc.z * (1.f - c4.z * c4.z); zc.w = dvv[r] * wc.w * (1.f - c4.w * c4.w);
+        out[g * 32 + lane] = zp;
+        out[H4 + g * 32 + lane] = zc;
+        acc_db2p[g].x += zp.x; acc_db2p[g].y += zp.y; acc_db2p[g].z += zp.z; acc_db2p[g].w += zp.w;
+        acc_db2c[g].x += zc.x; acc_db2c[g].y += zc.y; acc_db2c[g].z += zc.z; acc_db2c[g].w += zc.w;
+      }
+    }
+  }
+
+  float* my = sred + wib * npart;
+  if (own) {
+    my[lane] = acc_db3;
+    my[act + 1 + lane] = acc_dls;
+  } else if (lane == act) {
+    my[act] = acc_db3;
+  }
+  if (lane == 0) {
+    my[2 * act + 1] = acc_pg;
+    my[2 * act + 2] = acc_vl;
+    my[2 * act + 3] = acc_kl;
+    my[2 * act + 4] = acc_cf;
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float* q = my + 2 * act + 5 + g * 128 + 4 * lane;
+    q[0] = acc_db2p[g].x; q[1] = acc_db2p[g].y; q[2] = acc_db2p[g].z; q[3] = acc_db2p[g].w;
+    q[H_] = acc_db2c[g].x; q[H_ + 1] = acc_db2c[g].y; q[H_ + 2] = acc_db2c[g].z; q[H_ + 3] = acc_db2c[g].w;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npart; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sred[w * npart + i];
+    p.block_partials[(long long)blockIdx.x * npart + i] = s;
+  }
+}
+
+// ------------------------------------------ weight gradient of the head, one thread per (policy, critic) column pair
+template <int ACT_MAX>  // multiple of 4, >= act + 1
+__global__ void __launch_bounds__(1024) ppo_head_wgrad3_kernel(const HeadWgrad2P p) {
+  extern __shared__ __align__(16) float sd[];  // [rows_per_chunk][dh_ld]
+  const int chunk = blockIdx.x;
+  const long long r0 = (long long)chunk * p.rows_per_chunk;
+  const int nrows = (int)min((long long)p.rows_per_chunk, (long long)p.M - r0);
+  for (int i = threadIdx.x; i < nrows * p.dh_ld; i += blockDim.x) sd[i] = p.dhead[r0 * p.dh_ld + i];
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= p.H) return;
+  float accp[ACT_MAX], accc = 0.f;
+#pragma unroll
+  for (int a = 0; a < ACT_MAX; ++a) accp[a] = 0.f;
+  const float* __restrict__ base = p.H2 + r0 * (2LL * p.H) + t;
+  const long long pitch = 2LL * p.H;
+  int r = 0;
+  for (; r + 4 <= nrows; r += 4) {
+    float hpv[4], hcv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      hpv[u] = base[(long long)(r + u) * pitch];
+      hcv[u] = base[(long long)(r + u) * pitch + p.H];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4* dr = reinterpret_cast<const float4*>(sd + (r + u) * p.dh_ld);
+#pragma unroll
+      for (int q = 0; q < ACT_MAX / 4; ++q) {
+        if (4 * q < p.dh_ld) {
+          const float4 v = dr[q];
+          const float d[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int a = 4 * q + e;
+            if (a < p.act) accp[a] = fmaf(d[e], hpv[u], accp[a]);
+            else if (a == p.act) accc = fmaf(d[e], hcv[u], accc);
+          }
+        }
+      }
+    }
+  }
+  for (; r < nrows; ++r) {
+    const float hpv = base[(long long)r * pitch], hcv = base[(long long)r * pitch + p.H];
+#pragma unroll
+    for (int a = 0; a < ACT_MAX; ++a) {
+      if (a < p.act) accp[a] = fmaf(sd[r * p.dh_ld + a], hpv, accp[a]);
+      else if (a == p.act) accc = fmaf(sd[r * p.dh_ld + a], hcv, accc);
+    }
+  }
+  float* out = p.part + (long long)chunk * (p.act + 1) * p.H + t;
+#pragma unroll
+  for (int a = 0; a < ACT_MAX; ++a)
+    if (a < p.act) out[(long long)a * p.H] = accp[a];
+  out[(long long)p.act * p.H] = accc;
+}
+
 // ------------------------------------------------------------------ weight gradient of the head (thread per column)
 // part[chunk][(act+1)*H]: rows 0..act-1 = dW3p, row act = dW3c, summed over the chunk's rows.
 struct HeadWgradP {

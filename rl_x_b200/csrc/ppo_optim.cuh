@@ -32,42 +32,82 @@ struct GradReduceP {
   float m_local;
 };
 
-__global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP p) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < p.total) {
-    float s = 0.f;
+// Groups with few partials per element (split-K GEMM outputs) are summed by one thread per element with 8 loads in flight;
+// groups with many partials (per-CTA partials of the head kernels: hundreds per element) get one WARP per element, lanes
+// striding over the partials, then a fixed-order shuffle tree.  Both orders are fixed => bitwise reproducible.
+__device__ __forceinline__ float grad_sum_serial(const float* __restrict__ q, int nsplit, long long stride) {
+  float s = 0.f;
+  int sp = 0;
+  for (; sp + 8 <= nsplit; sp += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = q[(long long)(sp + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += v[u];
+  }
+  for (; sp < nsplit; ++sp) s += q[(long long)sp * stride];
+  return s;
+}
+__device__ __forceinline__ float grad_sum_warp(const float* __restrict__ q, int nsplit, long long stride, int lane) {
+  float s = 0.f;
+  for (int sp = lane; sp < nsplit; sp += 32) s += q[(long long)sp * stride];
+  return warp_sum(s);
+}
+constexpr int kTallSplit = 48;  // groups with more partials than this use a warp per element
+
+__global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP p, const int flat_blocks) {
+  if ((int)blockIdx.x < flat_blocks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.total) {
+      bool mine = true;
+      float s = 0.f;
+#pragma unroll
+      for (int gi = 0; gi < kNumGroups; ++gi) {
+        const GradGroup& g = p.g[gi];
+        if (i >= g.off && i < g.off + g.len) {
+          if (g.nsplit > kTallSplit) mine = false;
+          else s = grad_sum_serial(g.src + (i - g.off), g.nsplit, g.stride);
+        }
+      }
+      if (mine) {
+        if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
+        p.grads[i] = s;
+      }
+    }
+  } else {
+    // warp per element over the concatenation of the tall groups
+    const int lane = threadIdx.x & 31;
+    long long w = (long long)(blockIdx.x - flat_blocks) * (blockDim.x >> 5) + (threadIdx.x >> 5);
 #pragma unroll
     for (int gi = 0; gi < kNumGroups; ++gi) {
       const GradGroup& g = p.g[gi];
-      if (i >= g.off && i < g.off + g.len) {
-        const float* __restrict__ q = g.src + (i - g.off);
-        int sp = 0;
-        for (; sp + 8 <= g.nsplit; sp += 8) {  // 8 independent loads in flight, summed in a fixed order
-          float v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = q[(long long)(sp + u) * g.stride];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) s += v[u];
-        }
-        for (; sp < g.nsplit; ++sp) s += q[(long long)sp * g.stride];
+      if (g.nsplit <= kTallSplit) continue;
+      if (w >= 0 && w < g.len) {
+        float s = grad_sum_warp(g.src + w, g.nsplit, g.stride, lane);
+        const long long i = g.off + w;
+        if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
+        if (lane == 0) p.grads[i] = s;
+        w = -1;
+      } else if (w >= g.len) {
+        w -= g.len;
       }
     }
-    if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
-    p.grads[i] = s;
   }
   if (blockIdx.x == 0 && p.metrics != nullptr) {
-    // metric sums of this minibatch (ref: ppo.py:126-141,157): warp 0 reduces the head block partials in fixed order
-    const int npart = p.npart;
-    if (threadIdx.x < 4) {
+    // metric sums of this minibatch (ref: ppo.py:126-141,157): one warp per metric over the head block partials
+    const int npart = p.npart, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    if (wi < 4) {
       float s = 0.f;
-      for (int b = 0; b < p.nblk; ++b) s += p.head_partials[(long long)b * npart + 2 * p.act + 1 + threadIdx.x];
-      s *= p.inv_mg;
-      if (threadIdx.x == 0) p.metrics[0] = s;                  // pg_loss
-      if (threadIdx.x == 1) p.metrics[1] = p.critic_coef * s;  // critic_loss
-      if (threadIdx.x == 2) p.metrics[3] = s;                  // approx_kl
-      if (threadIdx.x == 3) p.metrics[4] = s;                  // clip_fraction
+      for (int b = lane; b < p.nblk; b += 32) s += p.head_partials[(long long)b * npart + 2 * p.act + 1 + wi];
+      s = warp_sum(s) * p.inv_mg;
+      if (lane == 0) {
+        if (wi == 0) p.metrics[0] = s;                  // pg_loss
+        if (wi == 1) p.metrics[1] = p.critic_coef * s;  // critic_loss
+        if (wi == 2) p.metrics[3] = s;                  // approx_kl
+        if (wi == 3) p.metrics[4] = s;                  // clip_fraction
+      }
     }
-    if (threadIdx.x == 32) {
+    if (threadIdx.x == 128) {
       // entropy.mean(): sum_a (0.5 + 0.5*log(2*pi) + log(std_a)), identical for every row (torch Normal.entropy)
       float e = 0.f;
       for (int a = 0; a < p.act; ++a) e += 0.5f + 0.5f * 1.8378770664093453f + logf(expf(p.logstd[a]));
