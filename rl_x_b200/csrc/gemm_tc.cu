@@ -509,8 +509,12 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   // global tensors: K-major [mn_rows, k_cols]; MN-major [k_rows, mn_cols]
   TcOperand A{g.A, a_rows, a_kmaj ? (long long)(p.a_k_off * (batch - 1) + g.K) : (long long)(p.a_mn_off * (batch - 1) + g.M), g.lda};
   TcOperand B{g.B, b_rows, b_kmaj ? (long long)(p.b_k_off * (batch - 1) + g.K) : (long long)(p.b_mn_off * (batch - 1) + g.N), g.ldb};
+  // BN = 256 halves the A-operand re-reads but has a single accumulator set (no epilogue/mainloop overlap): it only pays for
+  // long reductions with a trivial epilogue (the dW GEMMs).  Short-K GEMMs with tanh / tanh' epilogues use the double-buffered
+  // BN = 128 configuration (measured: profiles/r01_tc_minibatch_ncu_details_v1.txt).
   const long long tiles256 = ceil_div(g.M, BM) * ceil_div(g.N, 256) * batch * g.splits;
-  const bool use256 = (g.N % 256 == 0 || g.N > 256 + 128) && tiles256 >= sm_count() / 2;
+  const int k_per_tile = (g.splits > 1) ? g.kchunk : g.K;
+  const bool use256 = (g.N % 256 == 0) && epi == TC_EPI_NONE && k_per_tile >= 512 && tiles256 >= sm_count() / 2;
 #define RLX_TC_DISPATCH(BN_)                                                                                                   \
   do {                                                                                                                        \
     if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg<BN_, true, true, TC_EPI_BIAS_TANH>(A, B, p, kclass, stream); \
