@@ -303,6 +303,7 @@ def main():
             "train_tflops_per_step": FLOP_PER_SAMPLE_TRAIN * args.envs * C2["nr_steps"] * args.epochs / 1e12}
 
     # end-to-end through the host-buffer path (NUMPY-interface env: pinned host observations, H2D/D2H every step)
+    model._end_training()
     if not args.no_e2e:
         del model
         torch.cuda.empty_cache()
@@ -321,6 +322,7 @@ def main():
         line["e2e"] = {"value": steps_per_iter * args.steps / s2, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "ms_per_step": s2 / args.steps * 1e3,
                        "path": "PPO._train_iteration() with a NUMPY-interface env: obs/reward/done from pinned host buffers every env step, actions read back every env step"}
+        m2._end_training()
         del m2
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = calibrate_threads(available_cores())

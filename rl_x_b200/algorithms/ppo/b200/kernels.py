@@ -50,8 +50,14 @@ class PpoKernels:
         return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, params, obs, workspace, *, noise=None, rng_seed=0, rng_offset=0, act_low=None, act_high=None,
-                clip_rescale=True, deterministic=False, action=None, env_action=None, logp=None, value=None):
+    def forward(self, params, obs, workspace, **kw):
+        nt.check(self.lib.rlx_ppo_forward_f32(C.byref(self.forward_args(params, obs, workspace, **kw)), _stream()), "rlx_ppo_forward_f32")
+
+    def forward_prepared(self, a):
+        nt.check(self.lib.rlx_ppo_forward_f32(C.byref(a), _stream()), "rlx_ppo_forward_f32")
+
+    def forward_args(self, params, obs, workspace, *, noise=None, rng_seed=0, rng_offset=0, act_low=None, act_high=None,
+                     clip_rescale=True, deterministic=False, action=None, env_action=None, logp=None, value=None):
         a = nt.PpoForwardArgs()
         a.dims = self.dims
         a.n = obs.shape[0]
@@ -64,7 +70,7 @@ class PpoKernels:
         a.action, a.env_action = _f32(action, "action"), _f32(env_action, "env_action")
         a.logp, a.value = _f32(logp, "logp"), _f32(value, "value")
         a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel()
-        nt.check(self.lib.rlx_ppo_forward_f32(C.byref(a), _stream()), "rlx_ppo_forward_f32")
+        return a
 
     def critic_forward(self, params, obs, value, workspace):
         nt.check(self.lib.rlx_critic_forward_f32(C.byref(self.dims), _f32(params, "params"), _f32(obs, "obs"), obs.shape[0],

@@ -85,6 +85,65 @@ class FlatParameters:
         return pol, cri
 
 
+class PermutationStream:
+    """Background producer of the epoch permutations (ppo.py:273-276).
+
+    The permutation sequence depends only on the PCG64 stream and the batch size — never on data — so it is generated ahead of
+    time on a host thread (the native shuffle releases the GIL) into pinned staging slots while the GPU is busy with the rollout
+    and the previous epochs.  Order of RNG consumption is exactly the reference's: per iteration one np.arange(B), then nr_epochs
+    successive in-place shuffles.  For the env-sharded update the thread also extracts the rows this rank owns."""
+
+    def __init__(self, rng, batch_size, nr_epochs, slot_rows, transform=None, depth_iterations=2):
+        import queue
+        import threading
+        self.rng, self.B, self.E, self.transform = rng, int(batch_size), int(nr_epochs), transform
+        self.nslots = max(2, depth_iterations) * self.E
+        self.slots = [torch.zeros(slot_rows, dtype=torch.int64).pin_memory() for _ in range(self.nslots)]
+        self.free = queue.Queue()
+        for i in range(self.nslots):
+            self.free.put(i)
+        self.ready = queue.Queue()
+        self.stop = False
+        self.error = None
+        self.thread = threading.Thread(target=self._run, name="rlx-permutations", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            while not self.stop:
+                idx = np.arange(self.B)  # int64, re-created every iteration (ppo.py:273)
+                for _ in range(self.E):
+                    slot = self.free.get()
+                    if slot is None or self.stop:
+                        return
+                    self.rng.shuffle(idx)
+                    if self.transform is None:
+                        self.slots[slot].numpy()[:] = idx
+                        self.ready.put((slot, self.B, None))
+                    else:
+                        local_idx, counts = self.transform(idx)
+                        self.slots[slot].numpy()[:local_idx.shape[0]] = local_idx
+                        self.ready.put((slot, int(local_idx.shape[0]), counts))
+        except Exception as e:  # surfaced to the training thread
+            self.error = e
+            self.ready.put(None)
+
+    def next(self):
+        item = self.ready.get()
+        if item is None:
+            raise RuntimeError(f"permutation thread failed: {self.error}")
+        slot, count, counts = item
+        return slot, self.slots[slot], count, counts
+
+    def release(self, slots):
+        for s_ in slots:
+            self.free.put(s_)
+
+    def close(self):
+        self.stop = True
+        self.free.put(None)
+
+
 class PPO:
     def __init__(self, config, train_env, eval_env, run_path, writer):
         self.config = config
@@ -202,7 +261,8 @@ class PPO:
         self.g_states, self.g_actions = z(Bl, self.ldx), z(Bl, act)
         self.g_log_probs, self.g_advantages, self.g_returns = z(Bl), z(Bl), z(Bl)
         self.perm_dev = torch.zeros(Bl, dtype=torch.int64, device=dev)
-        self.perm_host = torch.zeros(self.nr_epochs, Bl, dtype=torch.int64).pin_memory()
+        self._perm_stream = None
+        self._perm_slots_in_flight = []
         self.nmb_epoch = -(-self.batch_size // self.minibatch_size)  # ceil: a short last minibatch is processed (ppo.py:277-279)
         self.adv_stats = z(self.nmb_epoch, 2)
         self.metrics_dev = z(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC)
@@ -226,16 +286,22 @@ class PPO:
             self.d_trunc = torch.zeros(N, dtype=torch.bool, device=dev)
             self.d_obs = z(N, obs)
         self.noise_buf = z(N, act) if self.rollout_noise == "torch" else None
+        b = self.batch
+        self._fwd_args = [self.kernels.forward_args(self.params.flat, b.states[t], self.fwd_ws, rng_seed=self.noise_seed, act_low=self.env_as_low,
+                                                    act_high=self.env_as_high, clip_rescale=self.action_clipping_and_rescaling,
+                                                    action=b.actions[t], env_action=self.env_action, logp=b.log_probs[t], value=b.values[t])
+                          for t in range(T)]
+        self._store_rows = [(b.rewards[t], b.terminations[t], b.states[t + 1]) for t in range(T)]
         self._alloc_done = True
 
     # ------------------------------------------------------------------------------------------------- acting
     def _policy_step(self, state, step):
         """ref: policy.get_action_logprob + critic.get_value + buffer writes of action/value/log_prob (ppo.py:207-209,233,238,243)."""
-        b = self.batch
         noise = self._draw_noise(step)
-        self.kernels.forward(self.params.flat, state, self.fwd_ws, noise=noise, rng_seed=self.noise_seed, rng_offset=self.noise_offset,
-                             act_low=self.env_as_low, act_high=self.env_as_high, clip_rescale=self.action_clipping_and_rescaling,
-                             action=b.actions[step], env_action=self.env_action, logp=b.log_probs[step], value=b.values[step])
+        a = self._fwd_args[step]  # pointer table of this rollout slot, built once (the buffers never move)
+        a.noise = noise.data_ptr() if noise is not None else None
+        a.rng_offset = self.noise_offset
+        self.kernels.forward_prepared(a)
         self.noise_offset += 1
 
     def _draw_noise(self, step):
@@ -265,8 +331,9 @@ class PPO:
                     reward = reward.float()
                 terminated = terminated if terminated.dtype == torch.bool else terminated.bool()
                 truncated = truncated if truncated.dtype == torch.bool else truncated.bool()
+                rr, tr, ns = self._store_rows[step]
                 self.kernels.rollout_store(reward.contiguous(), terminated.contiguous(), truncated.contiguous(), next_state.contiguous(),
-                                           b.rewards[step], b.terminations[step], b.states[step + 1], self.done_count)
+                                           rr, tr, ns, self.done_count)
             else:
                 self.h_action.copy_(self.env_action, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -320,32 +387,28 @@ class PPO:
         flat_states = b.states[:T].view(T * N, obs)
         flat_actions = b.actions.view(T * N, act)
         lp, adv, ret = b.log_probs.view(-1), b.advantages.view(-1), b.returns.view(-1)
-        batch_indices = np.arange(self.batch_size)  # int64, re-created every iteration (ppo.py:273)
         mbs = self.minibatch_size
         for epoch in range(self.nr_epochs):
-            self.rng.shuffle(batch_indices)
+            slot, perm_pinned, count, counts = self._perm_stream.next()  # self.rng.shuffle(batch_indices), done ahead of time
+            self._perm_slots_in_flight.append(slot)
             row0 = epoch * self.nmb_epoch
+            self.perm_dev.copy_(perm_pinned, non_blocking=True)
             if self.world_size == 1:
-                self.perm_host[epoch].copy_(torch.from_numpy(batch_indices))
-                self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
                 k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
                          self.g_advantages, self.g_returns, out_states_ld=self.ldx)
                 k.advantage_stats(self.g_advantages, self.batch_size, mbs, self.adv_stats)
                 k.update_epoch(self._first_minibatch_args(self.metrics_dev[row0]), self.batch_size, mbs)
             else:
-                self._optimize_epoch_sharded(batch_indices, epoch, flat_states, flat_actions, lp, adv, ret)
+                self._optimize_epoch_sharded(count, counts, epoch, flat_states, flat_actions, lp, adv, ret)
 
-    def _optimize_epoch_sharded(self, batch_indices, epoch, flat_states, flat_actions, lp, adv, ret):
+    def _optimize_epoch_sharded(self, local_count, counts, epoch, flat_states, flat_actions, lp, adv, ret):
         """Reference-exact data parallelism: every rank walks the same global permutation, computes the gradient SUM over the
         rows it owns, one all-reduce(sum) per minibatch makes the full-minibatch gradient (divided by the global minibatch
         size inside the kernels), then every rank applies the identical clip+Adam step (SURVEY §8 e)."""
         k, dist = self.kernels, self.dist
         mbs, row0 = self.minibatch_size, epoch * self.nmb_epoch
-        local_idx, counts = sharding.local_rows_of_permutation(batch_indices, mbs, self.global_nr_envs, self.nr_envs, self.rank)
-        self.perm_host[epoch][:local_idx.shape[0]].copy_(torch.from_numpy(local_idx))
-        self.perm_dev.copy_(self.perm_host[epoch], non_blocking=True)
         k.gather(self.perm_dev, flat_states, flat_actions, lp, adv, ret, self.g_states, self.g_actions, self.g_log_probs,
-                 self.g_advantages, self.g_returns, count=local_idx.shape[0], out_states_ld=self.ldx)
+                 self.g_advantages, self.g_returns, count=local_count, out_states_ld=self.ldx)
         offsets = np.concatenate([[0], np.cumsum(counts)])
         global_counts = sharding.global_minibatch_sizes(self.batch_size, mbs)
         # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
@@ -401,8 +464,16 @@ class PPO:
     # ---------------------------------------------------------------------------------------------------- train
     def train(self):
         self._begin_training()
-        while self.global_step < self.total_timesteps:
-            self._train_iteration()
+        try:
+            while self.global_step < self.total_timesteps:
+                self._train_iteration()
+        finally:
+            self._end_training()
+
+    def _end_training(self):
+        if self._perm_stream is not None:
+            self._perm_stream.close()
+            self._perm_stream = None
 
     def _begin_training(self):
         """Everything PPO.train() does before its while loop (ppo.py:169-193)."""
@@ -415,6 +486,11 @@ class PPO:
             k.rollout_store(None, None, None, state.float().contiguous(), None, None, b.states[0], None)
         else:
             self._to_device_obs(state, b.states[0])
+        if self._perm_stream is None:  # starts shuffling right away: the first permutations are ready before the first rollout ends
+            transform = None
+            if self.world_size > 1:
+                transform = lambda perm: sharding.local_rows_of_permutation(perm, self.minibatch_size, self.global_nr_envs, self.nr_envs, self.rank)
+            self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, transform)
         self.global_step = 0
         self.nr_updates = 0
         self.nr_episodes = 0
@@ -459,6 +535,9 @@ class PPO:
         self.metrics_host.copy_(self.metrics_dev, non_blocking=True)
         ev_host = ev_pair.cpu()
         dones_this_rollout = dones_host if not self.is_torch_data_interface else int(self.done_count.item())
+        if self._perm_stream is not None:  # the .cpu()/.item() above synchronised the stream: the staged permutations were consumed
+            self._perm_stream.release(self._perm_slots_in_flight)
+            self._perm_slots_in_flight = []
         if self.dist:
             t = torch.tensor([dones_this_rollout], device=self.device)
             self.dist.all_reduce(t)
