@@ -98,7 +98,8 @@ class PermutationStream:
         import threading
         self.rng, self.B, self.E, self.transform = rng, int(batch_size), int(nr_epochs), transform
         self.nslots = max(2, depth_iterations) * self.E
-        self.slots = [torch.zeros(slot_rows, dtype=torch.int64).pin_memory() for _ in range(self.nslots)]
+        pool = torch.zeros(self.nslots, max(int(slot_rows), 1), dtype=torch.int64).pin_memory()  # one pinned allocation
+        self.slots = [pool[i] for i in range(self.nslots)]
         self.free = queue.Queue()
         for i in range(self.nslots):
             self.free.put(i)
@@ -275,12 +276,15 @@ class PPO:
         self.train_ws = self.kernels.minibatch_workspace(mb_rows, dev)
         self.lr_host = torch.zeros(1, dtype=torch.float32).pin_memory()
         if not self.is_torch_data_interface:
+            # pinned staging, double-buffered so that step t+1 can be staged while the copies of step t are still in flight
             self.h_action = torch.zeros(N, act).pin_memory()
-            self.h_obs = torch.zeros(N, obs).pin_memory()
-            self.h_final = torch.zeros(N, obs).pin_memory()
-            self.h_reward = torch.zeros(N).pin_memory()
-            self.h_term = torch.zeros(N, dtype=torch.bool).pin_memory()
-            self.h_trunc = torch.zeros(N, dtype=torch.bool).pin_memory()
+            self.h_obs = [torch.zeros(N, obs).pin_memory() for _ in range(2)]
+            self.h_reward = [torch.zeros(N).pin_memory() for _ in range(2)]
+            self.h_term = [torch.zeros(N, dtype=torch.bool).pin_memory() for _ in range(2)]
+            self.h_trunc = [torch.zeros(N, dtype=torch.bool).pin_memory() for _ in range(2)]
+            self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+            self.h2d_pending = [False, False]
+            self.action_ready = torch.cuda.Event()
             self.d_reward = z(N)
             self.d_term = torch.zeros(N, dtype=torch.bool, device=dev)
             self.d_trunc = torch.zeros(N, dtype=torch.bool, device=dev)
@@ -311,9 +315,23 @@ class PPO:
             return self.noise_buf.normal_()
         return None
 
-    def _to_device_obs(self, obs_np, dst):
-        self.h_obs.copy_(torch.from_numpy(np.ascontiguousarray(obs_np, dtype=np.float32)))
-        dst.copy_(self.h_obs, non_blocking=True)
+    @staticmethod
+    def _as_host_tensor(x, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=dtype))
+        return t
+
+    def _h2d(self, src_np, dtype, staging, dst):
+        """Host -> device copy of one env output.  Arrays that already live in pinned memory (e.g. a simulator's own staging
+        buffers) are copied directly; pageable arrays go through this step's pinned slot first."""
+        t = self._as_host_tensor(src_np, dtype)
+        if t.is_pinned():
+            dst.copy_(t, non_blocking=True)
+        else:
+            staging.copy_(t)
+            dst.copy_(staging, non_blocking=True)
+
+    def _to_device_obs(self, obs_np, dst, slot=0):
+        self._h2d(obs_np, np.float32, self.h_obs[slot], dst)
 
     def _collect_rollout(self, state_is_in_slot0):
         """ref: the acting loop, ppo.py:203-246."""
@@ -336,27 +354,33 @@ class PPO:
                                            rr, tr, ns, self.done_count)
             else:
                 self.h_action.copy_(self.env_action, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
+                self.action_ready.record()
+                self.action_ready.synchronize()  # the simulator needs the actions on the host (ppo.py:211-213)
                 next_state, reward, terminated, truncated, info = env.step(self.h_action.numpy())
-                done = np.logical_or(terminated, truncated)
-                self._to_device_obs(next_state, b.states[step + 1])
-                self.h_reward.copy_(torch.from_numpy(np.asarray(reward, dtype=np.float32)))
-                self.h_term.copy_(torch.from_numpy(np.asarray(terminated, dtype=bool)))
-                self.h_trunc.copy_(torch.from_numpy(np.asarray(truncated, dtype=bool)))
-                self.d_reward.copy_(self.h_reward, non_blocking=True)
-                self.d_term.copy_(self.h_term, non_blocking=True)
-                self.d_trunc.copy_(self.h_trunc, non_blocking=True)
+                slot = step & 1
+                if self.h2d_pending[slot]:
+                    self.h2d_done[slot].synchronize()  # the pinned slot of step-2 must have been consumed
+                self._h2d(next_state, np.float32, self.h_obs[slot], b.states[step + 1])
+                self._h2d(reward, np.float32, self.h_reward[slot], self.d_reward)
+                self._h2d(terminated, bool, self.h_term[slot], self.d_term)
+                self._h2d(truncated, bool, self.h_trunc[slot], self.d_trunc)
                 # next_states[step] = next_state with final observations patched in for finished episodes (ppo.py:217-223)
                 self.kernels.rollout_store(self.d_reward, self.d_term, self.d_trunc, b.states[step + 1], b.rewards[step],
                                            b.terminations[step], b.next_states[step], None)
+                self.h2d_done[slot].record()
+                self.h2d_pending[slot] = True
+                done = np.logical_or(terminated, truncated)
                 if done.any():
                     idx = np.nonzero(done)[0]
-                    finals = np.stack([np.asarray(env.get_final_observation_at_index(info, int(i)), dtype=np.float32) for i in idx])
+                    batch_getter = getattr(env, "get_final_observations_batch", None)  # optional vectorised form of the per-index call
+                    if batch_getter is not None:
+                        finals = np.asarray(batch_getter(info, idx), dtype=np.float32)
+                    else:
+                        finals = np.stack([np.asarray(env.get_final_observation_at_index(info, int(i)), dtype=np.float32) for i in idx])
                     b.next_states[step][torch.from_numpy(idx).to(self.device)] = torch.from_numpy(finals).to(self.device)
                     for i in idx:
                         saving_returns.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
                     dones_host += len(idx)
-                torch.cuda.current_stream().synchronize()  # pinned staging buffers are reused next step
             for key, info_value in env.get_logging_info_dict(info).items():
                 step_info_collection.setdefault(key, []).extend(info_value)
         return step_info_collection, saving_returns, dones_host

@@ -13,6 +13,10 @@ class RLXInfo:
         # the synthetic next observation is i.i.d.: the "final" observation of a finished episode is the returned one
         return self.env._obs[self.env.t % self.env.ring_length][index].numpy()
 
+    def get_final_observations_batch(self, info, indices):
+        """Vectorised form of get_final_observation_at_index (optional extension used by rl_x_b200's PPO)."""
+        return self.env._obs[self.env.t % self.env.ring_length].numpy()[indices]
+
     def get_final_info_value_at_index(self, info, key, index):
         return 0.0
 
