@@ -206,3 +206,19 @@ def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch, g
         assert torch.equal(c1[k], c2[k])
     assert int(m2.adam_step.item()) == int(float(ck["policy_optimizer_state_dict"]["state"][0]["step"]))
     m2.test(1)
+
+
+def test_two_gpu_sharded_run_equals_single_gpu_run(tmp_path, gemm_engine):
+    """Env-sharded data parallelism over 2 GPUs (NCCL) reproduces the 1-GPU run on the same global batch."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "dist_check_ppo.py")
+    w1, w2 = str(tmp_path / "w1.pt"), str(tmp_path / "w2.pt")
+    subprocess.run([sys.executable, script, "--out", w1, "--engine", gemm_engine], check=True, timeout=600)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29631", script, "--out", w2, "--engine", gemm_engine], check=True, timeout=600)
+    subprocess.run([sys.executable, script, "--compare", w1, w2], check=True, timeout=120)
