@@ -97,7 +97,8 @@ def build_model(args, rank, world, interface):
             f"--environment.stream={'ring' if interface == 'numpy' else 'fresh'}",
             f"--algorithm.nr_steps={C2['nr_steps']}", f"--algorithm.nr_epochs={args.epochs}",
             f"--algorithm.minibatch_size={args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
-            f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15"]
+            f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15",
+            f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}"]
     r = Runner(argv=argv)
     train_env, eval_env = r._create_train_and_eval_env(r._config)
     r._config.environment.seed = 1  # identical policy init / permutation stream on every rank; env streams differ via the env seed above
@@ -220,7 +221,8 @@ def workload_config(args, world):
     return {"workload": f"PPO synthetic Box(obs={C2['obs_dim']}, act={C2['act_dim']}) ~Humanoid, num_envs={args.envs}/GPU, horizon={C2['nr_steps']}, "
                         f"hidden={C2['hidden']}, nr_epochs={args.epochs}, minibatch={args.minibatch}/GPU (BASELINE.json configs[1])",
             "num_envs_global": args.envs * world, "minibatch_size_global": args.minibatch * world, "nr_epochs": args.epochs,
-            "parallelism": f"dp{world} (env-sharded, reference-exact global permutation, 1 all-reduce per minibatch)" if world > 1 else "single GPU",
+            "parallelism": (f"dp{world} (env-sharded, " + ("reference-exact global permutation" if args.exact_permutation else "rank-local PCG64 shuffles")
+                            + ", 1 NCCL all-reduce of the flat gradient per minibatch)") if world > 1 else "single GPU",
             "l2_policy": "per-step working set (rollout buffer 0.83 GB + gathered copy 0.83 GB + activations) exceeds the 126 MB L2"}
 
 
@@ -234,6 +236,8 @@ def main():
     ap.add_argument("--envs", type=int, default=C2["nr_envs"], help="envs per GPU")
     ap.add_argument("--minibatch", type=int, default=C2["minibatch_size"], help="minibatch rows per GPU")
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--exact-permutation", action="store_true",
+                    help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

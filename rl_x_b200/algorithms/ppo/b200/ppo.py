@@ -423,6 +423,8 @@ class PPO:
                 k.advantage_stats(self.g_advantages, self.batch_size, mbs, self.adv_stats)
                 k.update_epoch(self._first_minibatch_args(self.metrics_dev[row0]), self.batch_size, mbs)
             else:
+                if counts is None:  # rank-local shuffle: fixed local minibatch size
+                    counts = sharding.global_minibatch_sizes(self.local_batch_size, mbs // self.world_size)
                 self._optimize_epoch_sharded(count, counts, epoch, flat_states, flat_actions, lp, adv, ret)
 
     def _optimize_epoch_sharded(self, local_count, counts, epoch, flat_states, flat_actions, lp, adv, ret):
@@ -435,6 +437,7 @@ class PPO:
                  self.g_advantages, self.g_returns, count=local_count, out_states_ld=self.ldx)
         offsets = np.concatenate([[0], np.cumsum(counts)])
         global_counts = sharding.global_minibatch_sizes(self.batch_size, mbs)
+        assert len(global_counts) == len(counts)
         # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
         seg = torch.from_numpy(np.repeat(np.arange(len(counts)), counts)).to(self.device)
         gc = torch.from_numpy(global_counts.astype(np.float32)).to(self.device)
@@ -511,10 +514,19 @@ class PPO:
         else:
             self._to_device_obs(state, b.states[0])
         if self._perm_stream is None:  # starts shuffling right away: the first permutations are ready before the first rollout ends
-            transform = None
-            if self.world_size > 1:
+            if self.world_size > 1 and self.exact_global_permutation:
+                # reference-exact: every rank walks the same GLOBAL permutation and keeps the rows it owns (host work O(global batch))
                 transform = lambda perm: sharding.local_rows_of_permutation(perm, self.minibatch_size, self.global_nr_envs, self.nr_envs, self.rank)
-            self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, transform)
+                self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, transform)
+            elif self.world_size > 1:
+                # scalable: each rank shuffles only its own rows with its own PCG64 stream; global minibatch k = union of the ranks'
+                # local minibatches k (host work O(local batch), same collectives)
+                if self.minibatch_size % self.world_size != 0:
+                    raise ValueError("minibatch_size must be divisible by the world size when exact_global_permutation=False")
+                self.local_rng = nt.Pcg64Generator((int(self.seed) * 1000003 + 7919 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF)
+                self._perm_stream = PermutationStream(self.local_rng, self.local_batch_size, self.nr_epochs, self.local_batch_size, None)
+            else:
+                self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, None)
         self.global_step = 0
         self.nr_updates = 0
         self.nr_episodes = 0
