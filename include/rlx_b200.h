@@ -222,6 +222,53 @@ int rlx_replay_sample_gather_f32(const int64_t* idx_t, const int64_t* idx_e, int
 /* ref: Polyak update loop  (sac/pytorch/sac.py:238-242):  target = (1-tau)*target + tau*online over a flat buffer. */
 int rlx_polyak_f32(float* target, const float* online, int64_t n, float tau, void* stream);
 
+/* SAC networks (ref: sac/pytorch/policy.py:34-43, q_network.py:27-33), flat fp32 parameter layouts:
+ *   policy [Pp]   : W1[H,O] b1[H] W2[H,H] b2[H] Wm[A,H] Ws[A,H] bm[A] bs[A]     (torso ReLU-ReLU, heads mean / log_std)
+ *   q      [4][Pq]: W1[H,O+A] b1[H] W2[H,H] b2[H] W3[1,H] b3[1]   in the order q1, q2, q1_target, q2_target */
+typedef struct rlx_sac_dims { int32_t obs_dim, act_dim, hidden; float log_std_min, log_std_max; } rlx_sac_dims;
+int64_t rlx_sac_policy_param_count(int32_t obs_dim, int32_t act_dim, int32_t hidden);
+int64_t rlx_sac_q_param_count(int32_t obs_dim, int32_t act_dim, int32_t hidden);
+size_t rlx_sac_workspace_bytes(int32_t obs_dim, int32_t act_dim, int32_t hidden, int64_t batch);
+
+/* ref: Policy.get_action / get_deterministic_action  (sac/pytorch/policy.py:45-73).  eps [n, act] = the standard-normal draws of
+ * normal.rsample().  Outputs (nullable): action_tanh [n, act], env_action [n, act] (rescaled to [low, high]), logp [n]. */
+int rlx_sac_act_f32(const rlx_sac_dims* d, const float* policy_params, const float* obs, const float* eps, int64_t n, const float* act_low,
+                    const float* act_high, int32_t deterministic, float* action_tanh, float* env_action, float* logp, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* ref: one full SAC update  (sac.py:219-259): critic_loss_fn (target, twin-Q MSE, Adam over q1 U q2), Polyak, then
+ * policy_and_entropy_loss_fn (actor loss through the updated critics, Adam; temperature loss, Adam).
+ * metrics [RLX_SAC_NMETRIC]: 0 entropy/alpha 1 entropy/entropy 2 gradients/policy_grad_norm 3 gradients/critic_grad_norm
+ *                            4 gradients/entropy_grad_norm 5 loss/q_loss 6 loss/policy_loss 7 loss/entropy_loss 8 q_value/q_value */
+#define RLX_SAC_NMETRIC 12
+typedef struct rlx_sac_update_args {
+  rlx_sac_dims dims;
+  int64_t batch;
+  float* policy;            /* [Pp] */
+  float* q;                 /* [4][Pq] */
+  float* log_alpha;         /* [1] */
+  const float* states;      /* [batch, obs]   sampled batch (rlx_replay_sample_gather_f32) */
+  const float* next_states; /* [batch, obs] */
+  const float* actions;     /* [batch, act] */
+  const float* rewards;     /* [batch] */
+  const float* terminations;/* [batch] */
+  const float* eps_next;    /* [batch, act] rsample noise of pi(next_states)  (critic_loss_fn, sac.py:132) */
+  const float* eps_cur;     /* [batch, act] rsample noise of pi(states)       (policy_and_entropy_loss_fn, sac.py:93) */
+  const float* act_low;     /* [act] */
+  const float* act_high;    /* [act] */
+  float gamma, tau, target_entropy;
+  float adam_beta1, adam_beta2, adam_eps;
+  float* g_policy; float* m_policy; float* v_policy;            /* [Pp] each */
+  float* g_q; float* m_q; float* v_q;                           /* [2*Pq] each (online nets) */
+  float* g_log_alpha; float* m_log_alpha; float* v_log_alpha;   /* [1] each */
+  const float* lr;          /* [1] device */
+  int64_t* steps;           /* [3] device: Adam step counters of policy, q, log_alpha */
+  float* metrics;           /* [RLX_SAC_NMETRIC] device */
+  void* workspace;
+  size_t workspace_bytes;
+} rlx_sac_update_args;
+int rlx_sac_update_f32(const rlx_sac_update_args* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

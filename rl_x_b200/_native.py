@@ -84,6 +84,23 @@ class PpoMinibatchArgs(C.Structure):
     ]
 
 
+class SacDims(C.Structure):
+    _fields_ = [("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("hidden", C.c_int32), ("log_std_min", C.c_float), ("log_std_max", C.c_float)]
+
+
+class SacUpdateArgs(C.Structure):
+    _fields_ = [("dims", SacDims), ("batch", C.c_int64)] + [(n, C.c_void_p) for n in (
+        "policy", "q", "log_alpha", "states", "next_states", "actions", "rewards", "terminations", "eps_next", "eps_cur", "act_low", "act_high")] + [
+        ("gamma", C.c_float), ("tau", C.c_float), ("target_entropy", C.c_float), ("adam_beta1", C.c_float), ("adam_beta2", C.c_float),
+        ("adam_eps", C.c_float)] + [(n, C.c_void_p) for n in (
+        "g_policy", "m_policy", "v_policy", "g_q", "m_q", "v_q", "g_log_alpha", "m_log_alpha", "v_log_alpha", "lr", "steps", "metrics", "workspace")] + [
+        ("workspace_bytes", C.c_size_t)]
+
+
+RLX_SAC_NMETRIC = 12
+SAC_METRIC_NAMES = ("entropy/alpha", "entropy/entropy", "gradients/policy_grad_norm", "gradients/critic_grad_norm", "gradients/entropy_grad_norm",
+                    "loss/q_loss", "loss/policy_loss", "loss/entropy_loss", "q_value/q_value")
+
 _SIGNATURES = {
     # name: (restype, argtypes)
     "rlx_version": (C.c_int, []),
@@ -117,6 +134,12 @@ _SIGNATURES = {
     "rlx_ppo_update_epoch_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_int64, C.c_int64, C.c_void_p]),
     "rlx_replay_sample_gather_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 10 + [C.c_void_p]),
     "rlx_polyak_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
+    "rlx_sac_policy_param_count": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "rlx_sac_q_param_count": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "rlx_sac_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "rlx_sac_act_f32": (C.c_int, [C.POINTER(SacDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rlx_sac_update_f32": (C.c_int, [C.POINTER(SacUpdateArgs), C.c_void_p]),
 }
 
 _lib = None
