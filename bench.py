@@ -217,6 +217,85 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def run_sac(args):
+    """BASELINE config 4: SAC, synthetic Box(17)/Box(6), replay 1e6, batch 4096, one update per env step (UTD = 1 / nr_envs = 1).
+    value = updates/s of sample + fused update on a full replay ring; e2e = the same through SAC._train_step() with a NUMPY-interface env."""
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.sac.b200.default_config import get_config
+    from rl_x_b200.algorithms.sac.b200.sac import SAC
+    from rl_x_b200.environments.synthetic.box.create_env import create_train_and_eval_env
+    from rl_x_b200.environments.synthetic.box.default_config import get_config as env_config
+    torch.cuda.set_device(0)
+    obs, act, batch, cap = 17, 6, 4096, 1_000_000
+    e = env_config("synthetic.box")
+    e.nr_envs, e.obs_dim, e.act_dim, e.data_interface, e.stream, e.ring_length, e.seed = 1, obs, act, "numpy", "ring", 64, 1
+    a = get_config("sac.b200")
+    a.batch_size, a.buffer_size, a.learning_starts, a.logging_frequency, a.total_timesteps = batch, cap, 5000, 10**9, 1e12
+    cfg = ConfigDict(algorithm=a, environment=e, runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    env, _ = create_train_and_eval_env(cfg)
+    model = SAC(cfg, env, env, "/tmp/rlx_bench_sac", None)
+    model._begin_training()
+    rb = model.replay_buffer
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in (rb.states, rb.next_states, rb.actions, rb.rewards):
+        t.normal_(generator=g)
+    rb.actions.tanh_()
+    rb.size, rb.pos = rb.capacity, 0
+    model.global_step = 6000  # past learning_starts
+    lib = nt.load()
+    for _ in range(max(args.warmup, 3) * 20):
+        model.update(rb.sample(batch))
+    torch.cuda.synchronize()
+    K = args.steps * 100
+    lib.rlx_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        model.update(rb.sample(batch))
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3
+    launches = int(lib.rlx_launch_count())
+    nt.timing_begin()
+    for _ in range(20):
+        model.update(rb.sample(batch))
+    classes = nt.timing_end()
+    # e2e: the full per-step loop (act, env.step on host arrays, replay add, sample, update)
+    for _ in range(50):
+        model._train_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        model._train_step()
+    torch.cuda.synchronize()
+    sec2 = time.perf_counter() - t0
+    line = {"metric": "SAC updates/sec (sample + twin-Q/actor/alpha update), batch 4096", "value": K / sec, "unit": "updates/s", "n_gpus": 1, "steps": K,
+            "warmup": max(args.warmup, 3) * 20, "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "SAC synthetic Box(obs=17, act=6), replay=1e6 (full), batch=4096, nr_envs=1, hidden=256 (BASELINE.json configs[3])"},
+            "gpu_launches": launches, "kernel_ms": {k: round(v["ms"] / 20, 4) for k, v in classes.items() if v["launches"]},
+            "e2e": {"value": K / sec2, "unit": "updates/s (= env-steps/s at nr_envs=1)", "h2d_bytes_per_step": 2 * batch * 8 + (2 * obs + act + 2) * 4,
+                    "d2h_bytes_per_step": act * 4, "path": "SAC._train_step(): act -> env.step(numpy) -> replay add -> sample -> fused update"}}
+    if not args.no_cpu:
+        from oracle import sac_oracle as S
+        threads = calibrate_threads(available_cores())
+        torch.set_num_threads(threads)
+        pol, q1, q2 = S.init_params(obs, act, 256, seed=1)
+        L = S.Learner(pol, q1, q2, torch.full((act,), -1.0), torch.full((act,), 1.0))
+        gg = torch.Generator().manual_seed(0)
+        mk = lambda: (torch.randn(batch, obs, generator=gg), torch.randn(batch, obs, generator=gg), torch.tanh(torch.randn(batch, act, generator=gg)),
+                      torch.randn(batch, generator=gg), torch.zeros(batch), torch.randn(batch, act, generator=gg), torch.randn(batch, act, generator=gg))
+        L.update(*mk())
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 10.0:
+            L.update(*mk())
+            n += 1
+        line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "updates/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} oracle updates at batch 4096 in ~10 s (batch generation included, replay sampling excluded)"}
+    print(json.dumps(line))
+
+
 def workload_config(args, world):
     return {"workload": f"PPO synthetic Box(obs={C2['obs_dim']}, act={C2['act_dim']}) ~Humanoid, num_envs={args.envs}/GPU, horizon={C2['nr_steps']}, "
                         f"hidden={C2['hidden']}, nr_epochs={args.epochs}, minibatch={args.minibatch}/GPU (BASELINE.json configs[1])",
@@ -238,6 +317,7 @@ def main():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -248,6 +328,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
+    if args.workload == "sac":
+        if rank == 0:
+            run_sac(args)
+        return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)

@@ -210,98 +210,106 @@ class SAC:
 
     # ----------------------------------------------------------------------------------------------------- train
     def train(self):
+        self._begin_training()
+        while self.global_step < self.total_timesteps:
+            self._train_step()
+
+    def _begin_training(self):
+        """Everything SAC.train() does before its while loop (sac.py:162-178)."""
         self.set_train_mode()
-        env = self.train_env
-        replay_buffer = ReplayBuffer(int(self.buffer_size), self.nr_envs, self.os_shape, self.as_shape, self.rng, self.device)
-        self.replay_buffer = replay_buffer
-        saving_return_buffer = deque(maxlen=100 * self.nr_envs)
-        state, _ = env.reset()
-        global_step, self.nr_updates, nr_episodes = 0, 0, 0
-        time_metrics_collection, step_info_collection = {}, {}
-        updates_since_log = 0
-        prev_saving_end_time = None
-        while global_step < self.total_timesteps:
-            start_time = time.time()
-            dones_this_rollout = 0
-            # Acting (sac.py:187-196)
-            if global_step < self.learning_starts:
-                processed_action = np.array([env.single_action_space.sample() for _ in range(self.nr_envs)], dtype=np.float32)
-                action = (processed_action - self.env_as_low) / (self.env_as_high - self.env_as_low) * 2.0 - 1.0
-                step_action = torch.from_numpy(processed_action).to(self.device) if self.is_torch_data_interface else processed_action
-            else:
-                action, env_action = self._act(state)
-                step_action = env_action if self.is_torch_data_interface else env_action.cpu().numpy()
-            next_state, reward, terminated, truncated, info = env.step(step_action)
-            done = terminated | truncated
-            if self.is_torch_data_interface:
-                actual_next_state = next_state  # auto-reset torch envs hand out the post-reset observation (same caveat as ppo.py:224-226)
-                dones_this_rollout = int(done.sum().item())
-            else:
-                actual_next_state = next_state.copy()
-                for i in np.nonzero(done)[0]:
-                    actual_next_state[i] = np.array(env.get_final_observation_at_index(info, int(i)))
-                    saving_return_buffer.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
-                    dones_this_rollout += 1
-            for key, info_value in env.get_logging_info_dict(info).items():
-                step_info_collection.setdefault(key, []).extend(info_value)
-            replay_buffer.add(state, actual_next_state, action, reward, terminated)
-            state = next_state
-            global_step += self.nr_envs
-            nr_episodes += dones_this_rollout
-            acting_end_time = time.time()
-            time_metrics_collection.setdefault("time/acting_time", []).append(acting_end_time - start_time)
+        self.replay_buffer = ReplayBuffer(int(self.buffer_size), self.nr_envs, self.os_shape, self.as_shape, self.rng, self.device)
+        self.saving_return_buffer = deque(maxlen=100 * self.nr_envs)
+        self.state, _ = self.train_env.reset()
+        self.global_step, self.nr_updates, self.nr_episodes = 0, 0, 0
+        self.time_metrics_collection, self.step_info_collection = {}, {}
+        self.updates_since_log = 0
+        self.prev_saving_end_time = None
 
-            should_learning_start = global_step > self.learning_starts
-            should_evaluate = global_step % self.evaluation_frequency == 0 and self.evaluation_frequency != -1
-            should_try_to_save = should_learning_start and self.save_model and dones_this_rollout > 0
-            should_log = global_step % self.logging_frequency == 0
+    def _train_step(self):
+        """One pass of the reference's while-loop body (sac.py:180-348): act, env.step, replay add, sample, update, eval/save/log."""
+        env, replay_buffer, state = self.train_env, self.replay_buffer, self.state
+        start_time = time.time()
+        dones_this_rollout = 0
+        # Acting (sac.py:187-196)
+        if self.global_step < self.learning_starts:
+            processed_action = np.array([env.single_action_space.sample() for _ in range(self.nr_envs)], dtype=np.float32)
+            action = (processed_action - self.env_as_low) / (self.env_as_high - self.env_as_low) * 2.0 - 1.0
+            step_action = torch.from_numpy(processed_action).to(self.device) if self.is_torch_data_interface else processed_action
+        else:
+            action, env_action = self._act(state)
+            step_action = env_action if self.is_torch_data_interface else env_action.cpu().numpy()
+        next_state, reward, terminated, truncated, info = env.step(step_action)
+        done = terminated | truncated
+        if self.is_torch_data_interface:
+            actual_next_state = next_state  # auto-reset torch envs hand out the post-reset observation (same caveat as ppo.py:224-226)
+            dones_this_rollout = int(done.sum().item())
+        else:
+            actual_next_state = next_state.copy()
+            for i in np.nonzero(done)[0]:
+                actual_next_state[i] = np.array(env.get_final_observation_at_index(info, int(i)))
+                self.saving_return_buffer.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
+                dones_this_rollout += 1
+        for key, info_value in env.get_logging_info_dict(info).items():
+            self.step_info_collection.setdefault(key, []).extend(info_value)
+        replay_buffer.add(state, actual_next_state, action, reward, terminated)
+        self.state = next_state
+        self.global_step += self.nr_envs
+        global_step = self.global_step
+        self.nr_episodes += dones_this_rollout
+        acting_end_time = time.time()
+        self.time_metrics_collection.setdefault("time/acting_time", []).append(acting_end_time - start_time)
 
-            if should_learning_start:
-                self.lr_dev.fill_(self.current_learning_rate())
-                self.update(replay_buffer.sample(self.batch_size))
-                self.nr_updates += 1
-                updates_since_log += 1
-            optimizing_end_time = time.time()
-            time_metrics_collection.setdefault("time/optimizing_time", []).append(optimizing_end_time - acting_end_time)
+        should_learning_start = global_step > self.learning_starts
+        should_evaluate = global_step % self.evaluation_frequency == 0 and self.evaluation_frequency != -1
+        should_try_to_save = should_learning_start and self.save_model and dones_this_rollout > 0
+        should_log = global_step % self.logging_frequency == 0
 
-            evaluation_metrics = {}
-            if should_evaluate:
-                evaluation_metrics = self._evaluate()
-            evaluating_end_time = time.time()
-            time_metrics_collection.setdefault("time/evaluating_time", []).append(evaluating_end_time - optimizing_end_time)
+        if should_learning_start:
+            self.lr_dev.fill_(self.current_learning_rate())
+            self.update(replay_buffer.sample(self.batch_size))
+            self.nr_updates += 1
+            self.updates_since_log += 1
+        optimizing_end_time = time.time()
+        self.time_metrics_collection.setdefault("time/optimizing_time", []).append(optimizing_end_time - acting_end_time)
 
-            if should_try_to_save and len(saving_return_buffer) > 0:
-                mean_return = np.mean(saving_return_buffer)
-                if mean_return > self.best_mean_return:
-                    self.best_mean_return = mean_return
-                    self.save()
-            saving_end_time = time.time()
-            if prev_saving_end_time:
-                time_metrics_collection.setdefault("time/sps", []).append(self.nr_envs / (saving_end_time - prev_saving_end_time))
-            prev_saving_end_time = saving_end_time
-            time_metrics_collection.setdefault("time/saving_time", []).append(saving_end_time - evaluating_end_time)
+        evaluation_metrics = {}
+        if should_evaluate:
+            evaluation_metrics = self._evaluate()
+        evaluating_end_time = time.time()
+        self.time_metrics_collection.setdefault("time/evaluating_time", []).append(evaluating_end_time - optimizing_end_time)
 
-            if should_log:
-                self.start_logging(global_step)
-                combined = {}
-                for info_name, values in step_info_collection.items():
-                    group = "rollout" if info_name in ["episode_return", "episode_length"] else "env_info"
-                    mean_value = np.mean(values)
-                    if mean_value == mean_value:
-                        combined[f"{group}/{info_name}"] = mean_value
-                combined.update({k: np.mean(v) for k, v in evaluation_metrics.items()})
-                combined.update({"steps/nr_env_steps": global_step, "steps/nr_updates": self.nr_updates, "steps/nr_episodes": nr_episodes})
-                combined.update({k: np.mean(v) for k, v in time_metrics_collection.items()})
-                if updates_since_log > 0:  # the one device->host read of the optimisation metrics (means since the last log, sac.py:334-337)
-                    sums = (self.metric_sums / updates_since_log).cpu().numpy()
-                    combined.update({name: float(sums[i]) for i, name in enumerate(nt.SAC_METRIC_NAMES)})
-                    combined["lr/learning_rate"] = self.current_learning_rate()
-                    self.metric_sums.zero_()
-                    updates_since_log = 0
-                for key, value in combined.items():
-                    self.log(f"{key}", value, global_step)
-                time_metrics_collection, step_info_collection = {}, {}
-                self.end_logging()
+        if should_try_to_save and len(self.saving_return_buffer) > 0:
+            mean_return = np.mean(self.saving_return_buffer)
+            if mean_return > self.best_mean_return:
+                self.best_mean_return = mean_return
+                self.save()
+        saving_end_time = time.time()
+        if self.prev_saving_end_time:
+            self.time_metrics_collection.setdefault("time/sps", []).append(self.nr_envs / (saving_end_time - self.prev_saving_end_time))
+        self.prev_saving_end_time = saving_end_time
+        self.time_metrics_collection.setdefault("time/saving_time", []).append(saving_end_time - evaluating_end_time)
+
+        if should_log:
+            self.start_logging(global_step)
+            combined = {}
+            for info_name, values in self.step_info_collection.items():
+                group = "rollout" if info_name in ["episode_return", "episode_length"] else "env_info"
+                mean_value = np.mean(values)
+                if mean_value == mean_value:
+                    combined[f"{group}/{info_name}"] = mean_value
+            combined.update({k: np.mean(v) for k, v in evaluation_metrics.items()})
+            combined.update({"steps/nr_env_steps": global_step, "steps/nr_updates": self.nr_updates, "steps/nr_episodes": self.nr_episodes})
+            combined.update({k: np.mean(v) for k, v in self.time_metrics_collection.items()})
+            if self.updates_since_log > 0:  # the one device->host read of the optimisation metrics (means since the last log, sac.py:334-337)
+                sums = (self.metric_sums / self.updates_since_log).cpu().numpy()
+                combined.update({name: float(sums[i]) for i, name in enumerate(nt.SAC_METRIC_NAMES)})
+                combined["lr/learning_rate"] = self.current_learning_rate()
+                self.metric_sums.zero_()
+                self.updates_since_log = 0
+            for key, value in combined.items():
+                self.log(f"{key}", value, global_step)
+            self.time_metrics_collection, self.step_info_collection = {}, {}
+            self.end_logging()
 
     def _evaluate(self):
         """ref: sac.py:264-283."""
