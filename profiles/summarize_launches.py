@@ -14,9 +14,9 @@ def main(path):
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
-    ours = sum(a[1] for k, a in agg.items() if "rlx::" in k)
+    ours = sum(a[1] for k, a in agg.items() if "rlx::" in k or "tc::tc_gemm" in k)
     print(f"# {path}: {sum(a[0] for a in agg.values())} launches, {tot / 1e6:.2f} ms total device time (cold-cache, serialised by ncu)")
-    print(f"# rlx:: kernels (this repo): {100 * ours / tot:.2f}% of device time; the rest are torch kernels of the synthetic env / metric plumbing")
+    print(f"# rlx:: / rlx::tc:: kernels (this repo): {100 * ours / tot:.2f}% of device time; the rest are torch kernels of the synthetic env / metric plumbing")
     print(f"{'total ms':>10} {'share':>7} {'launches':>9} {'avg us':>10}  kernel")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{t / 1e6:10.2f} {100 * t / tot:6.2f}% {n:9d} {t / n / 1e3:10.2f}  {k[:140]}")

@@ -27,4 +27,6 @@ def get_config(algorithm_name):
     config.evaluation_frequency = -1
     config.evaluation_episodes = 10
 
+    config.gemm_engine = "auto"  # auto | simt (fp32 FFMA) | tcgen05 (3xTF32 tensor cores)
+
     return config

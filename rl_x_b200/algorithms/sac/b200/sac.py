@@ -126,6 +126,7 @@ class SAC:
         self.os_shape, self.as_shape = tuple(os_shape), tuple(as_shape)
         O, A = int(os_shape[0]), int(as_shape[0])
         self.k = SacKernels(O, A, a.nr_hidden_units, a.log_std_min, a.log_std_max)
+        self.k.lib.rlx_set_gemm_engine({"simt": 0, "tcgen05": 1, "auto": 1}[a.get("gemm_engine", "auto")])
         self.env_as_low = np.broadcast_to(np.asarray(torch.as_tensor(self.train_env.single_action_space.low).cpu(), dtype=np.float32).reshape(-1), (A,)).copy()
         self.env_as_high = np.broadcast_to(np.asarray(torch.as_tensor(self.train_env.single_action_space.high).cpu(), dtype=np.float32).reshape(-1), (A,)).copy()
         self.d_low, self.d_high = torch.from_numpy(self.env_as_low).to(self.device), torch.from_numpy(self.env_as_high).to(self.device)

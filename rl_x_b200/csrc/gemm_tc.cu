@@ -7,12 +7,12 @@
 // resolution).  That is the accuracy class of an fp32 FMA loop (single-pass TF32 misses the 1e-5 loss-parity bar,
 // 3xTF32 does not) at one third of the TF32 tensor rate.
 //
-// Structure (one persistent CTA per SM, 320 threads, static tile schedule):
+// Structure (one persistent CTA per SM, 448 threads, static tile schedule):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (SWIZZLE_128B) of raw fp32 A and B into a shared-memory ring
 //   warps 2-5   splitter: read the raw tiles, write the lo tiles (same swizzled layout) next to them, fence.proxy.async
 //   warp 1      MMA issuer: ONE thread issues tcgen05.mma.cta_group::1.kind::tf32 (3 per k-slice of 8), tcgen05.commit frees the
 //               ring slot / publishes the accumulator
-//   warps 6-9   epilogue: tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (double-buffered: the next tile's MMAs overlap),
+//   warps 6-13  epilogue (two warp-groups): tcgen05.ld the 128 x BN fp32 accumulator out of TMEM (double-buffered: the next tile's MMAs overlap),
 //               bias+tanh / tanh' / plain, 128-bit global stores
 // Operand layouts: K-major (row = m or n, 32 consecutive k = one 128-byte swizzle row) or MN-major (row = k, 32 consecutive
 // m/n per 128-byte row; used by the weight-gradient GEMMs whose reduction runs over the minibatch rows).  Out-of-bounds parts
@@ -28,10 +28,10 @@ namespace tc {
 constexpr int BM = 128;        // UMMA M (cta_group::1)
 constexpr int BK = 32;         // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;      // tf32: 32 bytes of K per instruction
-constexpr int NUM_THREADS = 320;
-constexpr int SPLIT_WARP0 = 2, EPI_WARP0 = 6;
+constexpr int NUM_THREADS = 448;
+constexpr int SPLIT_WARP0 = 2, EPI_WARP0 = 6, EPI_WARPS = 8;  // two epilogue warp-groups: group g takes column chunks g, g+2, ...
 
-enum TcEpi { TC_EPI_NONE = 0, TC_EPI_BIAS_TANH = 1, TC_EPI_DTANH = 2 };
+enum TcEpi { TC_EPI_NONE = 0, TC_EPI_BIAS_TANH = 1, TC_EPI_DTANH = 2, TC_EPI_BIAS_RELU = 3, TC_EPI_DRELU = 4, TC_EPI_BIAS = 5 };
 
 struct TcParams {
   int M, N, K;               // per-z output is [M, N]; K = full reduction extent
@@ -156,7 +156,7 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 2 : 3;
   static constexpr int ACC_STAGES = (BN == 256) ? 1 : 2;
   static constexpr int TMEM_COLS = ACC_STAGES * 2 * BN;         // 512
-  static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + 4 * 32 * 33 * 4 /*epilogue transpose staging, one [32][33] tile per warp*/;
+  static constexpr int AUX_BYTES = 1024 /*barriers etc.*/ + EPI_WARPS * 32 * 33 * 4 /*epilogue transpose staging, one [32][33] tile per warp*/;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024 /*alignment slack*/;
 };
 
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       }
       for (int a = 0; a < ACC_STAGES; ++a) {
         mbar_init(&tmem_full_bar[a], 1);
-        mbar_init(&tmem_empty_bar[a], 4);
+        mbar_init(&tmem_empty_bar[a], EPI_WARPS);
       }
       fence_barrier_init();
     }
@@ -340,11 +340,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       tc_fence_after();
       const int row0 = m0 + q * 32;
       float* cbase = p.C + p.c_batch_off * zb + p.c_split_off * zs;
-      const float* abase = (EPI == TC_EPI_DTANH) ? (p.aux + p.aux_batch_off * zb) : nullptr;
-      const float* bias = (EPI == TC_EPI_BIAS_TANH) ? (p.bias + p.bias_batch_off * zb) : nullptr;
+      constexpr bool HAS_AUX = (EPI == TC_EPI_DTANH || EPI == TC_EPI_DRELU);
+      constexpr bool HAS_BIAS = (EPI == TC_EPI_BIAS_TANH || EPI == TC_EPI_BIAS_RELU || EPI == TC_EPI_BIAS);
+      const float* abase = HAS_AUX ? (p.aux + p.aux_batch_off * zb) : nullptr;
+      const float* bias = HAS_BIAS ? (p.bias + p.bias_batch_off * zb) : nullptr;
       const int rows_valid = min(32, p.M - row0);  // warp-uniform
+      const int eg = (warp - EPI_WARP0) >> 2;  // epilogue warp-group
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = eg; c < BN / 32; c += EPI_WARPS / 4) {
         uint32_t r[32], rc[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * BN + c * 32);
         tmem_ld_32x32b_x32(taddr, r);
@@ -358,22 +361,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
           const int n = nb + lane;
           const bool n_ok = n < p.N;
           float bv = 0.f;
-          if (EPI == TC_EPI_BIAS_TANH && n_ok) bv = bias[n];
+          if (HAS_BIAS && n_ok) bv = bias[n];
           // Math is unconditional and fully unrolled (32 independent chains per lane: a branch per row would serialise the
           // ~40-instruction tanhf sequences); only the global accesses are predicated.  Rows >= rows_valid hold zeros.
           float x[32];
 #pragma unroll
           for (int rr = 0; rr < 32; ++rr) x[rr] = tile[rr * 33 + lane];
-          if (EPI == TC_EPI_DTANH) {
+          if (HAS_AUX) {
             float hv[32];
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) x[rr] = x[rr] * (1.f - hv[rr] * hv[rr]);
+            for (int rr = 0; rr < 32; ++rr) x[rr] = (EPI == TC_EPI_DTANH) ? x[rr] * (1.f - hv[rr] * hv[rr]) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
           }
-          if (EPI == TC_EPI_BIAS_TANH) {
+          if (HAS_BIAS) {
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) x[rr] = tanhf(x[rr] + bv);
+            for (int rr = 0; rr < 32; ++rr) {
+              const float z = x[rr] + bv;
+              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? tanhf(z) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
+            }
           }
           if (n < p.n_main) {
             float* cp = cbase + (long long)row0 * p.ldc + n;
@@ -490,6 +496,25 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   if (g.M <= 0 || g.N <= 0) return RLX_OK;
   if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || g.lda % 4 || g.ldb % 4 || g.ldc % 4) return RLX_ERR_UNSUPPORTED;
   if (g.splits > 1 && g.kchunk % BK) return RLX_ERR_UNSUPPORTED;
+  if (batch > 1) {
+    // A batch stride must be a pure row offset or a pure column offset of the operand's 2-D tensor to become a TMA coordinate.
+    // Otherwise (e.g. parameter blocks of different nets that are not a whole number of rows apart) run the nets one by one.
+    auto expressible = [](long long off, int ld) { return off == 0 || off % ld == 0 || off < ld; };
+    if (!expressible(g.sA, g.lda) || !expressible(g.sB, g.ldb)) {
+      if (g.sA % 4 || g.sB % 4 || g.sC % 4 || g.sAux % 4) return RLX_ERR_UNSUPPORTED;
+      for (int b = 0; b < batch; ++b) {
+        GemmP gb = g;
+        gb.A = g.A + b * g.sA; gb.B = g.B + b * g.sB; gb.C = g.C + b * g.sC;
+        if (g.bias) gb.bias = g.bias + b * g.sBias;
+        if (g.aux) gb.aux = g.aux + b * g.sAux;
+        gb.sA = gb.sB = gb.sC = gb.sBias = gb.sAux = 0;
+        const long long ar = a_rows, br = b_kmaj ? (long long)g.N : (long long)g.K;
+        const int rc = tc_gemm(gb, a_kmaj, b_kmaj, epi, 1, kclass, ar, br, n_main, extra_col ? extra_col + b * extra_batch_off : nullptr, 0, extra_split_off, stream);
+        if (rc) return rc;
+      }
+      return RLX_OK;
+    }
+  }
   TcParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.batch = batch; p.splits = g.splits;
@@ -506,9 +531,12 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   p.extra_col = extra_col; p.extra_batch_off = extra_batch_off; p.extra_split_off = extra_split_off;
   p.bias = g.bias; p.bias_batch_off = g.sBias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.aux_batch_off = g.sAux;
-  // global tensors: K-major [mn_rows, k_cols]; MN-major [k_rows, mn_cols]
-  TcOperand A{g.A, a_rows, a_kmaj ? (long long)(p.a_k_off * (batch - 1) + g.K) : (long long)(p.a_mn_off * (batch - 1) + g.M), g.lda};
-  TcOperand B{g.B, b_rows, b_kmaj ? (long long)(p.b_k_off * (batch - 1) + g.K) : (long long)(p.b_mn_off * (batch - 1) + g.N), g.ldb};
+  // global tensors: K-major [mn_rows, k_cols]; MN-major [k_rows, mn_cols].  a_rows / b_rows are the VALID rows of one batch entry
+  // (TMA zero-fills beyond them); batch entries that sit at row offsets extend the tensor accordingly.
+  TcOperand A{g.A, (a_kmaj ? (long long)p.a_mn_off : (long long)p.a_k_off) * (batch - 1) + a_rows,
+              a_kmaj ? (long long)(p.a_k_off * (batch - 1) + g.K) : (long long)(p.a_mn_off * (batch - 1) + g.M), g.lda};
+  TcOperand B{g.B, (b_kmaj ? (long long)p.b_mn_off : (long long)p.b_k_off) * (batch - 1) + b_rows,
+              b_kmaj ? (long long)(p.b_k_off * (batch - 1) + g.K) : (long long)(p.b_mn_off * (batch - 1) + g.N), g.ldb};
   // BN = 256 halves the A-operand re-reads but has a single accumulator set (no epilogue/mainloop overlap): it only pays for
   // long reductions with a trivial epilogue (the dW GEMMs).  Short-K GEMMs with tanh / tanh' epilogues use the double-buffered
   // BN = 128 configuration (measured: profiles/r01_tc_minibatch_ncu_details_v1.txt).
@@ -519,6 +547,9 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   do {                                                                                                                        \
     if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg<BN_, true, true, TC_EPI_BIAS_TANH>(A, B, p, kclass, stream); \
     if (a_kmaj && b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, true, true, TC_EPI_NONE>(A, B, p, kclass, stream);       \
+    if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_RELU) return launch_cfg<BN_, true, true, TC_EPI_BIAS_RELU>(A, B, p, kclass, stream); \
+    if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS) return launch_cfg<BN_, true, true, TC_EPI_BIAS>(A, B, p, kclass, stream);       \
+    if (a_kmaj && !b_kmaj && epi == TC_EPI_DRELU) return launch_cfg<BN_, true, false, TC_EPI_DRELU>(A, B, p, kclass, stream);   \
     if (a_kmaj && !b_kmaj && epi == TC_EPI_DTANH) return launch_cfg<BN_, true, false, TC_EPI_DTANH>(A, B, p, kclass, stream);   \
     if (a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, true, false, TC_EPI_NONE>(A, B, p, kclass, stream);     \
     if (!a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg<BN_, false, false, TC_EPI_NONE>(A, B, p, kclass, stream);   \

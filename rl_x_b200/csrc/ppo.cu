@@ -9,30 +9,13 @@
 // no dX for layer 1.  Bias gradients fall out of the dW GEMMs as row sums of the dZ operand.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 #include "ppo_head.cuh"
 #include "ppo_optim.cuh"
 
 namespace rlx {
 
-// tcgen05 engine hooks (gemm_tc.cu). tc_gemm returns RLX_ERR_UNSUPPORTED when a shape / alignment is not covered.
-int tc_supported(const rlx_ppo_dims& d);
-int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
-            float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream);
-enum { TC_NONE = 0, TC_BIAS_TANH = 1, TC_DTANH = 2 };
-
 static bool use_tc(const rlx_ppo_dims& d) { return g_gemm_engine == 1 && tc_supported(d); }
-
-// One GEMM through the selected engine (tcgen05 when it covers the shape, fp32 SIMT otherwise).
-// a_rows / b_rows: number of rows of the operand tensors as laid out in memory (TMA needs the true extents for zero fill).
-template <bool A_KMAJ, bool B_KMAJ, int EPI>
-static int run_gemm(bool tc, const GemmP& g, int batch, cudaStream_t st, int kclass, long long a_rows, long long b_rows) {
-  if (tc && g.rowsum == nullptr) {
-    const int epi = (EPI == EPI_BIAS_TANH) ? TC_BIAS_TANH : (EPI == EPI_DTANH) ? TC_DTANH : TC_NONE;
-    const int rc = tc_gemm(g, A_KMAJ, B_KMAJ, epi, batch, kclass, a_rows, b_rows, 0, nullptr, 0, 0, st);
-    if (rc != RLX_ERR_UNSUPPORTED) return rc;
-  }
-  return launch_sgemm<A_KMAJ, B_KMAJ, EPI>(g, batch, st, kclass);
-}
 
 struct Splits {
   int splits, kchunk;
@@ -134,7 +117,7 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
   g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
   g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
-  return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, 2 * H);
+  return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, H);
 }
 
 #define RLX_DISPATCH_NCH(CLS, FLOPS, BYTES, H, KERNEL, grid, block, smem, stream, arg)                                              \
@@ -363,7 +346,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
     gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
     gd.splits = 1; gd.kchunk = (int)(ceil_div(H, 8) * 8);
-    rc = run_gemm<true, false, EPI_DTANH>(tc, gd, 2, st, KC_GEMM_DX, m, 2 * H);
+    rc = run_gemm<true, false, EPI_DTANH>(tc, gd, 2, st, KC_GEMM_DX, m, H);
     if (rc) return rc;
     // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i];  db1[o] = sum_rows dZ1[r, o]
     GemmP g1{};

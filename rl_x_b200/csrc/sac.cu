@@ -9,6 +9,7 @@
 // are issued back-to-back from C++; the GEMMs go through the exact-fp32 SIMT engine (gemm_simt.cuh) with ReLU epilogues.
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 
 namespace rlx {
 
@@ -37,7 +38,7 @@ static SacLayout sac_layout(int O, int A, int H) {
   L.qb2 = o; o += H;
   L.qW3 = o; o += H;
   L.qb3 = o; o += 1;
-  L.Pq = o;
+  L.Pq = (o + 63) / 64 * 64;  // per-net stride padded to 256 bytes: every net's tensors keep the 16-byte alignment TMA needs
   return L;
 }
 
@@ -239,7 +240,10 @@ static int layer_fwd(const float* A, int lda, long long sA, const float* W, long
   g.lda = lda; g.ldb = K; g.ldc = ldc;
   g.sA = sA; g.sB = sW; g.sC = sC; g.sBias = sb;
   g.splits = 1; g.kchunk = (int)(ceil_div(K, 8) * 8);
-  return relu ? launch_sgemm<true, true, EPI_BIAS_RELU>(g, batch, st, KC_GEMM_FWD) : launch_sgemm<true, true, EPI_BIAS>(g, batch, st, KC_GEMM_FWD);
+  const bool tc = g_gemm_engine == 1;
+  const long long a_rows = M, b_rows = N;
+  return relu ? run_gemm<true, true, EPI_BIAS_RELU>(tc, g, batch, st, KC_GEMM_FWD, a_rows, b_rows)
+              : run_gemm<true, true, EPI_BIAS>(tc, g, batch, st, KC_GEMM_FWD, a_rows, b_rows);
 }
 // dX = (dZ W) [* relu'(aux)],  W is [N_out, K_in] row-major so that dX[m, k] = sum_n dZ[m, n] W[n, k]
 static int layer_bwd_input(const float* dZ, int ldz, long long sZ, const float* W, int ldw, long long sW, const float* aux, int ldaux, long long sAux,
@@ -250,7 +254,10 @@ static int layer_bwd_input(const float* dZ, int ldz, long long sZ, const float* 
   g.lda = ldz; g.ldb = ldw; g.ldc = ldx; g.ldaux = ldaux;
   g.sA = sZ; g.sB = sW; g.sC = sX; g.sAux = sAux;
   g.splits = 1; g.kchunk = (int)(ceil_div(Nout, 8) * 8);
-  return aux ? launch_sgemm<true, false, EPI_DRELU>(g, batch, st, KC_GEMM_DX) : launch_sgemm<true, false, EPI_NONE>(g, batch, st, KC_GEMM_DX);
+  const bool tc = g_gemm_engine == 1;
+  const long long a_rows = M, b_rows = Nout;
+  return aux ? run_gemm<true, false, EPI_DRELU>(tc, g, batch, st, KC_GEMM_DX, a_rows, b_rows)
+             : run_gemm<true, false, EPI_NONE>(tc, g, batch, st, KC_GEMM_DX, a_rows, b_rows);
 }
 // dW[n, k] = sum_m dZ[m, n] X[m, k], db[n] = sum_m dZ[m, n]; split over rows into `part`/`rs`, then reduced into gW / gb (batched).
 static int layer_bwd_weight(const float* dZ, int ldz, long long sZ, const float* X, int ldx, long long sX, int M, int Nout, int Kin, int batch, float* part,

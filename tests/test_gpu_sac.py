@@ -12,6 +12,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True, params=["simt", "tcgen05"])
+def gemm_engine(request):
+    """Every test runs once per GEMM engine (the engine is a process-wide switch of the library)."""
+    from rl_x_b200 import _native as nt
+    yield request.param
+    nt.load().rlx_set_gemm_engine(0)
+
+
 class _Space:
     def __init__(self, shape, low=None, high=None):
         self.shape, self.low, self.high = shape, low, high
@@ -62,7 +70,13 @@ class StubEnv:
 
 
 def _model(N, obs, act, hidden, batch, low, high, seed=2, interface="NUMPY", **algo):
+    import inspect
     from rl_x_b200.config_dict import ConfigDict
+    # pick up the engine of the running parametrisation
+    for fr in inspect.stack():
+        if "gemm_engine" in fr.frame.f_locals and isinstance(fr.frame.f_locals["gemm_engine"], str):
+            algo.setdefault("gemm_engine", fr.frame.f_locals["gemm_engine"])
+            break
     from rl_x_b200.algorithms.sac.b200.default_config import get_config
     from rl_x_b200.algorithms.sac.b200.sac import SAC
     a = get_config("sac.b200")
@@ -84,7 +98,7 @@ def _rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def test_sac_updates_reproduce_reference_golden():
+def test_sac_updates_reproduce_reference_golden(gemm_engine):
     from conftest import GOLDEN_DIR
     from rl_x_b200 import _native as nt
     z = np.load(os.path.join(GOLDEN_DIR, "sac_small.npz"))
@@ -119,7 +133,7 @@ def test_sac_updates_reproduce_reference_golden():
     assert model.steps.cpu().tolist() == [nupd, nupd, nupd]
 
 
-def test_sac_update_vs_oracle_at_config4_sizes():
+def test_sac_update_vs_oracle_at_config4_sizes(gemm_engine):
     """Box(17) / Box(6), hidden 256, batch 4096 (BASELINE.json configs[3])."""
     from rl_x_b200 import _native as nt
     obs, act, hidden, B = 17, 6, 256, 4096
@@ -149,7 +163,7 @@ def test_sac_update_vs_oracle_at_config4_sizes():
             assert _rel(qs[net][k].numpy(), d[k].detach().numpy()) < 1e-5, (net, k)
 
 
-def test_sac_act_vs_oracle():
+def test_sac_act_vs_oracle(gemm_engine):
     obs, act, hidden, n = 17, 6, 256, 333
     model, _ = _model(n, obs, act, hidden, 64, -2.0, 0.5)
     pol, q1, q2 = S.init_params(obs, act, hidden, seed=4)
@@ -193,7 +207,7 @@ def test_replay_sampling_is_numpy_exact():
 
 
 @pytest.mark.parametrize("interface", ["NUMPY", "TORCH"])
-def test_sac_train_loop_runs(interface):
+def test_sac_train_loop_runs(interface, gemm_engine):
     model, env = _model(4, 17, 6, 64, 32, -2.0, 1.0, interface=interface, learning_starts=24, total_timesteps=120, logging_frequency=8, buffer_size=512)
     logged = []
     model.log = lambda name, value, step: logged.append((name, float(value), step))
