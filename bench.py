@@ -257,10 +257,12 @@ def run_sac(args):
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) / 1e3
     launches = int(lib.rlx_launch_count())
+    model.use_cuda_graph = False  # per-class event timing needs eager launches
     nt.timing_begin()
     for _ in range(20):
         model.update(rb.sample(batch))
     classes = nt.timing_end()
+    model.use_cuda_graph = True
     # e2e: the full per-step loop (act, env.step on host arrays, replay add, sample, update)
     for _ in range(50):
         model._train_step()
@@ -273,7 +275,7 @@ def run_sac(args):
     line = {"metric": "SAC updates/sec (sample + twin-Q/actor/alpha update), batch 4096", "value": K / sec, "unit": "updates/s", "n_gpus": 1, "steps": K,
             "warmup": max(args.warmup, 3) * 20, "ms_per_step": sec / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": "SAC synthetic Box(obs=17, act=6), replay=1e6 (full), batch=4096, nr_envs=1, hidden=256 (BASELINE.json configs[3])"},
-            "gpu_launches": launches, "kernel_ms": {k: round(v["ms"] / 20, 4) for k, v in classes.items() if v["launches"]},
+            "gpu_launches": launches, "cuda_graph": True, "kernel_ms_eager": {k: round(v["ms"] / 20, 4) for k, v in classes.items() if v["launches"]},
             "e2e": {"value": K / sec2, "unit": "updates/s (= env-steps/s at nr_envs=1)", "h2d_bytes_per_step": 2 * batch * 8 + (2 * obs + act + 2) * 4,
                     "d2h_bytes_per_step": act * 4, "path": "SAC._train_step(): act -> env.step(numpy) -> replay add -> sample -> fused update"}}
     if not args.no_cpu:

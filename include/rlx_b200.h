@@ -39,6 +39,7 @@ int rlx_version(void);                        /* ABI version, currently 1 */
 const char* rlx_last_error_string(void);      /* thread-local, never NULL */
 uint64_t rlx_launch_count(void);              /* kernels launched by this library since load / last reset */
 void rlx_reset_launch_count(void);
+void rlx_add_launch_count(uint64_t n);        /* account for kernels replayed through a captured CUDA graph */
 /* Optional per-kernel-class device timing (CUDA events recorded around every launch on the launching stream).
  * rlx_timing_begin() enables it and clears the records; rlx_timing_end() synchronises the device, disables it and fills four
  * arrays of RLX_NKCLASS entries: summed duration (ms), launch count, summed ALGORITHMIC flops and bytes of each class. */

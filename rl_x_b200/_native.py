@@ -107,6 +107,7 @@ _SIGNATURES = {
     "rlx_last_error_string": (C.c_char_p, []),
     "rlx_launch_count": (C.c_uint64, []),
     "rlx_reset_launch_count": (None, []),
+    "rlx_add_launch_count": (None, [C.c_uint64]),
     "rlx_timing_begin": (C.c_int, []),
     "rlx_timing_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rlx_kernel_class_name": (C.c_char_p, [C.c_int]),

@@ -27,6 +27,7 @@ def get_config(algorithm_name):
     config.evaluation_frequency = -1
     config.evaluation_episodes = 10
 
+    config.use_cuda_graph = True   # replay the whole update (noise + ~58 kernels) as one CUDA graph
     config.gemm_engine = "auto"  # auto | simt (fp32 FFMA) | tcgen05 (3xTF32 tensor cores)
 
     return config

@@ -147,6 +147,9 @@ class SAC:
         self.ws = self.k.workspace(max(self.batch_size, self.nr_envs), self.device)
         self.eps = torch.zeros(2, self.batch_size, A, device=self.device)
         self.is_torch_data_interface = same_member(self.train_env.general_properties.data_interface_type, DataInterfaceType.TORCH)
+        self.use_cuda_graph = bool(a.get("use_cuda_graph", True))
+        self._graph = None
+        self.replay_buffer = None
         if self.save_model:
             os.makedirs(self.save_path)
             self.best_mean_return = -np.inf
@@ -190,8 +193,43 @@ class SAC:
         return a
 
     def update(self, batch):
-        """One optimisation step of the reference loop (sac.py:219-259) on a sampled batch."""
-        self.k.update(self._update_args(batch))
+        """One optimisation step of the reference loop (sac.py:219-259) on a sampled batch.
+
+        The ~58 kernels of an update (noise draws, fused update, metric accumulation) only touch static buffers, so they are
+        captured ONCE into a CUDA graph and replayed per step: the update is launch-latency-bound at batch 4096.
+        Eager launches are used when the noise hook is overridden (tests) or `use_cuda_graph` is off."""
+        eager = (not self.use_cuda_graph or getattr(self._draw_eps, "__func__", None) is not SAC._draw_eps or self.replay_buffer is None
+                 or self.replay_buffer._out is None or batch[0] is not self.replay_buffer._out[0])
+        if eager:
+            self.k.update(self._update_args(batch))
+            self.metric_sums += self.metrics
+            return
+        if self._graph is None:
+            # warm-up on a side stream (first-touch allocations, cudaFuncSetAttribute, TMA descriptor encoding), then capture
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._graph_update(batch)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            before = int(self.k.lib.rlx_launch_count())
+            with torch.cuda.graph(self._graph):
+                self._graph_update(batch)
+            self._graph_launches = int(self.k.lib.rlx_launch_count()) - before  # kernels of this library inside one replay
+            return  # the capture pass is not an update; the warm-up pass was
+        self._graph.replay()
+        self.k.lib.rlx_add_launch_count(self._graph_launches)
+
+    def _graph_update(self, batch):
+        self.eps.normal_()
+        self._static_eps = (self.eps[0], self.eps[1])
+        saved = self._draw_eps
+        it = iter(self._static_eps)
+        self._draw_eps = lambda n: next(it)
+        try:
+            self.k.update(self._update_args(batch))
+        finally:
+            self._draw_eps = saved
         self.metric_sums += self.metrics
 
     def _act(self, state, deterministic=False):

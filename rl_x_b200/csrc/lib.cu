@@ -54,6 +54,7 @@ extern "C" int rlx_version(void) { return 1; }
 extern "C" const char* rlx_last_error_string(void) { return rlx::g_err; }
 extern "C" uint64_t rlx_launch_count(void) { return rlx::g_launch_count.load(); }
 extern "C" void rlx_reset_launch_count(void) { rlx::g_launch_count.store(0); }
+extern "C" void rlx_add_launch_count(uint64_t n) { rlx::g_launch_count.fetch_add(n); }
 extern "C" int rlx_get_gemm_engine(void) { return rlx::g_gemm_engine; }
 
 extern "C" int64_t rlx_ppo_param_count(const rlx_ppo_dims* d) {
