@@ -42,6 +42,8 @@ struct TcParams {
   float* C;
   long long ldc, c_batch_off, c_split_off;
   int n_main;                // columns >= n_main are not stored to C; column == n_main goes to extra_col (bias-gradient trick)
+  int transpose_out;         // store C^T: element (m, n) at C[n * ldc + m]; rows >= m_main are not stored, row == m_main goes to extra_col[n]
+  int m_main;
   float* extra_col;          // [z][M] or null
   long long extra_batch_off, extra_split_off;
   const float* bias;         // TC_EPI_BIAS_TANH
@@ -354,6 +356,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         tmem_ld_32x32b_x32(taddr + BN, rc);
         tmem_ld_wait();
         const int nb = n0 + c * 32;
+        if (p.transpose_out) {
+          // transposed store: each lane owns one accumulator row m, so for a fixed column n the warp writes 32 consecutive
+          // floats of C^T (coalesced) straight from the TMEM registers - no shared-memory transpose needed
+          const int m = row0 + lane;
+          if (m < p.M) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              const float v = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+              if (n < p.N) {
+                if (m < p.m_main) cbase[(long long)n * p.ldc + m] = v;
+                else if (m == p.m_main && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + n] = v;
+              }
+            }
+          }
+          continue;
+        }
         if (rows_valid > 0 && nb < p.N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);  // main + correction (fp32 RN)
@@ -491,8 +510,16 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Generic front end over the SIMT engine's GemmP (same meaning of every field).  Supported: all strides multiples of 4 floats,
 // 16-byte aligned bases, batch strides that are pure row or column offsets of the operand tensors.
+int tc_gemm_t(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
+              float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream, int transpose_out, int m_main);
+
 int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
             float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream) {
+  return tc_gemm_t(g, a_kmaj, b_kmaj, epi, batch, kclass, a_rows, b_rows, n_main, extra_col, extra_batch_off, extra_split_off, stream, 0, 0);
+}
+
+int tc_gemm_t(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kclass, long long a_rows, long long b_rows, int n_main,
+              float* extra_col, long long extra_batch_off, long long extra_split_off, cudaStream_t stream, int transpose_out, int m_main) {
   if (g.M <= 0 || g.N <= 0) return RLX_OK;
   if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || g.lda % 4 || g.ldb % 4 || g.ldc % 4) return RLX_ERR_UNSUPPORTED;
   if (g.splits > 1 && g.kchunk % BK) return RLX_ERR_UNSUPPORTED;
@@ -509,7 +536,8 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
         if (g.aux) gb.aux = g.aux + b * g.sAux;
         gb.sA = gb.sB = gb.sC = gb.sBias = gb.sAux = 0;
         const long long ar = a_rows, br = b_kmaj ? (long long)g.N : (long long)g.K;
-        const int rc = tc_gemm(gb, a_kmaj, b_kmaj, epi, 1, kclass, ar, br, n_main, extra_col ? extra_col + b * extra_batch_off : nullptr, 0, extra_split_off, stream);
+        const int rc = tc_gemm_t(gb, a_kmaj, b_kmaj, epi, 1, kclass, ar, br, n_main, extra_col ? extra_col + b * extra_batch_off : nullptr, 0, extra_split_off, stream,
+                                 transpose_out, m_main);
         if (rc) return rc;
       }
       return RLX_OK;
@@ -528,6 +556,8 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   split_off(g.sB, g.ldb, b_kmaj, p.b_mn_off, p.b_k_off);
   p.C = g.C; p.ldc = g.ldc; p.c_batch_off = g.sC; p.c_split_off = g.sSplitC;
   p.n_main = n_main > 0 ? n_main : g.N;
+  p.transpose_out = transpose_out;
+  p.m_main = (transpose_out && m_main > 0) ? m_main : g.M;
   p.extra_col = extra_col; p.extra_batch_off = extra_batch_off; p.extra_split_off = extra_split_off;
   p.bias = g.bias; p.bias_batch_off = g.sBias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.aux_batch_off = g.sAux;
@@ -542,7 +572,7 @@ int tc_gemm(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int kc
   // BN = 128 configuration (measured: profiles/r01_tc_minibatch_ncu_details_v1.txt).
   const long long tiles256 = ceil_div(g.M, BM) * ceil_div(g.N, 256) * batch * g.splits;
   const int k_per_tile = (g.splits > 1) ? g.kchunk : g.K;
-  const bool use256 = (g.N % 256 == 0) && epi == TC_EPI_NONE && k_per_tile >= 512 && tiles256 >= sm_count() / 2;
+  const bool use256 = (g.N % 256 == 0) && epi == TC_EPI_NONE && k_per_tile >= 256 && tiles256 >= sm_count() / 2;
 #define RLX_TC_DISPATCH(BN_)                                                                                                   \
   do {                                                                                                                        \
     if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg<BN_, true, true, TC_EPI_BIAS_TANH>(A, B, p, kclass, stream); \

@@ -23,18 +23,30 @@ struct Splits {
 // choose a split-K factor for a [M' x N'] output reduced over `rows`: ~2 CTAs per SM for the SIMT engine, one persistent
 // CTA per SM for the tcgen05 engine (k-chunks are multiples of 32 there: one 128-byte swizzle row of fp32)
 static Splits choose_splits(long long rows, int out_m, int out_n, int batch, bool tc) {
+  if (tc) {
+    // persistent kernel, one CTA per SM: pick the split count whose tile total fills whole waves of SMs.  The tensor core accumulates
+    // with round-toward-zero, so each TMEM accumulation chain is also kept <= 1024 rows (128 MMAs); the long part of the
+    // reduction happens in the fp32 grad_reduce kernel (profiles/tc_accuracy_probe.py).
+    const int bn = (out_n % 256 == 0) ? 256 : 128;
+    const long long tiles = ceil_div(out_m, 128) * ceil_div(out_n, bn) * batch;
+    const long long smin = std::max<long long>(1, ceil_div(rows, 1024)), smax = std::max<long long>(smin, std::min<long long>(smin + 64, rows / 64));
+    const long long sms = sm_count();
+    long long best = smin;
+    double best_fill = -1.0;
+    for (long long s = smin; s <= smax; ++s) {
+      const long long t = tiles * s;
+      const double fill = (double)t / (double)(ceil_div(t, sms) * sms);
+      if (fill > best_fill + 0.02) { best_fill = fill; best = s; }
+    }
+    long long kchunk = std::max<long long>(32, ceil_div(ceil_div(rows, best), 32) * 32);
+    return Splits{(int)ceil_div(rows, kchunk), (int)kchunk};
+  }
   const long long tiles = ceil_div(out_m, GBM) * ceil_div(out_n, GBN) * batch;
-  const long long target = (long long)sm_count() * (tc ? 1 : 2);
-  const long long gran = tc ? 32 : 8;
+  const long long target = (long long)sm_count() * 2;
   long long s = std::max<long long>(1, target / std::max<long long>(tiles, 1));
   s = std::min<long long>(s, std::max<long long>(1, rows / 256));  // at least 256 rows per split
-  // the tensor core accumulates with round-toward-zero: keep each TMEM accumulation chain <= 1024 rows (128 MMAs) and do the
-  // long part of the reduction in the fp32 grad_reduce kernel (profiles/tc_accuracy_probe.py)
-  if (tc) s = std::max<long long>(s, ceil_div(rows, 1024));
-  long long kchunk = ceil_div(ceil_div(rows, s), gran) * gran;
-  kchunk = std::max<long long>(kchunk, gran);
-  s = ceil_div(rows, kchunk);
-  return Splits{(int)s, (int)kchunk};
+  long long kchunk = std::max<long long>(8, ceil_div(ceil_div(rows, s), 8) * 8);
+  return Splits{(int)ceil_div(rows, kchunk), (int)kchunk};
 }
 
 struct FwdPlan {
@@ -54,7 +66,7 @@ constexpr int kHeadWgradRows = 64;
 
 struct TrainPlan {
   size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, total;
-  int max_s1, max_s2;
+  int max_s1, max_s2, max_s3;
   int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
 static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 16), (long long)sm_count() * 2); }
@@ -62,7 +74,7 @@ static int head_grid(long long m) { return (int)std::min<long long>(ceil_div(m, 
 static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   TrainPlan P;
   const long long H = d.hidden, O = d.obs_dim, A = d.act_dim;
-  P.max_s1 = std::max(choose_splits(m, (int)(2 * H), (int)O, 1, false).splits, choose_splits(m, (int)(2 * H), (int)O + 1, 1, true).splits);
+  P.max_s1 = std::max(choose_splits(m, (int)(2 * H), (int)O, 1, false).splits, choose_splits(m, (int)O + 1, (int)(2 * H), 1, true).splits);
   P.max_s2 = std::max(choose_splits(m, (int)H, (int)H, 2, false).splits, choose_splits(m, (int)H, (int)H, 2, true).splits);
   P.head_blocks = head_grid(m);
   P.head_npart = (int)(2 * A + 5 + 2 * H);
@@ -82,7 +94,9 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   take(P.off_part1, (size_t)P.max_s1 * 2 * H * O);
   take(P.off_rs1, (size_t)P.max_s1 * 2 * H);
   take(P.off_part2, (size_t)P.max_s2 * 2 * H * H);
-  take(P.off_part3, (size_t)P.wgrad_chunks * (A + 1) * H);
+  const size_t dh_ld_plan = (size_t)(ceil_div(A + 1, 4) * 4);
+  P.max_s3 = choose_splits(m, (int)dh_ld_plan, (int)H, 2, true).splits;
+  take(P.off_part3, std::max<size_t>((size_t)P.wgrad_chunks * (A + 1) * H, (size_t)P.max_s3 * 2 * dh_ld_plan * H));
   take(P.off_norm, (size_t)P.norm_blocks * 2);
   P.total = o;
   return P;
@@ -240,7 +254,8 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   const float inv_mg = 1.f / (float)a->m_global;
   const int npart = P.head_npart;
 
-  int head_blocks = 0, wgrad_chunks = 0, s1 = 0, s2 = 0;
+  int head_blocks = 0, wgrad_chunks = 0, s1 = 0, s2 = 0, w3_nsplit = 0;
+  long long w3_stride = (long long)(A + 1) * H, w3c_off = (long long)A * H;
   if (m > 0) {
     // ---- forward hidden layers
     rc = mlp_hidden_forward(d, L, a->params, a->states, ldx, m, H1, H2, st);
@@ -299,19 +314,43 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
 #undef RLX_HEAD2_ACT
 #undef RLX_HEAD2
       }
-      // ---- dW3: one thread per (policy, critic) column pair, 64 rows per CTA
-      HeadWgrad2P w{(int)m, H, A, dh_ld, kHeadWgradRows, H2, dhead, part3};
-      wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
-      const unsigned wthreads = (unsigned)(ceil_div(H, 32) * 32);
-      const size_t wsmem = (size_t)kHeadWgradRows * dh_ld * sizeof(float);
-      const double wflops = 2.0 * m * H * (A + 1), wbytes = 4.0 * m * (2.0 * H + A + 1);
-      if (A + 1 <= 4) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<4>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 8) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<8>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 12) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<12>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 16) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<16>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 20) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<20>, wgrad_chunks, wthreads, wsmem, st, w);
-      else if (A + 1 <= 24) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<24>, wgrad_chunks, wthreads, wsmem, st, w);
-      else RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<32>, wgrad_chunks, wthreads, wsmem, st, w);
+      // ---- dW3 = dhead^T [act+1, m] . H2 [m, 2H]
+      bool w3_done = false;
+      if (tc) {
+        // tensor cores: one MN-major GEMM per net half (batch 2); the act+1 (padded to dh_ld) gradient columns are the M side
+        const Splits S3 = choose_splits(m, dh_ld, H, 2, true);
+        GemmP g3{};
+        g3.A = dhead; g3.B = H2; g3.C = part3;
+        g3.M = dh_ld; g3.N = H; g3.K = (int)m;
+        g3.lda = dh_ld; g3.ldb = 2 * H; g3.ldc = H;
+        g3.sA = 0; g3.sB = H; g3.sC = (long long)dh_ld * H;
+        g3.splits = S3.splits; g3.kchunk = S3.kchunk; g3.sSplitC = 2LL * dh_ld * H;
+        rc = tc_gemm(g3, false, false, TC_NONE, 2, KC_HEAD_WGRAD, m, m, 0, nullptr, 0, 0, st);
+        if (rc == RLX_OK) {
+          w3_done = true;
+          w3_nsplit = S3.splits;
+          w3_stride = 2LL * dh_ld * H;
+          w3c_off = (long long)dh_ld * H + (long long)A * H;  // net 1 (critic half of H2), row `act` of its [dh_ld, H] block
+        } else if (rc != RLX_ERR_UNSUPPORTED) {
+          return rc;
+        }
+      }
+      if (!w3_done) {
+        // SIMT: one thread per (policy, critic) column pair, 64 rows per CTA
+        HeadWgrad2P w{(int)m, H, A, dh_ld, kHeadWgradRows, H2, dhead, part3};
+        wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
+        const unsigned wthreads = (unsigned)(ceil_div(H, 32) * 32);
+        const size_t wsmem = (size_t)kHeadWgradRows * dh_ld * sizeof(float);
+        const double wflops = 2.0 * m * H * (A + 1), wbytes = 4.0 * m * (2.0 * H + A + 1);
+        if (A + 1 <= 4) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<4>, wgrad_chunks, wthreads, wsmem, st, w);
+        else if (A + 1 <= 8) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<8>, wgrad_chunks, wthreads, wsmem, st, w);
+        else if (A + 1 <= 12) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<12>, wgrad_chunks, wthreads, wsmem, st, w);
+        else if (A + 1 <= 16) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<16>, wgrad_chunks, wthreads, wsmem, st, w);
+        else if (A + 1 <= 20) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<20>, wgrad_chunks, wthreads, wsmem, st, w);
+        else if (A + 1 <= 24) RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<24>, wgrad_chunks, wthreads, wsmem, st, w);
+        else RLX_LAUNCH_C(KC_HEAD_WGRAD, wflops, wbytes, ppo_head_wgrad3_kernel<32>, wgrad_chunks, wthreads, wsmem, st, w);
+        w3_nsplit = wgrad_chunks;
+      }
     } else {
       RLX_DISPATCH_NCH(KC_HEAD_TRAIN, head_flops, head_bytes, H, ppo_head_train_kernel, head_blocks, 256, smem, st, h);
       // ---- dW3 (thread per column, chunked over rows)
@@ -327,6 +366,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
         RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_wgrad_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
         RLX_LAUNCH_C(KC_HEAD_WGRAD, 2.0 * m * H * (A + 1), 4.0 * m * (2.0 * H + A + 1), ppo_head_wgrad_kernel<64>, wg, 256, wsmem, st, w);
       }
+      w3_nsplit = wgrad_chunks;
     }
     // ---- dW2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]   (db2 comes from the head kernel)
     const Splits S2 = choose_splits(m, H, H, 2, tc);
@@ -355,18 +395,21 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     g1.lda = 2 * H; g1.ldb = (int)ldx; g1.ldc = O;
     bool done = false;
     if (tc && a->states_ones_col) {
-      // tensor-core path: the constant-one column of X makes db1 the (O+1)-th output column of the same GEMM
-      const Splits S1 = choose_splits(m, 2 * H, O + 1, 1, true);
-      g1.N = O + 1;
-      g1.splits = S1.splits; g1.kchunk = S1.kchunk; g1.sSplitC = 2LL * H * O;
-      rc = tc_gemm(g1, false, false, TC_NONE, 1, KC_GEMM_DW, m, m, O, rs1, 0, 2LL * H, st);
+      // tensor-core path, computed TRANSPOSED: C^T[i, o] = sum_r X_aug[r, i] dZ1[r, o] with M = O+1 (the constant-one column of X
+      // makes db1 the last output row) and N = 2H = full 256-wide tiles; the epilogue stores C^T transposed back into [o][i].
+      const Splits S1 = choose_splits(m, O + 1, 2 * H, 1, true);
+      GemmP gt{};
+      gt.A = a->states; gt.B = dZ1; gt.C = part1;
+      gt.M = O + 1; gt.N = 2 * H; gt.K = (int)m;
+      gt.lda = (int)ldx; gt.ldb = 2 * H; gt.ldc = O;
+      gt.splits = S1.splits; gt.kchunk = S1.kchunk; gt.sSplitC = 2LL * H * O;
+      rc = tc_gemm_t(gt, false, false, TC_NONE, 1, KC_GEMM_DW, m, m, 0, rs1, 0, 2LL * H, st, 1, O);
       if (rc == RLX_OK) {
         done = true;
         s1 = S1.splits;
       } else if (rc != RLX_ERR_UNSUPPORTED) {
         return rc;
       }
-      g1.N = O;
     }
     if (!done) {
       const Splits S1 = choose_splits(m, 2 * H, O, 1, false);
@@ -383,8 +426,9 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   r.g[1] = GradGroup{L.off[B1P], 2LL * H, rs1, s1, 2LL * H};
   r.g[2] = GradGroup{L.off[W2P], 2LL * H * H, part2, s2, 2LL * H * H};
   r.g[3] = GradGroup{L.off[B2P], 2LL * H, headpart + (2 * A + 5), head_blocks, (long long)npart};
-  r.g[4] = GradGroup{L.off[W3P], (long long)(A + 1) * H, part3, wgrad_chunks, (long long)(A + 1) * H};
+  r.g[4] = GradGroup{L.off[W3P], (long long)A * H, part3, w3_nsplit, w3_stride};
   r.g[5] = GradGroup{L.off[B3P], 2LL * A + 1, headpart, head_blocks, (long long)npart};
+  r.g[6] = GradGroup{L.off[W3C], (long long)H, part3 + w3c_off, w3_nsplit, w3_stride};
   r.total = L.total();
   r.logstd_off = L.off[LOGSTD];
   r.act = A;
@@ -398,7 +442,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   for (int gi = 0; gi < kNumGroups; ++gi)
     if (r.g[gi].nsplit > kTallSplit) tall += r.g[gi].len;
   const int tall_blocks = (int)ceil_div(tall, 8);  // 8 warps per CTA, one element per warp
-  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * H + (double)wgrad_chunks * (A + 1) * H + L.total()),
+  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * H + (double)w3_nsplit * (A + 1) * H + L.total()),
                ppo_grad_reduce_kernel, (unsigned)(flat_blocks + tall_blocks), 256, 0, st, r, flat_blocks);
   return RLX_OK;
 }

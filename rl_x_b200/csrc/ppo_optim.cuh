@@ -13,7 +13,7 @@ struct GradGroup {
   int nsplit;
   long long stride;
 };
-constexpr int kNumGroups = 6;
+constexpr int kNumGroups = 7;
 
 struct GradReduceP {
   GradGroup g[kNumGroups];
