@@ -86,6 +86,10 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
                "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// pull a box into L2 ahead of time (no shared memory, no barrier): hides DRAM latency that the 2-3 stage smem ring cannot
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -228,27 +232,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int zb, zs, m0, n0, kbeg, nkb;
         tile_coords(tile, zb, zs, m0, n0, kbeg, nkb);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* st = smem + s * C_::STAGE_BYTES;
-          uint8_t* sa = st;
-          uint8_t* sb = st + C_::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], C_::A_BYTES + C_::B_BYTES);
+        auto issue = [&](int kb, bool prefetch_only, uint8_t* sa, uint8_t* sb, uint64_t* bar) {
           const int k0 = kbeg + kb * BK;
           if (A_KMAJ) {
-            tma_load_2d(&tmap_a, &full_bar[s], sa, p.a_k_off * zb + k0, p.a_mn_off * zb + m0);
+            const int c0 = p.a_k_off * zb + k0, c1 = p.a_mn_off * zb + m0;
+            if (prefetch_only) tma_prefetch_2d(&tmap_a, c0, c1); else tma_load_2d(&tmap_a, bar, sa, c0, c1);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 32; ++j)
-              tma_load_2d(&tmap_a, &full_bar[s], sa + j * (BK * 128), p.a_mn_off * zb + m0 + 32 * j, p.a_k_off * zb + k0);
+            for (int j = 0; j < BM / 32; ++j) {
+              const int c0 = p.a_mn_off * zb + m0 + 32 * j, c1 = p.a_k_off * zb + k0;
+              if (prefetch_only) tma_prefetch_2d(&tmap_a, c0, c1); else tma_load_2d(&tmap_a, bar, sa + j * (BK * 128), c0, c1);
+            }
           }
           if (B_KMAJ) {
-            tma_load_2d(&tmap_b, &full_bar[s], sb, p.b_k_off * zb + k0, p.b_mn_off * zb + n0);
+            const int c0 = p.b_k_off * zb + k0, c1 = p.b_mn_off * zb + n0;
+            if (prefetch_only) tma_prefetch_2d(&tmap_b, c0, c1); else tma_load_2d(&tmap_b, bar, sb, c0, c1);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 32; ++j)
-              tma_load_2d(&tmap_b, &full_bar[s], sb + j * (BK * 128), p.b_mn_off * zb + n0 + 32 * j, p.b_k_off * zb + k0);
+            for (int j = 0; j < BN / 32; ++j) {
+              const int c0 = p.b_mn_off * zb + n0 + 32 * j, c1 = p.b_k_off * zb + k0;
+              if (prefetch_only) tma_prefetch_2d(&tmap_b, c0, c1); else tma_load_2d(&tmap_b, bar, sb + j * (BK * 128), c0, c1);
+            }
           }
+        };
+        constexpr int PF = STAGES + 3;  // L2 prefetch distance in k-blocks
+        for (int kb = 0; kb < min(PF, nkb); ++kb) issue(kb, true, nullptr, nullptr, nullptr);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (kb + PF < nkb) issue(kb + PF, true, nullptr, nullptr, nullptr);
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * C_::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], C_::A_BYTES + C_::B_BYTES);
+          issue(kb, false, st, st + C_::A_BYTES, &full_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }

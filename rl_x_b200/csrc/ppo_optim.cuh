@@ -53,7 +53,7 @@ __device__ __forceinline__ float grad_sum_warp(const float* __restrict__ q, int 
   for (int sp = lane; sp < nsplit; sp += 32) s += q[(long long)sp * stride];
   return warp_sum(s);
 }
-constexpr int kTallSplit = 48;  // groups with more partials than this use a warp per element
+constexpr int kTallSplit = 160;  // groups with more partials than this (per-CTA partials of the head kernel) use a warp per element
 
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP p, const int flat_blocks) {
   if ((int)blockIdx.x < flat_blocks) {
