@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
   constexpr int STAGES = C_::STAGES;
   constexpr int ACC_STAGES = C_::ACC_STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as an OFFSET on the __shared__ pointer: a round trip through uintptr_t makes the compiler lose the shared
+  // address space and emit generic LD/ST for every access below (seen in profiles/r01_tc_minibatch_ncu_v2: splitter stalled on LD.E.128)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + STAGES * C_::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);            // [STAGES]  TMA landed
   uint64_t* split_bar = full_bar + STAGES;                          // [STAGES]  lo tiles written
