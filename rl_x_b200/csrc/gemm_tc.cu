@@ -278,6 +278,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
       constexpr uint32_t A_SBO = A_KMAJ ? 1024u : 512u, B_SBO = B_KMAJ ? 1024u : 512u;
       constexpr uint32_t A_LT = A_KMAJ ? 2u : 1u, B_LT = B_KMAJ ? 2u : 1u;
       constexpr uint32_t A_KSTEP = A_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128), B_KSTEP = B_KMAJ ? (UMMA_K * 4) : (UMMA_K * 128);
+      // stage-0 descriptors of the raw A / B tiles; the lo tiles sit A_BYTES + B_BYTES further in the same stage
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t da0 = make_smem_desc(s0, A_LBO, A_SBO, A_LT);
+      const uint64_t db0 = make_smem_desc(s0 + C_::A_BYTES, B_LBO, B_SBO, B_LT);
+      constexpr uint64_t LO_OFF = (uint64_t)((C_::A_BYTES + C_::B_BYTES) >> 4);
       int s = 0, acc = 0;
       uint32_t ph = 0, acc_ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -288,19 +293,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN);
         const uint32_t d_corr = d_main + (uint32_t)BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          mbar_wait(&split_bar[s], ph);
+          mbar_wait(&split_bar[s], ph);  // the splitter passed full_bar[s] before arriving here: TMA data + lo tiles are both in place
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
-          const uint32_t sb = sa + C_::A_BYTES;
-          const uint32_t sa_lo = sb + C_::B_BYTES;
-          const uint32_t sb_lo = sa_lo + C_::A_BYTES;
+          // descriptors differ from the stage-0 / slice-0 ones only in the 14-bit start-address field (units of 16 bytes): one add each
+          const uint64_t soff = (uint64_t)((uint32_t)(s * C_::STAGE_BYTES) >> 4);
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-            const uint64_t db = make_smem_desc(sb + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
-            const uint64_t da_lo = make_smem_desc(sa_lo + kk * A_KSTEP, A_LBO, A_SBO, A_LT);
-            const uint64_t db_lo = make_smem_desc(sb_lo + kk * B_KSTEP, B_LBO, B_SBO, B_LT);
+            const uint64_t da = da0 + soff + (uint64_t)((kk * A_KSTEP) >> 4);
+            const uint64_t db = db0 + soff + (uint64_t)((kk * B_KSTEP) >> 4);
+            const uint64_t da_lo = da + LO_OFF;
+            const uint64_t db_lo = db + LO_OFF;
             const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
             umma_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
             umma_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
