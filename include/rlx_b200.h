@@ -43,7 +43,7 @@ void rlx_add_launch_count(uint64_t n);        /* account for kernels replayed th
 /* Optional per-kernel-class device timing (CUDA events recorded around every launch on the launching stream).
  * rlx_timing_begin() enables it and clears the records; rlx_timing_end() synchronises the device, disables it and fills four
  * arrays of RLX_NKCLASS entries: summed duration (ms), launch count, summed ALGORITHMIC flops and bytes of each class. */
-#define RLX_NKCLASS 13
+#define RLX_NKCLASS 14
 int rlx_timing_begin(void);
 int rlx_timing_end(double* ms, uint64_t* launches, double* flops, double* bytes);
 const char* rlx_kernel_class_name(int cls);
@@ -211,6 +211,39 @@ int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void* stream);
  * from C with no host round trip.  states etc. point at the first row; minibatch k covers rows [k*mb, min((k+1)*mb, count)).
  * adv_stats [num_mb,2]; metrics [num_mb, RLX_PPO_NMETRIC].  Single-GPU only (no collective between the two halves). */
 int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int64_t count, int64_t mb, void* stream);
+
+/* --------------------------------------------------------------- multi-GPU gradient exchange (SURVEY.md §8 e) -- */
+/* The reference is single-process (one optimiser.step per minibatch, ppo.py:146-148,162-164); data-parallel ranks have to
+ * agree on the minibatch gradient in between loss.backward() and clip_grad_norm_.  rlx_comm is that exchange, done by the
+ * library's own kernel over NVLink peer memory instead of a host-launched NCCL call: every rank writes its partial gradient
+ * into a send slot that lives in ITS memory, and one kernel per rank waits on peer flags and sums all ranks' slots, in rank
+ * order, straight from peer memory (one-shot all-reduce; the result is bit-identical on every rank).  The slots are double
+ * buffered so no second barrier is needed.  One process per GPU; handles travel through any host channel the caller owns
+ * (torch.distributed all_gather in the PPO class). */
+#define RLX_COMM_MAX_WORLD 16
+#define RLX_COMM_HANDLE_BYTES 64
+typedef struct rlx_comm rlx_comm;
+/* allocates this rank's flags + two send slots of `nfloats` floats on the current device */
+int rlx_comm_create(int rank, int world, int64_t nfloats, rlx_comm** out);
+/* writes the CUDA IPC handle of this rank's allocation (RLX_COMM_HANDLE_BYTES bytes) */
+int rlx_comm_export_handle(rlx_comm* c, uint8_t* handle);
+/* handles: [world, RLX_COMM_HANDLE_BYTES] in rank order (own entry ignored); maps every peer's allocation */
+int rlx_comm_connect(rlx_comm* c, const uint8_t* handles);
+/* device pointer of the slot the NEXT rlx_comm_allreduce_sum_f32 call reads (write the partial sums there) */
+float* rlx_comm_send_buffer(rlx_comm* c);
+/* convenience: device-to-device copy of src[0..n) into the send buffer (for callers whose producer cannot write there directly) */
+int rlx_comm_stage_f32(rlx_comm* c, const float* src, int64_t n, void* stream);
+/* out[i] = sum over ranks r = 0..world-1 (in that order) of rank r's send buffer [i], i < n <= nfloats.  Every rank must call
+ * it the same number of times; the kernel spins on peer flags (and traps after ~20 s if a peer never arrives). */
+int rlx_comm_allreduce_sum_f32(rlx_comm* c, float* out, int64_t n, void* stream);
+int rlx_comm_destroy(rlx_comm* c);
+
+/* Sharded form of rlx_ppo_update_epoch_f32: minibatch k covers this rank's counts[k] consecutive gathered rows and is divided by
+ * global_counts[k]; per minibatch: fwdbwd into the send slot, peer all-reduce (gradient + metric sums) into first->grads
+ * [P + RLX_PPO_NMETRIC], clip + Adam, metrics row k.  No host round trip and no NCCL call inside the epoch. */
+int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_t num_mb, const int64_t* counts,
+                                     const int64_t* global_counts, rlx_comm* comm, void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------- SAC path -- */
 /* ref: ReplayBuffer.sample gathers  (sac/pytorch/replay_buffer.py:32-40):  rows states[idx1, idx2] etc. from the device ring.

@@ -98,6 +98,8 @@ class SacUpdateArgs(C.Structure):
 
 
 RLX_SAC_NMETRIC = 12
+RLX_COMM_MAX_WORLD = 16
+RLX_COMM_HANDLE_BYTES = 64
 SAC_METRIC_NAMES = ("entropy/alpha", "entropy/entropy", "gradients/policy_grad_norm", "gradients/critic_grad_norm", "gradients/entropy_grad_norm",
                     "loss/q_loss", "loss/policy_loss", "loss/entropy_loss", "q_value/q_value")
 
@@ -133,6 +135,14 @@ _SIGNATURES = {
     "rlx_ppo_minibatch_fwdbwd_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_void_p]),
     "rlx_gradnorm_clip_adam_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_void_p]),
     "rlx_ppo_update_epoch_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_int64, C.c_int64, C.c_void_p]),
+    "rlx_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p)]),
+    "rlx_comm_export_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rlx_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rlx_comm_send_buffer": (C.c_void_p, [C.c_void_p]),
+    "rlx_comm_stage_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "rlx_comm_allreduce_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "rlx_comm_destroy": (C.c_int, [C.c_void_p]),
+    "rlx_ppo_update_epoch_sharded_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rlx_replay_sample_gather_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 10 + [C.c_void_p]),
     "rlx_polyak_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p]),
     "rlx_sac_policy_param_count": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
@@ -196,7 +206,7 @@ def check(rc, what=""):
         raise RuntimeError(f"rl_x_b200 native call failed ({what}, code {rc}): {last_error()}")
 
 
-RLX_NKCLASS = 13
+RLX_NKCLASS = 14
 
 
 def timing_begin():

@@ -2,6 +2,7 @@
 Every function here ends in exactly one native call; there is no alternative implementation behind it."""
 import ctypes as C
 
+import numpy as np
 import torch
 
 from rl_x_b200 import _native as nt
@@ -146,7 +147,63 @@ class PpoKernels:
     def update_epoch(self, first_args, count, mb):
         nt.check(self.lib.rlx_ppo_update_epoch_f32(C.byref(first_args), int(count), int(mb), _stream()), "rlx_ppo_update_epoch_f32")
 
+    def update_epoch_sharded(self, first_args, counts, global_counts, comm):
+        """counts / global_counts: contiguous int64 numpy arrays [num_mb]; comm: PeerComm."""
+        assert counts.dtype == np.int64 and global_counts.dtype == np.int64 and len(counts) == len(global_counts)
+        nt.check(self.lib.rlx_ppo_update_epoch_sharded_f32(C.byref(first_args), len(counts), counts.ctypes.data, global_counts.ctypes.data,
+                                                           comm.handle, _stream()), "rlx_ppo_update_epoch_sharded_f32")
+
 
 def make_hparams(clip_range, entropy_coef, critic_coef, max_grad_norm, beta1=0.9, beta2=0.999, eps=1e-8):
     return nt.PpoHparams(float(clip_range), float(entropy_coef), float(critic_coef), float(max_grad_norm), float(beta1), float(beta2),
                          float(eps), 0.0)
+
+
+class PeerComm:
+    """The library's NVLink peer-memory gradient exchange (rlx_comm_*, include/rlx_b200.h; SURVEY.md §8 e).
+
+    `dist` is an initialised torch.distributed module: it is used ONCE, to pass the 64-byte CUDA-IPC handles around and as the
+    setup barrier; the all-reduces themselves are the library's own kernel.  Raises RuntimeError when the GPUs cannot map each
+    other's memory (the caller may then fall back to NCCL)."""
+
+    def __init__(self, dist, nfloats, device):
+        self.lib = nt.load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        if self.world > nt.RLX_COMM_MAX_WORLD:
+            raise RuntimeError(f"PeerComm supports up to {nt.RLX_COMM_MAX_WORLD} ranks")
+        self.nfloats = int(nfloats)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(device):
+            nt.check(self.lib.rlx_comm_create(self.rank, self.world, self.nfloats, C.byref(self.handle)), "rlx_comm_create")
+            mine = np.zeros(nt.RLX_COMM_HANDLE_BYTES, dtype=np.uint8)
+            nt.check(self.lib.rlx_comm_export_handle(self.handle, mine.ctypes.data), "rlx_comm_export_handle")
+            gathered = [torch.zeros(nt.RLX_COMM_HANDLE_BYTES, dtype=torch.uint8, device=device) for _ in range(self.world)]
+            dist.all_gather(gathered, torch.from_numpy(mine).to(device))
+            handles = np.ascontiguousarray(torch.stack(gathered).cpu().numpy())
+            rc = self.lib.rlx_comm_connect(self.handle, handles.ctypes.data)
+            ok = torch.tensor([1 if rc == 0 else 0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank takes the same decision
+            if int(ok.item()) == 0:
+                err = self.lib.rlx_last_error_string().decode() if rc != 0 else "a peer rank could not map this rank's buffer"
+                self.close()
+                raise RuntimeError("PeerComm: " + err)
+
+    def stage(self, src, n=None):
+        """copies src into the slot the next all-reduce reads (the PPO epoch writes its gradient there directly instead)."""
+        n = src.numel() if n is None else int(n)
+        nt.check(self.lib.rlx_comm_stage_f32(self.handle, _f32(src, "src"), n, _stream()), "rlx_comm_stage_f32")
+
+    def allreduce_sum(self, out, n=None):
+        n = out.numel() if n is None else int(n)
+        nt.check(self.lib.rlx_comm_allreduce_sum_f32(self.handle, _f32(out, "out"), n, _stream()), "rlx_comm_allreduce_sum_f32")
+
+    def close(self):
+        if self.handle:
+            self.lib.rlx_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

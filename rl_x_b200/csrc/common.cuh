@@ -36,7 +36,7 @@ inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memo
 
 // Kernel classes for the optional event-timing facility (rlx_timing_begin / rlx_timing_end).
 enum KClass { KC_GEMM_FWD = 0, KC_GEMM_DX, KC_GEMM_DW, KC_HEAD_ROLLOUT, KC_HEAD_TRAIN, KC_HEAD_WGRAD, KC_GRAD_REDUCE, KC_CLIP_ADAM,
-              KC_GATHER, KC_ADV_STATS, KC_GAE, KC_STORE, KC_OTHER, KC_COUNT };
+              KC_GATHER, KC_ADV_STATS, KC_GAE, KC_STORE, KC_ALLREDUCE, KC_OTHER, KC_COUNT };
 static_assert(KC_COUNT == RLX_NKCLASS, "kernel class count out of sync with rlx_b200.h");
 extern bool g_timing;
 void timing_before(int cls, double flops, double bytes, cudaStream_t stream);

@@ -106,6 +106,6 @@ extern "C" int rlx_timing_end(double* ms, uint64_t* launches, double* flops, dou
 
 extern "C" const char* rlx_kernel_class_name(int cls) {
   static const char* names[RLX_NKCLASS] = {"gemm_fwd", "gemm_dx", "gemm_dw", "head_rollout", "head_train", "head_wgrad", "grad_reduce",
-                                           "clip_adam", "gather", "adv_stats", "gae", "rollout_store", "other"};
+                                           "clip_adam", "gather", "adv_stats", "gae", "rollout_store", "peer_allreduce", "other"};
   return (cls >= 0 && cls < RLX_NKCLASS) ? names[cls] : "?";
 }

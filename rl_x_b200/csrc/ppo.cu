@@ -496,6 +496,44 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
   return RLX_OK;
 }
 
+extern "C" int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_t num_mb, const int64_t* counts,
+                                                const int64_t* global_counts, rlx_comm* comm, void* stream) {
+  RLX_CHECK_ARG(first != nullptr && num_mb >= 0 && counts && global_counts && comm, "bad arguments");
+  RLX_CHECK_ARG(first->metrics != nullptr, "metrics rows are required");
+  const int A = first->dims.act_dim;
+  const int64_t O = first->states_ld > 0 ? first->states_ld : first->dims.obs_dim;
+  const int64_t P = make_layout(first->dims).total();
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t r0 = 0;
+  for (int64_t k = 0; k < num_mb; ++k) {
+    RLX_CHECK_ARG(counts[k] >= 0 && global_counts[k] >= 1, "bad minibatch sizes");
+    rlx_ppo_minibatch_args a = *first;
+    a.m = counts[k];
+    a.m_global = global_counts[k];
+    a.states = first->states + r0 * O;
+    a.actions = first->actions + r0 * A;
+    a.log_probs = first->log_probs + r0;
+    a.advantages = first->advantages + r0;
+    a.returns = first->returns + r0;
+    a.adv_stats = first->adv_stats + 2 * k;
+    float* send = rlx_comm_send_buffer(comm);  // partial gradient [P] followed by the partial metric sums
+    a.grads = send;
+    a.metrics = send + P;
+    int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
+    if (rc) return rc;
+    rc = rlx_comm_allreduce_sum_f32(comm, first->grads, P + RLX_PPO_NMETRIC, stream);
+    if (rc) return rc;
+    a.grads = first->grads;
+    a.metrics = first->grads + P;
+    rc = rlx_gradnorm_clip_adam_f32(&a, stream);  // writes the two pre-clip norms next to the summed metrics
+    if (rc) return rc;
+    RLX_CHECK_CUDA(cudaMemcpyAsync(first->metrics + RLX_PPO_NMETRIC * k, first->grads + P, RLX_PPO_NMETRIC * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+    r0 += counts[k];
+  }
+  return RLX_OK;
+}
+
 // Test hook: one plain GEMM through either engine (single batch, no split): layout 0 = A k-major, B k-major (C = A B^T);
 // 1 = A k-major, B n-major (C = A B); 2 = A m-major, B n-major (C = A^T B, A is [K, M]).  epilogue 0 none, 1 bias+tanh, 2 tanh'.
 extern "C" int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
