@@ -98,7 +98,8 @@ def build_model(args, rank, world, interface):
             f"--algorithm.nr_steps={C2['nr_steps']}", f"--algorithm.nr_epochs={args.epochs}",
             f"--algorithm.minibatch_size={args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
             f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15",
-            f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}"]
+            f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}",
+            f"--algorithm.gradient_exchange={args.exchange}"]
     r = Runner(argv=argv)
     train_env, eval_env = r._create_train_and_eval_env(r._config)
     r._config.environment.seed = 1  # identical policy init / permutation stream on every rank; env streams differ via the env seed above
@@ -303,7 +304,8 @@ def workload_config(args, world):
                         f"hidden={C2['hidden']}, nr_epochs={args.epochs}, minibatch={args.minibatch}/GPU (BASELINE.json configs[1])",
             "num_envs_global": args.envs * world, "minibatch_size_global": args.minibatch * world, "nr_epochs": args.epochs,
             "parallelism": (f"dp{world} (env-sharded, " + ("reference-exact global permutation" if args.exact_permutation else "rank-local PCG64 shuffles")
-                            + ", 1 NCCL all-reduce of the flat gradient per minibatch)") if world > 1 else "single GPU",
+                            + (", 1 peer-memory all-reduce kernel (rlx_comm, NVLink loads) of the flat gradient per minibatch)" if args.exchange == "peer"
+                               else ", 1 NCCL all-reduce of the flat gradient per minibatch)")) if world > 1 else "single GPU",
             "l2_policy": "per-step working set (rollout buffer 0.83 GB + gathered copy 0.83 GB + activations) exceeds the 126 MB L2"}
 
 
@@ -319,6 +321,7 @@ def main():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -378,8 +381,21 @@ def main():
                 "unit": "TFLOP/s", "frac": achieved_tf / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
                 "share_of_step": gms / total_ms if total_ms else None,
                 "note": "fp32-equivalent algorithmic FLOPs (2*M*N*K) of the exact-fp32 path against the dense bf16 tensor peak"}
+    # DRAM traffic per GEMM launch from the committed ncu --set full capture (profiles/roofline_traffic.json), next to the algorithmic bytes
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            tr = json.load(fh)
+        roofline["traffic"] = tr["gemm_dram_bytes_per_minibatch"] / tr["gemm_launches_per_minibatch"]
+        roofline["traffic_source"] = tr["note"]
+    except (OSError, KeyError, ValueError):
+        pass
+    glaunch = sum(v["launches"] for v in gemm.values())
+    roofline["algorithmic_bytes_per_launch"] = sum(v["bytes"] for v in gemm.values()) / glaunch if glaunch else None
+    # what the tensor pipe actually executes: 3 TF32 MMAs per fp32 product, against the tf32 dense rate (half the measured bf16 rate)
+    roofline["mma"] = {"achieved": 3 * achieved_tf, "peak": peaks["tflops"] / 2, "unit": "TFLOP/s tf32", "frac": 3 * achieved_tf / (peaks["tflops"] / 2),
+                       "note": "3xTF32 split (hi*hi + hi*lo + lo*hi); tf32 peak taken as half of the measured bf16 peak"}
     hbm = {}
-    for name in ("gather", "gae", "clip_adam", "head_train"):
+    for name in ("gather", "gae", "clip_adam", "head_train", "peer_allreduce"):
         c = classes[name]
         if c["launches"]:
             gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9
@@ -390,6 +406,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "roofline_hbm": hbm, "kernel_ms": kernel_ms, "gemm_engine": engine,
+            "gradient_exchange": (model.gradient_exchange if world > 1 else None),
             "train_tflops_per_step": FLOP_PER_SAMPLE_TRAIN * args.envs * C2["nr_steps"] * args.epochs / 1e12}
 
     # end-to-end through the host-buffer path (NUMPY-interface env: pinned host observations, H2D/D2H every step)

@@ -33,6 +33,7 @@ def get_config(algorithm_name):
     # B200-specific
     config.gemm_engine = "auto"          # auto | simt (fp32 FFMA) | tcgen05 (3xTF32 tensor cores)
     config.exact_global_permutation = True   # multi-GPU: reference-exact global shuffle (ppo.py:273-276) vs per-rank local shuffles
+    config.gradient_exchange = "peer"    # multi-GPU: peer (library all-reduce kernel over NVLink peer memory) | nccl (torch.distributed)
     config.rollout_noise = "philox"      # philox (in-kernel counter-based normals) | torch (torch.randn on device, injected)
 
     return config

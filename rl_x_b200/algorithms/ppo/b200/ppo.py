@@ -28,7 +28,7 @@ import torch.nn as nn
 from rl_x_b200 import _native as nt
 from rl_x_b200.algorithms.ppo.b200.batch import Batch
 from rl_x_b200.algorithms.ppo.b200.general_properties import GeneralProperties
-from rl_x_b200.algorithms.ppo.b200.kernels import PpoKernels, make_hparams
+from rl_x_b200.algorithms.ppo.b200.kernels import PeerComm, PpoKernels, make_hparams
 from rl_x_b200.algorithms.ppo.b200 import sharding
 from rl_x_b200.environments.types import DataInterfaceType, same_member
 
@@ -187,6 +187,11 @@ class PPO:
         self.local_batch_size = self.nr_envs * self.nr_steps
         self.nr_minibatches = self.batch_size // self.minibatch_size   # ppo.py:55
         self.exact_global_permutation = bool(config.algorithm.get("exact_global_permutation", True))
+        self.gradient_exchange = str(config.algorithm.get("gradient_exchange", "peer"))  # "peer": library kernel over NVLink; "nccl"
+        if self.gradient_exchange not in ("peer", "nccl"):
+            raise ValueError("gradient_exchange must be 'peer' or 'nccl'")
+        self.peer_comm = None
+        self._seg_cache = None
 
         if self.evaluation_frequency % (self.nr_steps * self.nr_envs) != 0 and self.evaluation_frequency != -1:
             raise ValueError("Evaluation frequency must be a multiple of the number of steps and environments.")
@@ -219,6 +224,12 @@ class PPO:
         self.exp_avg = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros(P + nt.RLX_PPO_NMETRIC, dtype=torch.float32, device=self.device)  # metrics ride in the tail (one all-reduce)
+        if self.world_size > 1 and self.gradient_exchange == "peer" and self.peer_comm is None:
+            try:
+                self.peer_comm = PeerComm(self.dist, P + nt.RLX_PPO_NMETRIC, self.device)
+            except RuntimeError as err:  # GPUs without peer access: NCCL carries the gradient instead (slower, same numbers up to sum order)
+                rlx_logger.warning(f"{err}; falling back to gradient_exchange='nccl'")
+                self.gradient_exchange = "nccl"
         self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_dev = torch.full((1,), float(self.learning_rate), dtype=torch.float32, device=self.device)
         self.lr_iteration = 0
@@ -439,8 +450,11 @@ class PPO:
         global_counts = sharding.global_minibatch_sizes(self.batch_size, mbs)
         assert len(global_counts) == len(counts)
         # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
-        seg = torch.from_numpy(np.repeat(np.arange(len(counts)), counts)).to(self.device)
-        gc = torch.from_numpy(global_counts.astype(np.float32)).to(self.device)
+        key = np.asarray(counts, dtype=np.int64).tobytes()
+        if self._seg_cache is None or self._seg_cache[0] != key:  # rank-local shuffles: the same split every epoch
+            self._seg_cache = (key, torch.from_numpy(np.repeat(np.arange(len(counts)), counts)).to(self.device),
+                               torch.from_numpy(global_counts.astype(np.float32)).to(self.device))
+        seg, gc = self._seg_cache[1], self._seg_cache[2]
         sums = torch.zeros(len(counts), dtype=torch.float32, device=self.device).index_add_(0, seg, self.g_advantages[:offsets[-1]])
         dist.all_reduce(sums)
         mean = sums / gc
@@ -450,6 +464,16 @@ class PPO:
         self.adv_stats[:, 0] = mean
         self.adv_stats[:, 1] = torch.sqrt(ssq / (gc - 1.0))
         P = k.param_count
+        if self.peer_comm is not None:
+            # the whole epoch is one native call: fwdbwd -> peer all-reduce -> clip+Adam per minibatch, no host in between
+            first = self.kernels.minibatch_args(
+                m=0, m_global=1, states=self.g_states, actions=self.g_actions, log_probs=self.g_log_probs, advantages=self.g_advantages,
+                returns=self.g_returns, adv_stats=self.adv_stats, params=self.params.flat, grads=self.grads, exp_avg=self.exp_avg,
+                exp_avg_sq=self.exp_avg_sq, lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=self.metrics_dev[row0],
+                workspace=self.train_ws, states_ld=self.ldx, states_ones_col=True)
+            k.update_epoch_sharded(first, np.ascontiguousarray(counts, dtype=np.int64), np.ascontiguousarray(global_counts, dtype=np.int64),
+                                   self.peer_comm)
+            return
         for i in range(len(counts)):
             a = self.kernels.minibatch_args(
                 m=int(counts[i]), m_global=int(global_counts[i]), states=self.g_states[offsets[i]:], actions=self.g_actions[offsets[i]:],
@@ -458,7 +482,7 @@ class PPO:
                 lr=self.lr_dev, step_count=self.adam_step, hp=self.hp, metrics=self.grads[P:], workspace=self.train_ws,
                 states_ld=self.ldx, states_ones_col=True)
             k.fwdbwd(a)
-            dist.all_reduce(self.grads)          # gradient + metric sums, 1.32 MB over NVLink
+            dist.all_reduce(self.grads)          # gradient + metric sums, 1.32 MB (host-launched NCCL: the baseline exchange)
             k.clip_adam(a)                       # writes the two grad norms into grads[P+5..P+6]
             self.metrics_dev[row0 + i].copy_(self.grads[P:])
 

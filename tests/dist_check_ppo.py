@@ -61,7 +61,7 @@ class TableEnv:
         pass
 
 
-def run(out, engine):
+def run(out, engine, exchange="peer"):
     from rl_x_b200.config_dict import ConfigDict
     from rl_x_b200.algorithms.ppo.b200.default_config import get_config
     from rl_x_b200.algorithms.ppo.b200.ppo import PPO
@@ -76,7 +76,7 @@ def run(out, engine):
     dev = torch.device("cuda", local)
     a = get_config("ppo.b200")
     a.nr_steps, a.minibatch_size, a.nr_epochs, a.nr_hidden_units, a.total_timesteps = T, MB, EPOCHS, HID, NG * T * ITERS
-    a.entropy_coef, a.gemm_engine = 0.01, engine
+    a.entropy_coef, a.gemm_engine, a.gradient_exchange = 0.01, engine, exchange
     cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=5, nr_envs=nl),
                      runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
     env = TableEnv(lo, hi, dev)
@@ -93,6 +93,9 @@ def run(out, engine):
     logged = []
     model.log = lambda name, value, step: logged.append((name, float(value)))
     model.train()
+    if world > 1:
+        assert model.gradient_exchange == exchange, f"asked for the {exchange} exchange, ran {model.gradient_exchange}"
+        assert (model.peer_comm is not None) == (exchange == "peer")
     if rank == 0:
         pol, cri = model.params.state_dicts()
         metrics = {n: [v for m, v in logged if m == n] for n in ["loss/policy_gradient_loss", "loss/critic_loss", "gradients/policy_grad_norm",
@@ -124,9 +127,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--out")
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--compare", nargs=2)
     args = ap.parse_args()
     if args.compare:
         compare(*args.compare)
     else:
-        run(args.out, args.engine)
+        run(args.out, args.engine, args.exchange)

@@ -208,8 +208,10 @@ def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch, g
     m2.test(1)
 
 
-def test_two_gpu_sharded_run_equals_single_gpu_run(tmp_path, gemm_engine):
-    """Env-sharded data parallelism over 2 GPUs (NCCL) reproduces the 1-GPU run on the same global batch."""
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_two_gpu_sharded_run_equals_single_gpu_run(tmp_path, gemm_engine, exchange):
+    """Env-sharded data parallelism over 2 GPUs reproduces the 1-GPU run on the same global batch, with the gradient carried by
+    the library's peer-memory all-reduce kernel ("peer") or by NCCL ("nccl")."""
     import os
     import subprocess
     import sys
@@ -220,5 +222,20 @@ def test_two_gpu_sharded_run_equals_single_gpu_run(tmp_path, gemm_engine):
     w1, w2 = str(tmp_path / "w1.pt"), str(tmp_path / "w2.pt")
     subprocess.run([sys.executable, script, "--out", w1, "--engine", gemm_engine], check=True, timeout=600)
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                    "--master-port", "29631", script, "--out", w2, "--engine", gemm_engine], check=True, timeout=600)
+                    "--master-port", "29631", script, "--out", w2, "--engine", gemm_engine, "--exchange", exchange], check=True, timeout=600)
     subprocess.run([sys.executable, script, "--compare", w1, w2], check=True, timeout=120)
+
+
+def test_peer_allreduce_kernel_all_ranks_bit_identical(tmp_path):
+    """rlx_comm_allreduce_sum_f32 over every visible GPU: exact integer-valued sums, identical bits on every rank, 2000 back-to-back
+    calls (exercises the double-buffered slots and the flag protocol)."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "dist_check_comm.py")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 8)), "--master-addr", "127.0.0.1",
+                    "--master-port", "29633", script], check=True, timeout=600)
