@@ -153,6 +153,11 @@ int rlx_gather_minibatch_f32(const int64_t* idx, int64_t count, int64_t obs_dim,
 /* ref: minibatch_advantages.mean(), .std() (unbiased)  (ppo.py:133-134), for `num_mb` consecutive minibatches of size mb
  * (last one may be short) over gathered advantages adv [count].  stats [num_mb, 2] = (mean, unbiased std). */
 int rlx_advantage_stats_f32(const float* adv, int64_t count, int64_t mb, float* stats, void* stream);
+/* sharded form (SURVEY.md §8 e): segment k = rows [offsets[k], offsets[k+1]) of x (offsets: [nseg+1] int64 ON THE DEVICE).
+ * gsum == NULL: out[k] = sum of the segment.  Otherwise out[k] = sum (x - gsum[k]/gcount[k])^2.  The caller all-reduces `out` across
+ * ranks between the two calls; mean = gsum/gcount, std = sqrt(q/(gcount-1)) reproduce ppo.py:133-134 on the global minibatch. */
+int rlx_segment_moments_f32(const float* x, const int64_t* offsets, int64_t nseg, const float* gsum, const float* gcount, float* out,
+                            void* stream);
 
 /* ------------------------------------------------------------------------------- PPO minibatch update step -- */
 /* Device-resident optimiser state: one struct per (policy, critic) pair.  ref: optim.Adam(lr, betas=(0.9,0.999), eps=1e-8)

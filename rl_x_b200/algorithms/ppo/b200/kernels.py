@@ -110,6 +110,13 @@ class PpoKernels:
         nt.check(self.lib.rlx_advantage_stats_f32(_f32(adv, "adv"), int(count), int(mb), _f32(stats, "stats"), _stream()),
                  "rlx_advantage_stats_f32")
 
+    def segment_moments(self, x, offsets, gsum, gcount, out):
+        """offsets: int64 CUDA tensor [nseg+1]; gsum/gcount None -> segment sums, else centred sums of squares."""
+        if not (offsets.is_cuda and offsets.dtype == torch.int64 and offsets.is_contiguous()):
+            raise TypeError("offsets: expected a contiguous int64 CUDA tensor")
+        nt.check(self.lib.rlx_segment_moments_f32(_f32(x, "x"), offsets.data_ptr(), offsets.numel() - 1, _f32(gsum, "gsum"), _f32(gcount, "gcount"),
+                                                  _f32(out, "out"), _stream()), "rlx_segment_moments_f32")
+
     # ------------------------------------------------------------------------------------------------- update
     def minibatch_args(self, *, m, m_global, states, actions, log_probs, advantages, returns, adv_stats, params, grads, exp_avg,
                        exp_avg_sq, lr, step_count, hp, metrics, workspace, states_ld=0, states_ones_col=False):

@@ -277,6 +277,7 @@ class PPO:
         self._perm_slots_in_flight = []
         self.nmb_epoch = -(-self.batch_size // self.minibatch_size)  # ceil: a short last minibatch is processed (ppo.py:277-279)
         self.adv_stats = z(self.nmb_epoch, 2)
+        self.seg_tmp = z(2, self.nmb_epoch)
         self.metrics_dev = z(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC)
         self.metrics_host = torch.zeros(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC).pin_memory()
         self.ev_dev = z(4)
@@ -452,16 +453,15 @@ class PPO:
         # global per-minibatch advantage mean / unbiased std: two small all-reduces per epoch (advantages are frozen during the update)
         key = np.asarray(counts, dtype=np.int64).tobytes()
         if self._seg_cache is None or self._seg_cache[0] != key:  # rank-local shuffles: the same split every epoch
-            self._seg_cache = (key, torch.from_numpy(np.repeat(np.arange(len(counts)), counts)).to(self.device),
+            self._seg_cache = (key, torch.from_numpy(offsets.astype(np.int64)).to(self.device),
                                torch.from_numpy(global_counts.astype(np.float32)).to(self.device))
-        seg, gc = self._seg_cache[1], self._seg_cache[2]
-        sums = torch.zeros(len(counts), dtype=torch.float32, device=self.device).index_add_(0, seg, self.g_advantages[:offsets[-1]])
-        dist.all_reduce(sums)
-        mean = sums / gc
-        dev2 = (self.g_advantages[:offsets[-1]] - mean[seg]) ** 2
-        ssq = torch.zeros(len(counts), dtype=torch.float32, device=self.device).index_add_(0, seg, dev2)
-        dist.all_reduce(ssq)
-        self.adv_stats[:, 0] = mean
+        seg_offsets, gc = self._seg_cache[1], self._seg_cache[2]
+        sums, ssq = self.seg_tmp[0, :len(counts)], self.seg_tmp[1, :len(counts)]
+        k.segment_moments(self.g_advantages, seg_offsets, None, None, sums)
+        self._allreduce_small(sums)
+        k.segment_moments(self.g_advantages, seg_offsets, sums, gc, ssq)
+        self._allreduce_small(ssq)
+        self.adv_stats[:, 0] = sums / gc
         self.adv_stats[:, 1] = torch.sqrt(ssq / (gc - 1.0))
         P = k.param_count
         if self.peer_comm is not None:
@@ -485,6 +485,14 @@ class PPO:
             dist.all_reduce(self.grads)          # gradient + metric sums, 1.32 MB (host-launched NCCL: the baseline exchange)
             k.clip_adam(a)                       # writes the two grad norms into grads[P+5..P+6]
             self.metrics_dev[row0 + i].copy_(self.grads[P:])
+
+    def _allreduce_small(self, t):
+        """in-place sum over ranks of a small contiguous float32 tensor, through whichever exchange carries the gradient."""
+        if self.peer_comm is not None:
+            self.peer_comm.stage(t)
+            self.peer_comm.allreduce_sum(t)
+        else:
+            self.dist.all_reduce(t)
 
     def _explained_variance(self):
         """ref: ppo.py:298-300, computed on the device instead of on the host."""

@@ -118,6 +118,28 @@ __global__ void __launch_bounds__(512) advantage_stats_kernel(const float* __res
   }
 }
 
+// Sharded form of the statistics above: a rank holds only its rows of every minibatch, so the mean / centred sum of squares are
+// built from per-rank partial sums with an all-reduce in between.  One CTA per segment (minibatch); centre == nullptr: plain sums.
+__global__ void __launch_bounds__(512) segment_moments_kernel(const float* __restrict__ x, const long long* __restrict__ offsets,
+                                                              const float* __restrict__ gsum, const float* __restrict__ gcount,
+                                                              float* __restrict__ out) {
+  __shared__ float sh[34];
+  const long long b0 = offsets[blockIdx.x], n = offsets[blockIdx.x + 1] - b0;
+  const float* __restrict__ a = x + b0;
+  const float centre = gsum ? gsum[blockIdx.x] / gcount[blockIdx.x] : 0.f;
+  float s = 0.f;
+  if (gsum) {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float d = a[i] - centre;
+      s = fmaf(d, d, s);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += a[i];
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
 // ----------------------------------------------------------------------------------------- SAC replay gather
 struct ReplayGatherP {
   const long long *idx_t, *idx_e;
@@ -202,6 +224,16 @@ extern "C" int rlx_advantage_stats_f32(const float* adv, int64_t count, int64_t 
   RLX_CHECK_ARG(adv && stats, "null pointer");
   const unsigned grid = (unsigned)ceil_div(count, mb);
   RLX_LAUNCH_C(KC_ADV_STATS, 0, 4.0 * count, advantage_stats_kernel, grid, 512, 0, stream, adv, (long long)count, (long long)mb, stats);
+  return RLX_OK;
+}
+
+extern "C" int rlx_segment_moments_f32(const float* x, const int64_t* offsets, int64_t nseg, const float* gsum, const float* gcount,
+                                       float* out, void* stream) {
+  RLX_CHECK_ARG(nseg >= 0, "negative segment count");
+  if (nseg == 0) return RLX_OK;
+  RLX_CHECK_ARG(x && offsets && out, "null pointer");
+  RLX_CHECK_ARG((gsum == nullptr) == (gcount == nullptr), "gsum and gcount go together");
+  RLX_LAUNCH_C(KC_ADV_STATS, 0, 0, segment_moments_kernel, (unsigned)nseg, 512, 0, stream, x, (const long long*)offsets, gsum, gcount, out);
   return RLX_OK;
 }
 
