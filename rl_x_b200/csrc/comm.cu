@@ -41,8 +41,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // One launch per rank.  Block 0 publishes "my slot for `seq` is complete" (stream order put the gradient kernels before this
 // one) into every rank's flag array; every block then waits until all ranks have published, and sums the slots in rank order.
 // Peer data is read with ld.cv: peer lines must not be served from this SM's L1.
-__global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, int rank, int world, unsigned long long seq,
+// WORLD > 0: compile-time rank count, so that the peer loads of one element are all in flight before the first add (one NVLink round
+// trip per element instead of one per rank); WORLD == 0: any rank count.
+template <int WORLD>
+__global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, int rank, int world_rt, unsigned long long seq,
                                                                    float* __restrict__ out, long long n) {
+  const int world = WORLD > 0 ? WORLD : world_rt;
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
     st_release_sys(v.flags[threadIdx.x] + rank, seq);
@@ -61,12 +65,22 @@ __global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, in
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 acc = __ldcv(reinterpret_cast<const float4*>(v.slot[0]) + i);
-    for (int r = 1; r < world; ++r) {
-      const float4 x = __ldcv(reinterpret_cast<const float4*>(v.slot[r]) + i);
-      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    if (WORLD > 0) {
+      float4 x[WORLD > 0 ? WORLD : 1];
+#pragma unroll
+      for (int r = 0; r < WORLD; ++r) x[r] = __ldcv(reinterpret_cast<const float4*>(v.slot[r]) + i);
+      float4 acc = x[0];
+#pragma unroll
+      for (int r = 1; r < WORLD; ++r) { acc.x += x[r].x; acc.y += x[r].y; acc.z += x[r].z; acc.w += x[r].w; }  // rank order, as below
+      reinterpret_cast<float4*>(out)[i] = acc;
+    } else {
+      float4 acc = __ldcv(reinterpret_cast<const float4*>(v.slot[0]) + i);
+      for (int r = 1; r < world; ++r) {
+        const float4 x = __ldcv(reinterpret_cast<const float4*>(v.slot[r]) + i);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+      reinterpret_cast<float4*>(out)[i] = acc;
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
   }
   if (blockIdx.x == 0) {
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
@@ -156,8 +170,16 @@ extern "C" int rlx_comm_allreduce_sum_f32(rlx_comm* c, float* out, int64_t n, vo
   const int64_t n4 = std::max<int64_t>(n >> 2, 1);
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n4, kThreads), sm_count());
   // algorithmic bytes: every rank's slot read once + the result written once
-  RLX_LAUNCH_C(KC_ALLREDUCE, 0, 4.0 * n * (c->world + 1), comm_allreduce_kernel, grid, kThreads, 0, stream, v, c->rank, c->world,
-               (unsigned long long)c->seq, out, (long long)n);
+#define RLX_COMM_LAUNCH(W)                                                                                                     \
+  RLX_LAUNCH_C(KC_ALLREDUCE, 0, 4.0 * n * (c->world + 1), comm_allreduce_kernel<W>, grid, kThreads, 0, stream, v, c->rank, c->world, \
+               (unsigned long long)c->seq, out, (long long)n)
+  switch (c->world) {
+    case 2: RLX_COMM_LAUNCH(2); break;
+    case 4: RLX_COMM_LAUNCH(4); break;
+    case 8: RLX_COMM_LAUNCH(8); break;
+    default: RLX_COMM_LAUNCH(0); break;
+  }
+#undef RLX_COMM_LAUNCH
   return RLX_OK;
 }
 
