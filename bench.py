@@ -402,6 +402,26 @@ def main():
             hbm[name] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                          "bytes_per_launch": c["bytes"] / c["launches"], "us_per_launch": c["ms"] * 1e3 / c["launches"]}
 
+    # the GAE kernel at config 2 is one 10 MB wave (latency-bound); the same kernel on a rollout that fills the machine shows its HBM rate
+    if rank == 0:
+        Tg, Ng = C2["nr_steps"], 65536
+        gr, gt, gv = (torch.randn(Tg, Ng, device="cuda"), (torch.rand(Tg, Ng, device="cuda") < 0.02).float(), torch.randn(Tg, Ng, device="cuda"))
+        ga, gret, glv = torch.empty_like(gr), torch.empty_like(gr), torch.randn(Ng, device="cuda")
+        for _ in range(3):
+            model.kernels.gae(gr, gt, gv, model.gamma, model.gae_lambda, ga, gret, last_value=glv)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            model.kernels.gae(gr, gt, gv, model.gamma, model.gae_lambda, ga, gret, last_value=glv)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 10
+        gbs = 20.0 * Tg * Ng / (us * 1e-6) / 1e9
+        hbm["gae_65536_envs"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                 "bytes_per_launch": 20.0 * Tg * Ng, "us_per_launch": us,
+                                 "note": "same kernel, T=128 x 65 536 envs (168 MB working set > L2), 20 B per (t, env)"}
+        del gr, gt, gv, ga, gret, glv
+
     line = {"metric": "env-steps/sec (PPO update incl.)", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": seconds / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args, world), "gpu_launches": launches, "clocks": clocks,

@@ -56,19 +56,38 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeP p) {
       if (has_nv) s_x[tt][lane] = valid ? p.nv[g] : 0.f;
     }
     __syncthreads();
-    // phase 2: sequential recurrence, one warp, lane = env
-    if (wrp == 0) {
-#pragma unroll 4
-      for (int tt = nt - 1; tt >= 0; --tt) {
+    // phase 2a, all warps: everything that does not depend on the running lastgaelam.  s_r <- delta, s_t <- gamma*lambda*(1-term).
+    // (same fp32 operations, in the same order, as the reference's expression: only their scheduling changes)
+    {
+      const float v_after_tile = vnext;  // shortcut mode: value of the state after the tile's last step
+      for (int tt = wrp; tt < nt; tt += nw) {
         const float r = s_r[tt][lane], tm = s_t[tt][lane], v = s_v[tt][lane];
-        const float nv = has_nv ? s_x[tt][lane] : vnext;
+        const float nv = has_nv ? s_x[tt][lane] : (tt + 1 < nt ? s_v[tt + 1][lane] : v_after_tile);
         const float nonterm = __fsub_rn(1.f, tm);
         // delta = rewards + gamma * next_values * (1 - terminations) - values
         const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma_f, nv), nonterm)), v);
-        // lastgaelam = delta + gamma * gae_lambda * (1 - terminations) * lastgaelam
-        last = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gl_f, nonterm), last));
+        s_r[tt][lane] = delta;
+        s_t[tt][lane] = __fmul_rn(p.gl_f, nonterm);
+      }
+      vnext = s_v[0][lane];  // the tile below (earlier steps) continues from this tile's first value
+    }
+    __syncthreads();
+    // phase 2b: the sequential recurrence, one warp, lane = env: lastgaelam = delta + (gamma*lambda*(1-term)) * lastgaelam
+    if (wrp == 0) {
+      int tt = nt - 1;
+      for (; tt >= 7; tt -= 8) {
+        float d[8], k[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { d[j] = s_r[tt - j][lane]; k[j] = s_t[tt - j][lane]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          last = __fadd_rn(d[j], __fmul_rn(k[j], last));
+          s_x[tt - j][lane] = last;
+        }
+      }
+      for (; tt >= 0; --tt) {
+        last = __fadd_rn(s_r[tt][lane], __fmul_rn(s_t[tt][lane], last));
         s_x[tt][lane] = last;
-        vnext = v;
       }
     }
     __syncthreads();
