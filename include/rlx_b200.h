@@ -69,6 +69,9 @@ uint32_t rlx_pcg64_next32(rlx_pcg64* st);
 int rlx_pcg64_shuffle_i64(rlx_pcg64* st, int64_t* a, int64_t n);
 /* ref: self.rng.integers(high, size=n)  (sac/pytorch/replay_buffer.py:33-34) — int64 output, low = 0. HOST memory. */
 int rlx_pcg64_integers_i64(rlx_pcg64* st, int64_t high, int64_t* out, int64_t n);
+/* ref: self.rng.choice(self.batch_size, size=self.minibatch_size, replace=False)  (espo/pytorch/espo.py:256): bit-exact with
+ * numpy.random.Generator.choice for an integer population, replace=False, shuffle=True, p=None.  Host function. */
+int rlx_pcg64_choice_i64(rlx_pcg64* st, int64_t pop_size, int64_t size, int64_t* out);
 
 /* ------------------------------------------------------------------------------------- PPO network layout -- */
 /* Policy: obs -> hidden -> hidden -> act (tanh, tanh, linear) + logstd(act)   ref: policy.py:34-52
@@ -168,12 +171,13 @@ typedef struct rlx_ppo_hparams {
   float critic_coef;     /* ppo.py:48 */
   float max_grad_norm;   /* ppo.py:49 */
   float adam_beta1, adam_beta2, adam_eps;
-  float reserved;
+  float ratio_delta_metric; /* 0: metrics[4] = clip fraction (ppo.py:131).  != 0 (ESPO): metrics[4] = mean |ratio - 1| (espo.py:133, operator
+                               "mean"); ESPO's unclipped surrogate (espo.py:138) is clip_range = +inf */
 } rlx_ppo_hparams;
 
 /* Per-minibatch metric record written by the update (ref: ppo.py:285-294 .item() calls, kept on device instead). */
 #define RLX_PPO_NMETRIC 8
-/* 0 pg_loss 1 critic_loss 2 entropy_loss 3 approx_kl 4 clip_fraction 5 policy_grad_norm 6 critic_grad_norm 7 count */
+/* 0 pg_loss 1 critic_loss 2 entropy_loss 3 approx_kl 4 clip_fraction (or ratio_delta) 5 policy_grad_norm 6 critic_grad_norm 7 count */
 
 typedef struct rlx_ppo_minibatch_args {
   rlx_ppo_dims dims;

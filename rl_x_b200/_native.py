@@ -53,7 +53,7 @@ class PpoHparams(C.Structure):
         ("adam_beta1", C.c_float),
         ("adam_beta2", C.c_float),
         ("adam_eps", C.c_float),
-        ("reserved", C.c_float),
+        ("ratio_delta_metric", C.c_float),
     ]
 
 
@@ -120,6 +120,7 @@ _SIGNATURES = {
     "rlx_pcg64_next32": (C.c_uint32, [C.POINTER(Pcg64)]),
     "rlx_pcg64_shuffle_i64": (C.c_int, [C.POINTER(Pcg64), C.c_void_p, C.c_int64]),
     "rlx_pcg64_integers_i64": (C.c_int, [C.POINTER(Pcg64), C.c_int64, C.c_void_p, C.c_int64]),
+    "rlx_pcg64_choice_i64": (C.c_int, [C.POINTER(Pcg64), C.c_int64, C.c_int64, C.c_void_p]),
     "rlx_ppo_param_count": (C.c_int64, [C.POINTER(PpoDims)]),
     "rlx_ppo_param_layout": (C.c_int, [C.POINTER(PpoDims), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "rlx_ppo_forward_workspace_bytes": (C.c_size_t, [C.POINTER(PpoDims), C.c_int64]),
@@ -243,7 +244,7 @@ def stream_ptr(device=None):
 # ------------------------------------------------------------------------------------------------ host RNG (numpy-compatible)
 class Pcg64Generator:
     """Restatement-free binding of the library's PCG64 stream; mirrors the subset of numpy.random.Generator the reference uses
-    (`shuffle` ppo.py:276, `integers` sac/pytorch/replay_buffer.py:33-34)."""
+    (`shuffle` ppo.py:276, `integers` sac/pytorch/replay_buffer.py:33-34, `choice` espo.py:256)."""
 
     def __init__(self, seed):
         self._lib = load()
@@ -258,6 +259,14 @@ class Pcg64Generator:
     def integers(self, high, size):
         out = np.empty(int(size), dtype=np.int64)
         check(self._lib.rlx_pcg64_integers_i64(C.byref(self.state), int(high), out.ctypes.data, out.shape[0]), "pcg64_integers")
+        return out
+
+    def choice(self, a, size, replace=False):
+        """Generator.choice(int population, size, replace=False) (espo.py:256)."""
+        if replace or not isinstance(a, (int, np.integer)):
+            raise NotImplementedError("only choice(int, size, replace=False) is mirrored")
+        out = np.empty(int(size), dtype=np.int64)
+        check(self._lib.rlx_pcg64_choice_i64(C.byref(self.state), int(a), out.shape[0], out.ctypes.data), "pcg64_choice")
         return out
 
     def next_uint64(self):

@@ -161,9 +161,9 @@ class PpoKernels:
                                                            comm.handle, _stream()), "rlx_ppo_update_epoch_sharded_f32")
 
 
-def make_hparams(clip_range, entropy_coef, critic_coef, max_grad_norm, beta1=0.9, beta2=0.999, eps=1e-8):
+def make_hparams(clip_range, entropy_coef, critic_coef, max_grad_norm, beta1=0.9, beta2=0.999, eps=1e-8, ratio_delta_metric=False):
     return nt.PpoHparams(float(clip_range), float(entropy_coef), float(critic_coef), float(max_grad_norm), float(beta1), float(beta2),
-                         float(eps), 0.0)
+                         float(eps), 1.0 if ratio_delta_metric else 0.0)
 
 
 class PeerComm:

@@ -265,6 +265,7 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     fill_head_common(h, L, a->params, H2, m);
     h.actions = a->actions; h.logp_old = a->log_probs; h.adv = a->advantages; h.ret = a->returns; h.adv_stats = a->adv_stats;
     h.inv_mg = inv_mg; h.clip_range = a->hp.clip_range; h.critic_coef = a->hp.critic_coef;
+    h.ratio_delta_metric = a->hp.ratio_delta_metric != 0.f ? 1 : 0;
     h.dZ2 = dZ2; h.dhead = dhead; h.block_partials = headpart;
     head_blocks = P.head_blocks;
     const size_t smem = head_smem_bytes(d, true);

@@ -63,6 +63,7 @@ struct HeadP {
   const float* adv_stats;  // [2]
   float inv_mg;            // 1 / m_global
   float clip_range, critic_coef;
+  int ratio_delta_metric;  // != 0: the clip-fraction slot accumulates |ratio - 1| instead (ESPO, espo.py:133)
   float* dZ2;              // [M, 2H]
   float* dhead;            // [M, act+1]   (dmean | dv)
   float* block_partials;   // [gridDim.x, 2*act+5+2H]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac | db2p[H] | db2c[H])
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     acc_pg += pg;
     acc_vl += 0.5f * verr * verr;
     acc_kl += (ratio - 1.f) - logratio;
-    acc_cf += (fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f;
+    acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
     acc_db3c += dv;
 
     float dmean[2];
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
-        acc_cf += (fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f;
+        acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
         dm = dlogp * dmu;
         if (own) {
           acc_db3 += dm;
@@ -689,7 +690,7 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
-        acc_cf += (fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f;
+        acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
         dm = dlogp * dmu;
         if (own) {
           acc_db3 += dm;

@@ -9,8 +9,10 @@
 //   next_uint32: low half of a 64-bit draw first, high half buffered across calls
 //   shuffle: Fisher-Yates from the top with masked-rejection bounded draws (random_interval)
 //   integers: Lemire multiply-shift with rejection on the 32-bit stream (buffered_bounded_lemire_uint32)
-// Pinned against numpy 2.3.5 in tests/test_rng_host.py.
+// Pinned against numpy 2.3.5 in tests/test_host_logic.py (test_pcg64_*).
 #include <stdint.h>
+
+#include <vector>
 
 #include "../../include/rlx_b200.h"
 
@@ -183,6 +185,87 @@ extern "C" int rlx_pcg64_integers_i64(rlx_pcg64* st, int64_t high, int64_t* out,
       }
       out[i] = (int64_t)(m >> 64);
     }
+  }
+  *st = loc;
+  return RLX_OK;
+}
+
+namespace {
+// random_bounded_uint64(bitgen, 0, rng, 0, use_masked=false) of numpy/random/src/distributions/distributions.c: a value in [0, rng]
+inline uint64_t bounded_lemire(rlx_pcg64* loc, uint64_t rng) {
+  if (rng == 0) return 0;
+  if (rng == 0xFFFFFFFFULL) return next32(loc);
+  if (rng < 0xFFFFFFFFULL) {
+    const uint32_t rng_excl = (uint32_t)rng + 1u;
+    uint64_t m = (uint64_t)next32(loc) * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+      const uint32_t threshold = (0xFFFFFFFFu - (uint32_t)rng) % rng_excl;
+      while (leftover < threshold) {
+        m = (uint64_t)next32(loc) * rng_excl;
+        leftover = (uint32_t)m;
+      }
+    }
+    return m >> 32;
+  }
+  if (rng == 0xFFFFFFFFFFFFFFFFULL) return next64(loc);
+  const uint64_t rng_excl = rng + 1;
+  u128 m = (u128)next64(loc) * rng_excl;
+  uint64_t leftover = (uint64_t)m;
+  if (leftover < rng_excl) {
+    const uint64_t threshold = (0xFFFFFFFFFFFFFFFFULL - rng) % rng_excl;
+    while (leftover < threshold) {
+      m = (u128)next64(loc) * rng_excl;
+      leftover = (uint64_t)m;
+    }
+  }
+  return (uint64_t)(m >> 64);
+}
+// _shuffle_int of numpy/random/_generator.pyx: Fisher-Yates on positions [first, n)
+inline void shuffle_int(rlx_pcg64* loc, int64_t n, int64_t first, int64_t* data) {
+  for (int64_t i = n - 1; i >= first; --i) {
+    const int64_t j = (int64_t)bounded_lemire(loc, (uint64_t)i);
+    const int64_t t = data[i];
+    data[i] = data[j];
+    data[j] = t;
+  }
+}
+}  // namespace
+
+// Generator.choice(pop_size, size=size, replace=False)  (numpy/random/_generator.pyx, the `p is None`, shuffle=True branch):
+// a tail shuffle of arange(pop_size) when the sample is a large part of a large population, Floyd's algorithm with an open-addressing
+// hash set (followed by a shuffle of the sample) otherwise.  ref use: espo.py:256.
+extern "C" int rlx_pcg64_choice_i64(rlx_pcg64* st, int64_t pop_size, int64_t size, int64_t* out) {
+  RLX_CHECK_ARG(st != nullptr && pop_size >= 0 && size >= 0 && (out != nullptr || size == 0), "bad arguments");
+  RLX_CHECK_ARG(size <= pop_size, "cannot take a larger sample than population when replace is False");
+  if (size == 0) return RLX_OK;
+  rlx_pcg64 loc = *st;
+  const int64_t cutoff = 50;
+  if (pop_size > 10000 && size > pop_size / cutoff) {
+    std::vector<int64_t> idx((size_t)pop_size);
+    for (int64_t i = 0; i < pop_size; ++i) idx[(size_t)i] = i;
+    const int64_t first = (pop_size - size > 1) ? pop_size - size : 1;
+    shuffle_int(&loc, pop_size, first, idx.data());
+    for (int64_t i = 0; i < size; ++i) out[i] = idx[(size_t)(pop_size - size + i)];
+  } else {
+    uint64_t mask = (uint64_t)(1.2 * (double)size);
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16; mask |= mask >> 32;
+    std::vector<uint64_t> hash((size_t)mask + 1, ~0ULL);
+    for (int64_t j = pop_size - size; j < pop_size; ++j) {
+      const uint64_t val = bounded_lemire(&loc, (uint64_t)j);
+      uint64_t slot = val & mask;
+      while (hash[slot] != ~0ULL && hash[slot] != val) slot = (slot + 1) & mask;
+      if (hash[slot] == ~0ULL) {  // val not drawn yet
+        hash[slot] = val;
+        out[j - pop_size + size] = (int64_t)val;
+      } else {                    // already in the sample: take j itself
+        slot = (uint64_t)j & mask;
+        while (hash[slot] != ~0ULL) slot = (slot + 1) & mask;
+        hash[slot] = (uint64_t)j;
+        out[j - pop_size + size] = j;
+      }
+    }
+    shuffle_int(&loc, size, 1, out);
   }
   *st = loc;
   return RLX_OK;

@@ -58,6 +58,28 @@ class Golden:
         return self.lr * (1.0 - iteration / self.iterations)
 
 
+class GoldenEspo(Golden):
+    """Golden vectors of the executed ESPO reference (tests/golden/make_golden_espo.py); same layout as the PPO files except that
+    `epochs` is max_epochs, the third float is max_ratio_delta and the index arrays are `choice/<k>`."""
+
+    def __init__(self, tag):
+        self.z = np.load(os.path.join(GOLDEN_DIR, f"espo_{tag}.npz"))
+        m = self.z["meta"]
+        self.N, self.T, self.obs, self.act, self.hidden, self.mb, self.max_epochs, self.iterations, self.seed = (int(x) for x in m)
+        self.epochs = self.max_epochs
+        f = self.z["meta_f"]
+        (self.gamma, self.gae_lambda, self.max_ratio_delta, self.entropy_coef, self.critic_coef, self.max_grad_norm, self.lr,
+         self.std_dev, self.act_low, self.act_high) = (float(x) for x in f[:10])
+        self.clip_range = float("inf")
+        self.anneal = bool(f[10])
+        self.B = self.N * self.T
+
+
+@pytest.fixture(scope="session")
+def golden_espo():
+    return GoldenEspo("small")
+
+
 @pytest.fixture(scope="session", params=["small", "humanoid"])
 def golden(request):
     return Golden(request.param)

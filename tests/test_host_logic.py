@@ -54,6 +54,25 @@ def test_pcg64_stream_is_numpy_exact(seed):
     assert g.next_uint64() == int(r.bit_generator.random_raw())
 
 
+@pytest.mark.parametrize("seed", [0, 7, 123456789])
+def test_pcg64_choice_without_replacement_is_numpy_exact(seed):
+    """Generator.choice(pop, size, replace=False) (espo.py:256): both of numpy's branches (Floyd + hash set, tail shuffle), interleaved
+    with shuffles on the same stream, and the stream position afterwards."""
+    from rl_x_b200 import _native as nt
+    g, r = nt.Pcg64Generator(seed), np.random.default_rng(seed)
+    for pop, size in [(10, 3), (10, 10), (1, 1), (5, 0), (2048, 64), (2048, 2048), (10001, 100), (10001, 201), (20000, 400), (20000, 401),
+                      (32768, 4096), (131072, 64)]:
+        for _ in range(2):
+            assert np.array_equal(g.choice(pop, size), r.choice(pop, size=size, replace=False)), (pop, size)
+        a, b = np.arange(17), np.arange(17)
+        g.shuffle(a)
+        r.shuffle(b)
+        assert np.array_equal(a, b)
+    assert g.next_uint64() == int(r.bit_generator.random_raw())
+    with pytest.raises(RuntimeError):
+        g.choice(4, 5)
+
+
 def test_pcg64_matches_golden_permutations(golden):
     from rl_x_b200 import _native as nt
     g = nt.Pcg64Generator(golden.seed)
