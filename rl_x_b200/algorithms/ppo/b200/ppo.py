@@ -233,7 +233,7 @@ class PPO:
         self.adam_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.lr_dev = torch.full((1,), float(self.learning_rate), dtype=torch.float32, device=self.device)
         self.lr_iteration = 0
-        self.hp = make_hparams(self.clip_range, self.entropy_coef, self.critic_coef, self.max_grad_norm)
+        self.hp = self._make_hparams()
 
         low = np.asarray(torch.as_tensor(self.train_env.single_action_space.low).cpu(), dtype=np.float32).reshape(-1)
         high = np.asarray(torch.as_tensor(self.train_env.single_action_space.high).cpu(), dtype=np.float32).reshape(-1)
@@ -546,25 +546,49 @@ class PPO:
         else:
             self._to_device_obs(state, b.states[0])
         if self._perm_stream is None:  # starts shuffling right away: the first permutations are ready before the first rollout ends
-            if self.world_size > 1 and self.exact_global_permutation:
-                # reference-exact: every rank walks the same GLOBAL permutation and keeps the rows it owns (host work O(global batch))
-                transform = lambda perm: sharding.local_rows_of_permutation(perm, self.minibatch_size, self.global_nr_envs, self.nr_envs, self.rank)
-                self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, transform)
-            elif self.world_size > 1:
-                # scalable: each rank shuffles only its own rows with its own PCG64 stream; global minibatch k = union of the ranks'
-                # local minibatches k (host work O(local batch), same collectives)
-                if self.minibatch_size % self.world_size != 0:
-                    raise ValueError("minibatch_size must be divisible by the world size when exact_global_permutation=False")
-                self.local_rng = nt.Pcg64Generator((int(self.seed) * 1000003 + 7919 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF)
-                self._perm_stream = PermutationStream(self.local_rng, self.local_batch_size, self.nr_epochs, self.local_batch_size, None)
-            else:
-                self._perm_stream = PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, None)
+            self._perm_stream = self._make_index_stream()
         self.global_step = 0
         self.nr_updates = 0
         self.nr_episodes = 0
         self.prev_saving_end_time = None
         self.logging_time_prev = None
         self.iteration_times = []
+
+    def _optimization_metrics(self, m, ev_host):
+        """m: the per-minibatch metric records of this iteration [nr_epochs * minibatches, RLX_PPO_NMETRIC] (ppo.py:285-310)."""
+        optimization_metrics = {
+            "loss/policy_gradient_loss": m[:, 0].mean(),
+            "loss/critic_loss": m[:, 1].mean(),
+            "loss/entropy_loss": m[:, 2].mean(),
+            "policy_ratio/clip_fraction": m[:, 4].mean(),
+            "gradients/policy_grad_norm": m[:, 5].mean(),
+            "gradients/critic_grad_norm": m[:, 6].mean(),
+        }
+        # the reference logs get_last_lr() AFTER scheduler.step() (ppo.py:302-307)
+        optimization_metrics["lr/learning_rate"] = self.current_learning_rate()
+        optimization_metrics["v_value/explained_variance"] = np.nan if float(ev_host[0]) == 0 else float(ev_host[1])
+        optimization_metrics["policy_ratio/approx_kl"] = m[-self.nmb_epoch:, 3].mean()  # last epoch only (approx_kl_divs reset at ppo.py:275)
+        optimization_metrics["policy/std_dev"] = float(np.mean(np.exp(self.params.view(self.params.flat, "logstd").cpu().numpy())))
+        self.nr_updates += self.nr_epochs * self.nr_minibatches
+        return optimization_metrics
+
+    def _make_hparams(self):
+        return make_hparams(self.clip_range, self.entropy_coef, self.critic_coef, self.max_grad_norm)
+
+    def _make_index_stream(self):
+        """Background producer of the epoch permutations (ppo.py:273-276)."""
+        if self.world_size > 1 and self.exact_global_permutation:
+            # reference-exact: every rank walks the same GLOBAL permutation and keeps the rows it owns (host work O(global batch))
+            transform = lambda perm: sharding.local_rows_of_permutation(perm, self.minibatch_size, self.global_nr_envs, self.nr_envs, self.rank)
+            return PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, transform)
+        if self.world_size > 1:
+            # scalable: each rank shuffles only its own rows with its own PCG64 stream; global minibatch k = union of the ranks'
+            # local minibatches k (host work O(local batch), same collectives)
+            if self.minibatch_size % self.world_size != 0:
+                raise ValueError("minibatch_size must be divisible by the world size when exact_global_permutation=False")
+            self.local_rng = nt.Pcg64Generator((int(self.seed) * 1000003 + 7919 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF)
+            return PermutationStream(self.local_rng, self.local_batch_size, self.nr_epochs, self.local_batch_size, None)
+        return PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, None)
 
     def _train_iteration(self):
         """One pass of the reference's while-loop body (ppo.py:195-393): acting, advantages, optimising, eval, save, log."""
@@ -611,21 +635,7 @@ class PPO:
             self.dist.all_reduce(t)
             dones_this_rollout = int(t.item())
         self.nr_episodes += dones_this_rollout
-        m = self.metrics_host.numpy()
-        optimization_metrics = {
-            "loss/policy_gradient_loss": m[:, 0].mean(),
-            "loss/critic_loss": m[:, 1].mean(),
-            "loss/entropy_loss": m[:, 2].mean(),
-            "policy_ratio/clip_fraction": m[:, 4].mean(),
-            "gradients/policy_grad_norm": m[:, 5].mean(),
-            "gradients/critic_grad_norm": m[:, 6].mean(),
-        }
-        # the reference logs get_last_lr() AFTER scheduler.step() (ppo.py:302-307)
-        optimization_metrics["lr/learning_rate"] = self.current_learning_rate()
-        optimization_metrics["v_value/explained_variance"] = np.nan if float(ev_host[0]) == 0 else float(ev_host[1])
-        optimization_metrics["policy_ratio/approx_kl"] = m[-self.nmb_epoch:, 3].mean()  # last epoch only (approx_kl_divs reset at ppo.py:275)
-        optimization_metrics["policy/std_dev"] = float(np.mean(np.exp(self.params.view(self.params.flat, "logstd").cpu().numpy())))
-        self.nr_updates += self.nr_epochs * self.nr_minibatches
+        optimization_metrics = self._optimization_metrics(self.metrics_host.numpy(), ev_host)
 
         optimizing_end_time = time.time()
         time_metrics["time/optimizing_time"] = optimizing_end_time - calc_adv_return_end_time
@@ -796,13 +806,14 @@ class PPO:
             import wandb
             wandb.save(file_path, base_path=os.path.dirname(file_path))
 
-    def load(config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
+    @classmethod
+    def load(cls, config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
         checkpoint = torch.load(config.runner.load_model, weights_only=False)
         loaded_algorithm_config = checkpoint["config_algorithm"]
         for key, value in loaded_algorithm_config.items():
             if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device", "bf16_mixed_precision_training", "compile_mode"):
                 config.algorithm[key] = value
-        model = PPO(config, train_env, eval_env, run_path, writer)
+        model = cls(config, train_env, eval_env, run_path, writer)
         named = {**checkpoint["policy_state_dict"], **checkpoint["critic_state_dict"]}
         model.params.load_named(named)
         step = 0.0

@@ -133,6 +133,21 @@ def test_default_config_keys_cover_reference_keys():
     assert (c.nr_steps, c.nr_epochs, c.minibatch_size, c.gamma, c.gae_lambda, c.clip_range) == (2048, 10, 64, 0.99, 0.95, 0.2)
 
 
+def test_espo_plugin_registers_with_reference_keys():
+    """espo.b200 registers like the reference's espo.pytorch (espo/pytorch/__init__.py) and its default config carries every key of
+    rl_x/algorithms/espo/pytorch/default_config.py:4-30."""
+    import rl_x_b200.algorithms.espo.b200  # noqa: F401  (registers)
+    from rl_x_b200.algorithms.algorithm_manager import get_algorithm_config, get_algorithm_model_class
+    cfg = get_algorithm_config("espo.b200")
+    for key in ["name", "device", "compile_mode", "bf16_mixed_precision_training", "total_timesteps", "learning_rate", "anneal_learning_rate",
+                "nr_steps", "max_epochs", "minibatch_size", "gamma", "gae_lambda", "max_ratio_delta", "delta_calc_operator", "entropy_coef",
+                "critic_coef", "max_grad_norm", "std_dev", "action_clipping_and_rescaling", "nr_hidden_units", "evaluation_frequency",
+                "evaluation_episodes"]:
+        assert key in cfg, key
+    assert (cfg.max_epochs, cfg.max_ratio_delta, cfg.delta_calc_operator) == (300, 0.25, "mean")
+    assert get_algorithm_model_class("espo.b200").__name__ == "ESPO"
+
+
 def test_ppo_refuses_to_run_without_cuda():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
