@@ -47,13 +47,31 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeP p) {
   for (long long t_hi = p.T; t_hi > 0; t_hi -= GAE_TT) {
     const long long t_lo = (t_hi > GAE_TT) ? t_hi - GAE_TT : 0;
     const int nt = (int)(t_hi - t_lo);
-    // phase 1: coalesced tile loads (row = time step, 32 consecutive envs)
-    for (int tt = wrp; tt < nt; tt += nw) {
-      const long long g = (t_lo + tt) * p.N + n;
-      s_r[tt][lane] = valid ? p.r[g] : 0.f;
-      s_t[tt][lane] = valid ? p.term[g] : 0.f;
-      s_v[tt][lane] = valid ? p.v[g] : 0.f;
-      if (has_nv) s_x[tt][lane] = valid ? p.nv[g] : 0.f;
+    // phase 1: coalesced tile loads (row = time step, 32 consecutive envs).  All of a thread's loads are issued before the first
+    // shared-memory store, so the tile costs one DRAM round trip instead of one per row.
+    {
+      constexpr int ROWS = GAE_TT / 8;  // 8 warps (the launch uses 256 threads)
+      float rr[ROWS], tm[ROWS], vv[ROWS], xx[ROWS];
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int tt = wrp + j * 8;
+        const bool ok = valid && tt < nt;
+        const long long g = (t_lo + tt) * p.N + n;
+        rr[j] = ok ? p.r[g] : 0.f;
+        tm[j] = ok ? p.term[g] : 0.f;
+        vv[j] = ok ? p.v[g] : 0.f;
+        xx[j] = (ok && has_nv) ? p.nv[g] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) {
+        const int tt = wrp + j * 8;
+        if (tt < nt) {
+          s_r[tt][lane] = rr[j];
+          s_t[tt][lane] = tm[j];
+          s_v[tt][lane] = vv[j];
+          if (has_nv) s_x[tt][lane] = xx[j];
+        }
+      }
     }
     __syncthreads();
     // phase 2a, all warps: everything that does not depend on the running lastgaelam.  s_r <- delta, s_t <- gamma*lambda*(1-term).
