@@ -14,7 +14,6 @@
 namespace rlx {
 
 constexpr int GAE_ENVS = 32;   // envs per CTA (one 128-byte row segment)
-constexpr int GAE_TT = 128;    // time steps per shared-memory tile
 
 struct GaeP {
   const float* r;
@@ -29,6 +28,9 @@ struct GaeP {
   float gl_f;           // (float)(gamma * lambda), product taken in double as TorchScript does
 };
 
+// GAE_TT: time steps per shared-memory tile.  128 = the whole config-2 rollout in one DRAM round trip (few CTAs, latency matters);
+// 64 = half the registers and shared memory per CTA, so more CTAs overlap their load / scan / store phases (many envs, HBM matters).
+template <int GAE_TT>
 __global__ void __launch_bounds__(256) gae_kernel(const GaeP p) {
   extern __shared__ __align__(16) float gae_smem[];
   float (*s_r)[GAE_ENVS] = reinterpret_cast<float (*)[GAE_ENVS]>(gae_smem);
@@ -135,12 +137,17 @@ extern "C" int rlx_gae_f32(const float* rewards, const float* terminations, cons
   GaeP p{rewards, terminations, values, next_values, last_value, advantages, returns, T, N, (float)gamma,
          (float)(gamma * gae_lambda)};
   const unsigned grid = (unsigned)ceil_div(N, GAE_ENVS);
-  constexpr size_t smem = 4ull * GAE_TT * GAE_ENVS * sizeof(float);  // 64 KB
+  const double bytes = (next_values ? 24.0 : 20.0) * (double)T * (double)N;
   static bool attr_set = false;
   if (!attr_set) {
-    RLX_CHECK_CUDA(cudaFuncSetAttribute(gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(gae_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 128 * GAE_ENVS * (int)sizeof(float)));
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(gae_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * GAE_ENVS * (int)sizeof(float)));
     attr_set = true;
   }
-  RLX_LAUNCH_C(KC_GAE, 0, (next_values ? 24.0 : 20.0) * (double)T * (double)N, gae_kernel, grid, 256, smem, stream, p);
+  if ((long long)grid > 2LL * sm_count() && T > 64) {
+    RLX_LAUNCH_C(KC_GAE, 0, bytes, gae_kernel<64>, grid, 256, 4ull * 64 * GAE_ENVS * sizeof(float), stream, p);
+  } else {
+    RLX_LAUNCH_C(KC_GAE, 0, bytes, gae_kernel<128>, grid, 256, 4ull * 128 * GAE_ENVS * sizeof(float), stream, p);
+  }
   return RLX_OK;
 }

@@ -50,7 +50,8 @@ def _rel(a, b):
 
 
 # ------------------------------------------------------------------------------------------------------------ GAE
-@pytest.mark.parametrize("T,N", [(1, 1), (5, 3), (128, 4096), (129, 33), (300, 100), (64, 31)])
+# (130, 9601) and (65, 16384): more than 2 CTAs per SM -> the 64-step-tile instantiation, with a ragged last tile
+@pytest.mark.parametrize("T,N", [(1, 1), (5, 3), (128, 4096), (129, 33), (300, 100), (64, 31), (130, 9601), (65, 16384)])
 @pytest.mark.parametrize("shortcut", [False, True])
 def test_gae_bit_exact_vs_oracle(T, N, shortcut):
     k = _kern(8, 2, 32)
