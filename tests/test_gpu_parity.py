@@ -393,3 +393,68 @@ def test_library_reports_kernel_launches():
     k.gae(x[:, :4].contiguous(), x[:, :4].contiguous(), x[:, :4].contiguous(), 0.99, 0.95, torch.empty(4, 4, device=DEV),
           torch.empty(4, 4, device=DEV), last_value=torch.zeros(4, device=DEV))
     assert lib.rlx_launch_count() == 1
+
+
+# ------------------------------------------------------------------------------------- multi-GPU helpers on one GPU
+def test_segment_moments_reproduce_minibatch_mean_and_unbiased_std():
+    """rlx_segment_moments_f32 (sharded advantage statistics): with one rank the two passes give torch's mean / std(ddof=1) of every
+    ragged segment (ppo.py:133-134)."""
+    k = _kern(8, 2, 32)
+    g = torch.Generator().manual_seed(4)
+    counts = [1000, 1, 37, 4096, 2]
+    x = (torch.randn(sum(counts), generator=g) * 3 + 0.5).to(DEV)
+    offsets = torch.tensor(np.concatenate([[0], np.cumsum(counts)]), dtype=torch.int64, device=DEV)
+    gc = torch.tensor(counts, dtype=torch.float32, device=DEV)
+    sums, ssq = torch.empty(len(counts), device=DEV), torch.empty(len(counts), device=DEV)
+    k.segment_moments(x, offsets, None, None, sums)
+    k.segment_moments(x, offsets, sums, gc, ssq)
+    mean, std = (sums / gc).cpu(), torch.sqrt(ssq / (gc - 1)).cpu()
+    o = 0
+    for i, c in enumerate(counts):
+        seg = x[o:o + c].cpu()
+        o += c
+        assert abs(float(mean[i]) - float(seg.mean())) <= 1e-6 * max(1.0, abs(float(seg.mean())))
+        if c > 1:
+            assert abs(float(std[i]) - float(seg.std())) <= 2e-6 * float(seg.std())
+        else:
+            assert torch.isnan(std[i])  # like torch.std of one element
+
+
+def test_peer_comm_world_of_one_is_a_copy():
+    """rlx_comm_* with a single rank: no peers to map, the all-reduce kernel returns the staged buffer (covers create / stage /
+    double-buffered slots / destroy on a one-GPU box; the multi-rank protocol is tests/dist_check_comm.py)."""
+    from rl_x_b200.algorithms.ppo.b200.kernels import PeerComm
+
+    class OneRank:
+        @staticmethod
+        def get_rank():
+            return 0
+
+        @staticmethod
+        def get_world_size():
+            return 1
+
+        class ReduceOp:
+            MIN = None
+
+        @staticmethod
+        def all_gather(out, t):
+            out[0].copy_(t)
+
+        @staticmethod
+        def all_reduce(t, op=None):
+            return None
+
+    n = 1003
+    comm = PeerComm(OneRank, n, torch.device(DEV))
+    out = torch.empty(n, device=DEV)
+    for i in range(5):
+        src = torch.arange(n, device=DEV, dtype=torch.float32) * (i + 1)
+        comm.stage(src)
+        comm.allreduce_sum(out)
+        assert torch.equal(out, src)
+    comm.stage(src, 10)
+    comm.allreduce_sum(out, 10)
+    with pytest.raises(RuntimeError):
+        comm.allreduce_sum(out, n + 1)
+    comm.close()
