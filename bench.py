@@ -53,6 +53,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc = [], None
+        self.nvml_rows, self.nvml_stop = [], False
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -60,6 +61,24 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+        # NVML in-process as well (a sample every 20 ms; nvidia-smi alone manages only a few per second on a busy box)
+        self.nvml_thread = threading.Thread(target=self._read_nvml, args=(gpu_index,), daemon=True)
+        self.nvml_thread.start()
+
+    def _read_nvml(self, gpu_index):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self.nvml_stop:
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.nvml_rows.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx,
+                                       pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, [n for n, b in bits.items() if mask & b]))
+                time.sleep(0.02)
+        except Exception:
+            return
 
     def _read(self):
         for line in self.proc.stdout:
@@ -73,7 +92,14 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.nvml_stop = True
         sm, mx, reasons, power = [], [], set(), []
+        nv = [r for r in list(self.nvml_rows) if t0 <= r[0] <= t1]
+        if len(nv) >= 3:
+            for _, c, m, w, rs in nv:
+                sm.append(c); mx.append(m); power.append(w); reasons.update(rs)
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                    "power_w_max": max(power), "source": "nvml, 20 ms period"}
         for ts, line in self.rows:
             if not (t0 <= ts <= t1 + 0.15):
                 continue
