@@ -277,7 +277,7 @@ class PPO:
         self._perm_slots_in_flight = []
         self.nmb_epoch = -(-self.batch_size // self.minibatch_size)  # ceil: a short last minibatch is processed (ppo.py:277-279)
         self.adv_stats = z(self.nmb_epoch, 2)
-        self.seg_tmp = z(2, self.nmb_epoch)
+        self.seg_tmp = z(2, -(-self.nmb_epoch // 4) * 4)  # rows padded to 16 bytes: rlx_comm_allreduce_sum_f32 wants an aligned destination
         self.metrics_dev = z(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC)
         self.metrics_host = torch.zeros(self.nr_epochs * self.nmb_epoch, nt.RLX_PPO_NMETRIC).pin_memory()
         self.ev_dev = z(4)
