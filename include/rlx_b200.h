@@ -263,6 +263,22 @@ int rlx_replay_sample_gather_f32(const int64_t* idx_t, const int64_t* idx_e, int
                                  float* out_actions, float* out_rewards, float* out_terminations, void* stream);
 
 /* ref: Polyak update loop  (sac/pytorch/sac.py:238-242):  target = (1-tau)*target + tau*online over a flat buffer. */
+/* ref: FastSAC's device-resident n-step replay, ReplayBuffer.sample  (fastsac/pytorch/replay_buffer.py:34-96), with the two index
+ * draws (torch.randint, :37-38 / :63-64) passed in.  Ring arrays are [capacity, nr_envs, dim] (rewards / dones / truncations
+ * [capacity, nr_envs]); `size` rows are filled, `pos` is the next write slot.  For sample i starting at (t, e) = (idx_t[i], idx_e[i]):
+ *   states, actions: row (t, e);
+ *   n_steps == 1:  next_states / rewards / dones / truncations of row (t, e), effective_n_steps = 1   (:36-47);
+ *   n_steps  > 1:  rows t+j (mod capacity), j < n_steps; mask_j = prod_{l<j} (1 - dones[t+l]); reward = sum_j r_j * mask_j * discounts[j]
+ *                  (summed in j order); effective_n_steps = sum_j mask_j; final row = first done or first truncation among the n
+ *                  (the last one if none); next_states / dones / truncations are taken there.  When the ring is full the truncation
+ *                  flag of the newest row (pos - 1) reads as 1 unless that row is a done (:50-57).
+ * discounts: [n_steps] device array holding gamma ** arange(n_steps) as the caller's framework computes it (bit-exactness of the
+ * power function is the caller's).  n_steps <= 32. */
+int rlx_replay_sample_nstep_f32(const int64_t* idx_t, const int64_t* idx_e, int64_t n, int64_t capacity, int64_t nr_envs, int64_t obs_dim,
+                                int64_t act_dim, int32_t n_steps, const float* discounts, int64_t size, int64_t pos, const float* states,
+                                const float* next_states, const float* actions, const float* rewards, const float* dones,
+                                const float* truncations, float* out_states, float* out_next_states, float* out_actions,
+                                float* out_rewards, float* out_dones, float* out_truncations, float* out_effective_n_steps, void* stream);
 int rlx_polyak_f32(float* target, const float* online, int64_t n, float tau, void* stream);
 
 /* SAC networks (ref: sac/pytorch/policy.py:34-43, q_network.py:27-33), flat fp32 parameter layouts:

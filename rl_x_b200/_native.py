@@ -121,6 +121,8 @@ _SIGNATURES = {
     "rlx_pcg64_shuffle_i64": (C.c_int, [C.POINTER(Pcg64), C.c_void_p, C.c_int64]),
     "rlx_pcg64_integers_i64": (C.c_int, [C.POINTER(Pcg64), C.c_int64, C.c_void_p, C.c_int64]),
     "rlx_pcg64_choice_i64": (C.c_int, [C.POINTER(Pcg64), C.c_int64, C.c_int64, C.c_void_p]),
+    "rlx_replay_sample_nstep_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
+                                              C.c_int64, C.c_int64] + [C.c_void_p] * 14),
     "rlx_ppo_param_count": (C.c_int64, [C.POINTER(PpoDims)]),
     "rlx_ppo_param_layout": (C.c_int, [C.POINTER(PpoDims), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "rlx_ppo_forward_workspace_bytes": (C.c_size_t, [C.POINTER(PpoDims), C.c_int64]),
