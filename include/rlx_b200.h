@@ -254,6 +254,58 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
                                      const int64_t* global_counts, rlx_comm* comm, void* stream);
 
 
+/* ------------------------------------------------------------------------------------------ PPO + LSTM path -- */
+/* rl_x/algorithms/ppo_lstm/flax (policy.py:36-146, critic.py:18-30, ppo_lstm.py:107-231), default options
+ * (lstm_obs_combine_method = "concat", share_lstm_obs_encoder = False).  STATUS: written without GPU access — numerics are checked
+ * by running these very sources in a host emulation build against oracle/ppo_lstm_oracle.py (tests/test_lstm_emulation.py); first
+ * hardware run pending.  Exact-fp32 SIMT GEMMs; one launch per time step for the recurrent part.
+ *
+ * Flat parameter layouts (fp32).  All kernels are stored [in, out] like Flax.  Policy segments, in order:
+ *   0 We1 [obs,E] 1 be1 [E] 2 g1 [E] 3 n1 [E]      lstm_obs_encoder dense kernel/bias, LayerNorm scale/bias
+ *   4 We2 [obs,E] 5 be2 [E] 6 g2 [E] 7 n2 [E]      obs_encoder
+ *   8 Wi [E,4L] 9 Wh [L,4L] 10 bh [4L]             LSTM, gate blocks ordered i|f|g|o (Flax ii,if,ig,io / hi,hf,hg,ho)
+ *   11 gl [L] 12 nl [L]                            lstm_ln
+ *   13 Wt1 [E+L,H] 14 bt1 [H] 15 Wt2 [H,H] 16 bt2 [H] 17 Wm [H,A] 18 bm [A] 19 logstd [A]
+ * Critic segments: 0 Wc1 [obs,H] 1 bc1 [H] 2 Wc2 [H,H] 3 bc2 [H] 4 Wc3 [H,1] 5 bc3 [1]. */
+#define RLX_LSTM_POLICY_NSEG 20
+#define RLX_LSTM_CRITIC_NSEG 6
+typedef struct rlx_lstm_dims { int32_t obs_dim, act_dim, hidden, enc_dim, lstm_dim; } rlx_lstm_dims;
+int rlx_lstm_param_layout(const rlx_lstm_dims* d, int64_t* policy_offsets /*[NSEG+1]*/, int64_t* critic_offsets /*[NSEG+1]*/);
+size_t rlx_lstm_minibatch_workspace_bytes(const rlx_lstm_dims* d, int64_t T, int64_t n_env);
+
+typedef struct rlx_lstm_minibatch_args {
+  rlx_lstm_dims dims;
+  int64_t T, n_env;             /* sequence length, envs in this minibatch (ppo_lstm.py:58: minibatch_size // nr_steps) */
+  const float* states;          /* [T, n_env, obs]   time-major like the reference's states[:, minibatch_env_indices] */
+  const float* actions;         /* [T, n_env, act] */
+  const float* log_probs;       /* [T, n_env] */
+  const float* advantages;      /* [T, n_env] raw */
+  const float* returns;         /* [T, n_env] */
+  const float* dones;           /* [T, n_env] 0/1: done AFTER step t (policy.py:127-135) */
+  const float* init_c;          /* [n_env, L] carry valid for states[0] */
+  const float* init_h;          /* [n_env, L] */
+  const float* adv_stats;       /* [2] device: mean and POPULATION std (jnp.std, ddof 0) of this minibatch's advantages (ppo_lstm.py:196-197) */
+  const float* policy_params;
+  const float* critic_params;
+  float* policy_grads;          /* out, same layout as policy_params */
+  float* critic_grads;
+  float clip_range, entropy_coef, critic_coef, reserved;
+  float* metrics;               /* [8] device: pg_loss, critic_loss, entropy_loss, approx_kl, clip_fraction, -, -, rows */
+  void* workspace;
+  size_t workspace_bytes;
+} rlx_lstm_minibatch_args;
+/* ref: loss_fn + grad (ppo_lstm.py:143-208): forward_sequence with carry reset, combined loss, gradients of its mean wrt both trees */
+int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* a, void* stream);
+
+/* ref: optax.chain(clip_by_global_norm(max_norm), adam(lr))  (ppo_lstm.py:88-103) on one flat tree: g *= max_norm/||g|| iff ||g|| >= max_norm
+ * (no epsilon), then Adam with bias correction; step_count (device int64) is incremented; norm_out[0] = pre-clip ||g||.
+ * workspace: >= ceil(n / 1024) floats. */
+int rlx_optax_clip_adam_f32(float* params, const float* grads, float* mu, float* nu, int64_t n, const float* lr, int64_t* step_count,
+                            float max_norm, float beta1, float beta2, float eps, float* norm_out, float* workspace, void* stream);
+
+/* out[t, j, :] = src[t, env_idx[j], :]  for t < T, j < n  (the reference's x[:, minibatch_env_indices]); width = trailing dim (1 for [T, N]) */
+int rlx_gather_env_columns_f32(const float* src, const int64_t* env_idx, int64_t T, int64_t N, int64_t n, int64_t width, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- SAC path -- */
 /* ref: ReplayBuffer.sample gathers  (sac/pytorch/replay_buffer.py:32-40):  rows states[idx1, idx2] etc. from the device ring.
  * ring arrays are [capacity_per_env, nr_envs, dim]; idx_t/idx_e [n] int64. */

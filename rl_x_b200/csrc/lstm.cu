@@ -1,0 +1,604 @@
+// PPO + LSTM update path (rl_x/algorithms/ppo_lstm/flax): sequence forward with carry reset, combined PPO loss,
+// back-propagation through time, Optax clip + Adam.  See include/rlx_b200.h for the entry points and the flat parameter layout.
+//
+// Written so that the SAME source compiles twice:
+//   * nvcc (default): kernels + exact-fp32 SIMT GEMMs (gemm_simt.cuh), part of librlx_b200.so;
+//   * g++ -x c++ -DRLX_EMU (tests/test_lstm_emulation.py only): every kernel here is "one thread = one row or one element, no shared
+//     memory, no warp primitives, no barriers", so a launch is emulated exactly by loops over (block, thread), and a GEMM by an
+//     interpreter of the GemmP contract.  That build checks indexing / strides / gradients against the oracle without a GPU.
+// The emulation build is test scaffolding; nothing in the product loads it.
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/rlx_b200.h"
+
+#ifdef RLX_EMU
+#include <math.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <algorithm>
+namespace rlx {
+struct EmuDim { unsigned x, y, z; };
+static EmuDim threadIdx, blockIdx, blockDim, gridDim;
+typedef void* cudaStream_t;
+static char g_emu_err[512];
+static void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap); va_end(ap); }
+inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_DTANH = 3, EPI_BIAS_RELU = 4, EPI_DRELU = 5 };
+enum { KC_OTHER = 0, KC_GEMM_FWD = 0, KC_GEMM_DX = 0, KC_GEMM_DW = 0 };
+struct GemmP {
+  const float* A; const float* B; float* C; const float* bias; const float* aux; float* rowsum;
+  int M, N, K; int lda, ldb, ldc, ldaux;
+  long long sA, sB, sC, sBias, sAux, sRowsum;
+  int splits; int kchunk; long long sSplitC, sSplitRowsum;
+};
+// interpreter of the GemmP contract of gemm_simt.cuh (same fp32 fmaf accumulation in k order within a split)
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
+  for (int z = 0; z < batch * p.splits; ++z) {
+    const int b = z / p.splits, sp = z % p.splits;
+    const int kbeg = sp * p.kchunk, kend = std::min(p.K, kbeg + p.kchunk);
+    const float* A = p.A + b * p.sA; const float* B = p.B + b * p.sB;
+    float* C = p.C + b * p.sC + sp * p.sSplitC;
+    for (int m = 0; m < p.M; ++m)
+      for (int n = 0; n < p.N; ++n) {
+        float acc = 0.f;
+        for (int k = kbeg; k < kend; ++k) {
+          const float a = A_KMAJ ? A[(long long)m * p.lda + k] : A[(long long)k * p.lda + m];
+          const float w = B_KMAJ ? B[(long long)n * p.ldb + k] : B[(long long)k * p.ldb + n];
+          acc = fmaf(a, w, acc);
+        }
+        if (EPI == EPI_BIAS) acc += p.bias[b * p.sBias + n];
+        if (EPI == EPI_BIAS_TANH) acc = tanhf(acc + p.bias[b * p.sBias + n]);
+        if (EPI == EPI_DTANH) { const float h = p.aux[b * p.sAux + (long long)m * p.ldaux + n]; acc = acc * (1.f - h * h); }
+        C[(long long)m * p.ldc + n] = acc;
+      }
+  }
+  return RLX_OK;
+}
+}  // namespace rlx
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define RLX_CHECK_ARG(cond, msg) do { if (!(cond)) { rlx::set_error("%s: invalid argument: %s", __func__, msg); return RLX_ERR_INVALID_ARG; } } while (0)
+#define LSTM_LAUNCH(kernel, nthreads_total, stream, ...)                                          \
+  do {                                                                                            \
+    const long long _n = (nthreads_total);                                                        \
+    rlx::blockDim = {256, 1, 1};                                                                  \
+    rlx::gridDim = {(unsigned)rlx::ceil_div(_n, 256), 1, 1};                                      \
+    for (unsigned _b = 0; _b < rlx::gridDim.x; ++_b)                                              \
+      for (unsigned _t = 0; _t < 256; ++_t) {                                                     \
+        rlx::blockIdx = {_b, 0, 0};                                                               \
+        rlx::threadIdx = {_t, 0, 0};                                                              \
+        kernel(__VA_ARGS__);                                                                      \
+      }                                                                                           \
+  } while (0)
+#else
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#define LSTM_LAUNCH(kernel, nthreads_total, stream, ...)                                                                       \
+  do {                                                                                                                         \
+    const long long _n = (nthreads_total);                                                                                     \
+    if (_n > 0) RLX_LAUNCH_C(rlx::KC_OTHER, 0, 0, kernel, (unsigned)rlx::ceil_div(_n, 256), 256, 0, (cudaStream_t)(stream), __VA_ARGS__); \
+  } while (0)
+#endif
+
+namespace rlx {
+namespace lstm {
+
+constexpr float kLnEps = 1e-6f;             // flax.linen.LayerNorm default
+constexpr float kHalfLog2Pi = 0.9189385332046727f;
+constexpr int kColChunk = 256;              // rows per partial of the column-sum reductions
+constexpr int kWgradRows = 1024;            // rows per split of the weight-gradient GEMMs
+
+__device__ __forceinline__ long long gtid() { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------------------- layouts
+enum PSeg { WE1 = 0, BE1, G1, N1, WE2, BE2, G2, N2, WI, WH, BH, GL, NL, WT1, BT1, WT2, BT2, WM, BM, P_LOGSTD };
+enum CSeg { WC1 = 0, BC1, WC2, BC2, WC3, BC3 };
+struct Layout {
+  long long p[RLX_LSTM_POLICY_NSEG + 1], c[RLX_LSTM_CRITIC_NSEG + 1];
+};
+static Layout make_layout(const rlx_lstm_dims& d) {
+  const long long O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim;
+  const long long ps[RLX_LSTM_POLICY_NSEG] = {O * E, E, E, E, O * E, E, E, E, E * 4 * L, L * 4 * L, 4 * L, L, L, (E + L) * H, H, H * H, H, H * A, A, A};
+  const long long cs[RLX_LSTM_CRITIC_NSEG] = {O * H, H, H * H, H, H, 1};
+  Layout l;
+  long long o = 0;
+  for (int i = 0; i < RLX_LSTM_POLICY_NSEG; ++i) { l.p[i] = o; o += ps[i]; }
+  l.p[RLX_LSTM_POLICY_NSEG] = o;
+  o = 0;
+  for (int i = 0; i < RLX_LSTM_CRITIC_NSEG; ++i) { l.c[i] = o; o += cs[i]; }
+  l.c[RLX_LSTM_CRITIC_NSEG] = o;
+  return l;
+}
+static bool dims_ok(const rlx_lstm_dims& d) {
+  return d.obs_dim > 0 && d.act_dim > 0 && d.act_dim <= 64 && d.hidden > 0 && d.enc_dim > 0 && d.enc_dim <= 1024 && d.lstm_dim > 0 && d.lstm_dim <= 1024;
+}
+
+// workspace carve-up (floats); R = T * n_env rows, time-major (row = t * n_env + e)
+struct Ws {
+  size_t Z1, E1, Z2, TI, Gi, Gates, Call, Hall, Hm, Cm, T1, T2, C1, C2, Mean, V, dMean, dV, Terms, dLs, dT2, dT1, dTI, dHall, dG, dE1, dZ1, dZ2,
+      dC2, dC1, Gh, dHn, dCn, Small, Stats1, Stats2, StatsL, Part, Col, total;
+};
+static Ws plan(const rlx_lstm_dims& d, long long T, long long n) {
+  const size_t R = (size_t)(T * n), O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim;
+  (void)O;
+  Ws w;
+  size_t o = 0;
+  auto take = [&](size_t& f, size_t cnt) { f = o; o += align_up(cnt, 64); };
+  take(w.Z1, R * E); take(w.E1, R * E); take(w.Z2, R * E); take(w.TI, R * (E + L)); take(w.Gi, R * 4 * L); take(w.Gates, R * 4 * L);
+  take(w.Call, R * L); take(w.Hall, R * L); take(w.Hm, R * L); take(w.Cm, R * L); take(w.T1, R * H); take(w.T2, R * H); take(w.C1, R * H);
+  take(w.C2, R * H); take(w.Mean, R * A); take(w.V, R); take(w.dMean, R * A); take(w.dV, R); take(w.Terms, R * 4); take(w.dLs, R * A);
+  take(w.dT2, R * H); take(w.dT1, R * H); take(w.dTI, R * (E + L)); take(w.dHall, R * L); take(w.dG, R * 4 * L); take(w.dE1, R * E);
+  take(w.dZ1, R * E); take(w.dZ2, R * E); take(w.dC2, R * H); take(w.dC1, R * H);
+  take(w.Gh, (size_t)n * 4 * L); take(w.dHn, (size_t)n * L); take(w.dCn, (size_t)n * L); take(w.Small, 64);
+  take(w.Stats1, R * 2); take(w.Stats2, R * 2); take(w.StatsL, R * 2);
+  const size_t splits = (size_t)ceil_div((long long)R, kWgradRows);
+  size_t biggest = 0;  // largest weight matrix: one partial of it per row split
+  for (size_t v : {(size_t)d.obs_dim * E, E * 4 * L, L * 4 * L, (E + L) * H, H * H, H * A, (size_t)d.obs_dim * H, H}) biggest = std::max(biggest, v);
+  take(w.Part, splits * biggest);
+  const size_t chunks = (size_t)ceil_div((long long)R, kColChunk);
+  size_t widest = 8;   // widest column reduction; the LayerNorm parameter gradients keep two partial sets side by side
+  for (size_t v : {H, 4 * L, 2 * E, 2 * L, A}) widest = std::max(widest, v);
+  take(w.Col, chunks * widest);
+  w.total = o * sizeof(float);
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------- kernels
+// (one thread = one row unless stated; all comm-free)
+
+// y = tanh(LayerNorm(z) * g + b) per row; flax fast variance: var = max(0, E[z^2] - E[z]^2); stats = (mean, rstd)
+__global__ void ln_tanh_fwd_kernel(const float* __restrict__ Z, int ldz, long long R, int W, const float* __restrict__ g,
+                                   const float* __restrict__ b, float* __restrict__ out, int ldo, float* __restrict__ stats) {
+  const long long r = gtid();
+  if (r >= R) return;
+  const float* z = Z + r * ldz;
+  float s = 0.f, q = 0.f;
+  for (int j = 0; j < W; ++j) { s += z[j]; q += z[j] * z[j]; }
+  const float mean = s / (float)W;
+  const float var = fmaxf(q / (float)W - mean * mean, 0.f);
+  const float rstd = 1.f / sqrtf(var + kLnEps);
+  for (int j = 0; j < W; ++j) out[r * ldo + j] = tanhf((z[j] - mean) * (rstd * g[j]) + b[j]);
+  stats[2 * r] = mean;
+  stats[2 * r + 1] = rstd;
+}
+
+// dZ for y = tanh(LN(z)); dOut = dL/dy, Y = y.  dxhat = dOut (1 - y^2) g;  dz = rstd (dxhat - mean(dxhat) - xhat mean(dxhat xhat))
+__global__ void ln_tanh_bwd_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Y, int ldy, const float* __restrict__ Z,
+                                   int ldz, long long R, int W, const float* __restrict__ g, const float* __restrict__ stats,
+                                   float* __restrict__ dZ, int lddz) {
+  const long long r = gtid();
+  if (r >= R) return;
+  const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = 0; j < W; ++j) {
+    const float y = Y[r * ldy + j];
+    const float dx = dOut[r * ldd + j] * (1.f - y * y) * g[j];
+    const float xh = (Z[r * ldz + j] - mean) * rstd;
+    s1 += dx;
+    s2 += dx * xh;
+  }
+  s1 /= (float)W;
+  s2 /= (float)W;
+  for (int j = 0; j < W; ++j) {
+    const float y = Y[r * ldy + j];
+    const float dx = dOut[r * ldd + j] * (1.f - y * y) * g[j];
+    const float xh = (Z[r * ldz + j] - mean) * rstd;
+    dZ[r * lddz + j] = rstd * (dx - s1 - xh * s2);
+  }
+}
+
+// partial column sums of the LayerNorm parameter gradients: thread = (row chunk, column).  part_g / part_b: [nchunk, W]
+__global__ void ln_param_partial_kernel(const float* __restrict__ dOut, int ldd, const float* __restrict__ Y, int ldy, const float* __restrict__ Z,
+                                        int ldz, long long R, int W, const float* __restrict__ stats, float* __restrict__ part_g,
+                                        float* __restrict__ part_b) {
+  const long long id = gtid();
+  const long long nchunk = (R + kColChunk - 1) / kColChunk;
+  if (id >= nchunk * W) return;
+  const long long ch = id / W;
+  const int j = (int)(id % W);
+  const long long r1 = ch * kColChunk + kColChunk < R ? ch * kColChunk + kColChunk : R;
+  float sg = 0.f, sb = 0.f;
+  for (long long r = ch * kColChunk; r < r1; ++r) {
+    const float y = Y[r * ldy + j];
+    const float dy = dOut[r * ldd + j] * (1.f - y * y);
+    sg += dy * ((Z[r * ldz + j] - stats[2 * r]) * stats[2 * r + 1]);
+    sb += dy;
+  }
+  part_g[id] = sg;
+  part_b[id] = sb;
+}
+
+// partial column sums of X [R, W] (bias gradients): thread = (row chunk, column)
+__global__ void colsum_partial_kernel(const float* __restrict__ X, int ldx, long long R, int W, float* __restrict__ part) {
+  const long long id = gtid();
+  const long long nchunk = (R + kColChunk - 1) / kColChunk;
+  if (id >= nchunk * W) return;
+  const long long ch = id / W;
+  const int j = (int)(id % W);
+  const long long r1 = ch * kColChunk + kColChunk < R ? ch * kColChunk + kColChunk : R;
+  float s = 0.f;
+  for (long long r = ch * kColChunk; r < r1; ++r) s += X[r * ldx + j];
+  part[id] = s;
+}
+
+// out[i] = scale * sum_s part[s * len + i] (+ add)      thread = element
+__global__ void reduce_parts_kernel(const float* __restrict__ part, long long nparts, long long len, float scale, float add,
+                                    float* __restrict__ out) {
+  const long long i = gtid();
+  if (i >= len) return;
+  float s = 0.f;
+  for (long long k = 0; k < nparts; ++k) s += part[k * len + i];
+  out[i] = s * scale + add;
+}
+
+// carry reset before step t: Hm = Hprev * keep, Cm = Cprev * keep, keep = 1 - done[t-1] (keep = 1 at t = 0).  thread = (env, unit)
+__global__ void lstm_mask_kernel(const float* __restrict__ Hprev, const float* __restrict__ Cprev, const float* __restrict__ done_prev,
+                                 long long n, int L, float* __restrict__ Hm, float* __restrict__ Cm) {
+  const long long id = gtid();
+  if (id >= n * L) return;
+  const float keep = done_prev ? 1.f - done_prev[id / L] : 1.f;
+  Hm[id] = Hprev[id] * keep;
+  Cm[id] = Cprev[id] * keep;
+}
+
+// gates = act(Gi_t + Gh + bh), c = f * cm + i * g, h = o * tanh(c).  thread = (env, unit)
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ Gi, const float* __restrict__ Gh, const float* __restrict__ bh,
+                                     const float* __restrict__ Cm, long long n, int L, float* __restrict__ gates, float* __restrict__ C,
+                                     float* __restrict__ Hh) {
+  const long long id = gtid();
+  if (id >= n * L) return;
+  const long long e = id / L;
+  const int j = (int)(id % L);
+  const long long base = e * 4 * L;
+  const float zi = Gi[base + j] + Gh[base + j] + bh[j];
+  const float zf = Gi[base + L + j] + Gh[base + L + j] + bh[L + j];
+  const float zg = Gi[base + 2 * L + j] + Gh[base + 2 * L + j] + bh[2 * L + j];
+  const float zo = Gi[base + 3 * L + j] + Gh[base + 3 * L + j] + bh[3 * L + j];
+  const float i = sigmoidf_(zi), f = sigmoidf_(zf), g = tanhf(zg), o = sigmoidf_(zo);
+  const float c = f * Cm[id] + i * g;
+  gates[base + j] = i;
+  gates[base + L + j] = f;
+  gates[base + 2 * L + j] = g;
+  gates[base + 3 * L + j] = o;
+  C[id] = c;
+  Hh[id] = o * tanhf(c);
+}
+
+// BPTT step t.  dH = dHall_t + dHnext * keep_next, dC = dCnext (already masked) + dH o (1 - tanh(c)^2); writes the pre-activation gate
+// gradients dG_t and dCprev = (dC f) * keep_t (keep_t = 1 - done[t-1]).  dHnext is the GEMM output dG_{t+1} . Wh^T.  thread = (env, unit)
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dHall, const float* __restrict__ dHnext, const float* __restrict__ keep_next_done,
+                                     const float* __restrict__ dCnext, const float* __restrict__ gates, const float* __restrict__ C,
+                                     const float* __restrict__ Cm, const float* __restrict__ done_prev, long long n, int L,
+                                     float* __restrict__ dG, float* __restrict__ dCprev) {
+  const long long id = gtid();
+  if (id >= n * L) return;
+  const long long e = id / L;
+  const int j = (int)(id % L);
+  const long long base = e * 4 * L;
+  float dH = dHall[id];
+  if (dHnext) dH += dHnext[id] * (1.f - keep_next_done[e]);
+  const float i = gates[base + j], f = gates[base + L + j], g = gates[base + 2 * L + j], o = gates[base + 3 * L + j];
+  const float tc = tanhf(C[id]);
+  const float dC = (dCnext ? dCnext[id] : 0.f) + dH * o * (1.f - tc * tc);
+  dG[base + j] = dC * g * i * (1.f - i);
+  dG[base + L + j] = dC * Cm[id] * f * (1.f - f);
+  dG[base + 2 * L + j] = dC * i * (1.f - g * g);
+  dG[base + 3 * L + j] = dH * tc * o * (1.f - o);
+  const float keep = done_prev ? 1.f - done_prev[e] : 1.f;
+  dCprev[id] = dC * f * keep;
+}
+
+// per-row loss terms and the gradients wrt the head outputs.  terms[r] = (pg, 0.5 (v - R)^2, approx_kl, clipped?)   thread = row
+__global__ void loss_rows_kernel(const float* __restrict__ Mean, const float* __restrict__ V, const float* __restrict__ actions,
+                                 const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
+                                 const float* __restrict__ logstd, const float* __restrict__ adv_stats, long long R, int A, float clip_range,
+                                 float critic_coef, float inv_R, float* __restrict__ dMean, float* __restrict__ dV, float* __restrict__ dLs,
+                                 float* __restrict__ terms) {
+  const long long r = gtid();
+  if (r >= R) return;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float sd = expf(logstd[a]);
+    const float zz = (actions[r * A + a] - Mean[r * A + a]) / sd;
+    lp += -0.5f * zz * zz - kHalfLog2Pi - logstd[a];
+  }
+  const float logratio = lp - logp_old[r];
+  const float ratio = expf(logratio);
+  const float An = (adv[r] - adv_stats[0]) / (adv_stats[1] + 1e-8f);
+  const float lo = 1.f - clip_range, hi = 1.f + clip_range;
+  const float pg1 = -An * ratio, pg2 = -An * fminf(fmaxf(ratio, lo), hi);
+  // d max(pg1, pg2) / d ratio: ties split evenly (jnp.maximum), the clip passes gradient on the closed interval
+  const float w1 = (pg1 > pg2) ? 1.f : ((pg1 == pg2) ? 0.5f : 0.f);
+  const float inr = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+  const float dlogp = -An * (w1 + (1.f - w1) * inr) * ratio * inv_R;
+  for (int a = 0; a < A; ++a) {
+    const float sd = expf(logstd[a]);
+    const float d = actions[r * A + a] - Mean[r * A + a];
+    dMean[r * A + a] = dlogp * d / (sd * sd);
+    dLs[r * A + a] = dlogp * (d * d / (sd * sd) - 1.f);
+  }
+  const float verr = V[r] - ret[r];
+  dV[r] = critic_coef * verr * inv_R;
+  terms[4 * r + 0] = fmaxf(pg1, pg2);
+  terms[4 * r + 1] = 0.5f * verr * verr;
+  terms[4 * r + 2] = (ratio - 1.f) - logratio;
+  terms[4 * r + 3] = (fabsf(ratio - 1.f) > clip_range) ? 1.f : 0.f;
+}
+
+__global__ void finish_metrics_kernel(const float* __restrict__ sums4, const float* __restrict__ logstd, int A, float rows, float* __restrict__ metrics) {
+  if (gtid() != 0) return;
+  metrics[0] = sums4[0];
+  metrics[1] = sums4[1];
+  float ent = 0.f;
+  for (int a = 0; a < A; ++a) ent += logstd[a] + 0.5f + kHalfLog2Pi;  // log_std + 0.5 log(2 pi e)
+  metrics[2] = ent;
+  metrics[3] = sums4[2];
+  metrics[4] = sums4[3];
+  metrics[5] = 0.f;
+  metrics[6] = 0.f;
+  metrics[7] = rows;
+}
+
+// out[t, j, :] = src[t, idx[j], :]      thread = one float
+__global__ void gather_env_kernel(const float* __restrict__ src, const long long* __restrict__ idx, long long T, long long N, long long n,
+                                  long long width, float* __restrict__ out) {
+  const long long id = gtid();
+  if (id >= T * n * width) return;
+  const long long k = id % width, j = (id / width) % n, t = id / (width * n);
+  out[id] = src[(t * N + idx[j]) * width + k];
+}
+
+// sum of squares per 1024-element chunk; thread = chunk
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  const long long c = gtid();
+  const long long nchunk = (n + 1023) / 1024;
+  if (c >= nchunk) return;
+  const long long i1 = c * 1024 + 1024 < n ? c * 1024 + 1024 : n;
+  float s = 0.f;
+  for (long long i = c * 1024; i < i1; ++i) s += g[i] * g[i];
+  part[c] = s;
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ part, long long nchunk, float* __restrict__ norm_out, long long* __restrict__ step) {
+  if (gtid() != 0) return;
+  float s = 0.f;
+  for (long long c = 0; c < nchunk; ++c) s += part[c];
+  norm_out[0] = sqrtf(s);
+  step[0] += 1;
+}
+// optax: g = ||g|| < max_norm ? g : g / ||g|| * max_norm; Adam with bias correction.  thread = element
+__global__ void optax_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu, long long n,
+                                  const float* __restrict__ lr, const long long* __restrict__ step, const float* __restrict__ norm, float max_norm,
+                                  float b1, float b2, float eps) {
+  const long long i = gtid();
+  if (i >= n) return;
+  const float gn = norm[0];
+  float gi = g[i];
+  if (!(gn < max_norm)) gi = gi / gn * max_norm;
+  const float t = (float)step[0];
+  const float m = b1 * mu[i] + (1.f - b1) * gi;
+  const float v = b2 * nu[i] + (1.f - b2) * gi * gi;
+  mu[i] = m;
+  nu[i] = v;
+  const float mh = m / (1.f - powf(b1, t)), vh = v / (1.f - powf(b2, t));
+  p[i] -= lr[0] * mh / (sqrtf(vh) + eps);
+}
+
+// ------------------------------------------------------------------------------------------------------- GEMM helpers
+// forward dense: C[r, o] = act(sum_i X[r, i] W[i, o] + b[o]);  W stored [in, out]
+template <int EPI>
+static int dense_fwd(const float* X, int ldx, const float* W, int in, int out, const float* bias, float* C, int ldc, long long R, cudaStream_t st) {
+  GemmP g{};
+  g.A = X; g.B = W; g.C = C; g.bias = bias;
+  g.M = (int)R; g.N = out; g.K = in;
+  g.lda = ldx; g.ldb = out; g.ldc = ldc;
+  g.splits = 1; g.kchunk = (int)(ceil_div(in, 8) * 8);
+  return launch_sgemm<true, false, EPI>(g, 1, st, KC_GEMM_FWD);
+}
+// backward wrt the input: C[r, i] = (sum_o dY[r, o] W[i, o]) [* (1 - aux[r, i]^2)]
+template <int EPI>
+static int dense_bwd_input(const float* dY, int ldy, const float* W, int in, int out, const float* aux, int ldaux, float* C, int ldc, long long R,
+                           cudaStream_t st) {
+  GemmP g{};
+  g.A = dY; g.B = W; g.C = C; g.aux = aux;
+  g.M = (int)R; g.N = in; g.K = out;
+  g.lda = ldy; g.ldb = out; g.ldc = ldc; g.ldaux = ldaux;
+  g.splits = 1; g.kchunk = (int)(ceil_div(out, 8) * 8);
+  return launch_sgemm<true, true, EPI>(g, 1, st, KC_GEMM_DX);
+}
+// weight gradient: dW[i, o] = sum_r X[r, i] dY[r, o], split over rows in chunks of kWgradRows and summed by reduce_parts_kernel
+static int dense_bwd_weight(const float* X, int ldx, const float* dY, int ldy, int in, int out, long long R, float* part, float* dW, cudaStream_t st) {
+  const int splits = (int)ceil_div(R, kWgradRows);
+  GemmP g{};
+  g.A = X; g.B = dY; g.C = part;
+  g.M = in; g.N = out; g.K = (int)R;
+  g.lda = ldx; g.ldb = ldy; g.ldc = out;
+  g.splits = splits; g.kchunk = kWgradRows; g.sSplitC = (long long)in * out;
+  int rc = launch_sgemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW);
+  if (rc) return rc;
+  LSTM_LAUNCH(reduce_parts_kernel, (long long)in * out, st, part, (long long)splits, (long long)in * out, 1.f, 0.f, dW);
+  return RLX_OK;
+}
+// bias gradient: db[o] = sum_r dY[r, o]
+static int colsum(const float* X, int ldx, long long R, int W, float* col_ws, float scale, float add, float* out, cudaStream_t st) {
+  const long long nchunk = ceil_div(R, kColChunk);
+  LSTM_LAUNCH(colsum_partial_kernel, nchunk * W, st, X, ldx, R, W, col_ws);
+  LSTM_LAUNCH(reduce_parts_kernel, (long long)W, st, col_ws, nchunk, (long long)W, scale, add, out);
+  return RLX_OK;
+}
+// LayerNorm scale / bias gradients
+static int ln_param_grads(const float* dOut, int ldd, const float* Y, int ldy, const float* Z, int ldz, long long R, int W, const float* stats,
+                          float* col_ws, float* dg, float* db, cudaStream_t st) {
+  const long long nchunk = ceil_div(R, kColChunk);
+  float* pg = col_ws;
+  float* pb = col_ws + nchunk * W;
+  LSTM_LAUNCH(ln_param_partial_kernel, nchunk * W, st, dOut, ldd, Y, ldy, Z, ldz, R, W, stats, pg, pb);
+  LSTM_LAUNCH(reduce_parts_kernel, (long long)W, st, pg, nchunk, (long long)W, 1.f, 0.f, dg);
+  LSTM_LAUNCH(reduce_parts_kernel, (long long)W, st, pb, nchunk, (long long)W, 1.f, 0.f, db);
+  return RLX_OK;
+}
+
+}  // namespace lstm
+}  // namespace rlx
+
+using namespace rlx;
+using namespace rlx::lstm;
+
+#define LSTM_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+extern "C" int rlx_lstm_param_layout(const rlx_lstm_dims* d, int64_t* policy_offsets, int64_t* critic_offsets) {
+  RLX_CHECK_ARG(d != nullptr && dims_ok(*d), "unsupported dims");
+  const Layout l = make_layout(*d);
+  if (policy_offsets) for (int i = 0; i <= RLX_LSTM_POLICY_NSEG; ++i) policy_offsets[i] = l.p[i];
+  if (critic_offsets) for (int i = 0; i <= RLX_LSTM_CRITIC_NSEG; ++i) critic_offsets[i] = l.c[i];
+  return RLX_OK;
+}
+
+extern "C" size_t rlx_lstm_minibatch_workspace_bytes(const rlx_lstm_dims* d, int64_t T, int64_t n_env) {
+  if (d == nullptr || !dims_ok(*d) || T <= 0 || n_env <= 0) return 0;
+  return plan(*d, T, n_env).total;
+}
+
+extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* a, void* stream) {
+  RLX_CHECK_ARG(a != nullptr && dims_ok(a->dims), "unsupported dims");
+  RLX_CHECK_ARG(a->T > 0 && a->n_env > 0 && a->T * a->n_env < (1LL << 31), "bad sequence / minibatch size");
+  RLX_CHECK_ARG(a->states && a->actions && a->log_probs && a->advantages && a->returns && a->dones && a->init_c && a->init_h && a->adv_stats,
+                "null minibatch tensor");
+  RLX_CHECK_ARG(a->policy_params && a->critic_params && a->policy_grads && a->critic_grads && a->metrics, "null parameter / gradient / metrics");
+  const rlx_lstm_dims& d = a->dims;
+  const long long T = a->T, n = a->n_env, R = T * n;
+  const int O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim, EL = E + L;
+  const Ws w = plan(d, T, n);
+  if (a->workspace == nullptr || a->workspace_bytes < w.total) {
+    set_error("rlx_lstm_ppo_minibatch_fwdbwd_f32: workspace too small (%zu < %zu)", a->workspace_bytes, w.total);
+    return RLX_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(d);
+  float* ws = (float*)a->workspace;
+  const float* P = a->policy_params;
+  const float* Cp = a->critic_params;
+  float* gP = a->policy_grads;
+  float* gC = a->critic_grads;
+  const float* X = a->states;
+  float *Z1 = ws + w.Z1, *E1 = ws + w.E1, *Z2 = ws + w.Z2, *TI = ws + w.TI, *Gi = ws + w.Gi, *Gates = ws + w.Gates, *Call = ws + w.Call,
+        *Hall = ws + w.Hall, *Hm = ws + w.Hm, *Cm = ws + w.Cm, *T1 = ws + w.T1, *T2 = ws + w.T2, *C1 = ws + w.C1, *C2 = ws + w.C2,
+        *Mean = ws + w.Mean, *V = ws + w.V, *dMean = ws + w.dMean, *dV = ws + w.dV, *Terms = ws + w.Terms, *dLs = ws + w.dLs, *dT2 = ws + w.dT2,
+        *dT1 = ws + w.dT1, *dTI = ws + w.dTI, *dHall = ws + w.dHall, *dG = ws + w.dG, *dE1 = ws + w.dE1, *dZ1 = ws + w.dZ1, *dZ2 = ws + w.dZ2,
+        *dC2 = ws + w.dC2, *dC1 = ws + w.dC1, *Gh = ws + w.Gh, *dHn = ws + w.dHn, *dCn = ws + w.dCn, *Small = ws + w.Small, *S1 = ws + w.Stats1,
+        *S2 = ws + w.Stats2, *SL = ws + w.StatsL, *Part = ws + w.Part, *Col = ws + w.Col;
+
+  // ================================================================ forward
+  // encoders (policy.py:79-92): Z = X We + be; E = tanh(LN(Z)).  E2 lands in the left E columns of the torso input TI.
+  LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE1], O, E, P + l.p[BE1], Z1, E, R, st));
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z1, E, R, E, P + l.p[G1], P + l.p[N1], E1, E, S1);
+  LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, R, st));
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z2, E, R, E, P + l.p[G2], P + l.p[N2], TI, EL, S2);
+  // input-side gate pre-activations of all steps at once, then the recurrence (policy.py:115-146)
+  LSTM_TRY(dense_fwd<EPI_NONE>(E1, E, P + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, R, st));
+  for (long long t = 0; t < T; ++t) {
+    const float* hprev = t == 0 ? a->init_h : Hall + (t - 1) * n * L;
+    const float* cprev = t == 0 ? a->init_c : Call + (t - 1) * n * L;
+    const float* done_prev = t == 0 ? nullptr : a->dones + (t - 1) * n;
+    LSTM_LAUNCH(lstm_mask_kernel, n * L, st, hprev, cprev, done_prev, n, L, Hm + t * n * L, Cm + t * n * L);
+    LSTM_TRY(dense_fwd<EPI_NONE>(Hm + t * n * L, L, P + l.p[WH], L, 4 * L, nullptr, Gh, 4 * L, n, st));
+    LSTM_LAUNCH(lstm_cell_fwd_kernel, n * L, st, Gi + t * n * 4 * L, Gh, P + l.p[BH], Cm + t * n * L, n, L, Gates + t * n * 4 * L, Call + t * n * L,
+                Hall + t * n * L);
+  }
+  // decode (policy.py:95-112): lstm latent = tanh(LN(h)) into the right L columns of TI; torso; mean head
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Hall, L, R, L, P + l.p[GL], P + l.p[NL], TI + E, EL, SL);
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, EL, P + l.p[WT1], EL, H, P + l.p[BT1], T1, H, R, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(T1, H, P + l.p[WT2], H, H, P + l.p[BT2], T2, H, R, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS>(T2, H, P + l.p[WM], H, A, P + l.p[BM], Mean, A, R, st));
+  // critic (critic.py:22-30)
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(X, O, Cp + l.c[WC1], O, H, Cp + l.c[BC1], C1, H, R, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(C1, H, Cp + l.c[WC2], H, H, Cp + l.c[BC2], C2, H, R, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS>(C2, H, Cp + l.c[WC3], H, 1, Cp + l.c[BC3], V, 1, R, st));
+
+  // ================================================================ loss (ppo_lstm.py:146-172) and head gradients
+  const float inv_R = 1.f / (float)R;
+  LSTM_LAUNCH(loss_rows_kernel, R, st, Mean, V, a->actions, a->log_probs, a->advantages, a->returns, P + l.p[P_LOGSTD], a->adv_stats, R, A,
+              a->clip_range, a->critic_coef, inv_R, dMean, dV, dLs, Terms);
+  LSTM_TRY(colsum(Terms, 4, R, 4, Col, inv_R, 0.f, Small, st));
+  LSTM_LAUNCH(finish_metrics_kernel, 1, st, Small, P + l.p[P_LOGSTD], A, (float)R, a->metrics);
+  // d/dlogstd: sum_r dlogp (z^2 - 1)  -  entropy_coef  (mean over rows of -c * sum_a (logstd_a + const))
+  LSTM_TRY(colsum(dLs, A, R, A, Col, 1.f, -a->entropy_coef, gP + l.p[P_LOGSTD], st));
+
+  // ================================================================ backward: policy head and torso
+  LSTM_TRY(dense_bwd_weight(T2, H, dMean, A, H, A, R, Part, gP + l.p[WM], st));
+  LSTM_TRY(colsum(dMean, A, R, A, Col, 1.f, 0.f, gP + l.p[BM], st));
+  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dMean, A, P + l.p[WM], H, A, T2, H, dT2, H, R, st));          // dL/d(pre-tanh of torso 2)
+  LSTM_TRY(dense_bwd_weight(T1, H, dT2, H, H, H, R, Part, gP + l.p[WT2], st));
+  LSTM_TRY(colsum(dT2, H, R, H, Col, 1.f, 0.f, gP + l.p[BT2], st));
+  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dT2, H, P + l.p[WT2], H, H, T1, H, dT1, H, R, st));
+  LSTM_TRY(dense_bwd_weight(TI, EL, dT1, H, EL, H, R, Part, gP + l.p[WT1], st));
+  LSTM_TRY(colsum(dT1, H, R, H, Col, 1.f, 0.f, gP + l.p[BT1], st));
+  LSTM_TRY(dense_bwd_input<EPI_NONE>(dT1, H, P + l.p[WT1], EL, H, nullptr, 0, dTI, EL, R, st));     // [dE2 | dLstmLatent]
+  // lstm_ln (+ tanh) backward -> dHall
+  LSTM_TRY(ln_param_grads(dTI + E, EL, TI + E, EL, Hall, L, R, L, SL, Col, gP + l.p[GL], gP + l.p[NL], st));
+  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dTI + E, EL, TI + E, EL, Hall, L, R, L, P + l.p[GL], SL, dHall, L);
+  // obs_encoder backward
+  LSTM_TRY(ln_param_grads(dTI, EL, TI, EL, Z2, E, R, E, S2, Col, gP + l.p[G2], gP + l.p[N2], st));
+  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dTI, EL, TI, EL, Z2, E, R, E, P + l.p[G2], S2, dZ2, E);
+  LSTM_TRY(dense_bwd_weight(X, O, dZ2, E, O, E, R, Part, gP + l.p[WE2], st));
+  LSTM_TRY(colsum(dZ2, E, R, E, Col, 1.f, 0.f, gP + l.p[BE2], st));
+
+  // ================================================================ back-propagation through time
+  for (long long t = T - 1; t >= 0; --t) {
+    const bool last = (t == T - 1);
+    // dHn holds dG_{t+1} . Wh^T (gradient wrt the MASKED carry of step t+1); its mask is done[t]
+    LSTM_LAUNCH(lstm_cell_bwd_kernel, n * L, st, dHall + t * n * L, last ? nullptr : dHn, last ? nullptr : a->dones + t * n, last ? nullptr : dCn,
+                Gates + t * n * 4 * L, Call + t * n * L, Cm + t * n * L, t == 0 ? nullptr : a->dones + (t - 1) * n, n, L, dG + t * n * 4 * L, dCn);
+    if (t > 0) LSTM_TRY(dense_bwd_input<EPI_NONE>(dG + t * n * 4 * L, 4 * L, P + l.p[WH], L, 4 * L, nullptr, 0, dHn, L, n, st));
+  }
+  LSTM_TRY(dense_bwd_weight(Hm, L, dG, 4 * L, L, 4 * L, R, Part, gP + l.p[WH], st));
+  LSTM_TRY(colsum(dG, 4 * L, R, 4 * L, Col, 1.f, 0.f, gP + l.p[BH], st));
+  LSTM_TRY(dense_bwd_weight(E1, E, dG, 4 * L, E, 4 * L, R, Part, gP + l.p[WI], st));
+  LSTM_TRY(dense_bwd_input<EPI_NONE>(dG, 4 * L, P + l.p[WI], E, 4 * L, nullptr, 0, dE1, E, R, st));
+  // lstm_obs_encoder backward
+  LSTM_TRY(ln_param_grads(dE1, E, E1, E, Z1, E, R, E, S1, Col, gP + l.p[G1], gP + l.p[N1], st));
+  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dE1, E, E1, E, Z1, E, R, E, P + l.p[G1], S1, dZ1, E);
+  LSTM_TRY(dense_bwd_weight(X, O, dZ1, E, O, E, R, Part, gP + l.p[WE1], st));
+  LSTM_TRY(colsum(dZ1, E, R, E, Col, 1.f, 0.f, gP + l.p[BE1], st));
+
+  // ================================================================ backward: critic
+  LSTM_TRY(dense_bwd_weight(C2, H, dV, 1, H, 1, R, Part, gC + l.c[WC3], st));
+  LSTM_TRY(colsum(dV, 1, R, 1, Col, 1.f, 0.f, gC + l.c[BC3], st));
+  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dV, 1, Cp + l.c[WC3], H, 1, C2, H, dC2, H, R, st));
+  LSTM_TRY(dense_bwd_weight(C1, H, dC2, H, H, H, R, Part, gC + l.c[WC2], st));
+  LSTM_TRY(colsum(dC2, H, R, H, Col, 1.f, 0.f, gC + l.c[BC2], st));
+  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dC2, H, Cp + l.c[WC2], H, H, C1, H, dC1, H, R, st));
+  LSTM_TRY(dense_bwd_weight(X, O, dC1, H, O, H, R, Part, gC + l.c[WC1], st));
+  LSTM_TRY(colsum(dC1, H, R, H, Col, 1.f, 0.f, gC + l.c[BC1], st));
+  return RLX_OK;
+}
+
+extern "C" int rlx_optax_clip_adam_f32(float* params, const float* grads, float* mu, float* nu, int64_t n, const float* lr, int64_t* step_count,
+                                       float max_norm, float beta1, float beta2, float eps, float* norm_out, float* workspace, void* stream) {
+  RLX_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return RLX_OK;
+  RLX_CHECK_ARG(params && grads && mu && nu && lr && step_count && norm_out && workspace, "null pointer");
+  const long long nchunk = ceil_div(n, 1024);  // the workspace holds one partial sum of squares per 1024 elements
+  cudaStream_t st = (cudaStream_t)stream;
+  LSTM_LAUNCH(sumsq_partial_kernel, nchunk, st, grads, (long long)n, workspace);
+  LSTM_LAUNCH(sumsq_final_kernel, 1, st, workspace, nchunk, norm_out, (long long*)step_count);
+  LSTM_LAUNCH(optax_adam_kernel, (long long)n, st, params, grads, mu, nu, (long long)n, lr, (const long long*)step_count, norm_out, max_norm, beta1,
+              beta2, eps);
+  return RLX_OK;
+}
+
+extern "C" int rlx_gather_env_columns_f32(const float* src, const int64_t* env_idx, int64_t T, int64_t N, int64_t n, int64_t width, float* out,
+                                          void* stream) {
+  RLX_CHECK_ARG(T >= 0 && N > 0 && n >= 0 && width > 0, "bad sizes");
+  if (T == 0 || n == 0) return RLX_OK;
+  RLX_CHECK_ARG(src && env_idx && out, "null pointer");
+  LSTM_LAUNCH(gather_env_kernel, (long long)T * n * width, (cudaStream_t)stream, src, (const long long*)env_idx, (long long)T, (long long)N,
+              (long long)n, (long long)width, out);
+  return RLX_OK;
+}

@@ -1,0 +1,171 @@
+"""PPO+LSTM update path (rl_x_b200/csrc/lstm.cu) checked WITHOUT a GPU: the same source is compiled with g++ -DRLX_EMU (kernel launches
+become loops over threads, GEMMs an interpreter of the GemmP contract) and its outputs are compared with oracle/ppo_lstm_oracle.py's
+autograd.  This validates indexing, strides, the carry-reset rule, BPTT and every hand-derived gradient; what it cannot validate is
+anything specific to the device (the real SIMT GEMM kernels are covered by the PPO parity tests).  The emulation library is built
+into a temporary directory and is never loaded by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_lstm_oracle as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim")]
+
+
+class Args(C.Structure):
+    _fields_ = ([("dims", Dims), ("T", C.c_int64), ("n_env", C.c_int64)] +
+                [(n, C.c_void_p) for n in ("states", "actions", "log_probs", "advantages", "returns", "dones", "init_c", "init_h", "adv_stats",
+                                           "policy_params", "critic_params", "policy_grads", "critic_grads")] +
+                [(n, C.c_float) for n in ("clip_range", "entropy_coef", "critic_coef", "reserved")] +
+                [("metrics", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)])
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("lstm_emu") / "liblstm_emu.so"
+    src = os.path.join(ROOT, "rl_x_b200", "csrc", "lstm.cu")
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out), src], check=True)
+    lib = C.CDLL(str(out))
+    lib.rlx_lstm_minibatch_workspace_bytes.restype = C.c_size_t
+    lib.rlx_lstm_minibatch_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_int64]
+    return lib
+
+
+POLICY_SEGS = ["lstm_obs_encoder_dense.kernel", "lstm_obs_encoder_dense.bias", "lstm_obs_encoder_ln.scale", "lstm_obs_encoder_ln.bias",
+               "obs_encoder_dense.kernel", "obs_encoder_dense.bias", "obs_encoder_ln.scale", "obs_encoder_ln.bias", "Wi", "Wh", "bh",
+               "lstm_ln.scale", "lstm_ln.bias", "torso_dense1.kernel", "torso_dense1.bias", "torso_dense2.kernel", "torso_dense2.bias",
+               "mean_head.kernel", "mean_head.bias", "policy_logstd"]
+CRITIC_SEGS = ["Dense_0.kernel", "Dense_0.bias", "Dense_1.kernel", "Dense_1.bias", "Dense_2.kernel", "Dense_2.bias"]
+
+
+def _get(tree, dotted):
+    for k in dotted.split("."):
+        tree = tree[k]
+    return tree
+
+
+def flatten_policy(pol):
+    """oracle tree -> the flat layout of include/rlx_b200.h (gate blocks i|f|g|o side by side)."""
+    parts = []
+    for name in POLICY_SEGS:
+        if name == "Wi":
+            parts.append(torch.cat([pol["lstm"]["i" + k]["kernel"] for k in L.GATES], dim=1))
+        elif name == "Wh":
+            parts.append(torch.cat([pol["lstm"]["h" + k]["kernel"] for k in L.GATES], dim=1))
+        elif name == "bh":
+            parts.append(torch.cat([pol["lstm"]["h" + k]["bias"] for k in L.GATES]))
+        else:
+            parts.append(_get(pol, name))
+    return [p.detach().reshape(-1) for p in parts]
+
+
+def flatten_critic(cri):
+    return [_get(cri, n).detach().reshape(-1) for n in CRITIC_SEGS]
+
+
+def _np(t):
+    return np.ascontiguousarray(t.detach().numpy(), dtype=np.float32)
+
+
+@pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm", [(7, 5, 6, 2, 12, 8, 4), (5, 3, 9, 3, 16, 12, 8), (33, 40, 5, 2, 8, 8, 4)])
+def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, enc, lstm):
+    torch.manual_seed(T * 100 + n)
+    pol, cri = L.init_params(obs, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.8, seed=T)
+    # non-trivial LayerNorm parameters and biases so that every gradient path is exercised
+    for tree in (pol, cri):
+        for name, v in L.tree_leaves(tree):
+            if name.endswith("bias") or name.endswith("scale"):
+                v.add_(0.1 * torch.randn_like(v))
+    states, actions = torch.randn(T, n, obs), torch.randn(T, n, act)
+    log_probs = torch.randn(T, n) * 0.1 - 2.5
+    adv, ret = torch.randn(T, n), torch.randn(T, n)
+    dones = (torch.rand(T, n) < 0.2).float()
+    init = (torch.randn(n, lstm) * 0.5, torch.randn(n, lstm) * 0.5)
+    clip, ent, cc = 0.2, 0.01, 0.5
+
+    learner = L.Learner(pol, cri, clip_range=clip, entropy_coef=ent, critic_coef=cc)
+    mb = dict(states=states, actions=actions, log_probs=log_probs, returns=ret, advantages=adv, dones=dones, init_carry=init)
+    gp_ref, gc_ref, metrics_ref = learner.grads(mb)
+    # oracle gradients are per leaf of its (sorted) tree; bring them into the flat layout
+    gp_tree = dict(zip([nm for nm, _ in L.tree_leaves(learner.pol)], gp_ref))
+    gc_tree = dict(zip([nm for nm, _ in L.tree_leaves(learner.cri)], gc_ref))
+
+    def grad_seg(name):
+        if name == "Wi":
+            return torch.cat([gp_tree[f"lstm.i{k}.kernel"] for k in L.GATES], dim=1)
+        if name == "Wh":
+            return torch.cat([gp_tree[f"lstm.h{k}.kernel"] for k in L.GATES], dim=1)
+        if name == "bh":
+            return torch.cat([gp_tree[f"lstm.h{k}.bias"] for k in L.GATES])
+        return gp_tree[name]
+
+    d = Dims(obs, act, hid, enc, lstm)
+    P = np.concatenate([_np(x) for x in flatten_policy(pol)])
+    Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
+    poff, coff = (C.c_int64 * 21)(), (C.c_int64 * 7)()
+    assert emu.rlx_lstm_param_layout(C.byref(d), poff, coff) == 0
+    assert poff[20] == P.size and coff[6] == Cc.size
+    gP, gC = np.full_like(P, np.nan), np.full_like(Cc, np.nan)
+    stats = np.array([float(adv.mean()), float(adv.std(unbiased=False))], dtype=np.float32)
+    metrics = np.zeros(8, np.float32)
+    nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), T, n)
+    ws = np.zeros(nbytes // 4 + 16, np.float32)
+    arrs = dict(states=_np(states), actions=_np(actions), log_probs=_np(log_probs), advantages=_np(adv), returns=_np(ret), dones=_np(dones),
+                init_c=_np(init[0]), init_h=_np(init[1]))
+    a = Args()
+    a.dims, a.T, a.n_env = d, T, n
+    for k, v in arrs.items():
+        setattr(a, k, v.ctypes.data)
+    a.adv_stats, a.policy_params, a.critic_params = stats.ctypes.data, P.ctypes.data, Cc.ctypes.data
+    a.policy_grads, a.critic_grads, a.metrics = gP.ctypes.data, gC.ctypes.data, metrics.ctypes.data
+    a.clip_range, a.entropy_coef, a.critic_coef = clip, ent, cc
+    a.workspace, a.workspace_bytes = ws.ctypes.data, nbytes
+    assert emu.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), None) == 0
+    assert np.isfinite(gP).all() and np.isfinite(gC).all()
+
+    scale = max(float(np.abs(np.concatenate([_np(grad_seg(nm)).reshape(-1) for nm in POLICY_SEGS])).max()), 1e-6)
+    for i, name in enumerate(POLICY_SEGS):
+        ours, ref = gP[poff[i]:poff[i + 1]], _np(grad_seg(name)).reshape(-1)
+        np.testing.assert_allclose(ours, ref, rtol=2e-4, atol=2e-6 * max(scale, 1.0), err_msg=name)
+    for i, name in enumerate(CRITIC_SEGS):
+        ours, ref = gC[coff[i]:coff[i + 1]], _np(gc_tree[name]).reshape(-1)
+        np.testing.assert_allclose(ours, ref, rtol=2e-4, atol=2e-6, err_msg=name)
+    for j, key in enumerate(["loss/policy_gradient_loss", "loss/critic_loss", "loss/entropy_loss", "policy_ratio/approx_kl", "policy_ratio/clip_fraction"]):
+        assert abs(float(metrics[j]) - metrics_ref[key]) <= 2e-5 * max(1.0, abs(metrics_ref[key])), (key, metrics[j], metrics_ref[key])
+    assert metrics[7] == T * n
+
+
+def test_emulated_optax_step_and_env_gather(emu):
+    n = 5000
+    g0 = torch.Generator().manual_seed(3)
+    p = torch.randn(n, generator=g0)
+    ref_p = [p.clone().requires_grad_(True)]
+    opt = L.OptaxAdam(ref_p, 1e-2, max_norm=0.5)
+    ours = _np(p).copy()
+    mu, nu = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    lr, step, norm, ws = np.array([1e-2], np.float32), np.zeros(1, np.int64), np.zeros(1, np.float32), np.zeros(64, np.float32)
+    emu.rlx_optax_clip_adam_f32.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3
+    for s in range(4):
+        g = torch.randn(n, generator=g0) * (0.001 if s == 2 else 1.0)   # step 2 stays below the clip threshold
+        ref_norm = opt.step([g.clone()])
+        gg = _np(g)
+        assert emu.rlx_optax_clip_adam_f32(ours.ctypes.data, gg.ctypes.data, mu.ctypes.data, nu.ctypes.data, n, lr.ctypes.data, step.ctypes.data,
+                                           0.5, 0.9, 0.999, 1e-8, norm.ctypes.data, ws.ctypes.data, None) == 0
+        assert abs(float(norm[0]) - ref_norm) <= 1e-5 * ref_norm
+        np.testing.assert_allclose(ours, _np(ref_p[0]), rtol=1e-5, atol=1e-6)
+    assert int(step[0]) == 4
+    T, N, w = 3, 7, 4
+    src = np.arange(T * N * w, dtype=np.float32).reshape(T, N, w)
+    idx = np.array([5, 0, 5, 2], dtype=np.int64)
+    out = np.zeros((T, 4, w), np.float32)
+    emu.rlx_gather_env_columns_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    assert emu.rlx_gather_env_columns_f32(src.ctypes.data, idx.ctypes.data, T, N, 4, w, out.ctypes.data, None) == 0
+    assert np.array_equal(out, src[:, idx])
