@@ -297,6 +297,36 @@ typedef struct rlx_lstm_minibatch_args {
 /* ref: loss_fn + grad (ppo_lstm.py:143-208): forward_sequence with carry reset, combined loss, gradients of its mean wrt both trees */
 int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* a, void* stream);
 
+typedef struct rlx_lstm_step_args {
+  rlx_lstm_dims dims;
+  int64_t n;                    /* envs */
+  const float* obs;             /* [n, obs] */
+  float* c;                     /* [n, L] in: carry valid for obs (already reset where the previous step ended an episode); out: next carry */
+  float* h;                     /* [n, L] */
+  const float* noise;           /* [n, act] standard normal draws, or NULL: deterministic (action = mean, get_deterministic_action ppo_lstm.py:234-237) */
+  const float* policy_params;
+  const float* critic_params;   /* may be NULL together with `value` (evaluation) */
+  const float* act_low;         /* [act] */
+  const float* act_high;        /* [act] */
+  int32_t clip_rescale;         /* action_clipping_and_rescaling (policy.py:149-157) */
+  int32_t reserved;
+  float* action;                /* [n, act] unclipped sample */
+  float* env_action;            /* [n, act] what the env receives */
+  float* logp;                  /* [n] or NULL */
+  float* value;                 /* [n] or NULL */
+  void* workspace;              /* rlx_lstm_minibatch_workspace_bytes(d, 1, n) */
+  size_t workspace_bytes;
+} rlx_lstm_step_args;
+/* ref: get_action_and_value (ppo_lstm.py:107-118): Policy.apply_one_step + Gaussian sample + log-prob + critic value */
+int rlx_lstm_step_f32(const rlx_lstm_step_args* a, void* stream);
+/* ref: next_policy_lstm_carry * (1 - done) (ppo_lstm.py:283): done is [n] float 0/1 */
+int rlx_lstm_mask_carry_f32(float* c, float* h, const float* done, int64_t n, int64_t lstm_dim, void* stream);
+/* ref: critic.apply(params, x) (ppo_lstm.py:131): x [rows, obs] -> out [rows]; workspace: rlx_lstm_minibatch_workspace_bytes(d, 1, rows) */
+int rlx_lstm_critic_forward_f32(const rlx_lstm_dims* d, const float* critic_params, const float* x, int64_t rows, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+/* out[0] = mean(x), out[1] = population std (jnp.std) of x[0..n); workspace: >= n + 2 * ceil(n / 256) + 8 floats */
+int rlx_mean_popstd_f32(const float* x, int64_t n, float* out, float* workspace, void* stream);
+
 /* ref: optax.chain(clip_by_global_norm(max_norm), adam(lr))  (ppo_lstm.py:88-103) on one flat tree: g *= max_norm/||g|| iff ||g|| >= max_norm
  * (no epsilon), then Adam with bias correction; step_count (device int64) is incremented; norm_out[0] = pre-clip ||g||.
  * workspace: >= ceil(n / 1024) floats. */

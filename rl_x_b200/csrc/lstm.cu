@@ -249,9 +249,9 @@ __global__ void lstm_mask_kernel(const float* __restrict__ Hprev, const float* _
 }
 
 // gates = act(Gi_t + Gh + bh), c = f * cm + i * g, h = o * tanh(c).  thread = (env, unit)
+// (Cm and C may be the same buffer — the rollout step updates the carry in place — so neither is __restrict__)
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ Gi, const float* __restrict__ Gh, const float* __restrict__ bh,
-                                     const float* __restrict__ Cm, long long n, int L, float* __restrict__ gates, float* __restrict__ C,
-                                     float* __restrict__ Hh) {
+                                     const float* Cm, long long n, int L, float* __restrict__ gates, float* C, float* __restrict__ Hh) {
   const long long id = gtid();
   if (id >= n * L) return;
   const long long e = id / L;
@@ -344,6 +344,43 @@ __global__ void finish_metrics_kernel(const float* __restrict__ sums4, const flo
   metrics[5] = 0.f;
   metrics[6] = 0.f;
   metrics[7] = rows;
+}
+
+// a = mean + exp(logstd) * noise; logp; env action (policy.py:149-157).  noise == null: a = mean.  thread = row
+__global__ void sample_rows_kernel(const float* __restrict__ Mean, const float* __restrict__ logstd, const float* __restrict__ noise, long long n,
+                                   int A, const float* __restrict__ low, const float* __restrict__ high, int clip_rescale,
+                                   float* __restrict__ action, float* __restrict__ env_action, float* __restrict__ logp) {
+  const long long r = gtid();
+  if (r >= n) return;
+  float lp = 0.f;
+  for (int a = 0; a < A; ++a) {
+    const float sd = expf(logstd[a]);
+    const float m = Mean[r * A + a];
+    const float act = noise ? m + sd * noise[r * A + a] : m;
+    const float zz = (act - m) / sd;
+    lp += -0.5f * zz * zz - kHalfLog2Pi - logstd[a];
+    action[r * A + a] = act;
+    float ea = act;
+    if (clip_rescale) ea = low[a] + 0.5f * (fminf(fmaxf(act, -1.f), 1.f) + 1.f) * (high[a] - low[a]);
+    env_action[r * A + a] = ea;
+  }
+  if (logp) logp[r] = lp;
+}
+__global__ void carry_mask_kernel(float* __restrict__ c, float* __restrict__ h, const float* __restrict__ done, long long n, int L) {
+  const long long id = gtid();
+  if (id >= n * L) return;
+  const float keep = 1.f - done[id / L];
+  c[id] *= keep;
+  h[id] *= keep;
+}
+__global__ void centered_sq_kernel(const float* __restrict__ x, long long n, const float* __restrict__ mean, float* __restrict__ out) {
+  const long long i = gtid();
+  if (i >= n) return;
+  const float d = x[i] - mean[0];
+  out[i] = d * d;
+}
+__global__ void sqrt_inplace_kernel(float* __restrict__ x) {
+  if (gtid() == 0) x[0] = sqrtf(x[0]);
 }
 
 // out[t, j, :] = src[t, idx[j], :]      thread = one float
@@ -576,6 +613,89 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   LSTM_TRY(dense_bwd_input<EPI_DTANH>(dC2, H, Cp + l.c[WC2], H, H, C1, H, dC1, H, R, st));
   LSTM_TRY(dense_bwd_weight(X, O, dC1, H, O, H, R, Part, gC + l.c[WC1], st));
   LSTM_TRY(colsum(dC1, H, R, H, Col, 1.f, 0.f, gC + l.c[BC1], st));
+  return RLX_OK;
+}
+
+
+// policy.apply_one_step on n rows (policy.py:115-125): leaves Mean in the workspace, updates c / h in place
+static int policy_one_step(const rlx_lstm_dims& d, const Layout& l, const Ws& w, float* ws, const float* P, const float* obs, float* c, float* h,
+                           long long n, cudaStream_t st) {
+  const int O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim, EL = E + L;
+  float *Z1 = ws + w.Z1, *E1 = ws + w.E1, *Z2 = ws + w.Z2, *TI = ws + w.TI, *Gi = ws + w.Gi, *Gates = ws + w.Gates, *Gh = ws + w.Gh, *T1 = ws + w.T1,
+        *T2 = ws + w.T2, *Mean = ws + w.Mean, *S1 = ws + w.Stats1, *S2 = ws + w.Stats2, *SL = ws + w.StatsL;
+  LSTM_TRY(dense_fwd<EPI_BIAS>(obs, O, P + l.p[WE1], O, E, P + l.p[BE1], Z1, E, n, st));
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, Z1, E, n, E, P + l.p[G1], P + l.p[N1], E1, E, S1);
+  LSTM_TRY(dense_fwd<EPI_BIAS>(obs, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, n, st));
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, Z2, E, n, E, P + l.p[G2], P + l.p[N2], TI, EL, S2);
+  LSTM_TRY(dense_fwd<EPI_NONE>(E1, E, P + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, n, st));
+  LSTM_TRY(dense_fwd<EPI_NONE>(h, L, P + l.p[WH], L, 4 * L, nullptr, Gh, 4 * L, n, st));
+  LSTM_LAUNCH(lstm_cell_fwd_kernel, n * L, st, Gi, Gh, P + l.p[BH], c, n, L, Gates, c, h);  // element-wise in place: thread (e, j) reads and writes c[e, j] only
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, h, L, n, L, P + l.p[GL], P + l.p[NL], TI + E, EL, SL);
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, EL, P + l.p[WT1], EL, H, P + l.p[BT1], T1, H, n, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(T1, H, P + l.p[WT2], H, H, P + l.p[BT2], T2, H, n, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS>(T2, H, P + l.p[WM], H, A, P + l.p[BM], Mean, A, n, st));
+  return RLX_OK;
+}
+static int critic_rows(const rlx_lstm_dims& d, const Layout& l, const Ws& w, float* ws, const float* Cp, const float* x, long long rows, float* out,
+                       cudaStream_t st) {
+  const int O = d.obs_dim, H = d.hidden;
+  float *C1 = ws + w.C1, *C2 = ws + w.C2;
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(x, O, Cp + l.c[WC1], O, H, Cp + l.c[BC1], C1, H, rows, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(C1, H, Cp + l.c[WC2], H, H, Cp + l.c[BC2], C2, H, rows, st));
+  LSTM_TRY(dense_fwd<EPI_BIAS>(C2, H, Cp + l.c[WC3], H, 1, Cp + l.c[BC3], out, 1, rows, st));
+  return RLX_OK;
+}
+
+extern "C" int rlx_lstm_step_f32(const rlx_lstm_step_args* a, void* stream) {
+  RLX_CHECK_ARG(a != nullptr && dims_ok(a->dims) && a->n > 0, "bad arguments");
+  RLX_CHECK_ARG(a->obs && a->c && a->h && a->policy_params && a->action && a->env_action, "null pointer");
+  RLX_CHECK_ARG((a->value == nullptr) || a->critic_params, "value requested without critic parameters");
+  RLX_CHECK_ARG(!a->clip_rescale || (a->act_low && a->act_high), "action bounds are required for clipping / rescaling");
+  const Ws w = plan(a->dims, 1, a->n);
+  if (a->workspace == nullptr || a->workspace_bytes < w.total) {
+    set_error("rlx_lstm_step_f32: workspace too small (%zu < %zu)", a->workspace_bytes, w.total);
+    return RLX_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const Layout l = make_layout(a->dims);
+  float* ws = (float*)a->workspace;
+  LSTM_TRY(policy_one_step(a->dims, l, w, ws, a->policy_params, a->obs, a->c, a->h, a->n, st));
+  LSTM_LAUNCH(sample_rows_kernel, a->n, st, ws + w.Mean, a->policy_params + l.p[P_LOGSTD], a->noise, (long long)a->n, a->dims.act_dim, a->act_low,
+              a->act_high, a->clip_rescale, a->action, a->env_action, a->logp);
+  if (a->value) LSTM_TRY(critic_rows(a->dims, l, w, ws, a->critic_params, a->obs, a->n, a->value, st));
+  return RLX_OK;
+}
+
+extern "C" int rlx_lstm_mask_carry_f32(float* c, float* h, const float* done, int64_t n, int64_t lstm_dim, void* stream) {
+  RLX_CHECK_ARG(n >= 0 && lstm_dim > 0, "bad sizes");
+  if (n == 0) return RLX_OK;
+  RLX_CHECK_ARG(c && h && done, "null pointer");
+  LSTM_LAUNCH(carry_mask_kernel, (long long)n * lstm_dim, (cudaStream_t)stream, c, h, done, (long long)n, (int)lstm_dim);
+  return RLX_OK;
+}
+
+extern "C" int rlx_lstm_critic_forward_f32(const rlx_lstm_dims* d, const float* critic_params, const float* x, int64_t rows, float* out,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  RLX_CHECK_ARG(d != nullptr && dims_ok(*d) && rows >= 0, "bad arguments");
+  if (rows == 0) return RLX_OK;
+  RLX_CHECK_ARG(critic_params && x && out, "null pointer");
+  const Ws w = plan(*d, 1, rows);
+  if (workspace == nullptr || workspace_bytes < w.total) {
+    set_error("rlx_lstm_critic_forward_f32: workspace too small (%zu < %zu)", workspace_bytes, w.total);
+    return RLX_ERR_WORKSPACE;
+  }
+  return critic_rows(*d, make_layout(*d), w, (float*)workspace, critic_params, x, rows, out, (cudaStream_t)stream);
+}
+
+extern "C" int rlx_mean_popstd_f32(const float* x, int64_t n, float* out, float* workspace, void* stream) {
+  RLX_CHECK_ARG(n > 0 && x && out && workspace, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* sq = workspace;           // [n]
+  float* col = workspace + n;      // column-sum partials
+  LSTM_TRY(colsum(x, 1, n, 1, col, 1.f / (float)n, 0.f, out, st));
+  LSTM_LAUNCH(centered_sq_kernel, (long long)n, st, x, (long long)n, out, sq);
+  LSTM_TRY(colsum(sq, 1, n, 1, col, 1.f / (float)n, 0.f, out + 1, st));
+  LSTM_LAUNCH(sqrt_inplace_kernel, 1, st, out + 1);
   return RLX_OK;
 }
 

@@ -169,3 +169,80 @@ def test_emulated_optax_step_and_env_gather(emu):
     emu.rlx_gather_env_columns_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     assert emu.rlx_gather_env_columns_f32(src.ctypes.data, idx.ctypes.data, T, N, 4, w, out.ctypes.data, None) == 0
     assert np.array_equal(out, src[:, idx])
+
+
+class StepArgs(C.Structure):
+    _fields_ = ([("dims", Dims), ("n", C.c_int64)] +
+                [(k, C.c_void_p) for k in ("obs", "c", "h", "noise", "policy_params", "critic_params", "act_low", "act_high")] +
+                [("clip_rescale", C.c_int32), ("reserved", C.c_int32)] +
+                [(k, C.c_void_p) for k in ("action", "env_action", "logp", "value", "workspace")] + [("workspace_bytes", C.c_size_t)])
+
+
+def test_emulated_rollout_step_matches_oracle(emu):
+    """rlx_lstm_step_f32 == get_action_and_value (ppo_lstm.py:107-118) over a few consecutive steps with the carry threaded through and
+    reset by rlx_lstm_mask_carry_f32; plus the critic-only forward and the population-std helper."""
+    obs_d, act, hid, enc, lstm, n = 7, 3, 16, 12, 8, 6
+    torch.manual_seed(4)
+    pol, cri = L.init_params(obs_d, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.6, seed=9)
+    for tree in (pol, cri):
+        for name, v in L.tree_leaves(tree):
+            if name.endswith("bias") or name.endswith("scale"):
+                v.add_(0.1 * torch.randn_like(v))
+    d = Dims(obs_d, act, hid, enc, lstm)
+    P = np.concatenate([_np(x) for x in flatten_policy(pol)])
+    Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
+    low, high = np.full(act, -2.0, np.float32), np.full(act, 0.5, np.float32)
+    nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, n)
+    ws = np.zeros(nbytes // 4 + 16, np.float32)
+    c, h = np.zeros((n, lstm), np.float32), np.zeros((n, lstm), np.float32)
+    carry = (torch.zeros(n, lstm), torch.zeros(n, lstm))
+    emu.rlx_lstm_mask_carry_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+    for step in range(4):
+        obs, noise = torch.randn(n, obs_d), torch.randn(n, act)
+        with torch.no_grad():
+            proc, action, value, logp, carry = L.get_action_and_value(pol, cri, obs, carry, noise, torch.from_numpy(low), torch.from_numpy(high))
+        o, nz = _np(obs), _np(noise)
+        out_a, out_e, out_lp, out_v = (np.zeros((n, act), np.float32), np.zeros((n, act), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32))
+        a = StepArgs()
+        a.dims, a.n = d, n
+        a.obs, a.c, a.h, a.noise = o.ctypes.data, c.ctypes.data, h.ctypes.data, nz.ctypes.data
+        a.policy_params, a.critic_params, a.act_low, a.act_high = P.ctypes.data, Cc.ctypes.data, low.ctypes.data, high.ctypes.data
+        a.clip_rescale = 1
+        a.action, a.env_action, a.logp, a.value = out_a.ctypes.data, out_e.ctypes.data, out_lp.ctypes.data, out_v.ctypes.data
+        a.workspace, a.workspace_bytes = ws.ctypes.data, nbytes
+        assert emu.rlx_lstm_step_f32(C.byref(a), None) == 0
+        np.testing.assert_allclose(out_a, _np(action), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out_e, _np(proc), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out_lp, _np(logp), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(out_v, _np(value), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(c, _np(carry[0]), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(h, _np(carry[1]), rtol=1e-5, atol=1e-6)
+        done = (torch.rand(n) < 0.4).float()
+        carry = (carry[0] * (1 - done)[:, None], carry[1] * (1 - done)[:, None])   # ppo_lstm.py:283
+        dn = _np(done)
+        assert emu.rlx_lstm_mask_carry_f32(c.ctypes.data, h.ctypes.data, dn.ctypes.data, n, lstm, None) == 0
+        np.testing.assert_allclose(c, _np(carry[0]), rtol=1e-5, atol=1e-6)
+    # deterministic mode (noise == NULL): action = mean
+    a.noise, a.logp, a.value, a.critic_params = None, None, None, None
+    obs = torch.randn(n, obs_d)
+    o = _np(obs)
+    a.obs = o.ctypes.data
+    with torch.no_grad():
+        mean, _, _ = L.apply_one_step(pol, obs, carry)
+    assert emu.rlx_lstm_step_f32(C.byref(a), None) == 0
+    np.testing.assert_allclose(out_a, _np(mean), rtol=1e-5, atol=1e-6)
+    # critic-only forward over many rows, population std
+    rows = 300
+    x = torch.randn(rows, obs_d)
+    xv, outv = _np(x), np.zeros(rows, np.float32)
+    nb = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, rows)
+    ws2 = np.zeros(nb // 4 + 16, np.float32)
+    emu.rlx_lstm_critic_forward_f32.argtypes = [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    assert emu.rlx_lstm_critic_forward_f32(C.byref(d), Cc.ctypes.data, xv.ctypes.data, rows, outv.ctypes.data, ws2.ctypes.data, nb, None) == 0
+    with torch.no_grad():
+        np.testing.assert_allclose(outv, _np(L.critic_value(cri, x).reshape(-1)), rtol=1e-5, atol=1e-6)
+    y = (torch.randn(1000) * 2 + 3)
+    yv, st2, wsp = _np(y), np.zeros(2, np.float32), np.zeros(1000 + 2 * 4 + 8, np.float32)
+    emu.rlx_mean_popstd_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert emu.rlx_mean_popstd_f32(yv.ctypes.data, 1000, st2.ctypes.data, wsp.ctypes.data, None) == 0
+    assert abs(st2[0] - float(y.mean())) < 1e-5 and abs(st2[1] - float(y.std(unbiased=False))) < 1e-5
