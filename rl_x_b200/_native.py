@@ -97,6 +97,30 @@ class SacUpdateArgs(C.Structure):
         ("workspace_bytes", C.c_size_t)]
 
 
+
+class LstmDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim")]
+
+
+class LstmMinibatchArgs(C.Structure):
+    _fields_ = ([("dims", LstmDims), ("T", C.c_int64), ("n_env", C.c_int64)] +
+                [(n, C.c_void_p) for n in ("states", "actions", "log_probs", "advantages", "returns", "dones", "init_c", "init_h", "adv_stats",
+                                           "policy_params", "critic_params", "policy_grads", "critic_grads")] +
+                [(n, C.c_float) for n in ("clip_range", "entropy_coef", "critic_coef", "reserved")] +
+                [("metrics", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)])
+
+
+class LstmStepArgs(C.Structure):
+    _fields_ = ([("dims", LstmDims), ("n", C.c_int64)] +
+                [(k, C.c_void_p) for k in ("obs", "c", "h", "noise", "policy_params", "critic_params", "act_low", "act_high")] +
+                [("clip_rescale", C.c_int32), ("reserved", C.c_int32)] +
+                [(k, C.c_void_p) for k in ("action", "env_action", "logp", "value", "workspace")] + [("workspace_bytes", C.c_size_t)])
+
+
+RLX_LSTM_POLICY_NSEG, RLX_LSTM_CRITIC_NSEG = 20, 6
+LSTM_POLICY_SEGMENTS = ("We1", "be1", "g1", "n1", "We2", "be2", "g2", "n2", "Wi", "Wh", "bh", "gl", "nl", "Wt1", "bt1", "Wt2", "bt2", "Wm", "bm", "logstd")
+LSTM_CRITIC_SEGMENTS = ("Wc1", "bc1", "Wc2", "bc2", "Wc3", "bc3")
+
 RLX_SAC_NMETRIC = 12
 RLX_COMM_MAX_WORLD = 16
 RLX_COMM_HANDLE_BYTES = 64
@@ -123,6 +147,15 @@ _SIGNATURES = {
     "rlx_pcg64_choice_i64": (C.c_int, [C.POINTER(Pcg64), C.c_int64, C.c_int64, C.c_void_p]),
     "rlx_replay_sample_nstep_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p,
                                               C.c_int64, C.c_int64] + [C.c_void_p] * 14),
+    "rlx_lstm_param_layout": (C.c_int, [C.POINTER(LstmDims), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rlx_lstm_minibatch_workspace_bytes": (C.c_size_t, [C.POINTER(LstmDims), C.c_int64, C.c_int64]),
+    "rlx_lstm_ppo_minibatch_fwdbwd_f32": (C.c_int, [C.POINTER(LstmMinibatchArgs), C.c_void_p]),
+    "rlx_lstm_step_f32": (C.c_int, [C.POINTER(LstmStepArgs), C.c_void_p]),
+    "rlx_lstm_mask_carry_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "rlx_lstm_critic_forward_f32": (C.c_int, [C.POINTER(LstmDims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rlx_mean_popstd_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rlx_optax_clip_adam_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3),
+    "rlx_gather_env_columns_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "rlx_ppo_param_count": (C.c_int64, [C.POINTER(PpoDims)]),
     "rlx_ppo_param_layout": (C.c_int, [C.POINTER(PpoDims), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "rlx_ppo_forward_workspace_bytes": (C.c_size_t, [C.POINTER(PpoDims), C.c_int64]),

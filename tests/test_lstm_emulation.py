@@ -246,3 +246,109 @@ def test_emulated_rollout_step_matches_oracle(emu):
     emu.rlx_mean_popstd_f32.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     assert emu.rlx_mean_popstd_f32(yv.ctypes.data, 1000, st2.ctypes.data, wsp.ctypes.data, None) == 0
     assert abs(st2[0] - float(y.mean())) < 1e-5 and abs(st2[1] - float(y.std(unbiased=False))) < 1e-5
+
+
+def test_plugin_class_runs_under_emulation(emu, tmp_path):
+    """Host logic of rl_x_b200/algorithms/ppo_lstm/b200/ppo_lstm.py (rollout bookkeeping, env-column minibatches, schedules, logging,
+    evaluation) exercised on CPU: the module source is loaded with its three device hooks rewritten (device -> cpu, stream -> NULL,
+    library -> the emulation build + an oracle GAE), which the shipped module never does — it raises without CUDA."""
+    import types
+    from oracle import ppo_oracle as O
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.ppo_lstm.b200.default_config import get_config
+    from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
+    real = nt.load()
+
+    class Lib:
+        def __getattr__(self, name):
+            if name == "rlx_gae_f32":
+                def gae(r, term, v, nv, last, T, N, gamma, lam, adv, ret, stream):
+                    t = lambda ptr: torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(T, N)))
+                    a, rr = O.gae(t(r), t(term), t(v), t(nv), gamma, lam)
+                    t(adv).copy_(a)
+                    t(ret).copy_(rr)
+                    return 0
+                return gae
+            f = getattr(emu, name)
+            f.argtypes, f.restype = getattr(real, name).argtypes, getattr(real, name).restype
+            return f
+
+    path = os.path.join(ROOT, "rl_x_b200", "algorithms", "ppo_lstm", "b200", "ppo_lstm.py")
+    src = open(path).read()
+    for old, new in [('torch.device("cuda", torch.cuda.current_device())', 'torch.device("cpu")'),
+                     ('if a.device != "gpu" or not torch.cuda.is_available():', 'if False:'),
+                     ("return C.c_void_p(torch.cuda.current_stream().cuda_stream)", "return None"), ("self.lib = nt.load()", "self.lib = LIB")]:
+        assert old in src
+        src = src.replace(old, new)
+    mod = types.ModuleType("ppo_lstm_emulated")
+    mod.LIB = Lib()
+    exec(compile(src, "ppo_lstm_emulated", "exec"), mod.__dict__)
+    N, T, obs, act = 8, 16, 12, 3
+
+    class Sp:
+        def __init__(self, shape, low=None, high=None):
+            self.shape, self.low, self.high = shape, low, high
+
+    results = {}
+    for iface in ("TORCH", "NUMPY"):
+        class P:
+            observation_space_type, action_space_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS
+            data_interface_type = getattr(DataInterfaceType, iface)
+
+        class Env:
+            general_properties = P
+            single_observation_space = Sp((obs,))
+            single_action_space = Sp((act,), np.full(act, -1.0, np.float32), np.full(act, 1.0, np.float32))
+
+            def __init__(self):
+                self.g = torch.Generator().manual_seed(3)
+
+            def _o(self, x):
+                return x if iface == "TORCH" else x.numpy()
+
+            def reset(self):
+                return self._o(torch.randn(N, obs, generator=self.g)), {}
+
+            def step(self, action):
+                assert tuple(action.shape) == (N, act)
+                self.last = torch.randn(N, obs, generator=self.g)
+                return (self._o(self.last), self._o(torch.randn(N, generator=self.g)), self._o(torch.rand(N, generator=self.g) < 0.1),
+                        self._o(torch.zeros(N, dtype=torch.bool)), {})
+
+            def get_logging_info_dict(self, info):
+                return {}
+
+            def get_final_observation_at_index(self, info, i):
+                return self.last[i].numpy()
+
+            def get_final_info_value_at_index(self, info, key, i):
+                return 1.0
+
+            def close(self):
+                pass
+
+        a = get_config("ppo_lstm.b200")
+        a.nr_steps, a.minibatch_size, a.nr_epochs, a.total_timesteps = T, 4 * T, 2, 3 * N * T
+        a.nr_hidden_units, a.obs_encoding_dim, a.lstm_hidden_dim, a.learning_rate, a.anneal_learning_rate = 32, 16, 8, 1e-3, True
+        a.evaluation_frequency, a.evaluation_episodes = N * T, 2
+        cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=5, nr_envs=N),
+                         runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+        env = Env()
+        model = mod.PPO_LSTM(cfg, env, env, str(tmp_path), None)
+        before = model.policy_params.clone()
+        logged = []
+        model.log = lambda name, value, step: logged.append((name, float(value)))
+        model.train()
+        assert all(np.isfinite(v) for nme, v in logged if not nme.startswith("time/"))
+        names = {nme for nme, _ in logged}
+        for nme in ["loss/policy_gradient_loss", "loss/critic_loss", "loss/entropy_loss", "policy_ratio/approx_kl", "policy_ratio/clip_fraction",
+                    "gradients/policy_grad_norm", "gradients/critic_grad_norm", "lr/learning_rate", "v_value/explained_variance", "policy/std_dev",
+                    "steps/nr_env_steps", "steps/nr_updates", "steps/nr_episodes", "eval/episode_return"]:
+            assert nme in names, nme
+        # linear schedule (ppo_lstm.py:78-81): the rate of the last optimiser step of each of the 3 iterations
+        np.testing.assert_allclose([v for nme, v in logged if nme == "lr/learning_rate"], [1e-3, 1e-3 * 2 / 3, 1e-3 / 3], rtol=1e-6)
+        assert [v for nme, v in logged if nme == "steps/nr_updates"] == [4.0, 8.0, 12.0]
+        assert float((model.policy_params - before).abs().max()) > 1e-4
+        results[iface] = [v for nme, v in logged if nme == "loss/critic_loss"]
+    assert results["TORCH"] == results["NUMPY"]  # the two data interfaces drive the same computation
