@@ -355,12 +355,13 @@ int rlx_replay_sample_gather_f32(const int64_t* idx_t, const int64_t* idx_e, int
  *                  (the last one if none); next_states / dones / truncations are taken there.  When the ring is full the truncation
  *                  flag of the newest row (pos - 1) reads as 1 unless that row is a done (:50-57).
  * discounts: [n_steps] device array holding gamma ** arange(n_steps) as the caller's framework computes it (bit-exactness of the
- * power function is the caller's).  n_steps <= 32. */
+ * power function is the caller's).  n_steps <= 32.  workspace: n int64 (the bootstrap row of every sample). */
 int rlx_replay_sample_nstep_f32(const int64_t* idx_t, const int64_t* idx_e, int64_t n, int64_t capacity, int64_t nr_envs, int64_t obs_dim,
                                 int64_t act_dim, int32_t n_steps, const float* discounts, int64_t size, int64_t pos, const float* states,
                                 const float* next_states, const float* actions, const float* rewards, const float* dones,
                                 const float* truncations, float* out_states, float* out_next_states, float* out_actions,
-                                float* out_rewards, float* out_dones, float* out_truncations, float* out_effective_n_steps, void* stream);
+                                float* out_rewards, float* out_dones, float* out_truncations, float* out_effective_n_steps, int64_t* workspace,
+                                void* stream);
 int rlx_polyak_f32(float* target, const float* online, int64_t n, float tau, void* stream);
 
 /* SAC networks (ref: sac/pytorch/policy.py:34-43, q_network.py:27-33), flat fp32 parameter layouts:

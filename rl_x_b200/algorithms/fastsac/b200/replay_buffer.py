@@ -61,12 +61,14 @@ class ReplayBuffer:
         obs, act = self.os_shape[0], self.as_shape[0]
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
         out = (e(n, obs), e(n, obs), e(n, act), e(n), e(n), e(n), e(n))
+        scratch = torch.empty(n, dtype=torch.int64, device=self.device)  # bootstrap row of every sample (stays alive until the call is queued)
         if not (idx_t.dtype == torch.int64 and idx_e.dtype == torch.int64 and idx_t.is_contiguous() and idx_e.is_contiguous()):
             raise TypeError("indices: contiguous int64 CUDA tensors expected")
         nt.check(self.lib.rlx_replay_sample_nstep_f32(
             idx_t.data_ptr(), idx_e.data_ptr(), n, self.capacity, self.nr_envs, obs, act, self.n_steps, self.discounts.data_ptr(), self.size, self.pos,
             self.states.data_ptr(), self.next_states.data_ptr(), self.actions.data_ptr(), self.rewards.data_ptr(), self.dones.data_ptr(),
-            self.truncations.data_ptr(), *[t.data_ptr() for t in out], C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+            self.truncations.data_ptr(), *[t.data_ptr() for t in out], scratch.data_ptr(),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)),
             "rlx_replay_sample_nstep_f32")
         return out
 

@@ -176,76 +176,6 @@ __global__ void __launch_bounds__(256) polyak_kernel(float* __restrict__ target,
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 
-// ----------------------------------------------------------------------------------- FastSAC n-step replay sample
-// One warp per sample.  Lane j < n_steps loads the scalars of step j; every lane then walks the (<= 32) steps through shuffles, so the
-// whole warp knows the final row and copies the observation / action rows with coalesced 128-byte accesses.
-struct NStepP {
-  const long long *idx_t, *idx_e;
-  long long n, capacity, nr_envs, size, pos;
-  int obs, act, n_steps;
-  const float *discounts, *states, *next_states, *actions, *rewards, *dones, *truncs;
-  float *o_states, *o_next, *o_actions, *o_rewards, *o_dones, *o_truncs, *o_eff;
-};
-__global__ void __launch_bounds__(256) replay_nstep_kernel(const NStepP p) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const bool full = p.size >= p.capacity;
-  const long long last_idx = ((p.pos - 1) % p.capacity + p.capacity) % p.capacity;
-  for (long long i = warp; i < p.n; i += nwarps) {
-    const long long t0 = p.idx_t[i], e = p.idx_e[i];
-    const long long src0 = t0 * p.nr_envs + e;
-    long long fin = src0;  // ring row the next state / done / truncation are read from
-    float reward, done, trunc, eff;
-    if (p.n_steps == 1) {
-      reward = p.rewards[src0];
-      done = p.dones[src0];
-      trunc = p.truncs[src0];
-      eff = 1.f;
-    } else {
-      float r = 0.f, d = 0.f, tr = 0.f, disc = 0.f;
-      if (lane < p.n_steps) {
-        const long long t = (t0 + lane) % p.capacity;
-        const long long src = t * p.nr_envs + e;
-        r = p.rewards[src];
-        d = p.dones[src];
-        tr = p.truncs[src];
-        if (full && t == last_idx) tr = (d > 0.f) ? tr : 1.f;  // newest row: the episode continues outside the ring
-        disc = p.discounts[lane];
-      }
-      float mask = 1.f, acc = 0.f;
-      eff = 0.f;
-      int first_done = p.n_steps - 1, first_trunc = p.n_steps - 1;
-      bool seen_done = false, seen_trunc = false;
-      for (int j = 0; j < p.n_steps; ++j) {
-        const float rj = __shfl_sync(0xffffffffu, r, j), dj = __shfl_sync(0xffffffffu, d, j), tj = __shfl_sync(0xffffffffu, tr, j);
-        const float cj = __shfl_sync(0xffffffffu, disc, j);
-        acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(rj, mask), cj));  // (r * mask) * discount, summed in step order
-        eff += mask;
-        if (!seen_done && dj > 0.f) { first_done = j; seen_done = true; }
-        if (!seen_trunc && tj > 0.f) { first_trunc = j; seen_trunc = true; }
-        mask = __fmul_rn(mask, __fsub_rn(1.f, dj));  // cumprod(1 - dones shifted by one step)
-      }
-      const int off = min(first_done, first_trunc);
-      reward = acc;
-      done = __shfl_sync(0xffffffffu, d, off);
-      trunc = __shfl_sync(0xffffffffu, tr, off);
-      fin = ((t0 + off) % p.capacity) * p.nr_envs + e;
-    }
-    for (int k = lane; k < p.obs; k += 32) {
-      p.o_states[i * p.obs + k] = p.states[src0 * p.obs + k];
-      p.o_next[i * p.obs + k] = p.next_states[fin * p.obs + k];
-    }
-    for (int k = lane; k < p.act; k += 32) p.o_actions[i * p.act + k] = p.actions[src0 * p.act + k];
-    if (lane == 0) {
-      p.o_rewards[i] = reward;
-      p.o_dones[i] = done;
-      p.o_truncs[i] = trunc;
-      p.o_eff[i] = eff;
-    }
-  }
-}
-
 }  // namespace rlx
 
 using namespace rlx;
@@ -330,29 +260,5 @@ extern "C" int rlx_polyak_f32(float* target, const float* online, int64_t n, flo
   RLX_CHECK_ARG(target && online, "null pointer");
   const unsigned grid = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 8);
   RLX_LAUNCH(polyak_kernel, grid, 256, 0, stream, target, online, (long long)n, tau);
-  return RLX_OK;
-}
-
-extern "C" int rlx_replay_sample_nstep_f32(const int64_t* idx_t, const int64_t* idx_e, int64_t n, int64_t capacity, int64_t nr_envs,
-                                           int64_t obs_dim, int64_t act_dim, int32_t n_steps, const float* discounts, int64_t size,
-                                           int64_t pos, const float* states, const float* next_states, const float* actions,
-                                           const float* rewards, const float* dones, const float* truncations, float* out_states,
-                                           float* out_next_states, float* out_actions, float* out_rewards, float* out_dones,
-                                           float* out_truncations, float* out_effective_n_steps, void* stream) {
-  RLX_CHECK_ARG(n >= 0 && capacity > 0 && nr_envs > 0 && obs_dim > 0 && act_dim > 0, "bad sizes");
-  RLX_CHECK_ARG(n_steps >= 1 && n_steps <= 32, "n_steps must be in [1, 32]");
-  RLX_CHECK_ARG(size >= 0 && size <= capacity && pos >= 0 && pos < capacity, "bad ring state");
-  if (n == 0) return RLX_OK;
-  RLX_CHECK_ARG(idx_t && idx_e && states && next_states && actions && rewards && dones && truncations, "null input");
-  RLX_CHECK_ARG(n_steps == 1 || discounts != nullptr, "discounts is required for n_steps > 1");
-  RLX_CHECK_ARG(out_states && out_next_states && out_actions && out_rewards && out_dones && out_truncations && out_effective_n_steps,
-                "null output");
-  NStepP p{(const long long*)idx_t, (const long long*)idx_e, n, capacity, nr_envs, size, pos, (int)obs_dim, (int)act_dim, n_steps,
-           discounts, states, next_states, actions, rewards, dones, truncations, out_states, out_next_states, out_actions, out_rewards,
-           out_dones, out_truncations, out_effective_n_steps};
-  const unsigned grid = (unsigned)std::min<long long>(ceil_div(n, 8), (long long)sm_count() * 16);
-  // algorithmic bytes: two index words, the n_steps scalar triples, two observation rows and one action row read, the same rows written
-  const double bytes = (double)n * (16.0 + 12.0 * n_steps + 4.0 * (4.0 * obs_dim + 2.0 * act_dim + 4.0));
-  RLX_LAUNCH_C(KC_GATHER, 0, bytes, replay_nstep_kernel, grid, 256, 0, stream, p);
   return RLX_OK;
 }

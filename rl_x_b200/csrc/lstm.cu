@@ -7,84 +7,8 @@
 //     memory, no warp primitives, no barriers", so a launch is emulated exactly by loops over (block, thread), and a GEMM by an
 //     interpreter of the GemmP contract.  That build checks indexing / strides / gradients against the oracle without a GPU.
 // The emulation build is test scaffolding; nothing in the product loads it.
-#include <stdint.h>
-#include <stddef.h>
-
-#include "../../include/rlx_b200.h"
-
-#ifdef RLX_EMU
-#include <math.h>
-#include <stdio.h>
-#include <stdarg.h>
-#include <algorithm>
-namespace rlx {
-struct EmuDim { unsigned x, y, z; };
-static EmuDim threadIdx, blockIdx, blockDim, gridDim;
-typedef void* cudaStream_t;
-static char g_emu_err[512];
-static void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap); va_end(ap); }
-inline long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
-inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-enum Epi { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_TANH = 2, EPI_DTANH = 3, EPI_BIAS_RELU = 4, EPI_DRELU = 5 };
-enum { KC_OTHER = 0, KC_GEMM_FWD = 0, KC_GEMM_DX = 0, KC_GEMM_DW = 0 };
-struct GemmP {
-  const float* A; const float* B; float* C; const float* bias; const float* aux; float* rowsum;
-  int M, N, K; int lda, ldb, ldc, ldaux;
-  long long sA, sB, sC, sBias, sAux, sRowsum;
-  int splits; int kchunk; long long sSplitC, sSplitRowsum;
-};
-// interpreter of the GemmP contract of gemm_simt.cuh (same fp32 fmaf accumulation in k order within a split)
-template <bool A_KMAJ, bool B_KMAJ, int EPI>
-int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
-  for (int z = 0; z < batch * p.splits; ++z) {
-    const int b = z / p.splits, sp = z % p.splits;
-    const int kbeg = sp * p.kchunk, kend = std::min(p.K, kbeg + p.kchunk);
-    const float* A = p.A + b * p.sA; const float* B = p.B + b * p.sB;
-    float* C = p.C + b * p.sC + sp * p.sSplitC;
-    for (int m = 0; m < p.M; ++m)
-      for (int n = 0; n < p.N; ++n) {
-        float acc = 0.f;
-        for (int k = kbeg; k < kend; ++k) {
-          const float a = A_KMAJ ? A[(long long)m * p.lda + k] : A[(long long)k * p.lda + m];
-          const float w = B_KMAJ ? B[(long long)n * p.ldb + k] : B[(long long)k * p.ldb + n];
-          acc = fmaf(a, w, acc);
-        }
-        if (EPI == EPI_BIAS) acc += p.bias[b * p.sBias + n];
-        if (EPI == EPI_BIAS_TANH) acc = tanhf(acc + p.bias[b * p.sBias + n]);
-        if (EPI == EPI_DTANH) { const float h = p.aux[b * p.sAux + (long long)m * p.ldaux + n]; acc = acc * (1.f - h * h); }
-        C[(long long)m * p.ldc + n] = acc;
-      }
-  }
-  return RLX_OK;
-}
-}  // namespace rlx
-#define __global__
-#define __device__
-#define __forceinline__ inline
-#define __restrict__
-#define __launch_bounds__(...)
-#define RLX_CHECK_ARG(cond, msg) do { if (!(cond)) { rlx::set_error("%s: invalid argument: %s", __func__, msg); return RLX_ERR_INVALID_ARG; } } while (0)
-#define LSTM_LAUNCH(kernel, nthreads_total, stream, ...)                                          \
-  do {                                                                                            \
-    const long long _n = (nthreads_total);                                                        \
-    rlx::blockDim = {256, 1, 1};                                                                  \
-    rlx::gridDim = {(unsigned)rlx::ceil_div(_n, 256), 1, 1};                                      \
-    for (unsigned _b = 0; _b < rlx::gridDim.x; ++_b)                                              \
-      for (unsigned _t = 0; _t < 256; ++_t) {                                                     \
-        rlx::blockIdx = {_b, 0, 0};                                                               \
-        rlx::threadIdx = {_t, 0, 0};                                                              \
-        kernel(__VA_ARGS__);                                                                      \
-      }                                                                                           \
-  } while (0)
-#else
-#include "common.cuh"
-#include "gemm_simt.cuh"
-#define LSTM_LAUNCH(kernel, nthreads_total, stream, ...)                                                                       \
-  do {                                                                                                                         \
-    const long long _n = (nthreads_total);                                                                                     \
-    if (_n > 0) RLX_LAUNCH_C(rlx::KC_OTHER, 0, 0, kernel, (unsigned)rlx::ceil_div(_n, 256), 256, 0, (cudaStream_t)(stream), __VA_ARGS__); \
-  } while (0)
-#endif
+#include "dual_build.cuh"
+#define LSTM_LAUNCH RLX_FLAT_LAUNCH
 
 namespace rlx {
 namespace lstm {

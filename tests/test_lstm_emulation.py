@@ -352,3 +352,38 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
         assert float((model.policy_params - before).abs().max()) > 1e-4
         results[iface] = [v for nme, v in logged if nme == "loss/critic_loss"]
     assert results["TORCH"] == results["NUMPY"]  # the two data interfaces drive the same computation
+
+
+def test_emulated_nstep_replay_matches_reference_golden(tmp_path):
+    """rl_x_b200/csrc/replay_nstep.cu (FastSAC n-step sampling) compiled for the host and run on the golden rings of the executed reference:
+    gathers, flags and effective lengths bit-exact; the n-step reward equals the oracle's step-ordered float32 sum bit for bit and the
+    reference's torch.sum to one rounding."""
+    from conftest import GOLDEN_DIR
+    from oracle import fastsac_replay_oracle as F
+    out = tmp_path / "libnstep_emu.so"
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
+                    os.path.join(ROOT, "rl_x_b200", "csrc", "replay_nstep.cu")], check=True)
+    lib = C.CDLL(str(out))
+    lib.rlx_replay_sample_nstep_f32.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int64] * 5 + [C.c_int32, C.c_void_p, C.c_int64, C.c_int64] +
+                                                [C.c_void_p] * 15)
+    z = np.load(os.path.join(GOLDEN_DIR, "fastsac_replay.npz"))
+    names = ["states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps"]
+    for tag in [str(c) for c in z["cases"]]:
+        cap, nr_envs, obs, act, n_steps, size, pos, ns = (int(x) for x in z[f"{tag}/meta"])
+        ring = {k: np.ascontiguousarray(z[f"{tag}/ring/{k}"]) for k in names[:6]}
+        idx_t, idx_e = np.ascontiguousarray(z[f"{tag}/idx_t"]), np.ascontiguousarray(z[f"{tag}/idx_e"])
+        disc = np.ascontiguousarray(z[f"{tag}/discounts"])
+        n = len(idx_t)
+        outs = [np.zeros((n, obs), np.float32), np.zeros((n, obs), np.float32), np.zeros((n, act), np.float32)] + [np.zeros(n, np.float32) for _ in range(4)]
+        scratch = np.zeros(n, np.int64)
+        rc = lib.rlx_replay_sample_nstep_f32(idx_t.ctypes.data, idx_e.ctypes.data, n, cap, nr_envs, obs, act, n_steps, disc.ctypes.data, size, pos,
+                                             *[ring[k].ctypes.data for k in names[:6]], *[o.ctypes.data for o in outs], scratch.ctypes.data, None)
+        assert rc == 0
+        want = F.sample(ring, idx_t, idx_e, n_steps, disc, size, pos)
+        for name, got, w in zip(names, outs, want):
+            assert np.array_equal(got, w), f"{tag}/{name} vs oracle"
+            ref = z[f"{tag}/out/{name}"]
+            if name == "rewards":
+                np.testing.assert_allclose(got, ref, rtol=3e-7, atol=3e-7, err_msg=f"{tag}/{name}")
+            else:
+                assert np.array_equal(got, ref), f"{tag}/{name} vs reference"
