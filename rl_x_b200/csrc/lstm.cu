@@ -7,18 +7,17 @@
 //     memory, no warp primitives, no barriers", so a launch is emulated exactly by loops over (block, thread), and a GEMM by an
 //     interpreter of the GemmP contract.  That build checks indexing / strides / gradients against the oracle without a GPU.
 // The emulation build is test scaffolding; nothing in the product loads it.
-#include "dual_build.cuh"
+#include "flat_ops.cuh"
 #define LSTM_LAUNCH RLX_FLAT_LAUNCH
 
 namespace rlx {
 namespace lstm {
+using namespace rlx::flat;
 
 constexpr float kLnEps = 1e-6f;             // flax.linen.LayerNorm default
 constexpr float kHalfLog2Pi = 0.9189385332046727f;
-constexpr int kColChunk = 256;              // rows per partial of the column-sum reductions
 constexpr int kWgradRows = 1024;            // rows per split of the weight-gradient GEMMs
 
-__device__ __forceinline__ long long gtid() { return (long long)blockIdx.x * blockDim.x + threadIdx.x; }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------- layouts
@@ -137,29 +136,6 @@ __global__ void ln_param_partial_kernel(const float* __restrict__ dOut, int ldd,
   }
   part_g[id] = sg;
   part_b[id] = sb;
-}
-
-// partial column sums of X [R, W] (bias gradients): thread = (row chunk, column)
-__global__ void colsum_partial_kernel(const float* __restrict__ X, int ldx, long long R, int W, float* __restrict__ part) {
-  const long long id = gtid();
-  const long long nchunk = (R + kColChunk - 1) / kColChunk;
-  if (id >= nchunk * W) return;
-  const long long ch = id / W;
-  const int j = (int)(id % W);
-  const long long r1 = ch * kColChunk + kColChunk < R ? ch * kColChunk + kColChunk : R;
-  float s = 0.f;
-  for (long long r = ch * kColChunk; r < r1; ++r) s += X[r * ldx + j];
-  part[id] = s;
-}
-
-// out[i] = scale * sum_s part[s * len + i] (+ add)      thread = element
-__global__ void reduce_parts_kernel(const float* __restrict__ part, long long nparts, long long len, float scale, float add,
-                                    float* __restrict__ out) {
-  const long long i = gtid();
-  if (i >= len) return;
-  float s = 0.f;
-  for (long long k = 0; k < nparts; ++k) s += part[k * len + i];
-  out[i] = s * scale + add;
 }
 
 // carry reset before step t: Hm = Hprev * keep, Cm = Cprev * keep, keep = 1 - done[t-1] (keep = 1 at t = 0).  thread = (env, unit)
@@ -316,23 +292,6 @@ __global__ void gather_env_kernel(const float* __restrict__ src, const long long
   out[id] = src[(t * N + idx[j]) * width + k];
 }
 
-// sum of squares per 1024-element chunk; thread = chunk
-__global__ void sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
-  const long long c = gtid();
-  const long long nchunk = (n + 1023) / 1024;
-  if (c >= nchunk) return;
-  const long long i1 = c * 1024 + 1024 < n ? c * 1024 + 1024 : n;
-  float s = 0.f;
-  for (long long i = c * 1024; i < i1; ++i) s += g[i] * g[i];
-  part[c] = s;
-}
-__global__ void sumsq_final_kernel(const float* __restrict__ part, long long nchunk, float* __restrict__ norm_out, long long* __restrict__ step) {
-  if (gtid() != 0) return;
-  float s = 0.f;
-  for (long long c = 0; c < nchunk; ++c) s += part[c];
-  norm_out[0] = sqrtf(s);
-  step[0] += 1;
-}
 // optax: g = ||g|| < max_norm ? g : g / ||g|| * max_norm; Adam with bias correction.  thread = element
 __global__ void optax_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mu, float* __restrict__ nu, long long n,
                                   const float* __restrict__ lr, const long long* __restrict__ step, const float* __restrict__ norm, float max_norm,
@@ -384,13 +343,6 @@ static int dense_bwd_weight(const float* X, int ldx, const float* dY, int ldy, i
   int rc = launch_sgemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW);
   if (rc) return rc;
   LSTM_LAUNCH(reduce_parts_kernel, (long long)in * out, st, part, (long long)splits, (long long)in * out, 1.f, 0.f, dW);
-  return RLX_OK;
-}
-// bias gradient: db[o] = sum_r dY[r, o]
-static int colsum(const float* X, int ldx, long long R, int W, float* col_ws, float scale, float add, float* out, cudaStream_t st) {
-  const long long nchunk = ceil_div(R, kColChunk);
-  LSTM_LAUNCH(colsum_partial_kernel, nchunk * W, st, X, ldx, R, W, col_ws);
-  LSTM_LAUNCH(reduce_parts_kernel, (long long)W, st, col_ws, nchunk, (long long)W, scale, add, out);
   return RLX_OK;
 }
 // LayerNorm scale / bias gradients
