@@ -336,6 +336,62 @@ int rlx_optax_clip_adam_f32(float* params, const float* grads, float* mu, float*
 /* out[t, j, :] = src[t, env_idx[j], :]  for t < T, j < n  (the reference's x[:, minibatch_env_indices]); width = trailing dim (1 for [T, N]) */
 int rlx_gather_env_columns_f32(const float* src, const int64_t* env_idx, int64_t T, int64_t N, int64_t n, int64_t width, float* out, void* stream);
 
+/* -------------------------------------------------------------------------------------------- FastSAC update -- */
+/* SURVEY.md §8 f4 (second half): rl_x/algorithms/fastsac/pytorch, fp32 path, clipped_double_q_learning = False.  STATUS: written
+ * without GPU access; numerics checked by running these sources in a host emulation build against oracle/fastsac_oracle.py, which
+ * is pinned to the executed reference (tests/test_fastsac_emulation.py); first hardware run pending.
+ * Networks (fixed widths like the reference): policy Linear-LayerNorm-SiLU x3 (512, 256, 128) + mean / log_std heads (policy.py:36-48);
+ * Q network Linear-LayerNorm-SiLU x3 (768, 384, 192) + nr_atoms logits on [state | action] (q_network.py:24-35).
+ * Flat parameter layouts, torch [out, in] weights in state_dict order:
+ *   policy: (W, b, ln_w, ln_b) x 3, mean.W [act,128], mean.b, log_std.W [act,128], log_std.b            -> 16 segments
+ *   Q:      (W, b, ln_w, ln_b) x 3, head.W [atoms,192], head.b                                          -> 14 segments; q buffers hold q1 | q2 */
+#define RLX_FASTSAC_POLICY_NSEG 16
+#define RLX_FASTSAC_Q_NSEG 14
+typedef struct rlx_fastsac_dims { int32_t obs_dim, act_dim, nr_atoms; } rlx_fastsac_dims;
+int rlx_fastsac_param_layout(const rlx_fastsac_dims* d, int64_t* policy_offsets /*[17]*/, int64_t* q_offsets /*[15], one network*/);
+size_t rlx_fastsac_workspace_bytes(const rlx_fastsac_dims* d, int64_t n);
+
+typedef struct rlx_fastsac_hparams {
+  float gamma, tau, v_min, v_max, target_entropy, log_std_min, log_std_max;
+  float weight_decay, adam_beta1, adam_beta2, adam_eps, max_grad_norm;  /* max_grad_norm < 0: no clipping (fastsac.py:126-133) */
+} rlx_fastsac_hparams;
+
+typedef struct rlx_fastsac_update_args {
+  rlx_fastsac_dims dims;
+  int64_t n;                        /* batch rows */
+  const float* states;              /* [n, obs] normalised */
+  const float* next_states;         /* [n, obs] normalised (critic update only) */
+  const float* actions;             /* [n, act] (critic update only) */
+  const float* rewards;             /* [n] n-step rewards */
+  const float* dones;               /* [n] */
+  const float* truncations;         /* [n] */
+  const float* effective_n_steps;   /* [n] */
+  const float* noise;               /* [n, act] standard normal draws of Normal.rsample() */
+  const float* action_scale;        /* [act] policy.py:29-33 */
+  float* policy_params;  float* policy_grads;  float* policy_m;  float* policy_v;
+  float* q_params;       float* q_grads;       float* q_m;       float* q_v;        /* q1 | q2 */
+  float* q_target_params;                                                           /* q1_target | q2_target */
+  float* log_alpha;      float* alpha_state;   /* alpha_state [3]: grad, m, v */
+  const float* lr;                  /* [1] device */
+  int64_t* steps;                   /* [3] device: q, entropy, policy optimiser step counters */
+  rlx_fastsac_hparams hp;
+  float* metrics;                   /* critic update: q_loss, entropy_loss, q_min, q_max, entropy, critic_grad_norm, entropy_grad_norm (sq);
+                                       policy update: policy_loss, alpha, policy_grad_norm */
+  void* workspace;
+  size_t workspace_bytes;
+} rlx_fastsac_update_args;
+/* ref: critic_and_entropy_loss_fn + both optimiser steps (fastsac.py:141-238) + the polyak update that follows it (:316-320) */
+int rlx_fastsac_critic_update_f32(const rlx_fastsac_update_args* a, void* stream);
+/* ref: policy_loss_fn + optimiser step (fastsac.py:106-138) */
+int rlx_fastsac_policy_update_f32(const rlx_fastsac_update_args* a, void* stream);
+/* ref: policy.get_action (policy.py:78-92); noise NULL: deterministic.  workspace as above */
+int rlx_fastsac_act_f32(const rlx_fastsac_dims* d, const float* policy_params, const float* obs, const float* noise, const float* action_scale,
+                        float log_std_min, float log_std_max, int64_t n, float* action, void* workspace, size_t workspace_bytes, void* stream);
+/* ref: ObservationNormalizer (observation_normalizer.py:20-47): out = (x - mean) / (std + eps); update folds the batch statistics of x
+ * into mean / var / std / count (Chan's formula) first when `update` != 0.  count: device int64[1]; workspace: >= 4 * obs * (n / 256 + 2) floats */
+int rlx_fastsac_normalize_f32(const float* x, int64_t n, int64_t obs_dim, float* mean, float* var, float* std, int64_t* count, int32_t update,
+                              float eps, float* out, float* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- SAC path -- */
 /* ref: ReplayBuffer.sample gathers  (sac/pytorch/replay_buffer.py:32-40):  rows states[idx1, idx2] etc. from the device ring.
  * ring arrays are [capacity_per_env, nr_envs, dim]; idx_t/idx_e [n] int64. */

@@ -1,0 +1,153 @@
+"""FastSAC update (rl_x_b200/csrc/fastsac.cu) checked WITHOUT a GPU: the source is compiled with g++ -DRLX_EMU (see csrc/dual_build.cuh) and
+driven through the batches and normal draws of the executed reference run (tests/golden/fastsac_update.npz), side by side with
+oracle/fastsac_oracle.py, which is itself pinned to that run.  After every critic / policy update the emulated library's parameters,
+optimiser moments, target networks and metrics must match the oracle's; at the end they must match the reference's logged metrics."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fastsac_oracle as FS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "nr_atoms")]
+
+
+class HP(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("gamma", "tau", "v_min", "v_max", "target_entropy", "log_std_min", "log_std_max", "weight_decay",
+                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm")]
+
+
+class Args(C.Structure):
+    _fields_ = ([("dims", Dims), ("n", C.c_int64)] +
+                [(k, C.c_void_p) for k in ("states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps", "noise",
+                                           "action_scale", "policy_params", "policy_grads", "policy_m", "policy_v", "q_params", "q_grads", "q_m", "q_v",
+                                           "q_target_params", "log_alpha", "alpha_state", "lr", "steps")] +
+                [("hp", HP), ("metrics", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)])
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = tmp_path_factory.mktemp("fastsac_emu") / "libfastsac_emu.so"
+    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
+                    os.path.join(ROOT, "rl_x_b200", "csrc", "fastsac.cu")], check=True)
+    lib = C.CDLL(str(out))
+    lib.rlx_fastsac_workspace_bytes.restype = C.c_size_t
+    lib.rlx_fastsac_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64]
+    return lib
+
+
+def flat(net):
+    return np.concatenate([t.detach().numpy().reshape(-1) for t in FS._leaves(net)]).astype(np.float32)
+
+
+def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fastsac_update.npz"))
+    N, obs, act, batch, n_steps, nopt, seed, ncu, npu, atoms, stride = (int(x) for x in z["meta"])
+    gamma, tau, lr, lsmin, lsmax, tgt_ent, vmin, vmax, wd, b1, b2, alpha0, low, high, scale = (float(x) for x in z["meta_f"])
+    torch.set_num_threads(1)
+    pol, q1, q2 = FS.reference_init(obs, act, atoms, seed)
+    center = (low + high) / 2
+    action_scale = torch.full((act,), max(abs(low - center), abs(high - center)) / scale)
+    L = FS.Learner(pol, q1, q2, action_scale, lr, wd, (b1, b2), gamma, tau, vmin, vmax, atoms, tgt_ent, alpha0, lsmin, lsmax)
+    nrm = FS.Normalizer(obs)
+
+    d = Dims(obs, act, atoms)
+    poff, qoff = (C.c_int64 * 17)(), (C.c_int64 * 15)()
+    assert emu.rlx_fastsac_param_layout(C.byref(d), poff, qoff) == 0
+    P, Q = flat(L.pol), np.concatenate([flat(L.q1), flat(L.q2)])
+    assert poff[16] == P.size and 2 * qoff[14] == Q.size
+    QT = Q.copy()
+    gP, mP, vP = np.zeros_like(P), np.zeros_like(P), np.zeros_like(P)
+    gQ, mQ, vQ = np.zeros_like(Q), np.zeros_like(Q), np.zeros_like(Q)
+    la, astate = np.array([np.log(alpha0)], np.float32), np.zeros(3, np.float32)
+    lr_a, steps = np.array([lr], np.float32), np.zeros(3, np.int64)
+    sc = action_scale.numpy().astype(np.float32)
+    nbytes = emu.rlx_fastsac_workspace_bytes(C.byref(d), batch)
+    ws = np.zeros(nbytes // 4 + 64, np.float32)
+    hp = HP(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, -1.0)
+    nmean, nvar, nstd, ncount = np.zeros(obs, np.float32), np.ones(obs, np.float32), np.ones(obs, np.float32), np.zeros(1, np.int64)
+    emu.rlx_fastsac_normalize_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def call(fn, s, ns, a_, r, dn, tr, eff, noise, metrics):
+        arrs = [np.ascontiguousarray(t.numpy() if torch.is_tensor(t) else t, dtype=np.float32) if t is not None else None
+                for t in (s, ns, a_, r, dn, tr, eff, noise)]
+        a = Args()
+        a.dims, a.n = d, batch
+        for name, arr in zip(("states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps", "noise"), arrs):
+            setattr(a, name, arr.ctypes.data if arr is not None else None)
+        a.action_scale = sc.ctypes.data
+        a.policy_params, a.policy_grads, a.policy_m, a.policy_v = P.ctypes.data, gP.ctypes.data, mP.ctypes.data, vP.ctypes.data
+        a.q_params, a.q_grads, a.q_m, a.q_v, a.q_target_params = Q.ctypes.data, gQ.ctypes.data, mQ.ctypes.data, vQ.ctypes.data, QT.ctypes.data
+        a.log_alpha, a.alpha_state, a.lr, a.steps = la.ctypes.data, astate.ctypes.data, lr_a.ctypes.data, steps.ctypes.data
+        a.hp, a.metrics, a.workspace, a.workspace_bytes = hp, metrics.ctypes.data, ws.ctypes.data, nbytes
+        rc = fn(C.byref(a), None)
+        assert rc == 0, rc
+
+    def close(ours, ref, what, rtol=3e-4, atol=3e-6):
+        np.testing.assert_allclose(ours, ref, rtol=rtol, atol=atol, err_msg=what)
+
+    def close_params(ours, ref, what):
+        """parameters after AdamW steps: Adam divides by sqrt(v), which turns fp32 rounding of a near-zero gradient entry into a difference
+        of a fraction of lr in that entry — bound single entries by 0.1 * lr and the tensor as a whole by its relative norm."""
+        np.testing.assert_allclose(ours, ref, rtol=3e-4, atol=0.1 * lr, err_msg=what)
+        rel = float(np.linalg.norm(ours - ref) / np.linalg.norm(ref))
+        assert rel <= 2e-5, (what, rel)
+
+    logged = {}
+    for u in range(nopt):
+        b = {k: z[f"step{u}/{k}"] for k in ["states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps"]}
+        total = b["states"].shape[0]
+        wsn = np.zeros(4 * obs * (total // 256 + 2), np.float32)
+        s_emu, ns_emu = np.zeros_like(b["states"]), np.zeros_like(b["next_states"])
+        for src, dst in ((b["states"], s_emu), (b["next_states"], ns_emu)):
+            src = np.ascontiguousarray(src)
+            assert emu.rlx_fastsac_normalize_f32(src.ctypes.data, total, obs, nmean.ctypes.data, nvar.ctypes.data, nstd.ctypes.data, ncount.ctypes.data, 1,
+                                                 1e-8, dst.ctypes.data, wsn.ctypes.data, None) == 0
+        s = nrm.normalize(torch.from_numpy(b["states"]), update=True)
+        ns = nrm.normalize(torch.from_numpy(b["next_states"]), update=True)
+        close(s_emu, s.numpy(), "normalised states", 1e-5, 1e-5)
+        close(ns_emu, ns.numpy(), "normalised next states", 1e-5, 1e-5)
+        close(nmean, nrm.mean.numpy().reshape(-1), "running mean", 1e-5, 1e-6)
+        close(nvar, nrm.var.numpy().reshape(-1), "running var", 1e-5, 1e-6)
+        assert int(ncount[0]) == nrm.count
+        view = lambda t: torch.as_tensor(t).view(npu, ncu, batch, *t.shape[1:])
+        s, ns = view(s), view(ns)
+        a_, r, dn, tr, eff = (view(b[k]) for k in ["actions", "rewards", "dones", "truncations", "effective_n_steps"])
+        normals = torch.from_numpy(z[f"step{u}/normals"])
+        k, step_metrics = 0, []
+        for i in range(npu):
+            for j in range(ncu):
+                m = L.critic_and_entropy_step(s[i, j], ns[i, j], a_[i, j], r[i, j], dn[i, j], tr[i, j], eff[i, j], normals[k])
+                mc = np.zeros(8, np.float32)
+                call(emu.rlx_fastsac_critic_update_f32, s[i, j], ns[i, j], a_[i, j], r[i, j], dn[i, j], tr[i, j], eff[i, j], normals[k], mc)
+                k += 1
+                for idx, name in enumerate(["loss/q_loss", "loss/entropy_loss", "q/q_min", "q/q_max", "entropy/entropy", "gradients/critic_grad_norm",
+                                            "gradients/entropy_grad_norm"]):
+                    assert abs(float(mc[idx]) - m[name]) <= 3e-4 * max(1.0, abs(m[name])), (u, i, j, name, mc[idx], m[name])
+                close_params(Q, np.concatenate([flat(L.q1), flat(L.q2)]), f"q params after critic update {u}.{i}.{j}")
+                close_params(QT, np.concatenate([flat(L.q1t), flat(L.q2t)]), "target params")
+                close(la, L.log_alpha.detach().numpy(), "log_alpha", 1e-5, 1e-7)
+            mo = L.policy_step(s[i, -1], normals[k])
+            mp = np.zeros(8, np.float32)
+            call(emu.rlx_fastsac_policy_update_f32, s[i, -1], None, None, None, None, None, None, normals[k], mp)
+            k += 1
+            for idx, name in enumerate(["loss/policy_loss", "entropy/alpha", "gradients/policy_grad_norm"]):
+                assert abs(float(mp[idx]) - mo[name]) <= 3e-4 * max(1.0, abs(mo[name])), (u, i, name, mp[idx], mo[name])
+            close_params(P, flat(L.pol), f"policy params after policy update {u}.{i}")
+            m = dict(m)
+            m.update(mo)
+            step_metrics.append({**m, **{"emu/" + nm: float(v) for nm, v in zip(["loss/q_loss", "loss/policy_loss"], [mc[0], mp[0]])}})
+        for name in ("emu/loss/q_loss", "emu/loss/policy_loss"):
+            logged.setdefault(name, []).append(float(np.mean([sm[name] for sm in step_metrics])))
+    # the emulated library's own losses against what the executed reference logged
+    np.testing.assert_allclose(logged["emu/loss/q_loss"], z["metric/loss/q_loss"], rtol=3e-4)
+    np.testing.assert_allclose(logged["emu/loss/policy_loss"], z["metric/loss/policy_loss"], rtol=3e-4, atol=3e-6)
+    assert list(steps) == [nopt * npu * ncu, nopt * npu * ncu, nopt * npu]
