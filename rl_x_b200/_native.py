@@ -121,6 +121,23 @@ RLX_LSTM_POLICY_NSEG, RLX_LSTM_CRITIC_NSEG = 20, 6
 LSTM_POLICY_SEGMENTS = ("We1", "be1", "g1", "n1", "We2", "be2", "g2", "n2", "Wi", "Wh", "bh", "gl", "nl", "Wt1", "bt1", "Wt2", "bt2", "Wm", "bm", "logstd")
 LSTM_CRITIC_SEGMENTS = ("Wc1", "bc1", "Wc2", "bc2", "Wc3", "bc3")
 
+
+class FastSacDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "nr_atoms")]
+
+
+class FastSacHparams(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("gamma", "tau", "v_min", "v_max", "target_entropy", "log_std_min", "log_std_max", "weight_decay",
+                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm")]
+
+
+class FastSacUpdateArgs(C.Structure):
+    _fields_ = ([("dims", FastSacDims), ("n", C.c_int64)] +
+                [(k, C.c_void_p) for k in ("states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps", "noise",
+                                           "action_scale", "policy_params", "policy_grads", "policy_m", "policy_v", "q_params", "q_grads", "q_m", "q_v",
+                                           "q_target_params", "log_alpha", "alpha_state", "lr", "steps")] +
+                [("hp", FastSacHparams), ("metrics", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)])
+
 RLX_SAC_NMETRIC = 12
 RLX_COMM_MAX_WORLD = 16
 RLX_COMM_HANDLE_BYTES = 64
@@ -156,6 +173,14 @@ _SIGNATURES = {
     "rlx_mean_popstd_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rlx_optax_clip_adam_f32": (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3),
     "rlx_gather_env_columns_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "rlx_fastsac_param_layout": (C.c_int, [C.POINTER(FastSacDims), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rlx_fastsac_workspace_bytes": (C.c_size_t, [C.POINTER(FastSacDims), C.c_int64]),
+    "rlx_fastsac_critic_update_f32": (C.c_int, [C.POINTER(FastSacUpdateArgs), C.c_void_p]),
+    "rlx_fastsac_policy_update_f32": (C.c_int, [C.POINTER(FastSacUpdateArgs), C.c_void_p]),
+    "rlx_fastsac_act_f32": (C.c_int, [C.POINTER(FastSacDims), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rlx_fastsac_normalize_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "rlx_ppo_param_count": (C.c_int64, [C.POINTER(PpoDims)]),
     "rlx_ppo_param_layout": (C.c_int, [C.POINTER(PpoDims), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "rlx_ppo_forward_workspace_bytes": (C.c_size_t, [C.POINTER(PpoDims), C.c_int64]),

@@ -151,3 +151,112 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
     np.testing.assert_allclose(logged["emu/loss/q_loss"], z["metric/loss/q_loss"], rtol=3e-4)
     np.testing.assert_allclose(logged["emu/loss/policy_loss"], z["metric/loss/policy_loss"], rtol=3e-4, atol=3e-6)
     assert list(steps) == [nopt * npu * ncu, nopt * npu * ncu, nopt * npu]
+
+
+def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path):
+    """The whole plugin (rl_x_b200/algorithms/fastsac/b200: FastSAC class + n-step ReplayBuffer) on CPU: the two modules are loaded with
+    their device hooks rewritten (device -> cpu, stream -> NULL, library -> host emulation builds of fastsac.cu and replay_nstep.cu; the
+    shipped modules raise without CUDA).  With the golden run's seed and environment the torch generator is consumed in the reference's
+    order (module init, acting noise, torch.randint sampling, update noise), so the run must reproduce the metrics the executed
+    reference logged at every step."""
+    import types
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.fastsac.b200.default_config import get_config
+    from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
+    emus = []
+    for name in ("fastsac", "replay_nstep"):
+        out = tmp_path / f"lib{name}_emu.so"
+        subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
+                        os.path.join(ROOT, "rl_x_b200", "csrc", f"{name}.cu")], check=True)
+        emus.append(C.CDLL(str(out)))
+    real = nt.load()
+
+    class Lib:
+        def __getattr__(self, name):
+            for e in emus:
+                try:
+                    f = getattr(e, name)
+                except AttributeError:
+                    continue
+                f.argtypes, f.restype = getattr(real, name).argtypes, getattr(real, name).restype
+                return f
+            raise AttributeError(name)
+
+    lib = Lib()
+
+    def load_patched(relpath, modname, drop_import=None, extra=None):
+        src = open(os.path.join(ROOT, *relpath)).read()
+        if drop_import:
+            assert drop_import in src
+            src = src.replace(drop_import, "")
+        for old, new in [('torch.device("cuda", torch.cuda.current_device())', 'torch.device("cpu")'),
+                         ('if a.device != "gpu" or not torch.cuda.is_available():', 'if False:'), ('if not torch.cuda.is_available():', 'if False:'),
+                         ("return C.c_void_p(torch.cuda.current_stream().cuda_stream)", "return None"),
+                         ("C.c_void_p(torch.cuda.current_stream().cuda_stream)", "None"), ("self.lib = nt.load()", "self.lib = LIB")]:
+            src = src.replace(old, new)
+        mod = types.ModuleType(modname)
+        mod.LIB = lib
+        mod.__dict__.update(extra or {})
+        exec(compile(src, modname, "exec"), mod.__dict__)
+        return mod
+
+    rb = load_patched(("rl_x_b200", "algorithms", "fastsac", "b200", "replay_buffer.py"), "fastsac_replay_emulated")
+    fs = load_patched(("rl_x_b200", "algorithms", "fastsac", "b200", "fastsac.py"), "fastsac_emulated",
+                      drop_import="from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer", extra={"ReplayBuffer": rb.ReplayBuffer})
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fastsac_update.npz"))
+    N, obs, act, batch, n_steps, nopt, seed, ncu, npu, atoms, stride = (int(x) for x in z["meta"])
+
+    class Sp:
+        def __init__(self, shape, **kw):
+            self.shape = shape
+            self.__dict__.update(kw)
+
+    class Props:
+        observation_space_type, action_space_type, data_interface_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS, DataInterfaceType.TORCH
+
+    class Env:  # the environment of tests/golden/make_golden_fastsac.py
+        general_properties, horizon = Props, 5
+
+        def __init__(self):
+            self.g = torch.Generator().manual_seed(seed + 100)
+            self.single_observation_space = Sp((obs,))
+            low, high = np.full(act, -1.5, np.float32), np.full(act, 0.5, np.float32)
+            self.single_action_space = Sp((act,), low=low, high=high, center=(low + high) / 2, scale=np.full(act, 0.8, np.float32))
+            self.t = 0
+
+        def reset(self):
+            return torch.randn(N, obs, generator=self.g) * 2 + 1, {}
+
+        def step(self, action):
+            self.t += 1
+            return (torch.randn(N, obs, generator=self.g) * 2 + 1, torch.randn(N, generator=self.g), torch.rand(N, generator=self.g) < 0.2,
+                    torch.full((N,), self.t % 4 == 0), {})
+
+        def get_logging_info_dict(self, info):
+            return {}
+
+        def close(self):
+            pass
+
+    a = get_config("fastsac.b200")
+    a.batch_size, a.buffer_size_per_env, a.learning_starts, a.total_timesteps, a.n_steps = batch, 8, 3, N * 9, n_steps
+    a.nr_critic_updates_per_policy_update, a.nr_policy_updates_per_step, a.logging_frequency, a.save_frequency = ncu, npu, N, -1
+    a.learning_rate, a.target_entropy = 1e-3, -float(act)
+    cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=seed, nr_envs=N),
+                     runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    torch.set_num_threads(1)
+    env = Env()
+    model = fs.FastSAC(cfg, env, env, str(tmp_path), None)
+    logged = []
+    model.log = lambda name, value, step: logged.append((name, float(value)))
+    model.train()
+    checked = 0
+    for key in z.files:
+        if not key.startswith("metric/"):
+            continue
+        name = key[len("metric/"):]
+        ours = [v for nme, v in logged if nme == name]
+        np.testing.assert_allclose(ours, z[key], rtol=5e-4, atol=5e-6, err_msg=name)
+        checked += 1
+    assert checked >= 15
