@@ -122,6 +122,9 @@ LSTM_POLICY_SEGMENTS = ("We1", "be1", "g1", "n1", "We2", "be2", "g2", "n2", "Wi"
 LSTM_CRITIC_SEGMENTS = ("Wc1", "bc1", "Wc2", "bc2", "Wc3", "bc3")
 
 
+RLX_FASTSAC_POLICY_NSEG, RLX_FASTSAC_Q_NSEG = 16, 14
+
+
 class FastSacDims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "nr_atoms")]
 

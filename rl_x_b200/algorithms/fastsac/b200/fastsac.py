@@ -107,7 +107,7 @@ class FastSAC:
         self.lib = nt.load()
         obs, act = int(self.train_env.single_observation_space.shape[0]), int(np.prod(self.train_env.single_action_space.shape))
         self.dims = nt.FastSacDims(obs, act, int(a.nr_atoms))
-        poff, qoff = (C.c_int64 * (nt_nseg_p() + 1))(), (C.c_int64 * (nt_nseg_q() + 1))()
+        poff, qoff = (C.c_int64 * (nt.RLX_FASTSAC_POLICY_NSEG + 1))(), (C.c_int64 * (nt.RLX_FASTSAC_Q_NSEG + 1))()
         nt.check(self.lib.rlx_fastsac_param_layout(C.byref(self.dims), poff, qoff), "rlx_fastsac_param_layout")
         self.policy_offsets, self.q_offsets = list(poff), list(qoff)
 
@@ -393,10 +393,3 @@ class FastSAC:
         from rl_x_b200.algorithms.fastsac.b200.general_properties import GeneralProperties
         return GeneralProperties
 
-
-def nt_nseg_p():
-    return 16
-
-
-def nt_nseg_q():
-    return 14
