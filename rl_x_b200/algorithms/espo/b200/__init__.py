@@ -1,8 +1,4 @@
-from rl_x_b200.algorithms.algorithm_manager import extract_algorithm_name_from_file, register_algorithm
-from rl_x_b200.algorithms.espo.b200.espo import ESPO
-from rl_x_b200.algorithms.espo.b200.default_config import get_config
-from rl_x_b200.algorithms.espo.b200.general_properties import GeneralProperties
+"""Plugin package `espo.b200`: importing it registers the algorithm (the reference's registration contract, rl_x/algorithms/algorithm_manager.py)."""
+from rl_x_b200.algorithms.algorithm_manager import register_algorithm_package
 
-
-ESPO_B200 = extract_algorithm_name_from_file(__file__)
-register_algorithm(ESPO_B200, get_config, ESPO, GeneralProperties)
+NAME = register_algorithm_package(__file__, "espo", "ESPO")

@@ -1,8 +1,4 @@
-from rl_x_b200.algorithms.algorithm_manager import extract_algorithm_name_from_file, register_algorithm
-from rl_x_b200.algorithms.ppo.b200.ppo import PPO
-from rl_x_b200.algorithms.ppo.b200.default_config import get_config
-from rl_x_b200.algorithms.ppo.b200.general_properties import GeneralProperties
+"""Plugin package `ppo.b200`: importing it registers the algorithm (the reference's registration contract, rl_x/algorithms/algorithm_manager.py)."""
+from rl_x_b200.algorithms.algorithm_manager import register_algorithm_package
 
-
-PPO_B200 = extract_algorithm_name_from_file(__file__)
-register_algorithm(PPO_B200, get_config, PPO, GeneralProperties)
+NAME = register_algorithm_package(__file__, "ppo", "PPO")

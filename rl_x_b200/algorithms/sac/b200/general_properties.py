@@ -1,11 +1,5 @@
-from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
-from rl_x_b200.algorithms.deep_learning_framework_type import DeepLearningFrameworkType
+from rl_x_b200.plugin_properties import algorithm_properties
 
-
-class GeneralProperties:
-    """ref: rl_x/algorithms/sac/pytorch/general_properties.py (FLAT_VALUES x CONTINUOUS); both data interfaces are accepted here."""
-    observation_space_types = [ObservationSpaceType.FLAT_VALUES]
-    action_space_types = [ActionSpaceType.CONTINUOUS]
-    data_interface_types = [DataInterfaceType.NUMPY, DataInterfaceType.TORCH]
-
-    deep_learning_framework_type = DeepLearningFrameworkType.TORCH
+GeneralProperties = algorithm_properties(
+    'ref: rl_x/algorithms/sac/pytorch/general_properties.py.',
+    observations=("FLAT_VALUES",), actions=("CONTINUOUS",), interfaces=('NUMPY', 'TORCH'))

@@ -23,6 +23,14 @@ class ConfigDict(dict):
         return ConfigDict({k: (v.copy_and_resolve_references() if isinstance(v, ConfigDict) else v) for k, v in self.items()})
 
 
+def config_from_defaults(name, defaults):
+    """A plugin's default config tree from its (key, value) table; `name` is the registered plugin name."""
+    config = ConfigDict(name=name)
+    for key, value in defaults:
+        config[key] = value
+    return config
+
+
 def _coerce(text, default):
     if isinstance(default, bool):
         if text.lower() in ("true", "1", "yes"):

@@ -1,0 +1,27 @@
+"""One registry implementation behind both plugin managers.  The contract is the reference's (rl_x/algorithms/algorithm_manager.py:8-25,
+rl_x/environments/environment_manager.py:8-25): a plugin package's `__init__.py` derives its dotted name from its own path and registers
+three objects under it; the runner looks them up by that name."""
+import os
+from collections import namedtuple
+
+
+class PluginRegistry:
+    def __init__(self, kind, fields):
+        self.kind = kind                      # directory name that anchors the dotted plugin name ("algorithms" / "environments")
+        self.Entry = namedtuple(f"{kind.capitalize()}Entry", ("name",) + tuple(fields))
+        self.entries = {}
+
+    def name_from_file(self, init_file):
+        """'.../<kind>/ppo/b200/__init__.py' -> 'ppo.b200'"""
+        parts = os.path.normpath(init_file).split(os.sep)
+        start = len(parts) - 1 - parts[::-1].index(self.kind)
+        return ".".join(parts[start + 1:-1])
+
+    def register(self, name, *objects):
+        self.entries[name] = self.Entry(name, *objects)
+
+    def lookup(self, name):
+        try:
+            return self.entries[name]
+        except KeyError:
+            raise KeyError(f"no {self.kind[:-1]} plugin registered under {name!r} (registered: {sorted(self.entries)})") from None
