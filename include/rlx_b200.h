@@ -337,7 +337,7 @@ int rlx_optax_clip_adam_f32(float* params, const float* grads, float* mu, float*
 int rlx_gather_env_columns_f32(const float* src, const int64_t* env_idx, int64_t T, int64_t N, int64_t n, int64_t width, float* out, void* stream);
 
 /* -------------------------------------------------------------------------------------------- FastSAC update -- */
-/* SURVEY.md §8 f4 (second half): rl_x/algorithms/fastsac/pytorch, fp32 path, clipped_double_q_learning = False.  STATUS: written
+/* SURVEY.md §8 f4 (second half): rl_x/algorithms/fastsac/pytorch, fp32 path.  STATUS: written
  * without GPU access; numerics checked by running these sources in a host emulation build against oracle/fastsac_oracle.py, which
  * is pinned to the executed reference (tests/test_fastsac_emulation.py); first hardware run pending.
  * Networks (fixed widths like the reference): policy Linear-LayerNorm-SiLU x3 (512, 256, 128) + mean / log_std heads (policy.py:36-48);
@@ -354,6 +354,8 @@ size_t rlx_fastsac_workspace_bytes(const rlx_fastsac_dims* d, int64_t n);
 typedef struct rlx_fastsac_hparams {
   float gamma, tau, v_min, v_max, target_entropy, log_std_min, log_std_max;
   float weight_decay, adam_beta1, adam_beta2, adam_eps, max_grad_norm;  /* max_grad_norm < 0: no clipping (fastsac.py:126-133) */
+  float clipped_double_q;           /* != 0: both critics learn the target distribution of the smaller next value, the actor maximises
+                                       min(q1, q2) (fastsac.py:117-120,179-182) */
 } rlx_fastsac_hparams;
 
 typedef struct rlx_fastsac_update_args {

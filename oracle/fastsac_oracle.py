@@ -128,7 +128,8 @@ class Normalizer:
 
 class Learner:
     def __init__(self, pol, q1, q2, action_scale, lr, weight_decay, betas, gamma, tau, v_min, v_max, nr_atoms, target_entropy, alpha_init,
-                 log_std_min, log_std_max):
+                 log_std_min, log_std_max, clipped_double_q=False, max_grad_norm=-1.0):
+        self.clipped, self.max_grad_norm = clipped_double_q, max_grad_norm
         self.pol, self.q1, self.q2 = _clone(pol, True), _clone(q1, True), _clone(q2, True)
         self.q1t, self.q2t = _clone(q1, False), _clone(q2, False)
         self.log_alpha = torch.full((1,), math.log(alpha_init), requires_grad=True)
@@ -140,7 +141,7 @@ class Learner:
         self.support = torch.linspace(v_min, v_max, nr_atoms)
 
     def critic_and_entropy_step(self, s, ns, a, r, dones, truncs, eff, eps_next):
-        """fastsac.py:141-238 (clipped_double_q_learning = False), then the polyak update of :316-320."""
+        """fastsac.py:141-238, then the polyak update of :316-320."""
         with torch.no_grad():
             na, nlp = action_and_log_prob(self.pol, ns, eps_next, self.action_scale, self.lsmin, self.lsmax)
             delta_z = (self.v_max - self.v_min) / (self.nr_atoms - 1)
@@ -161,12 +162,18 @@ class Learner:
                 proj.scatter_add_(1, lo, d * wl)
                 proj.scatter_add_(1, up, d * wu)
             q1_next_value = (proj1 * self.support).sum(1)
+            if self.clipped:  # fastsac.py:179-182: both critics learn the distribution of the smaller next value
+                q2_next_value = (proj2 * self.support).sum(1)
+                proj1 = proj2 = torch.where(q1_next_value.unsqueeze(1) < q2_next_value.unsqueeze(1), proj1, proj2)
         l1 = -(proj1 * F.log_softmax(q_forward(self.q1, s, a), dim=1)).sum(1).mean()
         l2 = -(proj2 * F.log_softmax(q_forward(self.q2, s, a), dim=1)).sum(1).mean()
         q_loss = l1 + l2
         self.qopt.zero_grad()
         q_loss.backward()
-        cg = math.sqrt(sum(float(p.grad.norm(2) ** 2) for p in _leaves(self.q1) + _leaves(self.q2)))
+        if self.max_grad_norm != -1.0:   # fastsac.py:203-210
+            cg = float(torch.nn.utils.clip_grad_norm_(_leaves(self.q1) + _leaves(self.q2), self.max_grad_norm))
+        else:
+            cg = math.sqrt(sum(float(p.grad.norm(2) ** 2) for p in _leaves(self.q1) + _leaves(self.q2)))
         self.qopt.step()
         entropy = -nlp
         ent_loss = (self.log_alpha.exp() * (entropy - self.target_entropy)).mean()
@@ -185,13 +192,18 @@ class Learner:
     def policy_step(self, s, eps):
         """fastsac.py:106-138."""
         a, lp = action_and_log_prob(self.pol, s, eps, self.action_scale, self.lsmin, self.lsmax)
-        qv = 0.5 * ((F.softmax(q_forward(self.q1, s, a), dim=1) * self.support).sum(1) + (F.softmax(q_forward(self.q2, s, a), dim=1) * self.support).sum(1))
+        v1 = (F.softmax(q_forward(self.q1, s, a), dim=1) * self.support).sum(1)
+        v2 = (F.softmax(q_forward(self.q2, s, a), dim=1) * self.support).sum(1)
+        qv = torch.minimum(v1, v2) if self.clipped else (v1 + v2) / 2.0   # fastsac.py:117-120
         alpha = self.log_alpha.exp().detach()
         loss = (alpha * lp - qv).mean()
         self.popt.zero_grad()
         for p in _leaves(self.q1) + _leaves(self.q2):
             p.grad = None
         loss.backward()
-        pg = math.sqrt(sum(float(p.grad.norm(2) ** 2) for p in _leaves(self.pol)))
+        if self.max_grad_norm != -1.0:   # fastsac.py:126-133
+            pg = float(torch.nn.utils.clip_grad_norm_(_leaves(self.pol), self.max_grad_norm))
+        else:
+            pg = math.sqrt(sum(float(p.grad.norm(2) ** 2) for p in _leaves(self.pol)))
         self.popt.step()
         return {"loss/policy_loss": loss.item(), "entropy/alpha": alpha.item(), "gradients/policy_grad_norm": pg}

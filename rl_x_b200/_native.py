@@ -131,7 +131,7 @@ class FastSacDims(C.Structure):
 
 class FastSacHparams(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("gamma", "tau", "v_min", "v_max", "target_entropy", "log_std_min", "log_std_max", "weight_decay",
-                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm")]
+                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm", "clipped_double_q")]
 
 
 class FastSacUpdateArgs(C.Structure):

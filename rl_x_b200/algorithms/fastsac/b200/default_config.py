@@ -1,6 +1,6 @@
 """Keys and default values of rl_x/algorithms/fastsac/pytorch/default_config.py (the plugin surface: `--algorithm.<key>=...` flags and checkpoints
 address them by name), except `bf16_mixed_precision_training` (False: this build is the fp32 path) and `compile_mode` (accepted, ignored).
-`device` must stay "gpu": there is no CPU fallback.  `clipped_double_q_learning=True` is not built."""
+`device` must stay "gpu": there is no CPU fallback."""
 from rl_x_b200.config_dict import config_from_defaults
 
 _DEFAULTS = (

@@ -8,8 +8,7 @@ Host side: Python/PyTorch for device memory and the TORCH-interface environment;
                  policy_loss_fn (fastsac.py:106-138)                                             rlx_fastsac_policy_update_f32
 
 Parameters are initialised exactly like the reference (the same torch modules built in the same order under torch.manual_seed(seed),
-fastsac.py:77-84) and live in the library's flat layout; action noise is torch.randn on the device.  Not built: bf16 autocast,
-clipped_double_q_learning.  STATUS: first hardware run pending (numerics validated in host emulation, tests/test_fastsac_emulation.py).
+fastsac.py:77-84) and live in the library's flat layout; action noise is torch.randn on the device.  Not built: bf16 autocast.  STATUS: first hardware run pending (numerics validated in host emulation, tests/test_fastsac_emulation.py).
 """
 import ctypes as C
 import logging
@@ -97,8 +96,6 @@ class FastSAC:
             raise ValueError("The save frequency must be a multiple of the number of environments.")
         if a.get("bf16_mixed_precision_training", False):
             raise ValueError("rl_x_b200 FastSAC implements the reference's fp32 path; set algorithm.bf16_mixed_precision_training=False.")
-        if a.clipped_double_q_learning:
-            raise NotImplementedError("rl_x_b200 FastSAC implements clipped_double_q_learning=False (the reference default).")
         if a.device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("rl_x_b200 FastSAC needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -129,7 +126,8 @@ class FastSAC:
         self.lr_dev = torch.full((1,), float(self.learning_rate), dtype=torch.float32, device=dev)
         self.lr_step = 0
         self.hp = nt.FastSacHparams(float(a.gamma), float(a.tau), float(a.v_min), float(a.v_max), float(target_entropy), float(a.log_std_min),
-                                    float(a.log_std_max), float(a.weight_decay), float(a.adam_beta1), float(a.adam_beta2), 1e-8, float(a.max_grad_norm))
+                                    float(a.log_std_max), float(a.weight_decay), float(a.adam_beta1), float(a.adam_beta2), 1e-8, float(a.max_grad_norm),
+                                    1.0 if a.clipped_double_q_learning else 0.0)
         sp = self.train_env.single_action_space
         low, high, center, scale = (torch.as_tensor(np.asarray(getattr(sp, k), dtype=np.float32)) for k in ("low", "high", "center", "scale"))
         self.action_scale = (torch.maximum(torch.abs(low - center), torch.abs(high - center)) / scale).to(dev).contiguous()  # policy.py:29-33

@@ -219,11 +219,32 @@ __global__ void expect_rows_kernel(const float* __restrict__ logits, long long n
       dlogits[r * K + k] = coef * p * ((v_min + dz * (float)k) - v);
     }
 }
+// gradient of -mean(q) wrt one critic's logits, q = (v1 + v2) / 2 or min(v1, v2) (ties split evenly like torch.minimum).  thread = row
+__global__ void value_grad_rows_kernel(const float* __restrict__ logits, const float* __restrict__ v_self, const float* __restrict__ v_other,
+                                       long long n, int K, float v_min, float v_max, int clipped, float inv_n, float* __restrict__ dlogits) {
+  const long long r = gtid();
+  if (r >= n) return;
+  const float vs = v_self[r], vo = v_other[r];
+  const float coef = clipped ? (vs < vo ? 1.f : (vs == vo ? 0.5f : 0.f)) : 0.5f;
+  const float* l = logits + r * K;
+  float mx = l[0];
+  for (int k = 1; k < K; ++k) mx = fmaxf(mx, l[k]);
+  float den = 0.f;
+  for (int k = 0; k < K; ++k) den += expf(l[k] - mx);
+  const float dz = (v_max - v_min) / (float)(K - 1);
+  for (int k = 0; k < K; ++k) dlogits[r * K + k] = -coef * inv_n * (expf(l[k] - mx) / den) * ((v_min + dz * (float)k) - vs);
+}
+__global__ void combine_values_kernel(const float* __restrict__ v1, const float* __restrict__ v2, long long n, int clipped, float* __restrict__ out) {
+  const long long r = gtid();
+  if (r >= n) return;
+  out[r] = clipped ? fminf(v1[r], v2[r]) : (v1[r] + v2[r]) / 2.f;
+}
 // C51 target of one row (fastsac.py:146-186): both target distributions are projected with the same bins.  thread = row
 __global__ void c51_project_kernel(const float* __restrict__ tl1, const float* __restrict__ tl2, const float* __restrict__ rewards,
                                    const float* __restrict__ dones, const float* __restrict__ truncs, const float* __restrict__ eff,
                                    const float* __restrict__ next_logp, const float* __restrict__ log_alpha, long long n, int K, float gamma,
-                                   float v_min, float v_max, float* __restrict__ proj1, float* __restrict__ proj2, float* __restrict__ q1_next_value) {
+                                   float v_min, float v_max, int clipped, float* __restrict__ proj1, float* __restrict__ proj2,
+                                   float* __restrict__ q1_next_value) {
   const long long r = gtid();
   if (r >= n) return;
   const float dz = (v_max - v_min) / (float)(K - 1);
@@ -247,9 +268,16 @@ __global__ void c51_project_kernel(const float* __restrict__ tl1, const float* _
     proj1[r * K + lo] += p1 * wl; proj1[r * K + up] += p1 * wu;
     proj2[r * K + lo] += p2 * wl; proj2[r * K + up] += p2 * wu;
   }
-  float v = 0.f;
-  for (int k = 0; k < K; ++k) v += proj1[r * K + k] * (v_min + dz * (float)k);
+  float v = 0.f, v2 = 0.f;
+  for (int k = 0; k < K; ++k) { v += proj1[r * K + k] * (v_min + dz * (float)k); v2 += proj2[r * K + k] * (v_min + dz * (float)k); }
   q1_next_value[r] = v;
+  if (clipped) {  // torch.where(q1_next < q2_next, proj1, proj2) for BOTH critics (fastsac.py:179-182)
+    for (int k = 0; k < K; ++k) {
+      const float sel = (v < v2) ? proj1[r * K + k] : proj2[r * K + k];
+      proj1[r * K + k] = sel;
+      proj2[r * K + k] = sel;
+    }
+  }
 }
 // cross-entropy of one row against its projected target: loss = -sum_k proj_k log_softmax(logits)_k; dlogits = (softmax * sum(proj) - proj) / n
 __global__ void ce_rows_kernel(const float* __restrict__ logits, const float* __restrict__ proj, long long n, int K, float inv_n,
@@ -298,7 +326,7 @@ __global__ void critic_finish_kernel(const float* __restrict__ sums, const float
 __global__ void policy_finish_kernel(const float* __restrict__ sums, float n, const float* __restrict__ log_alpha, float* __restrict__ metrics) {
   if (gtid() != 0) return;
   const float al = expf(log_alpha[0]);
-  metrics[0] = al * sums[0] / n - 0.5f * (sums[1] + sums[2]) / n;  // mean(alpha * logp - (q1 + q2) / 2)
+  metrics[0] = al * sums[0] / n - sums[1] / n;  // mean(alpha * logp - q), q = (q1 + q2) / 2 or min(q1, q2)
   metrics[1] = al;
 }
 // torch.optim.AdamW (single tensor): p *= 1 - lr wd; m, v updates; p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps).  Optional clip_grad_norm_.
@@ -513,7 +541,8 @@ extern "C" int rlx_fastsac_critic_update_f32(const rlx_fastsac_update_args* a, v
   FS_TRY(q_fwd(d, l, a->q_target_params, XA, n, q0, ws + w.Logits[0], st));
   FS_TRY(q_fwd(d, l, a->q_target_params + nq, XA, n, q1, ws + w.Logits[1], st));
   RLX_FLAT_LAUNCH(c51_project_kernel, n, st, ws + w.Logits[0], ws + w.Logits[1], a->rewards, a->dones, a->truncations, a->effective_n_steps, Logp,
-                  a->log_alpha, n, K, hp.gamma, hp.v_min, hp.v_max, ws + w.Proj[0], ws + w.Proj[1], RowA /*q1_next_value*/);
+                  a->log_alpha, n, K, hp.gamma, hp.v_min, hp.v_max, hp.clipped_double_q != 0.f ? 1 : 0, ws + w.Proj[0], ws + w.Proj[1],
+                  RowA /*q1_next_value*/);
   const long long nchunk = ceil_div(n, kColChunk);
   RLX_FLAT_LAUNCH(minmax_partial_kernel, nchunk, st, RowA, n, RowB);
   // ---- current critics on (s, a): cross-entropy and its gradient (fastsac.py:188-196)
@@ -558,20 +587,23 @@ extern "C" int rlx_fastsac_policy_update_f32(const rlx_fastsac_update_args* a, v
   // a ~ pi(s); q = (E[q1] + E[q2]) / 2 on (s, a); L = mean(alpha logp - q)   (fastsac.py:108-124)
   FS_TRY(policy_fwd(d, l, w, ws, a->policy_params, a->states, a->noise, a->action_scale, hp.log_std_min, hp.log_std_max, n, Act, Logp, st));
   RLX_FLAT_LAUNCH(concat_kernel, n * (O + A), st, a->states, Act, n, O, A, XA);
+  const int clipped = hp.clipped_double_q != 0.f ? 1 : 0;
+  for (int q = 0; q < 2; ++q) {
+    FS_TRY(q_fwd(d, l, a->q_params + q * nq, XA, n, acts_q(ws, w, q), ws + w.Logits[q], st));
+    RLX_FLAT_LAUNCH(expect_rows_kernel, n, st, ws + w.Logits[q], n, K, hp.v_min, hp.v_max, RowA + (1 + q) * n, 0.f, (float*)nullptr);
+  }
   for (int q = 0; q < 2; ++q) {
     const Acts aq = acts_q(ws, w, q);
-    FS_TRY(q_fwd(d, l, a->q_params + q * nq, XA, n, aq, ws + w.Logits[q], st));
-    // dL/dlogits = -(0.5 / n) * p * (z - E[z]); back through the critic to its input (the critic's own gradients land in scratch and are dropped)
-    RLX_FLAT_LAUNCH(expect_rows_kernel, n, st, ws + w.Logits[q], n, K, hp.v_min, hp.v_max, RowA + (1 + q) * n, -0.5f * inv_n, ws + w.dLogits);
+    // back through the critic to its input only (its own parameter gradients are not needed: the next critic update zeroes them)
+    RLX_FLAT_LAUNCH(value_grad_rows_kernel, n, st, ws + w.Logits[q], RowA + (1 + q) * n, RowA + (2 - q) * n, n, K, hp.v_min, hp.v_max, clipped, inv_n,
+                    ws + w.dLogits);
     FS_TRY(lin_bwd_input(ws + w.dLogits, K, a->q_params + q * nq + l.q[12], 192, K, ws + w.dY, 192, n, st));
-    float* dout = ws + w.dY;
-    for (int k = 2; k >= 0; --k) {  // input-gradient-only pass through the torso
+    for (int k = 2; k >= 0; --k) {
       const int W = kQW[k], in = k == 0 ? O + A : kQW[k - 1];
-      RLX_FLAT_LAUNCH(ln_silu_bwd_kernel, n, st, dout, aq.Z[k], n, W, a->q_params + q * nq + l.q[4 * k + 2], a->q_params + q * nq + l.q[4 * k + 3],
+      RLX_FLAT_LAUNCH(ln_silu_bwd_kernel, n, st, ws + w.dY, aq.Z[k], n, W, a->q_params + q * nq + l.q[4 * k + 2], a->q_params + q * nq + l.q[4 * k + 3],
                       aq.S[k], ws + w.dZ);
       float* dst = k == 0 ? (q == 0 ? dXA : ws + w.dXA2) : ws + w.dY;
       FS_TRY(lin_bwd_input(ws + w.dZ, W, a->q_params + q * nq + l.q[4 * k], in, W, dst, in, n, st));
-      dout = ws + w.dY;
     }
   }
   // dAct = action columns of both critics' input gradients; back through the squashed-Gaussian head and the policy torso
@@ -590,8 +622,8 @@ extern "C" int rlx_fastsac_policy_update_f32(const rlx_fastsac_update_args* a, v
   FS_TRY(torso_bwd(P, G, l.p, kPW, a->states, O, n, pa, ws + w.dY, ws + w.dZ, ws + w.dY, nullptr, ws + w.Part, Col, st));
   // metrics: policy_loss, alpha; then AdamW (its pre-clip gradient norm is metrics[2])
   FS_TRY(colsum(Logp, 1, n, 1, Col, 1.f, 0.f, Small + 0, st));
-  FS_TRY(colsum(RowA + n, 1, n, 1, Col, 1.f, 0.f, Small + 1, st));
-  FS_TRY(colsum(RowA + 2 * n, 1, n, 1, Col, 1.f, 0.f, Small + 2, st));
+  RLX_FLAT_LAUNCH(combine_values_kernel, n, st, RowA + n, RowA + 2 * n, n, clipped, RowA + 3 * n);
+  FS_TRY(colsum(RowA + 3 * n, 1, n, 1, Col, 1.f, 0.f, Small + 1, st));
   RLX_FLAT_LAUNCH(policy_finish_kernel, 1, st, Small, (float)n, a->log_alpha, a->metrics);
   FS_TRY(adamw(a->policy_params, a->policy_grads, a->policy_m, a->policy_v, l.p[RLX_FASTSAC_POLICY_NSEG], a->lr, (long long*)a->steps + 2, hp,
                a->metrics + 2, ws + w.Part, st));

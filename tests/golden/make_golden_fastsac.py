@@ -9,7 +9,7 @@ Normal.rsample() ([batch, act]: per critic update one for the next-state action,
 the observation-normaliser statistics before the step, the logged metrics (logging_frequency = nr_envs: every logged value is the mean
 over that step's policy updates) and, at the end, all small parameter tensors plus every 61st element of the large matrices.
 Initial parameters are NOT stored (1.4 M floats): the test rebuilds them by constructing the same torch modules in the same order
-under torch.manual_seed(seed), as FastSAC.__init__ does (fastsac.py:77-84).  Output: tests/golden/fastsac_update.npz
+under torch.manual_seed(seed), as FastSAC.__init__ does (fastsac.py:77-84).  Output: tests/golden/fastsac_update.npz, fastsac_update_clipped.npz
 """
 import os
 import sys
@@ -72,7 +72,7 @@ class SyntheticTorchEnv:
         pass
 
 
-def run(N=4, obs=7, act=3, batch=16, n_steps=3, steps=9, seed=4, ncu=2, npu=2):
+def run(tag="update", N=4, obs=7, act=3, batch=16, n_steps=3, steps=9, seed=4, ncu=2, npu=2, clipped=False, max_grad_norm=-1.0):
     torch.set_num_threads(1)
     batches, normals, norm_states = [], [], []
 
@@ -98,6 +98,7 @@ def run(N=4, obs=7, act=3, batch=16, n_steps=3, steps=9, seed=4, ncu=2, npu=2):
     a.batch_size, a.buffer_size_per_env, a.learning_starts, a.total_timesteps, a.n_steps = batch, 8, 3, N * steps, n_steps
     a.nr_critic_updates_per_policy_update, a.nr_policy_updates_per_step, a.logging_frequency, a.save_frequency = ncu, npu, N, -1
     a.learning_rate, a.target_entropy = 1e-3, -float(act)
+    a.clipped_double_q_learning, a.max_grad_norm = clipped, max_grad_norm
     env = SyntheticTorchEnv(N, obs, act, seed + 100)
     model = ref.FastSAC(cfg, env, env, "/tmp/golden_fastsac", None)
     nrm = model.observation_normalizer
@@ -140,8 +141,8 @@ def run(N=4, obs=7, act=3, batch=16, n_steps=3, steps=9, seed=4, ncu=2, npu=2):
     out["final/norm_mean"], out["final/norm_var"], out["final/norm_count"] = nrm.running_mean.numpy().copy(), nrm.running_var.numpy().copy(), np.array(int(nrm.count))
     out["meta"] = np.array([N, obs, act, batch, n_steps, nopt, seed, ncu, npu, a.nr_atoms, STRIDE], dtype=np.int64)
     out["meta_f"] = np.array([a.gamma, a.tau, a.learning_rate, a.log_std_min, a.log_std_max, a.target_entropy, a.v_min, a.v_max, a.weight_decay,
-                              a.adam_beta1, a.adam_beta2, a.alpha_init, -1.5, 0.5, 0.8], dtype=np.float64)
-    path = os.path.join(HERE, "fastsac_update.npz")
+                              a.adam_beta1, a.adam_beta2, a.alpha_init, -1.5, 0.5, 0.8, float(clipped), max_grad_norm], dtype=np.float64)
+    path = os.path.join(HERE, f"fastsac_{tag}.npz")
     np.savez_compressed(path, **out)
     print("->", path, os.path.getsize(path) // 1024, "KiB; optimising steps:", nopt, "metrics:", sorted({m[0] for m in metrics if not m[0].startswith("time/")}))
     print({n: out[f"metric/{n}"][:3] for n in ["loss/q_loss", "loss/policy_loss", "entropy/alpha"]})
@@ -149,3 +150,5 @@ def run(N=4, obs=7, act=3, batch=16, n_steps=3, steps=9, seed=4, ncu=2, npu=2):
 
 if __name__ == "__main__":
     run()
+    # the two non-default options: clipped double-Q targets / min-Q actor loss, and clip_grad_norm_ on both optimisers
+    run("update_clipped", n_steps=1, seed=6, clipped=True, max_grad_norm=0.5)

@@ -21,7 +21,7 @@ class Dims(C.Structure):
 
 class HP(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("gamma", "tau", "v_min", "v_max", "target_entropy", "log_std_min", "log_std_max", "weight_decay",
-                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm")]
+                                         "adam_beta1", "adam_beta2", "adam_eps", "max_grad_norm", "clipped_double_q")]
 
 
 class Args(C.Structure):
@@ -47,15 +47,17 @@ def flat(net):
     return np.concatenate([t.detach().numpy().reshape(-1) for t in FS._leaves(net)]).astype(np.float32)
 
 
-def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
-    z = np.load(os.path.join(ROOT, "tests", "golden", "fastsac_update.npz"))
+@pytest.mark.parametrize("tag", ["update", "update_clipped"])
+def test_emulated_fastsac_updates_track_the_pinned_oracle(emu, tag):
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"fastsac_{tag}.npz"))
     N, obs, act, batch, n_steps, nopt, seed, ncu, npu, atoms, stride = (int(x) for x in z["meta"])
-    gamma, tau, lr, lsmin, lsmax, tgt_ent, vmin, vmax, wd, b1, b2, alpha0, low, high, scale = (float(x) for x in z["meta_f"])
+    gamma, tau, lr, lsmin, lsmax, tgt_ent, vmin, vmax, wd, b1, b2, alpha0, low, high, scale, clipped, max_gn = (float(x) for x in z["meta_f"])
     torch.set_num_threads(1)
     pol, q1, q2 = FS.reference_init(obs, act, atoms, seed)
     center = (low + high) / 2
     action_scale = torch.full((act,), max(abs(low - center), abs(high - center)) / scale)
-    L = FS.Learner(pol, q1, q2, action_scale, lr, wd, (b1, b2), gamma, tau, vmin, vmax, atoms, tgt_ent, alpha0, lsmin, lsmax)
+    L = FS.Learner(pol, q1, q2, action_scale, lr, wd, (b1, b2), gamma, tau, vmin, vmax, atoms, tgt_ent, alpha0, lsmin, lsmax,
+                   clipped_double_q=bool(clipped), max_grad_norm=max_gn)
     nrm = FS.Normalizer(obs)
 
     d = Dims(obs, act, atoms)
@@ -71,7 +73,7 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
     sc = action_scale.numpy().astype(np.float32)
     nbytes = emu.rlx_fastsac_workspace_bytes(C.byref(d), batch)
     ws = np.zeros(nbytes // 4 + 64, np.float32)
-    hp = HP(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, -1.0)
+    hp = HP(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, max_gn, clipped)
     nmean, nvar, nstd, ncount = np.zeros(obs, np.float32), np.ones(obs, np.float32), np.ones(obs, np.float32), np.zeros(1, np.int64)
     emu.rlx_fastsac_normalize_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
@@ -96,8 +98,9 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
 
     def close_params(ours, ref, what):
         """parameters after AdamW steps: Adam divides by sqrt(v), which turns fp32 rounding of a near-zero gradient entry into a difference
-        of a fraction of lr in that entry — bound single entries by 0.1 * lr and the tensor as a whole by its relative norm."""
-        np.testing.assert_allclose(ours, ref, rtol=3e-4, atol=0.1 * lr, err_msg=what)
+        of a fraction of lr in that entry (more entries are in that regime when clip_grad_norm_ scales the gradient down) — bound single
+        entries by one full step (lr) and the tensor as a whole by its relative norm."""
+        np.testing.assert_allclose(ours, ref, rtol=3e-4, atol=lr, err_msg=what)
         rel = float(np.linalg.norm(ours - ref) / np.linalg.norm(ref))
         assert rel <= 2e-5, (what, rel)
 
@@ -149,11 +152,12 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu):
             logged.setdefault(name, []).append(float(np.mean([sm[name] for sm in step_metrics])))
     # the emulated library's own losses against what the executed reference logged
     np.testing.assert_allclose(logged["emu/loss/q_loss"], z["metric/loss/q_loss"], rtol=3e-4)
-    np.testing.assert_allclose(logged["emu/loss/policy_loss"], z["metric/loss/policy_loss"], rtol=3e-4, atol=3e-6)
+    np.testing.assert_allclose(logged["emu/loss/policy_loss"], z["metric/loss/policy_loss"], rtol=3e-4, atol=2e-5)  # a difference of O(1) terms
     assert list(steps) == [nopt * npu * ncu, nopt * npu * ncu, nopt * npu]
 
 
-def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path):
+@pytest.mark.parametrize("tag", ["update", "update_clipped"])
+def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path, tag):
     """The whole plugin (rl_x_b200/algorithms/fastsac/b200: FastSAC class + n-step ReplayBuffer) on CPU: the two modules are loaded with
     their device hooks rewritten (device -> cpu, stream -> NULL, library -> host emulation builds of fastsac.cu and replay_nstep.cu; the
     shipped modules raise without CUDA).  With the golden run's seed and environment the torch generator is consumed in the reference's
@@ -204,8 +208,9 @@ def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path):
     rb = load_patched(("rl_x_b200", "algorithms", "fastsac", "b200", "replay_buffer.py"), "fastsac_replay_emulated")
     fs = load_patched(("rl_x_b200", "algorithms", "fastsac", "b200", "fastsac.py"), "fastsac_emulated",
                       drop_import="from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer", extra={"ReplayBuffer": rb.ReplayBuffer})
-    z = np.load(os.path.join(ROOT, "tests", "golden", "fastsac_update.npz"))
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"fastsac_{tag}.npz"))
     N, obs, act, batch, n_steps, nopt, seed, ncu, npu, atoms, stride = (int(x) for x in z["meta"])
+    clipped, max_gn = bool(z["meta_f"][15]), float(z["meta_f"][16])
 
     class Sp:
         def __init__(self, shape, **kw):
@@ -242,7 +247,7 @@ def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path):
     a = get_config("fastsac.b200")
     a.batch_size, a.buffer_size_per_env, a.learning_starts, a.total_timesteps, a.n_steps = batch, 8, 3, N * 9, n_steps
     a.nr_critic_updates_per_policy_update, a.nr_policy_updates_per_step, a.logging_frequency, a.save_frequency = ncu, npu, N, -1
-    a.learning_rate, a.target_entropy = 1e-3, -float(act)
+    a.learning_rate, a.target_entropy, a.clipped_double_q_learning, a.max_grad_norm = 1e-3, -float(act), clipped, max_gn
     cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=seed, nr_envs=N),
                      runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
     torch.set_num_threads(1)

@@ -21,7 +21,7 @@ def test_fastsac_updates_match_oracle_on_golden_batches():
     lib = nt.load()
     z = np.load(os.path.join(ROOT, "tests", "golden", "fastsac_update.npz"))
     N, obs, act, batch, n_steps, nopt, seed, ncu, npu, atoms, stride = (int(x) for x in z["meta"])
-    gamma, tau, lr, lsmin, lsmax, tgt_ent, vmin, vmax, wd, b1, b2, alpha0, low, high, scale = (float(x) for x in z["meta_f"])
+    gamma, tau, lr, lsmin, lsmax, tgt_ent, vmin, vmax, wd, b1, b2, alpha0, low, high, scale = (float(x) for x in z["meta_f"][:15])
     torch.set_num_threads(1)
     pol, q1, q2 = FS.reference_init(obs, act, atoms, seed)
     center = (low + high) / 2
@@ -38,7 +38,7 @@ def test_fastsac_updates_match_oracle_on_golden_batches():
     sc = action_scale.to(DEV)
     nbytes = lib.rlx_fastsac_workspace_bytes(C.byref(d), batch)
     ws = torch.zeros(nbytes // 4 + 64, device=DEV)
-    hp = nt.FastSacHparams(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, -1.0)
+    hp = nt.FastSacHparams(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, -1.0, 0.0)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def call(fn, metrics, **tensors):
