@@ -333,25 +333,100 @@ class FastSAC:
                 episode_return += float(torch.as_tensor(reward).float().mean())
             rlx_logger.info(f"Episode {i + 1} - Return: {episode_return}")
 
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    # The reference's file layout and state_dict key names (fastsac.py:463-500), so that models move between the two implementations.
+    def _named(self, flat, net):
+        """flat parameter-like vector -> {state_dict key: tensor} for "policy" or one Q network."""
+        obs, act, atoms = self.dims.obs_dim, self.dims.act_dim, self.dims.nr_atoms
+        widths, inp, prefix = (POLICY_WIDTHS, obs, "torso") if net == "policy" else (Q_WIDTHS, obs + act, "critic")
+        shapes, last = [], inp
+        for k, w in enumerate(widths):
+            shapes += [(f"{prefix}.{3 * k}.weight", (w, last)), (f"{prefix}.{3 * k}.bias", (w,)), (f"{prefix}.{3 * k + 1}.weight", (w,)),
+                       (f"{prefix}.{3 * k + 1}.bias", (w,))]
+            last = w
+        if net == "policy":
+            shapes += [("mean.weight", (act, 128)), ("mean.bias", (act,)), ("log_std.weight", (act, 128)), ("log_std.bias", (act,))]
+        else:
+            shapes += [("critic.9.weight", (atoms, 192)), ("critic.9.bias", (atoms,))]
+        out, o = {}, 0
+        for name, shape in shapes:
+            n = int(np.prod(shape))
+            out[name] = flat[o:o + n].view(shape)
+            o += n
+        assert o == flat.numel()
+        return out
+
+    def _adamw_state(self, m, v, step, named_like):
+        state, o = {}, 0
+        for i, (name, t) in enumerate(named_like.items()):
+            n = t.numel()
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": m[o:o + n].view(t.shape).cpu().clone(), "exp_avg_sq": v[o:o + n].view(t.shape).cpu().clone()}
+            o += n
+        group = {"lr": self.current_learning_rate(), "betas": (self.hp.adam_beta1, self.hp.adam_beta2), "eps": 1e-08, "weight_decay": self.hp.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": True, "params": list(range(len(state)))}
+        return {"state": state, "param_groups": [group]}
+
     def save(self):
-        torch.save({"config_algorithm": dict(self.config.algorithm), "policy_params": self.policy_params.cpu(), "q_params": self.q_params.cpu(),
-                    "q_target_params": self.q_target_params.cpu(), "log_alpha": self.log_alpha.cpu(),
-                    "optimizer": {k: getattr(self, k).cpu() for k in ("policy_m", "policy_v", "q_m", "q_v", "alpha_state", "steps")},
-                    "normalizer": {k: getattr(self, k).cpu() for k in ("norm_mean", "norm_var", "norm_std", "norm_count")}},
-                   os.path.join(self.save_path, "best.model"))
+        nq = self.q_offsets[-1]
+        cpu = lambda d: {k: v.detach().cpu().clone() for k, v in d.items()}
+        steps = self.steps.cpu().tolist()
+        pol = self._named(self.policy_params, "policy")
+        q1, q2 = self._named(self.q_params[:nq], "q"), self._named(self.q_params[nq:], "q")
+        q_both = {**{"q1." + k: v for k, v in q1.items()}, **{"q2." + k: v for k, v in q2.items()}}
+        torch.save({
+            "config_algorithm": self.config.algorithm,
+            "policy_state_dict": cpu(pol),
+            "q1_state_dict": cpu(q1), "q2_state_dict": cpu(q2),
+            "q1_target_state_dict": cpu(self._named(self.q_target_params[:nq], "q")), "q2_target_state_dict": cpu(self._named(self.q_target_params[nq:], "q")),
+            "log_alpha": self.log_alpha.detach().cpu().clone(),
+            "policy_optimizer_state_dict": self._adamw_state(self.policy_m, self.policy_v, steps[2], pol),
+            "q_optimizer_state_dict": self._adamw_state(self.q_m, self.q_v, steps[0], q_both),
+            "entropy_optimizer_state_dict": self._adamw_state(self.alpha_state[1:2], self.alpha_state[2:3], steps[1], {"log_alpha": self.log_alpha}),
+            "observation_normalizer_state_dict": {"running_mean": self.norm_mean.cpu().view(1, -1).clone(), "running_var": self.norm_var.cpu().view(1, -1).clone(),
+                                                  "running_std_dev": self.norm_std.cpu().view(1, -1).clone(), "count": self.norm_count.cpu()[0].clone()},
+        }, os.path.join(self.save_path, "latest.model"))
 
     @classmethod
     def load(cls, config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
         ck = torch.load(config.runner.load_model, weights_only=False)
         for key, value in ck["config_algorithm"].items():
-            if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device"):
+            if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device", "bf16_mixed_precision_training", "compile_mode"):
                 config.algorithm[key] = value
         model = cls(config, train_env, eval_env, run_path, writer)
-        for k in ("policy_params", "q_params", "q_target_params", "log_alpha"):
-            getattr(model, k).copy_(ck[k])
-        for group in ("optimizer", "normalizer"):
-            for k, v in ck[group].items():
-                getattr(model, k).copy_(v)
+        nq = model.q_offsets[-1]
+
+        def fill(flat, net, sd):
+            for name, dst in model._named(flat, net).items():
+                src = sd[name] if name in sd else sd["_orig_mod." + name]   # torch.compile'd reference modules prefix their keys
+                dst.copy_(torch.as_tensor(src, dtype=torch.float32).reshape(dst.shape))
+
+        def fill_moments(m, v, named_like, osd):
+            o, step = 0, 0.0
+            for i, t in enumerate(named_like.values()):
+                n = t.numel()
+                if i in osd["state"]:
+                    m[o:o + n].copy_(osd["state"][i]["exp_avg"].reshape(-1))
+                    v[o:o + n].copy_(osd["state"][i]["exp_avg_sq"].reshape(-1))
+                    step = max(step, float(osd["state"][i]["step"]))
+                o += n
+            return int(step)
+
+        fill(model.policy_params, "policy", ck["policy_state_dict"])
+        fill(model.q_params[:nq], "q", ck["q1_state_dict"]); fill(model.q_params[nq:], "q", ck["q2_state_dict"])
+        fill(model.q_target_params[:nq], "q", ck["q1_target_state_dict"]); fill(model.q_target_params[nq:], "q", ck["q2_target_state_dict"])
+        model.log_alpha.copy_(torch.as_tensor(ck["log_alpha"]).detach().reshape(1))
+        pol = model._named(model.policy_params, "policy")
+        q_both = {**{"q1." + k: v for k, v in model._named(model.q_params[:nq], "q").items()},
+                  **{"q2." + k: v for k, v in model._named(model.q_params[nq:], "q").items()}}
+        steps = [fill_moments(model.q_m, model.q_v, q_both, ck["q_optimizer_state_dict"]),
+                 fill_moments(model.alpha_state[1:2], model.alpha_state[2:3], {"log_alpha": model.log_alpha}, ck["entropy_optimizer_state_dict"]),
+                 fill_moments(model.policy_m, model.policy_v, pol, ck["policy_optimizer_state_dict"])]
+        model.steps.copy_(torch.tensor(steps, dtype=torch.int64))
+        n = ck["observation_normalizer_state_dict"]
+        if "running_mean" in n:
+            model.norm_mean.copy_(n["running_mean"].reshape(-1)); model.norm_var.copy_(n["running_var"].reshape(-1))
+            model.norm_std.copy_(n["running_std_dev"].reshape(-1)); model.norm_count.fill_(int(n["count"]))
         return model
 
     def log(self, name, value, step):

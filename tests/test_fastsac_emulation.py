@@ -265,3 +265,98 @@ def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path, tag
         np.testing.assert_allclose(ours, z[key], rtol=5e-4, atol=5e-6, err_msg=name)
         checked += 1
     assert checked >= 15
+
+
+def test_plugin_checkpoint_has_the_reference_layout(tmp_path):
+    """FastSAC.save() writes the reference's file (fastsac.py:463-478): the state dicts load with strict=True into torch modules shaped like
+    the reference's Policy / QNetwork and its three AdamW optimisers accept the optimiser states; FastSAC.load() restores the flat
+    buffers exactly.  (Run on CPU with the same source rewrites as above.)"""
+    import types
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.fastsac.b200.default_config import get_config
+    from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
+    src = open(os.path.join(ROOT, "rl_x_b200", "algorithms", "fastsac", "b200", "fastsac.py")).read()
+    src = src.replace("from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer", "ReplayBuffer = None")
+    for old, new in [('torch.device("cuda", torch.cuda.current_device())', 'torch.device("cpu")'),
+                     ('if a.device != "gpu" or not torch.cuda.is_available():', 'if False:'), ("self.lib = nt.load()", "self.lib = nt.load()")]:
+        assert old in src
+        src = src.replace(old, new)
+    mod = types.ModuleType("fastsac_ckpt")
+    exec(compile(src, "fastsac_ckpt", "exec"), mod.__dict__)   # only the layout query of the real library is used here (host function)
+    obs, act, atoms = 9, 4, 21
+
+    class Sp:
+        def __init__(self, shape, **kw):
+            self.shape = shape
+            self.__dict__.update(kw)
+
+    class Props:
+        observation_space_type, action_space_type, data_interface_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS, DataInterfaceType.TORCH
+
+    class Env:
+        general_properties, horizon = Props, 3
+        single_observation_space = Sp((obs,))
+        single_action_space = Sp((act,), low=np.full(act, -1.0, np.float32), high=np.full(act, 1.0, np.float32), center=np.zeros(act, np.float32),
+                                 scale=np.ones(act, np.float32))
+
+    a = get_config("fastsac.b200")
+    a.nr_atoms = atoms
+    cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=8, nr_envs=4),
+                     runner=ConfigDict(save_model=True, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    model = mod.FastSAC(cfg, Env(), Env(), str(tmp_path / "run"), None)
+    g = torch.Generator().manual_seed(0)
+    for t in (model.policy_m, model.policy_v, model.q_m, model.q_v, model.q_target_params, model.alpha_state, model.norm_mean):
+        t.copy_(torch.rand(t.shape, generator=g))
+    model.steps.copy_(torch.tensor([12, 12, 3]))
+    model.norm_count.fill_(77)
+    model.save()
+    path = tmp_path / "run" / "models" / "latest.model"
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"config_algorithm", "policy_state_dict", "q1_state_dict", "q2_state_dict", "q1_target_state_dict", "q2_target_state_dict", "log_alpha",
+                       "policy_optimizer_state_dict", "q_optimizer_state_dict", "entropy_optimizer_state_dict", "observation_normalizer_state_dict"}
+
+    def torso(inp, widths):
+        layers, last = [], inp
+        for w in widths:
+            layers += [torch.nn.Linear(last, w), torch.nn.LayerNorm(w), torch.nn.SiLU()]
+            last = w
+        return layers
+
+    class Policy(torch.nn.Module):       # module structure of rl_x/algorithms/fastsac/pytorch/policy.py:36-48
+        def __init__(self):
+            super().__init__()
+            self.torso = torch.nn.Sequential(*torso(obs, (512, 256, 128)))
+            self.mean, self.log_std = torch.nn.Linear(128, act), torch.nn.Linear(128, act)
+
+    class QNetwork(torch.nn.Module):     # q_network.py:24-35
+        def __init__(self):
+            super().__init__()
+            self.critic = torch.nn.Sequential(*torso(obs + act, (768, 384, 192)), torch.nn.Linear(192, atoms))
+
+    pol, q1, q2 = Policy(), QNetwork(), QNetwork()
+    pol.load_state_dict(ck["policy_state_dict"], strict=True)
+    q1.load_state_dict(ck["q1_state_dict"], strict=True)
+    q2.load_state_dict(ck["q2_state_dict"], strict=True)
+    QNetwork().load_state_dict(ck["q1_target_state_dict"], strict=True)
+    torch.optim.AdamW(pol.parameters(), lr=1e-3).load_state_dict(ck["policy_optimizer_state_dict"])
+    torch.optim.AdamW(list(q1.parameters()) + list(q2.parameters()), lr=1e-3).load_state_dict(ck["q_optimizer_state_dict"])
+    torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=1e-3).load_state_dict(ck["entropy_optimizer_state_dict"])
+    # the module built from the checkpoint computes what the oracle computes from the plugin's flat parameters
+    x = torch.randn(5, obs)
+    with torch.no_grad():
+        latent = pol.torso(x)
+        opol = {"torso": [(l.weight, l.bias) for l in pol.torso if not isinstance(l, torch.nn.SiLU)], "mean": (pol.mean.weight, pol.mean.bias),
+                "log_std": (pol.log_std.weight, pol.log_std.bias)}
+        assert torch.allclose(latent, FS.torso_forward(opol, x), atol=1e-6)
+        assert torch.equal(torch.cat([t.reshape(-1) for t in FS._leaves(opol)]), model.policy_params)
+    # round trip
+    cfg.runner.load_model = str(path)
+    cfg.runner.save_model = False
+    again = mod.FastSAC.load(cfg, Env(), Env(), str(tmp_path / "run2"), None, [])
+    for name in ("policy_params", "q_params", "q_target_params", "log_alpha", "policy_m", "policy_v", "q_m", "q_v", "alpha_state", "norm_mean", "norm_var",
+                 "norm_std", "norm_count", "steps"):
+        a_, b_ = getattr(model, name), getattr(again, name)
+        if name == "alpha_state":
+            a_, b_ = a_[1:], b_[1:]   # element 0 is the transient gradient
+        assert torch.equal(a_, b_), name
