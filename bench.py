@@ -325,6 +325,101 @@ def run_sac(args):
     print(json.dumps(line))
 
 
+def run_fastsac(args):
+    """FastSAC at the reference's default update shape: batch 8192, 4 critic updates per policy update, 2 policy updates per
+    environment step (rl_x/algorithms/fastsac/pytorch/default_config.py), 1024 x 4096 ring, synthetic Box(48) / Box(12).  One "step" =
+    what the reference does after one vector-env step: sample 8 x 8192 rows (n-step gather), normalise states and next states (updating
+    the running statistics), 8 critic + entropy updates with polyak, 2 policy updates.  value = critic updates/s.
+    (Written for the first hardware run of this path; not yet executed on a GPU.)"""
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.fastsac.b200.default_config import get_config
+    from rl_x_b200.algorithms.fastsac.b200.fastsac import FastSAC
+    from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer
+    from rl_x_b200.environments.types import ActionSpaceType, ObservationSpaceType, DataInterfaceType
+    torch.cuda.set_device(0)
+    N, obs, act, n_steps = 4096, 48, 12, 3
+
+    class Space:
+        def __init__(self, shape, **kw):
+            self.shape = shape
+            self.__dict__.update(kw)
+
+    class Props:
+        observation_space_type, action_space_type, data_interface_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS, DataInterfaceType.TORCH
+
+    class Env:
+        general_properties, horizon = Props, 1000
+        single_observation_space = Space((obs,))
+        single_action_space = Space((act,), low=np.full(act, -1.0, np.float32), high=np.full(act, 1.0, np.float32), center=np.zeros(act, np.float32),
+                                    scale=np.ones(act, np.float32))
+
+    a = get_config("fastsac.b200")
+    a.n_steps = n_steps
+    cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=1, nr_envs=N),
+                     runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    model = FastSAC(cfg, Env(), Env(), "/tmp/rlx_bench_fastsac", None)
+    model.set_train_mode()
+    rb = ReplayBuffer(a.buffer_size_per_env, N, (obs,), (act,), n_steps, a.gamma, model.device)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in (rb.states, rb.next_states, rb.actions, rb.rewards):
+        t.normal_(generator=g)
+    rb.actions.tanh_()
+    rb.dones.copy_((torch.rand(rb.dones.shape, device="cuda", generator=g) < 0.01).float())
+    rb.size, rb.pos = rb.capacity, 0
+    npu, ncu, B = a.nr_policy_updates_per_step, a.nr_critic_updates_per_policy_update, a.batch_size
+    cm, pm = torch.zeros(8, device="cuda"), torch.zeros(8, device="cuda")
+
+    def step():
+        ts, tns, ta, tr, td, ttr, teff = rb.sample(npu * ncu * B)
+        ts = model.normalize(ts, update=True).view(npu, ncu, B, -1)
+        tns = model.normalize(tns, update=True).view(npu, ncu, B, -1)
+        ta = ta.view(npu, ncu, B, -1)
+        tr, td, ttr, teff = (t.view(npu, ncu, B) for t in (tr, td, ttr, teff))
+        for i in range(npu):
+            for j in range(ncu):
+                model.critic_update(ts[i, j], tns[i, j], ta[i, j], tr[i, j], td[i, j], ttr[i, j], teff[i, j], cm)
+            model.policy_update(ts[i, -1], pm)
+
+    lib = nt.load()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    K = args.steps * 4
+    lib.rlx_reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) / 1e3
+    line = {"metric": "FastSAC critic updates/sec (n-step sample + C51 twin-critic / actor / alpha updates), batch 8192", "value": K * npu * ncu / sec,
+            "unit": "critic updates/s", "n_gpus": 1, "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": sec / K * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"FastSAC synthetic Box(obs={obs}, act={act}), ring 1024 x {N}, n_steps={n_steps}, batch={B}, {ncu} critic per policy update, "
+                                   f"{npu} policy updates per step (reference defaults)"},
+            "gpu_launches": int(lib.rlx_launch_count()), "q_loss": float(cm[0]), "policy_loss": float(pm[0])}
+    if not args.no_cpu:
+        from oracle import fastsac_oracle as FS
+        threads = calibrate_threads(available_cores())
+        torch.set_num_threads(threads)
+        pol, q1, q2 = FS.reference_init(obs, act, int(a.nr_atoms), 1)
+        L = FS.Learner(pol, q1, q2, torch.ones(act), a.learning_rate, a.weight_decay, (a.adam_beta1, a.adam_beta2), a.gamma, a.tau, a.v_min, a.v_max, int(a.nr_atoms),
+                       a.target_entropy, a.alpha_init, a.log_std_min, a.log_std_max)
+        gg = torch.Generator().manual_seed(0)
+        rn = lambda *s_: torch.randn(*s_, generator=gg)
+        mk = lambda: (rn(B, obs), rn(B, obs), torch.tanh(rn(B, act)), rn(B), torch.zeros(B), torch.zeros(B), torch.ones(B), rn(B, act))
+        L.critic_and_entropy_step(*mk())
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 10.0:
+            L.critic_and_entropy_step(*mk())
+            n += 1
+        line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "critic updates/s", "cores": threads, "kind": "port",
+                                "sample": f"{n} oracle critic updates at batch {B} in ~10 s (policy updates and sampling excluded)"}
+    print(json.dumps(line))
+
+
 def workload_config(args, world):
     return {"workload": f"PPO synthetic Box(obs={C2['obs_dim']}, act={C2['act_dim']}) ~Humanoid, num_envs={args.envs}/GPU, horizon={C2['nr_steps']}, "
                         f"hidden={C2['hidden']}, nr_epochs={args.epochs}, minibatch={args.minibatch}/GPU (BASELINE.json configs[1])",
@@ -348,7 +443,7 @@ def main():
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
-    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac"])
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -359,9 +454,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
-    if args.workload == "sac":
+    if args.workload in ("sac", "fastsac"):
         if rank == 0:
-            run_sac(args)
+            (run_sac if args.workload == "sac" else run_fastsac)(args)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
