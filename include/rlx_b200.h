@@ -254,6 +254,17 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
                                      const int64_t* global_counts, rlx_comm* comm, void* stream);
 
 
+/* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused kernel (default), 1 = the GEMM formulation of csrc/ppo_head_gemm.cu
+ * (logits and dZ2 as GEMMs around one flat loss kernel; emulation-validated, first hardware run pending).  Returns the engine in effect. */
+int rlx_set_head_engine(int engine);
+/* bring-up / test entry of the GEMM head on caller buffers: H2 [m, 2*hidden] (policy | critic halves), torch-layout head weights; outputs
+ * dZ2 [m, 2*hidden], dhead [m, round_up(act+1, 4)] (dMean | dV | 0) and ONE partial block headpart [2*act + 5 + 2*hidden] =
+ * db3p | db3c | dlogstd | pg vl kl cf sums | db2p | db2c.  scratch: >= m * (2*act + 8) + (m / 256 + 2) * max(2*hidden, 8) floats. */
+int rlx_debug_ppo_head_gemm_f32(int64_t m, int32_t hidden, int32_t act_dim, const float* H2, const float* W3p, const float* W3c, const float* b3p,
+                                const float* b3c, const float* logstd, const float* actions, const float* logp_old, const float* adv,
+                                const float* ret, const float* adv_stats, float inv_mg, float clip_range, float critic_coef,
+                                int32_t ratio_delta_metric, float* dZ2, float* dhead, float* headpart, float* scratch, void* stream);
+
 /* ------------------------------------------------------------------------------------------ PPO + LSTM path -- */
 /* rl_x/algorithms/ppo_lstm/flax (policy.py:36-146, critic.py:18-30, ppo_lstm.py:107-231), default options
  * (lstm_obs_combine_method = "concat", share_lstm_obs_encoder = False).  STATUS: written without GPU access — numerics are checked

@@ -11,6 +11,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_dispatch.cuh"
 #include "ppo_head.cuh"
+#include "ppo_head_gemm.cuh"
 #include "ppo_optim.cuh"
 
 namespace rlx {
@@ -148,6 +149,9 @@ static bool head_dims_ok(const rlx_ppo_dims& d) {
   return dims_ok(d) && d.hidden <= 1024 && head_smem_bytes(d, true) <= 200 * 1024;
 }
 
+int ppo_head_gemm_path(const HeadGemmArgs& a, cudaStream_t st);  // ppo_head_gemm.cu
+static int g_head_engine = 0;                                       // 0 fused kernel, 1 GEMM formulation (rlx_set_head_engine)
+
 static void fill_head_common(HeadP& h, const PpoLayout& L, const float* params, const float* H2, long long rows) {
   h.M = (int)rows; h.H = L.H; h.act = L.act;
   h.H2 = H2;
@@ -272,10 +276,22 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
     const int dh_ld = (int)(ceil_div(A + 1, 4) * 4);
     const bool fast_head = (A <= 31) && (H % 2 == 0) && (H <= 1024);
     const double head_flops = 4.0 * m * H * (A + 1), head_bytes = 4.0 * m * (4.0 * H + 2.0 * A + 5);
+    // opt-in GEMM formulation of the head (ppo_head_gemm.cu); dZ1 is free until the dX GEMM and serves as its scratch
+    const bool gemm_head = fast_head && g_head_engine == 1 && head_gemm_scratch_floats(m, H, A) <= m * 2LL * H;
+    if (gemm_head) {
+      HeadGemmArgs ha{m, H, A, dh_ld, H2, a->params + L.off[W3P], a->params + L.off[W3C], a->params + L.off[B3P], a->params + L.off[B3C],
+                      a->params + L.off[LOGSTD], a->actions, a->log_probs, a->advantages, a->returns, a->adv_stats, inv_mg, a->hp.clip_range,
+                      a->hp.critic_coef, a->hp.ratio_delta_metric != 0.f ? 1 : 0, dZ2, dhead, headpart, dZ1};
+      rc = ppo_head_gemm_path(ha, st);
+      if (rc) return rc;
+      head_blocks = 1;  // the path writes ONE partial block in the fused kernel's layout
+    }
     if (fast_head) {
       HeadTrain2Extra ex{dh_ld};
       const bool vec_head = (H == 128 || H == 256 || H == 512);
-      if (vec_head) {
+      if (gemm_head) {
+        // loss, dZ2, dhead and the partial block are done
+      } else if (vec_head) {
 #define RLX_HEAD3(H_, AM_)                                                                                                       \
   do {                                                                                                                           \
     RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train3_kernel<H_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -560,6 +576,12 @@ extern "C" int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t 
   if (layout == 1 && epilogue == 2) return launch_sgemm<true, false, EPI_DTANH>(g, 1, st);
   if (layout == 1) return launch_sgemm<true, false, EPI_NONE>(g, 1, st);
   return launch_sgemm<false, false, EPI_NONE>(g, 1, st);
+}
+
+extern "C" int rlx_set_head_engine(int engine) {
+  if (engine == 0 || engine == 1) g_head_engine = engine;
+  else set_error("rlx_set_head_engine: unknown engine %d", engine);
+  return g_head_engine;
 }
 
 extern "C" int rlx_set_gemm_engine(int engine) {
