@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 run() { echo "=== $*"; timeout 600 python -m pytest "$@" -q --runxfail --timeout 300 -x 2>&1 | tail -15 | cut -c1-220; }
 run tests/test_gpu_train_espo.py -m gpu
 run tests/test_gpu_zz_fastsac_replay.py -m gpu
+run tests/test_gpu_zz_head_gemm.py -m gpu
 run tests/test_gpu_zzzz_fastsac.py -m gpu
 run tests/test_gpu_zzz_ppo_lstm.py -m gpu
 if [ "${1:-1}" -ge 2 ]; then
