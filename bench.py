@@ -443,6 +443,7 @@ def main():
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
+    ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -468,6 +469,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from rl_x_b200 import _native as nt
     lib = nt.load()
+    lib.rlx_set_head_engine(1 if args.head_engine == "gemm" else 0)
 
     model = build_model(args, rank, world, "torch")
     model._begin_training()
