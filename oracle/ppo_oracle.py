@@ -105,6 +105,27 @@ def gae(rewards, terminations, values, next_values, gamma, gae_lambda):
     return advantages, returns
 
 
+# ----------------------------------------------------------------------------------------------- bf16 autocast variant
+def autocast_bf16(enabled):
+    """The reference's mixed-precision mode (`bf16_mixed_precision_training`, ppo.py:123,155,208,253): torch autocast around the forward and
+    loss computations, backward / clipping / Adam outside.  The reference hard-codes device_type="cuda" and refuses the mode elsewhere
+    (ppo.py:66-67); here — and in tests/golden/make_golden_ppo.py's bf16 run — the CPU autocast context stands in for it: the cast rules
+    that matter on this path are the same (Linear runs in bf16 with bf16 outputs, tanh stays in its input dtype, everything that mixes
+    a bf16 and an fp32 tensor promotes to fp32)."""
+    return torch.autocast("cpu", dtype=torch.bfloat16, enabled=enabled)
+
+
+def gae_mixed_precision(rewards, terminations, values, next_values, gamma, gae_lambda):
+    """ref: calculate_gae_advantages_and_returns_mixed_precision (ppo.py:98-107).  `next_values` arrives as a bf16 tensor, so
+    `gamma * next_values` is rounded to bf16 before it meets the fp32 operands; the recurrence itself is fp32."""
+    delta = rewards + gamma * next_values * (1 - terminations) - values
+    advantages = torch.zeros_like(rewards)
+    lastgaelam = torch.zeros_like(rewards[0])
+    for t in range(values.shape[0] - 1, -1, -1):
+        lastgaelam = advantages[t] = delta[t] + gamma * gae_lambda * (1 - terminations[t]) * lastgaelam
+    return advantages, advantages + values
+
+
 # ----------------------------------------------------------------------------------------------- losses / update
 def policy_loss(pol, states, actions, log_probs, advantages, clip_range, entropy_coef):
     """ref: ppo.py:124-141. Returns (loss, pg_loss, entropy_loss, approx_kl, clip_fraction)."""
@@ -132,7 +153,8 @@ def critic_loss(cri, states, returns, critic_coef):
 class Learner:
     """Policy + critic + two Adam optimisers, as PPO.__init__ builds them (ref: ppo.py:79-88)."""
 
-    def __init__(self, pol, cri, lr=3e-4, clip_range=0.2, entropy_coef=0.0, critic_coef=0.5, max_grad_norm=0.5):
+    def __init__(self, pol, cri, lr=3e-4, clip_range=0.2, entropy_coef=0.0, critic_coef=0.5, max_grad_norm=0.5, bf16=False):
+        self.bf16 = bf16  # bf16_mixed_precision_training: the two loss functions run under autocast (ppo.py:123,155)
         self.pol = {k: v.clone().requires_grad_(True) for k, v in pol.items()}
         self.cri = {k: v.clone().requires_grad_(True) for k, v in cri.items()}
         self.popt = torch.optim.Adam([self.pol[k] for k in POLICY_KEYS], lr=lr)
@@ -159,12 +181,14 @@ class Learner:
     def minibatch_step(self, states, actions, log_probs, advantages, returns):
         """ref: policy_loss_fn + critic_loss_fn (ppo.py:121-166): backward, clip_grad_norm_, Adam.step for each net."""
         self.popt.zero_grad()
-        loss, pg, ent, kl, cf = policy_loss(self.pol, states, actions, log_probs, advantages, self.clip_range, self.entropy_coef)
+        with autocast_bf16(self.bf16):
+            loss, pg, ent, kl, cf = policy_loss(self.pol, states, actions, log_probs, advantages, self.clip_range, self.entropy_coef)
         loss.backward()
         pnorm = torch.nn.utils.clip_grad_norm_([self.pol[k] for k in POLICY_KEYS], self.max_grad_norm)
         self.popt.step()
         self.copt.zero_grad()
-        closs = critic_loss(self.cri, states, returns, self.critic_coef)
+        with autocast_bf16(self.bf16):
+            closs = critic_loss(self.cri, states, returns, self.critic_coef)
         closs.backward()
         cnorm = torch.nn.utils.clip_grad_norm_([self.cri[k] for k in CRITIC_KEYS], self.max_grad_norm)
         self.copt.step()

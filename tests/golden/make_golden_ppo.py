@@ -158,7 +158,7 @@ def run(tag, N, T, obs_dim, act_dim, hidden, mb, epochs, iterations, seed, act_l
     def get_value(x):
         out = orig_get_value(x)
         if x.dim() == 3:
-            next_values_log.append(out.detach().squeeze(-1).numpy().copy())
+            next_values_log.append(out.detach().float().squeeze(-1).numpy().copy())
         return out
 
     model.critic.get_value = get_value
