@@ -174,9 +174,9 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ Gi, const float* 
 // BPTT step t.  dH = dHall_t + dHnext * keep_next, dC = dCnext (already masked) + dH o (1 - tanh(c)^2); writes the pre-activation gate
 // gradients dG_t and dCprev = (dC f) * keep_t (keep_t = 1 - done[t-1]).  dHnext is the GEMM output dG_{t+1} . Wh^T.  thread = (env, unit)
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dHall, const float* __restrict__ dHnext, const float* __restrict__ keep_next_done,
-                                     const float* __restrict__ dCnext, const float* __restrict__ gates, const float* __restrict__ C,
+                                     const float* dCnext, const float* __restrict__ gates, const float* __restrict__ C,
                                      const float* __restrict__ Cm, const float* __restrict__ done_prev, long long n, int L,
-                                     float* __restrict__ dG, float* __restrict__ dCprev) {
+                                     float* __restrict__ dG, float* dCprev) {  // dCnext and dCprev are the same buffer (element-wise in place)
   const long long id = gtid();
   if (id >= n * L) return;
   const long long e = id / L;
