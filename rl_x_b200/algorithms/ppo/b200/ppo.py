@@ -58,6 +58,17 @@ def init_reference_parameters(obs_dim, act_dim, hidden, std_dev, seed):
     return out
 
 
+# torch.optim.Adam(module.parameters()) numbers the parameters in nn.Module.parameters() order: the module's OWN Parameters first
+# (policy_logstd, reference policy.py:52), then the children's (policy_mean.0.weight, ...).  state_dict() uses the same order.  The
+# reference modules are torch.compile wrappers (policy.py:27, critic.py:19): the installed torch strips their "_orig_mod." prefix in
+# state_dict() (what the executed reference wrote here: tests/golden/ppo_ref_checkpoint.model), older builds kept it - load accepts both,
+# save writes the bare names like the installed torch.
+POLICY_PARAM_ORDER = ("policy_logstd", "policy_mean.0.weight", "policy_mean.0.bias", "policy_mean.2.weight", "policy_mean.2.bias",
+                      "policy_mean.4.weight", "policy_mean.4.bias")
+CRITIC_PARAM_ORDER = ("critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias", "critic.4.weight", "critic.4.bias")
+COMPILED_PREFIX = "_orig_mod."
+
+
 class FlatParameters:
     """One flat fp32 device buffer for policy + critic (layout: include/rlx_b200.h), with named views that carry the
     reference's state_dict keys so checkpoints interoperate (ppo.py:426-451)."""
@@ -78,11 +89,36 @@ class FlatParameters:
                 src = named[key] if key in named else named["_orig_mod." + key]  # torch.compile'd reference modules prefix keys
                 self.view(flat, seg).copy_(torch.as_tensor(src, dtype=torch.float32).reshape(self.shapes[seg]))
 
-    def state_dicts(self, flat=None):
+    def state_dicts(self, flat=None, prefix=""):
+        """(policy, critic) dicts in the reference's state_dict() order; prefix="_orig_mod." gives the compiled modules' keys."""
         flat = self.flat if flat is None else flat
-        pol = {key: self.view(flat, seg).detach().cpu().clone() for key, seg in nt.POLICY_KEYS.items()}
-        cri = {key: self.view(flat, seg).detach().cpu().clone() for key, seg in nt.CRITIC_KEYS.items()}
+        pol = {prefix + key: self.view(flat, nt.POLICY_KEYS[key]).detach().cpu().clone() for key in POLICY_PARAM_ORDER}
+        cri = {prefix + key: self.view(flat, nt.CRITIC_KEYS[key]).detach().cpu().clone() for key in CRITIC_PARAM_ORDER}
         return pol, cri
+
+    def adam_state_dict(self, order, keys, exp_avg, exp_avg_sq, step, lr):
+        """torch.optim.Adam.state_dict() of the reference's optimiser over one net (ppo.py:83-84,426-436): parameter i is order[i]."""
+        state = {i: {"step": torch.tensor(float(step)), "exp_avg": self.view(exp_avg, keys[key]).detach().cpu().clone(),
+                     "exp_avg_sq": self.view(exp_avg_sq, keys[key]).detach().cpu().clone()} for i, key in enumerate(order)}
+        group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": list(range(len(order)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_adam_state(self, opt_state, order, keys, exp_avg, exp_avg_sq):
+        """Inverse of adam_state_dict for a checkpoint written by the reference or by save().  Returns the step count; a parameter whose
+        moment shape does not match the layout raises (a silently permuted optimiser state is worse than no state)."""
+        st, step = opt_state["state"], 0.0
+        for i, key in enumerate(order):
+            if i not in st:
+                continue  # the reference saves an empty state before the first optimiser step
+            seg = keys[key]
+            for name, dst in (("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+                src = torch.as_tensor(st[i][name], dtype=torch.float32)
+                if tuple(src.shape) != tuple(self.shapes[seg]):
+                    raise ValueError(f"optimizer state {i} ({key}): {name} has shape {tuple(src.shape)}, expected {tuple(self.shapes[seg])}")
+                self.view(dst, seg).copy_(src)
+            step = max(step, float(st[i]["step"]))
+        return step
 
 
 class PermutationStream:
@@ -202,7 +238,14 @@ class PPO:
         self.device = torch.device("cuda", torch.cuda.current_device())
         rlx_logger.info(f"Using device: {self.device}")
 
-        self.rng = nt.Pcg64Generator(self.seed)  # np.random.default_rng(self.seed), ppo.py:72
+        # Replicas must start from identical weights and (reference-exact mode) walk one permutation stream: both derive from RANK 0's
+        # seed, whatever per-rank environment.seed the launcher used to decorrelate the env streams.
+        self.model_seed = int(self.seed)
+        if self.dist:
+            t = torch.tensor([self.model_seed], dtype=torch.int64, device=self.device)
+            self.dist.broadcast(t, src=0)
+            self.model_seed = int(t.item())
+        self.rng = nt.Pcg64Generator(self.model_seed)  # np.random.default_rng(self.seed), ppo.py:72
 
         self.os_shape = self.train_env.single_observation_space.shape
         self.as_shape = self.train_env.single_action_space.shape
@@ -219,7 +262,9 @@ class PPO:
         lib = self.kernels.lib
         lib.rlx_set_gemm_engine({"simt": 0, "tcgen05": 1, "auto": 1}[engine])
         self.params = FlatParameters(self.kernels, self.device)
-        self.params.load_named(init_reference_parameters(obs_dim, act_dim, self.nr_hidden_units, self.std_dev, self.seed))
+        self.params.load_named(init_reference_parameters(obs_dim, act_dim, self.nr_hidden_units, self.std_dev, self.model_seed))
+        if self.dist:
+            self.dist.broadcast(self.params.flat, src=0)  # bit-identical replicas even if a rank's torch build initialises differently
         P = self.kernels.param_count
         self.exp_avg = torch.zeros(P, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(P, dtype=torch.float32, device=self.device)
@@ -586,7 +631,7 @@ class PPO:
             # local minibatches k (host work O(local batch), same collectives)
             if self.minibatch_size % self.world_size != 0:
                 raise ValueError("minibatch_size must be divisible by the world size when exact_global_permutation=False")
-            self.local_rng = nt.Pcg64Generator((int(self.seed) * 1000003 + 7919 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF)
+            self.local_rng = nt.Pcg64Generator((int(self.model_seed) * 1000003 + 7919 * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF)
             return PermutationStream(self.local_rng, self.local_batch_size, self.nr_epochs, self.local_batch_size, None)
         return PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, None)
 
@@ -780,27 +825,18 @@ class PPO:
             rlx_logger.info("└" + "─" * 31 + "┴" + "─" * 16 + "┘")
 
     # ------------------------------------------------------------------------------------- checkpointing
-    def _adam_state_dict(self, keys):
-        """torch.optim.Adam.state_dict() layout of the reference checkpoints (ppo.py:426-436)."""
-        state = {}
-        for i, (key, seg) in enumerate(keys.items()):
-            state[i] = {"step": torch.tensor(float(self.adam_step.item())),
-                        "exp_avg": self.params.view(self.exp_avg, seg).detach().cpu().clone(),
-                        "exp_avg_sq": self.params.view(self.exp_avg_sq, seg).detach().cpu().clone()}
-        group = {"lr": self.current_learning_rate(), "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False,
-                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
-                 "decoupled_weight_decay": False, "params": list(range(len(keys)))}
-        return {"state": state, "param_groups": [group]}
-
     def save(self):
+        """ref: ppo.py:426-436.  Same dict keys, the reference modules' parameter names and order and the reference optimisers' parameter
+        numbering, so that the reference's own load() (strict load_state_dict, ppo.py:439-451) accepts the file and vice versa."""
         file_path = self.save_path + "/best.model"
         pol, cri = self.params.state_dicts()
+        step, lr = float(self.adam_step.item()), self.current_learning_rate()
         torch.save({
             "config_algorithm": self.config.algorithm,
             "policy_state_dict": pol,
             "critic_state_dict": cri,
-            "policy_optimizer_state_dict": self._adam_state_dict(nt.POLICY_KEYS),
-            "critic_optimizer_state_dict": self._adam_state_dict(nt.CRITIC_KEYS),
+            "policy_optimizer_state_dict": self.params.adam_state_dict(POLICY_PARAM_ORDER, nt.POLICY_KEYS, self.exp_avg, self.exp_avg_sq, step, lr),
+            "critic_optimizer_state_dict": self.params.adam_state_dict(CRITIC_PARAM_ORDER, nt.CRITIC_KEYS, self.exp_avg, self.exp_avg_sq, step, lr),
         }, file_path)
         if self.track_wandb:
             import wandb
@@ -816,15 +852,9 @@ class PPO:
         model = cls(config, train_env, eval_env, run_path, writer)
         named = {**checkpoint["policy_state_dict"], **checkpoint["critic_state_dict"]}
         model.params.load_named(named)
-        step = 0.0
-        for opt_key, keys in (("policy_optimizer_state_dict", nt.POLICY_KEYS), ("critic_optimizer_state_dict", nt.CRITIC_KEYS)):
-            st = checkpoint[opt_key]["state"]
-            for i, (key, seg) in enumerate(keys.items()):
-                if i in st:
-                    model.params.view(model.exp_avg, seg).copy_(st[i]["exp_avg"].reshape(model.params.shapes[seg]))
-                    model.params.view(model.exp_avg_sq, seg).copy_(st[i]["exp_avg_sq"].reshape(model.params.shapes[seg]))
-                    step = max(step, float(st[i]["step"]))
-        model.adam_step.fill_(int(step))
+        step_p = model.params.load_adam_state(checkpoint["policy_optimizer_state_dict"], POLICY_PARAM_ORDER, nt.POLICY_KEYS, model.exp_avg, model.exp_avg_sq)
+        step_c = model.params.load_adam_state(checkpoint["critic_optimizer_state_dict"], CRITIC_PARAM_ORDER, nt.CRITIC_KEYS, model.exp_avg, model.exp_avg_sq)
+        model.adam_step.fill_(int(max(step_p, step_c)))
         return model
 
     def set_train_mode(self):

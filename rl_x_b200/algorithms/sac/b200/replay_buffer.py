@@ -45,11 +45,23 @@ class ReplayBuffer:
         if self._out is None or self._out[0].shape[0] != n:
             z = lambda *s: torch.empty(*s, dtype=torch.float32, device=self.device)
             self._out = (z(n, *self.os_shape), z(n, *self.os_shape), z(n, *self.as_shape), z(n), z(n))
-            self._idx_host = torch.empty(2, n, dtype=torch.int64).pin_memory()
+            # two pinned staging slots, each guarded by the event of its last H2D copy: the host never rewrites a slot whose copy is
+            # still queued (back-to-back sample() calls without a sync in between, e.g. CUDA-graph replays of the update)
+            self._idx_host = [torch.empty(2, n, dtype=torch.int64).pin_memory() for _ in range(2)]
+            self._idx_event = [torch.cuda.Event(), torch.cuda.Event()]
+            self._idx_pending = [False, False]
+            self._idx_slot = 0
             self._idx_dev = torch.empty(2, n, dtype=torch.int64, device=self.device)
-        self._idx_host[0].numpy()[:] = self.rng.integers(self.size, n)
-        self._idx_host[1].numpy()[:] = self.rng.integers(self.nr_envs, n)
-        self._idx_dev.copy_(self._idx_host, non_blocking=True)
+        slot = self._idx_slot
+        self._idx_slot ^= 1
+        if self._idx_pending[slot]:
+            self._idx_event[slot].synchronize()
+        host = self._idx_host[slot]
+        host[0].numpy()[:] = self.rng.integers(self.size, n)
+        host[1].numpy()[:] = self.rng.integers(self.nr_envs, n)
+        self._idx_dev.copy_(host, non_blocking=True)
+        self._idx_event[slot].record()
+        self._idx_pending[slot] = True
         s, ns, a, r, t = self._out
         obs_dim, act_dim = int(np.prod(self.os_shape)), int(np.prod(self.as_shape))
         nt.check(self._lib.rlx_replay_sample_gather_f32(self._idx_dev[0].data_ptr(), self._idx_dev[1].data_ptr(), n, self.nr_envs, obs_dim, act_dim,

@@ -28,6 +28,32 @@ POLICY_SEGMENTS = [("torso.0.weight", "H,O"), ("torso.0.bias", "H"), ("torso.2.w
 Q_SEGMENTS = [("critic.0.weight", "H,OA"), ("critic.0.bias", "H"), ("critic.2.weight", "H,H"), ("critic.2.bias", "H"), ("critic.4.weight", "1,H"),
               ("critic.4.bias", "1")]
 Q_NETS = ("q1", "q2", "q1_target", "q2_target")
+# nn.Module.parameters() order of the reference modules = the numbering inside their torch.optim.Adam state dicts (sac.py:75-77)
+POLICY_PARAM_ORDER = ("torso.0.weight", "torso.0.bias", "torso.2.weight", "torso.2.bias", "mean.weight", "mean.bias", "log_std.weight", "log_std.bias")
+Q_PARAM_ORDER = tuple(k for k, _ in Q_SEGMENTS)
+
+
+def _adam_state_dict(views_m, views_v, step, lr):
+    """torch.optim.Adam.state_dict() layout over an ordered list of (exp_avg view, exp_avg_sq view) pairs."""
+    state = {i: {"step": torch.tensor(float(step)), "exp_avg": m.detach().cpu().clone(), "exp_avg_sq": v.detach().cpu().clone()}
+             for i, (m, v) in enumerate(zip(views_m, views_v))}
+    group = {"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False, "maximize": False, "foreach": None,
+             "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False, "params": list(range(len(state)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def _load_adam_state(osd, views_m, views_v, what):
+    step = 0
+    for i, (m, v) in enumerate(zip(views_m, views_v)):
+        if i not in osd["state"]:
+            continue
+        st = osd["state"][i]
+        if tuple(st["exp_avg"].shape) != tuple(m.shape):
+            raise ValueError(f"{what} optimizer state {i}: exp_avg has shape {tuple(st['exp_avg'].shape)}, expected {tuple(m.shape)}")
+        m.copy_(torch.as_tensor(st["exp_avg"], dtype=torch.float32))
+        v.copy_(torch.as_tensor(st["exp_avg_sq"], dtype=torch.float32))
+        step = max(step, int(float(st["step"])))
+    return step
 
 
 def _shape(spec, O, A, H):
@@ -404,13 +430,41 @@ class SAC:
         if self.track_console:
             rlx_logger.info("└" + "─" * 31 + "┴" + "─" * 16 + "┘")
 
+    def _optimizer_views(self):
+        """(exp_avg views, exp_avg_sq views) per reference optimiser, in the reference's parameter numbering: policy (sac.py:75),
+        q1 then q2 (sac.py:76), log_alpha (sac.py:77)."""
+        pm, pv = self.k.policy_views(self.m_policy), self.k.policy_views(self.v_policy)
+        Pq = self.k.Pq
+
+        def q_pair(flat):
+            out, o = [], 0
+            for net in range(2):
+                for key, spec in Q_SEGMENTS:
+                    shp = _shape(spec, self.k.O, self.k.A, self.k.H)
+                    n = int(np.prod(shp))
+                    out.append(flat[o:o + n].view(shp))
+                    o += n
+            assert o == 2 * Pq
+            return out
+
+        return {"policy": ([pm[k] for k in POLICY_PARAM_ORDER], [pv[k] for k in POLICY_PARAM_ORDER]),
+                "q": (q_pair(self.m_q), q_pair(self.v_q)),
+                "entropy": ([self.m_la.view(1)], [self.v_la.view(1)])}
+
     def save(self):
-        """Checkpoint with the reference's keys (sac.py:381-396): module state_dicts; optimiser moments stored flat under *_flat keys."""
+        """Checkpoint with the reference's keys and optimizer layout (sac.py:381-396): module state_dicts in parameters() order, log_alpha,
+        and the three torch.optim.Adam state dicts, so that either side's load() accepts the other's file."""
         pol, qs = self.state_dicts()
+        pol = {k: pol[k] for k in POLICY_PARAM_ORDER}
+        steps = [int(x) for x in self.steps.cpu().tolist()]  # policy, q, entropy
+        ov = self._optimizer_views()
+        lr = float(self.lr_dev.item())
         file_path = self.save_path + "/best.model"
         torch.save({"config_algorithm": self.config.algorithm, "policy_state_dict": pol, "q1_state_dict": qs["q1"], "q2_state_dict": qs["q2"],
-                    "q1_target_state_dict": qs["q1_target"], "q2_target_state_dict": qs["q2_target"], "log_alpha": self.log_alpha.cpu(),
-                    "optimizer_flat": {k: getattr(self, k).cpu() for k in ("m_policy", "v_policy", "m_q", "v_q", "m_la", "v_la", "steps")}}, file_path)
+                    "q1_target_state_dict": qs["q1_target"], "q2_target_state_dict": qs["q2_target"], "log_alpha": self.log_alpha.detach().cpu().clone(),
+                    "policy_optimizer_state_dict": _adam_state_dict(*ov["policy"], steps[0], lr),
+                    "q_optimizer_state_dict": _adam_state_dict(*ov["q"], steps[1], lr),
+                    "entropy_optimizer_state_dict": _adam_state_dict(*ov["entropy"], steps[2], lr)}, file_path)
 
     def load(config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
         ck = torch.load(config.runner.load_model, weights_only=False)
@@ -419,9 +473,15 @@ class SAC:
                 config.algorithm[key] = value
         model = SAC(config, train_env, eval_env, run_path, writer)
         model.load_named(ck["policy_state_dict"], ck["q1_state_dict"], ck["q2_state_dict"], ck["q1_target_state_dict"], ck["q2_target_state_dict"])
-        model.log_alpha.copy_(ck["log_alpha"])
-        for k, v in ck.get("optimizer_flat", {}).items():
-            getattr(model, k).copy_(v)
+        model.log_alpha.copy_(torch.as_tensor(ck["log_alpha"]).detach().reshape(1))
+        ov = model._optimizer_views()
+        steps = [_load_adam_state(ck[f"{name}_optimizer_state_dict"], *ov[name], name) if f"{name}_optimizer_state_dict" in ck else 0
+                 for name in ("policy", "q", "entropy")]
+        if "optimizer_flat" in ck:  # files written by round 1 of this build
+            for k, v in ck["optimizer_flat"].items():
+                getattr(model, k).copy_(v)
+        else:
+            model.steps.copy_(torch.tensor(steps, dtype=torch.int64))
         return model
 
     def set_train_mode(self):

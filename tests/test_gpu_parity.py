@@ -251,7 +251,7 @@ def _run_fwdbwd(k, fp, mbatch, hp, m_global=None):
 
 
 @pytest.mark.parametrize("obs,act,hidden,m,ent", [(11, 3, 64, 40, 0.01), (376, 17, 256, 1000, 0.0), (376, 17, 256, 4099, 0.02), (24, 33, 96, 257, 0.0),
-                                                 (5, 2, 8, 1, 0.0)])
+                                                 (5, 2, 8, 1, 0.0), (376, 17, 256, 32768, 0.0)])  # last: the bench's own minibatch (BASELINE configs[1])
 def test_minibatch_gradients_vs_oracle_autograd(obs, act, hidden, m, ent):
     from rl_x_b200.algorithms.ppo.b200.kernels import make_hparams
     k = _kern(obs, act, hidden)
@@ -382,6 +382,67 @@ def test_update_epochs_vs_reference_golden(golden):
             for name in O.POLICY_KEYS:
                 assert _rel(mp[name].numpy(), g[f"iter{it}/policy_opt/{name}/exp_avg"]) <= 1e-4, name
     assert int(step.item()) == g.iterations * g.epochs * nmb
+
+
+def test_one_epoch_at_bench_shape_vs_oracle():
+    """BASELINE configs[1] update shape (obs 376, act 17, hidden 256, minibatch 32768): one epoch of 4 minibatches from a gathered
+    batch of 131 072 rows (the split-K chains, dW reductions and head grids are those of the benchmark; only the batch is 4x shorter
+    so that the CPU oracle finishes in seconds).  Weights after the epoch, Adam moments and every logged metric against the oracle."""
+    from rl_x_b200.algorithms.ppo.b200.kernels import make_hparams
+    obs, act, hidden, mb, nmb = 376, 17, 256, 32768, 4
+    B = mb * nmb
+    k = _kern(obs, act, hidden)
+    pol, cri = O.init_params(obs, act, hidden, seed=1)
+    g = torch.Generator().manual_seed(5)
+    data = _random_minibatch(obs, act, B, seed=6)
+    with torch.no_grad():
+        lp, _ = O.get_logprob_entropy(pol, data["states"], data["actions"])
+    data["log_probs"] = lp + 0.1 * torch.randn(B, generator=g)
+    L = O.Learner(pol, cri, lr=3e-4, clip_range=0.2, entropy_coef=0.0, critic_coef=0.5, max_grad_norm=0.5)
+    ref_metrics = [L.minibatch_step(*(data[n][i * mb:(i + 1) * mb] for n in ("states", "actions", "log_probs", "advantages", "returns"))) for i in range(nmb)]
+    fp = _flat_from_named(k, pol, cri)
+    P = k.param_count
+    ldx = k.states_pitch()
+    xs = torch.zeros(B, ldx, device=DEV)
+    xs[:, :obs] = data["states"].to(DEV)
+    xs[:, obs] = 1.0
+    d = {n: v.to(DEV).contiguous() for n, v in data.items() if n != "states"}
+    stats, metrics = torch.empty(nmb, 2, device=DEV), torch.zeros(nmb, 8, device=DEV)
+    k.advantage_stats(d["advantages"], B, mb, stats)
+    exp_avg, exp_avg_sq, grads = torch.zeros(P, device=DEV), torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+    args = k.minibatch_args(m=0, m_global=1, states=xs, actions=d["actions"], log_probs=d["log_probs"], advantages=d["advantages"], returns=d["returns"],
+                            adv_stats=stats, params=fp.flat, grads=grads, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, lr=torch.full((1,), 3e-4, device=DEV),
+                            step_count=torch.zeros(1, dtype=torch.int64, device=DEV), hp=make_hparams(0.2, 0.0, 0.5, 0.5), metrics=metrics,
+                            workspace=k.minibatch_workspace(mb, DEV), states_ld=ldx, states_ones_col=True)
+    k.update_epoch(args, B, mb)
+    torch.cuda.synchronize()
+    # Adam's moments are LINEAR in the gradients: they carry the 1e-5 bar.  The weights themselves move by lr * m / (sqrt(v) + eps), which
+    # for gradient components of the order of eps = 1e-8 (many at this batch size: the mean over 32768 rows of a policy whose last layer
+    # starts at gain 0.01) turns a 1e-6 relative gradient difference into a visible fraction of one step - both engines, the exact-fp32
+    # SIMT one included, sit at ~3.5e-5 of the weight norm = 0.2 % of the update here.  Hence: moments 1e-5, weights 1e-4 of the norm and
+    # never further apart than a tenth of the four lr-sized steps.
+    pol_now, cri_now = fp.state_dicts()
+    mom1, mom2 = fp.__class__(k, DEV), fp.__class__(k, DEV)
+    mom1.flat.copy_(exp_avg)
+    mom2.flat.copy_(exp_avg_sq)
+    m1p, m1c = mom1.state_dicts()
+    m2p, m2c = mom2.state_dicts()
+    for keys, opt, cur, params, m1, m2 in ((O.POLICY_KEYS, L.popt, pol_now, L.pol, m1p, m2p), (O.CRITIC_KEYS, L.copt, cri_now, L.cri, m1c, m2c)):
+        for i, name in enumerate(keys):
+            st = opt.state[opt.param_groups[0]["params"][i]]
+            assert _rel(m1[name].numpy(), st["exp_avg"].numpy()) <= 1e-5, (name, "exp_avg", _rel(m1[name].numpy(), st["exp_avg"].numpy()))
+            assert _rel(m2[name].numpy(), st["exp_avg_sq"].numpy()) <= 2e-5, (name, "exp_avg_sq", _rel(m2[name].numpy(), st["exp_avg_sq"].numpy()))
+            ours, ref = cur[name].numpy(), params[name].detach().numpy()
+            assert _rel(ours, ref) <= 1e-4, (name, _rel(ours, ref))
+            assert float(np.abs(ours - ref).max()) <= 0.1 * nmb * 3e-4, (name, float(np.abs(ours - ref).max()))
+    m = metrics.cpu().numpy()
+    for i, r in enumerate(ref_metrics):
+        assert abs(m[i, 0] - r["pg_loss"]) <= 1e-5 * max(abs(r["pg_loss"]), 0.5), (i, m[i, 0], r["pg_loss"])
+        assert abs(m[i, 1] - r["critic_loss"]) <= 1e-5 * abs(r["critic_loss"])
+        assert abs(m[i, 3] - r["approx_kl"]) <= 1e-5 * max(abs(r["approx_kl"]), 1e-2)
+        assert abs(m[i, 4] - r["clip_fraction"]) <= 2.0 / mb
+        assert abs(m[i, 5] - r["policy_grad_norm"]) <= 1e-5 * r["policy_grad_norm"]
+        assert abs(m[i, 6] - r["critic_grad_norm"]) <= 1e-5 * r["critic_grad_norm"]
 
 
 def test_library_reports_kernel_launches():

@@ -218,3 +218,39 @@ def test_sac_train_loop_runs(interface, gemm_engine):
     assert all(np.isfinite(v) for _, v, _ in logged)
     assert model.nr_updates == (120 - 24) // 4  # updates run once global_step > learning_starts (sac.py:212)
     assert int(model.steps[0].item()) == model.nr_updates
+
+
+def test_sac_checkpoint_has_the_reference_optimizer_layout(tmp_path):
+    """save() writes the reference's keys (sac.py:381-396) incl. the three torch.optim.Adam state dicts in parameters() order
+    (policy: torso, mean, log_std; q: q1 then q2), and load() restores moments and step counters from them."""
+    from rl_x_b200.algorithms.sac.b200.sac import SAC, POLICY_PARAM_ORDER
+    N, obs, act, hidden = 2, 9, 3, 32
+    model, env = _model(N, obs, act, hidden, 16, np.full(act, -1.0, np.float32), np.full(act, 1.0, np.float32))
+    model.save_path = str(tmp_path)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in (model.m_policy, model.m_q, model.m_la, model.policy, model.q):
+        t.normal_(generator=g)
+    for t in (model.v_policy, model.v_q, model.v_la):
+        t.uniform_(generator=g)
+    model.steps.copy_(torch.tensor([7, 9, 8]))
+    model.log_alpha.fill_(-0.3)
+    model.save()
+    ck = torch.load(str(tmp_path / "best.model"), weights_only=False)
+    assert set(ck) == {"config_algorithm", "policy_state_dict", "q1_state_dict", "q2_state_dict", "q1_target_state_dict", "q2_target_state_dict",
+                       "log_alpha", "policy_optimizer_state_dict", "q_optimizer_state_dict", "entropy_optimizer_state_dict"}
+    assert list(ck["policy_state_dict"]) == list(POLICY_PARAM_ORDER)
+    po, qo, eo = ck["policy_optimizer_state_dict"], ck["q_optimizer_state_dict"], ck["entropy_optimizer_state_dict"]
+    assert len(po["state"]) == 8 and len(qo["state"]) == 12 and len(eo["state"]) == 1
+    assert tuple(po["state"][4]["exp_avg"].shape) == (act, hidden) and tuple(po["state"][5]["exp_avg"].shape) == (act,)  # mean.weight, mean.bias
+    assert tuple(qo["state"][6]["exp_avg"].shape) == (hidden, obs + act) and float(qo["state"][0]["step"]) == 9.0
+    # the dicts drive real torch optimizers over modules shaped like the reference's
+    pol = torch.nn.ParameterList([torch.nn.Parameter(v.clone()) for v in ck["policy_state_dict"].values()])
+    opt = torch.optim.Adam(pol.parameters(), lr=1e-3)
+    opt.load_state_dict(po)
+    assert torch.equal(opt.state[pol[6]]["exp_avg"], po["state"][6]["exp_avg"])
+    # round trip
+    cfg = model.config
+    cfg.runner.load_model = str(tmp_path / "best.model")
+    m2 = SAC.load(cfg, env, env, "/tmp/rlx_sac_test2", None, [])
+    for name in ("policy", "q", "log_alpha", "m_policy", "v_policy", "m_q", "v_q", "m_la", "v_la", "steps"):
+        assert torch.equal(getattr(m2, name), getattr(model, name)), name

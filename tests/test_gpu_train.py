@@ -141,7 +141,15 @@ def test_train_reproduces_reference_run(golden, interface, gemm_engine):
     assert calls["n"] == g.T * g.iterations and len(snaps) == g.iterations
     # the env received the clipped / rescaled actions the reference sent
     np.testing.assert_allclose(torch.stack(env.actions).numpy(), g["env_actions"], rtol=1e-4, atol=5e-6)
+    # north_star: <= 1e-5 relative on losses / advantages.  The norm: ||ours - ref||_2 <= 1e-5 * ||ref||_2 per tensor, in the
+    # FIRST iteration, where both sides act with identical weights.  From the second iteration on the run follows its own weights, which
+    # Adam's eps-regime components have moved ~1e-5 of their norm away from the reference's (see test_one_epoch_at_bench_shape_vs_oracle):
+    # there the bound is 1e-4 of the norm.  The elementwise allclose is the coarse guard against single outliers.
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
     for it, s in enumerate(snaps):
+        bar = 1e-5 if it == 0 else 1e-4
+        for key, name in (("val", "values"), ("lp", "log_probs"), ("adv", "advantages"), ("ret", "returns")):
+            assert rel(s[key], g[f"iter{it}/{name}"]) <= bar, (it, name, rel(s[key], g[f"iter{it}/{name}"]))
         np.testing.assert_allclose(s["val"], g[f"iter{it}/values"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(s["lp"], g[f"iter{it}/log_probs"], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(s["adv"], g[f"iter{it}/advantages"], rtol=1e-4, atol=2e-5)
@@ -162,8 +170,11 @@ def test_train_reproduces_reference_run(golden, interface, gemm_engine):
               "v_value/explained_variance", "policy/std_dev", "steps/nr_env_steps", "steps/nr_updates", "steps/nr_episodes"]:
         ours = [v for m, v, _ in logged if m == n]
         ref = g[f"metric/{n}"]
+        np.testing.assert_allclose(ours[:1], ref[:1], rtol=1e-5, atol=1e-7, err_msg=n + " (first iteration: identical weights on both sides)")
         np.testing.assert_allclose(ours, ref, rtol=2e-4, atol=1e-6, err_msg=n)
+    # pg_loss is a mean of signed terms with near-zero mean: its scale is the summand scale E|A_hat| ~ 0.8, not its own value
     ours = [v for m, v, _ in logged if m == "loss/policy_gradient_loss"]
+    np.testing.assert_allclose(ours[:1], g["metric/loss/policy_gradient_loss"][:1], rtol=0, atol=1e-5 * 0.8)
     np.testing.assert_allclose(ours, g["metric/loss/policy_gradient_loss"], rtol=0, atol=2e-5)
 
 
@@ -206,6 +217,36 @@ def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch, g
         assert torch.equal(c1[k], c2[k])
     assert int(m2.adam_step.item()) == int(float(ck["policy_optimizer_state_dict"]["state"][0]["step"]))
     m2.test(1)
+
+
+def test_load_checkpoint_written_by_the_reference(tmp_path, monkeypatch):
+    """PPO.load() on a best.model written by the executed reference's own save() (tests/golden/make_golden_ppo_ckpt.py): weights and both
+    Adam states arrive where the reference had them (its optimizer numbers policy_logstd as parameter 0), training continues from it, and
+    the file save() writes afterwards has the reference's layout again."""
+    import os
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.runner.runner import Runner
+    monkeypatch.chdir(tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = np.load(os.path.join(root, "tests", "golden", "ppo_ref_checkpoint_expect.npz"))
+    N, T, obs, act, hid, mb, E = (int(x) for x in ex["meta"])
+    argv = [f"--environment.nr_envs={N}", f"--environment.obs_dim={obs}", f"--environment.act_dim={act}", "--runner.save_model=True",
+            "--runner.run_name=fromref", "--runner.load_model=" + os.path.join(root, "tests", "golden", "ppo_ref_checkpoint.model"),
+            f"--algorithm.total_timesteps={2 * N * T}"]
+    r = Runner(argv=argv)
+    model, env, _ = r._build_model(str(tmp_path / "run"), None)
+    assert (model.nr_steps, model.nr_epochs, model.minibatch_size, model.nr_hidden_units) == (T, E, mb, hid)  # taken from the checkpoint's config
+    for tag, keys in (("policy", nt.POLICY_KEYS), ("critic", nt.CRITIC_KEYS)):
+        for name, seg in keys.items():
+            assert np.array_equal(model.params.view(model.params.flat, seg).cpu().numpy(), ex[f"{tag}/{name}/param"]), name
+            assert np.array_equal(model.params.view(model.exp_avg, seg).cpu().numpy(), ex[f"{tag}/{name}/exp_avg"]), name
+            assert np.array_equal(model.params.view(model.exp_avg_sq, seg).cpu().numpy(), ex[f"{tag}/{name}/exp_avg_sq"]), name
+    assert int(model.adam_step.item()) == int(ex["policy/policy_logstd/step"])
+    model.train()
+    assert int(model.adam_step.item()) > int(ex["policy/policy_logstd/step"])
+    model.save()
+    ck = torch.load(str(tmp_path / "run" / "models" / "best.model"), weights_only=False)
+    assert list(ck["policy_state_dict"])[0] == "policy_logstd" and tuple(ck["policy_optimizer_state_dict"]["state"][0]["exp_avg"].shape) == (1, act)
 
 
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])

@@ -84,8 +84,6 @@ def test_espo_train_reproduces_reference_run(golden_espo, interface, gemm_engine
         np.testing.assert_allclose(ours, g[f"metric/{n}"], rtol=1e-3, atol=atol, err_msg=n)
 
 
-@pytest.mark.xfail(strict=False, reason="tolerance for zero-initialised biases revised after the round's last hardware run (stop step and all weight "
-                                       "matrices matched there); remove once it has passed on a B200")
 def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine):
     """One ESPO iteration on random rollout data of Humanoid-like width (376 -> 256 -> 256 -> 17) against oracle/espo_oracle.py: same stop
     step, same weights."""

@@ -1,13 +1,12 @@
 """FastSAC n-step replay sampling kernel (rlx_replay_sample_nstep_f32) against the executed reference (tests/golden/fastsac_replay.npz)
 and against oracle/fastsac_replay_oracle.py on a large random ring.
 
-This file sorts last and its tests are xfail(strict=False): the kernel was written after the round's GPU budget was spent, so its
-first hardware run is the driver's; a defect here must not mask the verified suites.  Remove the marker once it has passed on a B200."""
+First passed on a B200 at the round-1 driver run (GPUTEST_r01.json); strict since round 2."""
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 NAMES = ["states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps"]
 

@@ -1,7 +1,7 @@
 """PPO+LSTM path on the GPU (rl_x_b200/csrc/lstm.cu through librlx_b200.so) against oracle/ppo_lstm_oracle.py.
 
-Sorts last and is xfail(strict=False): the path was written after the round's GPU budget was spent (its numerics are validated in host
-emulation, tests/test_lstm_emulation.py); the first hardware run is the driver's.  Remove the marker once it has passed on a B200."""
+The same sources are validated in host emulation (tests/test_lstm_emulation.py).  First passed on a B200 at the round-1 driver run;
+strict since round 2."""
 import ctypes as C
 
 import numpy as np
@@ -11,7 +11,7 @@ import torch
 from oracle import ppo_lstm_oracle as L
 from test_lstm_emulation import CRITIC_SEGS, POLICY_SEGS, flatten_critic, flatten_policy
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 

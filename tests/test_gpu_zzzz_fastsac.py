@@ -1,6 +1,6 @@
 """FastSAC update path on the GPU (rl_x_b200/csrc/fastsac.cu through librlx_b200.so) against oracle/fastsac_oracle.py, and a short run of
-the fastsac.b200 plugin.  Sorts last and is xfail(strict=False): written after the round's GPU budget was spent; its numerics are
-validated in host emulation against the executed reference (tests/test_fastsac_emulation.py).  Remove the marker after the first pass."""
+the fastsac.b200 plugin.  The same sources are also validated in host emulation against the executed reference
+(tests/test_fastsac_emulation.py).  First passed on a B200 at the round-1 driver run; strict since round 2."""
 import ctypes as C
 import os
 
@@ -10,7 +10,7 @@ import torch
 
 from oracle import fastsac_oracle as FS
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first hardware run pending (written without GPU access)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

@@ -270,3 +270,89 @@ def test_sharded_gradient_equals_single_process_gloo_world2():
         assert p.exitcode == 0
     for rank, err in results:
         assert err < 5e-7, (rank, err)
+
+
+# ------------------------------------------------------------------------------------------- checkpoint interoperability
+def _ckpt_fixture():
+    from rl_x_b200.algorithms.ppo.b200.kernels import PpoKernels
+    from rl_x_b200.algorithms.ppo.b200.ppo import FlatParameters
+    ck = torch.load(os.path.join(ROOT, "tests", "golden", "ppo_ref_checkpoint.model"), weights_only=False)
+    ex = np.load(os.path.join(ROOT, "tests", "golden", "ppo_ref_checkpoint_expect.npz"))
+    N, T, obs, act, hid, mb, E = (int(x) for x in ex["meta"])
+    k = PpoKernels(obs, act, hid)
+    return ck, ex, k, FlatParameters(k, "cpu")
+
+
+def test_checkpoint_written_by_the_reference_maps_onto_the_flat_layout():
+    """tests/golden/ppo_ref_checkpoint.model was written by the executed reference's own PPO.save() (make_golden_ppo_ckpt.py).  Its
+    optimizer states are numbered in nn.Module.parameters() order - policy_logstd FIRST - and must land on the right segments."""
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.algorithms.ppo.b200.ppo import CRITIC_PARAM_ORDER, POLICY_PARAM_ORDER
+    ck, ex, k, fp = _ckpt_fixture()
+    assert list(ck["policy_state_dict"]) == list(POLICY_PARAM_ORDER) and list(ck["critic_state_dict"]) == list(CRITIC_PARAM_ORDER)
+    fp.load_named({**ck["policy_state_dict"], **ck["critic_state_dict"]})
+    m1, m2 = torch.zeros(k.param_count), torch.zeros(k.param_count)
+    sp = fp.load_adam_state(ck["policy_optimizer_state_dict"], POLICY_PARAM_ORDER, nt.POLICY_KEYS, m1, m2)
+    sc = fp.load_adam_state(ck["critic_optimizer_state_dict"], CRITIC_PARAM_ORDER, nt.CRITIC_KEYS, m1, m2)
+    for tag, keys in (("policy", nt.POLICY_KEYS), ("critic", nt.CRITIC_KEYS)):
+        for name, seg in keys.items():
+            assert np.array_equal(fp.view(fp.flat, seg).numpy(), ex[f"{tag}/{name}/param"]), name
+            assert np.array_equal(fp.view(m1, seg).numpy(), ex[f"{tag}/{name}/exp_avg"]), name
+            assert np.array_equal(fp.view(m2, seg).numpy(), ex[f"{tag}/{name}/exp_avg_sq"]), name
+            assert float(ex[f"{tag}/{name}/step"]) == sp == sc
+    # and back: what save() writes is, tensor for tensor and index for index, what the reference wrote
+    pol, cri = fp.state_dicts()
+    assert list(pol) == list(ck["policy_state_dict"]) and all(torch.equal(pol[n], ck["policy_state_dict"][n]) for n in pol)
+    assert list(cri) == list(ck["critic_state_dict"]) and all(torch.equal(cri[n], ck["critic_state_dict"][n]) for n in cri)
+    for key, order, keys in (("policy_optimizer_state_dict", POLICY_PARAM_ORDER, nt.POLICY_KEYS), ("critic_optimizer_state_dict", CRITIC_PARAM_ORDER, nt.CRITIC_KEYS)):
+        ours, ref = fp.adam_state_dict(order, keys, m1, m2, sp, 3e-4), ck[key]
+        assert ours["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+        assert set(ours["param_groups"][0]) == set(ref["param_groups"][0])
+        for i in ref["state"]:
+            for f in ("exp_avg", "exp_avg_sq"):
+                assert torch.equal(ours["state"][i][f], ref["state"][i][f]), (key, i, f)
+            assert float(ours["state"][i]["step"]) == float(ref["state"][i]["step"])
+    # a permuted optimizer state (the round-1 bug: logstd last) is rejected instead of being mis-assigned
+    bad = {"state": {i: ck["policy_optimizer_state_dict"]["state"][(i + 1) % 7] for i in range(7)}}
+    with pytest.raises(ValueError, match="expected"):
+        fp.load_adam_state(bad, POLICY_PARAM_ORDER, nt.POLICY_KEYS, m1, m2)
+    # torch builds that keep the compile wrapper's prefix in state_dict()
+    fp2 = fp.__class__(k, "cpu")
+    fp2.load_named({"_orig_mod." + n: v for n, v in {**ck["policy_state_dict"], **ck["critic_state_dict"]}.items()})
+    assert torch.equal(fp2.flat, fp.flat)
+
+
+def test_checkpoint_written_here_loads_into_the_reference_modules():
+    """The other direction, with the reference's own classes (staged copy oracle/_ref): strict load_state_dict + optimizer.load_state_dict
+    as in the reference's load() (ppo.py:447-450)."""
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+    from oracle import ref_arm
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.algorithms.ppo.b200.ppo import CRITIC_PARAM_ORDER, POLICY_PARAM_ORDER
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    refppo = ref_arm.import_reference()
+    from rl_x.algorithms.ppo.pytorch.default_config import get_config
+    ck, ex, k, fp = _ckpt_fixture()
+    N, T, obs, act, hid, mb, E = (int(x) for x in ex["meta"])
+    g = torch.Generator().manual_seed(0)
+    fp.flat.copy_(torch.randn(k.param_count, generator=g))
+    m1, m2 = torch.randn(k.param_count, generator=g), torch.rand(k.param_count, generator=g)
+    pol, cri = fp.state_dicts()
+    a = get_config("ppo.pytorch")
+    a.device, a.bf16_mixed_precision_training, a.nr_steps, a.nr_epochs, a.minibatch_size, a.nr_hidden_units = "cpu", False, T, E, mb, hid
+    cfg = ref_arm._ConfigDict(algorithm=a, environment=ref_arm._ConfigDict(seed=0, nr_envs=N),
+                              runner=ref_arm._ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False))
+    env = ref_arm.SyntheticTorchEnv(N, obs, act)
+    model = refppo.PPO(cfg, env, env, "/tmp/rlx_ckpt_interop", None)
+    model.policy.load_state_dict(pol)
+    model.critic.load_state_dict(cri)
+    model.policy_optimizer.load_state_dict(fp.adam_state_dict(POLICY_PARAM_ORDER, nt.POLICY_KEYS, m1, m2, 5, 3e-4))
+    model.critic_optimizer.load_state_dict(fp.adam_state_dict(CRITIC_PARAM_ORDER, nt.CRITIC_KEYS, m1, m2, 5, 3e-4))
+    for net, opt, keys in ((model.policy, model.policy_optimizer, nt.POLICY_KEYS), (model.critic, model.critic_optimizer, nt.CRITIC_KEYS)):
+        for name, p in net.named_parameters():
+            seg = keys[name.replace("_orig_mod.", "")]
+            assert torch.equal(p.detach(), fp.view(fp.flat, seg)), name
+            assert torch.equal(opt.state[p]["exp_avg"], fp.view(m1, seg)) and torch.equal(opt.state[p]["exp_avg_sq"], fp.view(m2, seg)), name
+            assert float(opt.state[p]["step"]) == 5.0
