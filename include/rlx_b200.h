@@ -128,6 +128,15 @@ int rlx_critic_forward_f32(const rlx_ppo_dims* d, const float* params, const flo
 int rlx_rollout_store_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* next_obs,
                           int64_t n, int64_t obs_dim, float* rewards_row, float* terminations_row, float* next_obs_dst,
                           int64_t* done_count, void* stream);
+/* Same, plus device-side episode statistics with the semantics of the reference's torch-interface envs
+ * (rl_x/environments/custom_mujoco/ant/warp_torch/environment.py:159-178, wrappers.py:15-33): episode_return[n] / episode_length[n]
+ * (in/out running accumulators, zero-initialised by the caller) take this step's reward / +1; for an env whose episode ended
+ * (terminated | truncated) done_return_row[i] / done_length_row[i] receive the finished episode's return / length and the accumulators
+ * restart from zero; elsewhere the rows receive 0 (length 0 = "no episode ended here").  All four may be NULL (= rlx_rollout_store_f32). */
+int rlx_rollout_store_stats_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* next_obs,
+                                int64_t n, int64_t obs_dim, float* rewards_row, float* terminations_row, float* next_obs_dst,
+                                int64_t* done_count, float* episode_return, float* episode_length, float* done_return_row,
+                                float* done_length_row, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ GAE -- */
 /* ref: calculate_gae_advantages_and_returns  (ppo.py:110-118)

@@ -78,13 +78,15 @@ class PpoKernels:
                                                  _f32(value, "value"), workspace.data_ptr(), workspace.numel(), _stream()),
                  "rlx_critic_forward_f32")
 
-    def rollout_store(self, reward, terminated, truncated, next_obs, rewards_row, terminations_row, next_obs_dst, done_count):
+    def rollout_store(self, reward, terminated, truncated, next_obs, rewards_row, terminations_row, next_obs_dst, done_count, episode_stats=None):
+        """episode_stats: (episode_return [n], episode_length [n], done_return_row [n], done_length_row [n]) or None."""
         n = reward.shape[0] if reward is not None else next_obs.shape[0]
-        nt.check(self.lib.rlx_rollout_store_f32(_f32(reward, "reward"), _bool_u8(terminated, "terminated"), _bool_u8(truncated, "truncated"),
-                                                _f32(next_obs, "next_obs"), n, self.obs_dim, _f32(rewards_row, "rewards_row"),
-                                                _f32(terminations_row, "terminations_row"), _f32(next_obs_dst, "next_obs_dst"),
-                                                done_count.data_ptr() if done_count is not None else None, _stream()),
-                 "rlx_rollout_store_f32")
+        es = [_f32(t, "episode_stats") for t in episode_stats] if episode_stats is not None else [None] * 4
+        nt.check(self.lib.rlx_rollout_store_stats_f32(_f32(reward, "reward"), _bool_u8(terminated, "terminated"), _bool_u8(truncated, "truncated"),
+                                                      _f32(next_obs, "next_obs"), n, self.obs_dim, _f32(rewards_row, "rewards_row"),
+                                                      _f32(terminations_row, "terminations_row"), _f32(next_obs_dst, "next_obs_dst"),
+                                                      done_count.data_ptr() if done_count is not None else None, *es, _stream()),
+                 "rlx_rollout_store_stats_f32")
 
     # ---------------------------------------------------------------------------------------------------- GAE
     def gae(self, rewards, terminations, values, gamma, gae_lambda, advantages, returns, next_values=None, last_value=None):

@@ -347,12 +347,22 @@ class PPO:
             self.d_trunc = torch.zeros(N, dtype=torch.bool, device=dev)
             self.d_obs = z(N, obs)
         self.noise_buf = z(N, act) if self.rollout_noise == "torch" else None
+        # device-side episode statistics for TORCH-interface envs (semantics of warp_torch/environment.py:159-178 and
+        # wrappers.py:15-33): running return / length per env, and per rollout step the return / length of the episodes that ended there.
+        # Read back ONCE per iteration with the metric records - no per-step .cpu() as in the reference's wrapper.
+        self.device_episode_stats = self.is_torch_data_interface and bool(self.config.algorithm.get("device_episode_statistics", True))
+        if self.device_episode_stats:
+            self.ep_return, self.ep_length = z(N), z(N)
+            self.done_stats_dev = z(2, T, N)   # [0] finished-episode return, [1] finished-episode length (0 = none ended)
+            self.done_stats_host = torch.zeros(2, T, N).pin_memory()
         b = self.batch
         self._fwd_args = [self.kernels.forward_args(self.params.flat, b.states[t], self.fwd_ws, rng_seed=self.noise_seed, act_low=self.env_as_low,
                                                     act_high=self.env_as_high, clip_rescale=self.action_clipping_and_rescaling,
                                                     action=b.actions[t], env_action=self.env_action, logp=b.log_probs[t], value=b.values[t])
                           for t in range(T)]
         self._store_rows = [(b.rewards[t], b.terminations[t], b.states[t + 1]) for t in range(T)]
+        self._stat_rows = ([(self.ep_return, self.ep_length, self.done_stats_dev[0, t], self.done_stats_dev[1, t]) for t in range(T)]
+                           if self.device_episode_stats else [None] * T)
         self._alloc_done = True
 
     # ------------------------------------------------------------------------------------------------- acting
@@ -408,7 +418,7 @@ class PPO:
                 truncated = truncated if truncated.dtype == torch.bool else truncated.bool()
                 rr, tr, ns = self._store_rows[step]
                 self.kernels.rollout_store(reward.contiguous(), terminated.contiguous(), truncated.contiguous(), next_state.contiguous(),
-                                           rr, tr, ns, self.done_count)
+                                           rr, tr, ns, self.done_count, self._stat_rows[step])
             else:
                 self.h_action.copy_(self.env_action, non_blocking=True)
                 self.action_ready.record()
@@ -586,6 +596,9 @@ class PPO:
         self.set_train_mode()
         self.saving_return_buffer = deque(maxlen=100 * self.nr_envs)
         state, _ = self.train_env.reset()
+        if self.device_episode_stats:
+            self.ep_return.zero_()
+            self.ep_length.zero_()
         if self.is_torch_data_interface:
             k.rollout_store(None, None, None, state.float().contiguous(), None, None, b.states[0], None)
         else:
@@ -670,8 +683,19 @@ class PPO:
 
         # the only device->host transfers of the iteration: per-minibatch metric records, explained variance, done count
         self.metrics_host.copy_(self.metrics_dev, non_blocking=True)
+        if self.device_episode_stats:
+            self.done_stats_host.copy_(self.done_stats_dev, non_blocking=True)
         ev_host = ev_pair.cpu()
         dones_this_rollout = dones_host if not self.is_torch_data_interface else int(self.done_count.item())
+        if self.device_episode_stats and dones_this_rollout > 0:
+            # what the reference's wrapper would have handed over step by step (`v[done_mask].tolist()`, wrappers.py:29-32): finished
+            # episodes in step order, env order within a step
+            lengths = self.done_stats_host[1].numpy()
+            mask = lengths > 0
+            finished_returns = self.done_stats_host[0].numpy()[mask]
+            step_info_collection.setdefault("episode_return", []).extend(finished_returns.tolist())
+            step_info_collection.setdefault("episode_length", []).extend(lengths[mask].tolist())
+            self.saving_return_buffer.extend(finished_returns.tolist())
         if self._perm_stream is not None:  # the .cpu()/.item() above synchronised the stream: the staged permutations were consumed
             self._perm_stream.release(self._perm_slots_in_flight)
             self._perm_slots_in_flight = []

@@ -19,7 +19,9 @@ __global__ void __launch_bounds__(256) rollout_store_kernel(const float* __restr
                                                             const uint8_t* __restrict__ truncated, const float* __restrict__ next_obs,
                                                             long long n, long long obs_dim, float* __restrict__ rewards_row,
                                                             float* __restrict__ term_row, float* __restrict__ next_dst,
-                                                            long long* done_count, int vec) {
+                                                            long long* done_count, int vec, float* __restrict__ ep_return,
+                                                            float* __restrict__ ep_length, float* __restrict__ done_return_row,
+                                                            float* __restrict__ done_length_row) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   if (next_obs != nullptr && next_dst != nullptr) {
@@ -40,6 +42,18 @@ __global__ void __launch_bounds__(256) rollout_store_kernel(const float* __restr
       if (rewards_row && reward) rewards_row[i] = reward[i];
       if (term_row) term_row[i] = te ? 1.f : 0.f;
       dones += (te || tr) ? 1 : 0;
+      if (ep_return != nullptr) {
+        // device-side episode statistics with the semantics of the reference's torch-interface env
+        // (custom_mujoco/ant/warp_torch/environment.py:159-178): step count and return accumulate, a finished episode publishes both
+        // for this step and restarts from zero.  A length of 0 in the row means "no episode ended here".
+        const float ret = ep_return[i] + reward[i];
+        const float len = ep_length[i] + 1.f;
+        const bool done = te || tr;
+        done_return_row[i] = done ? ret : 0.f;
+        done_length_row[i] = done ? len : 0.f;
+        ep_return[i] = done ? 0.f : ret;
+        ep_length[i] = done ? 0.f : len;
+      }
     }
   }
   if (done_count != nullptr) {
@@ -183,15 +197,25 @@ using namespace rlx;
 extern "C" int rlx_rollout_store_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* next_obs,
                                      int64_t n, int64_t obs_dim, float* rewards_row, float* terminations_row, float* next_obs_dst,
                                      int64_t* done_count, void* stream) {
+  return rlx_rollout_store_stats_f32(reward, terminated, truncated, next_obs, n, obs_dim, rewards_row, terminations_row, next_obs_dst, done_count,
+                                     nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int rlx_rollout_store_stats_f32(const float* reward, const uint8_t* terminated, const uint8_t* truncated, const float* next_obs,
+                                           int64_t n, int64_t obs_dim, float* rewards_row, float* terminations_row, float* next_obs_dst,
+                                           int64_t* done_count, float* episode_return, float* episode_length, float* done_return_row,
+                                           float* done_length_row, void* stream) {
   RLX_CHECK_ARG(n >= 0 && obs_dim >= 0, "negative size");
   if (n == 0) return RLX_OK;
   RLX_CHECK_ARG((reward && terminated) || (next_obs && next_obs_dst), "nothing to store");
   RLX_CHECK_ARG(!rewards_row || reward, "rewards_row given without reward");
+  RLX_CHECK_ARG(!episode_return || (reward && terminated && episode_length && done_return_row && done_length_row),
+                "episode statistics need reward, terminated and all four statistics arrays");
   const int vec = (next_obs && next_obs_dst && aligned16(next_obs) && aligned16(next_obs_dst) && ((n * obs_dim) % 4 == 0)) ? 1 : 0;
   const long long work = (next_obs && next_obs_dst) ? (vec ? n * obs_dim / 4 : n * obs_dim) : n;
   const unsigned grid = (unsigned)std::min<long long>(ceil_div(std::max<long long>(work, n), 256), (long long)sm_count() * 8);
   RLX_LAUNCH_C(KC_STORE, 0, ((next_obs && next_obs_dst) ? 8.0 * n * obs_dim : 0.0) + 10.0 * n, rollout_store_kernel, grid, 256, 0, stream, reward, terminated, truncated, next_obs, (long long)n, (long long)obs_dim,
-             rewards_row, terminations_row, next_obs_dst, (long long*)done_count, vec);
+             rewards_row, terminations_row, next_obs_dst, (long long*)done_count, vec, episode_return, episode_length, done_return_row, done_length_row);
   return RLX_OK;
 }
 

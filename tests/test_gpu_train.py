@@ -219,6 +219,78 @@ def test_runner_trains_on_synthetic_env_and_checkpoints(tmp_path, monkeypatch, g
     m2.test(1)
 
 
+def test_config1_pendulum_trains_evaluates_and_saves_best(tmp_path, monkeypatch):
+    """BASELINE.json configs[0]: PPO on Pendulum-v1 with nr_envs=4 through the runner (NUMPY data interface, gym-style autoreset infos).
+    Covers PPO._evaluate() (ppo.py:319-345 of the reference): deterministic actions until `evaluation_episodes` episodes finished."""
+    from rl_x_b200.runner.runner import Runner
+    monkeypatch.chdir(tmp_path)
+    argv = ["--environment.name=synthetic.pendulum", "--algorithm.nr_steps=256", "--algorithm.minibatch_size=64", "--algorithm.nr_epochs=2",
+            "--algorithm.nr_hidden_units=64", "--algorithm.total_timesteps=3072", "--algorithm.evaluation_frequency=1024",
+            "--algorithm.evaluation_episodes=3", "--runner.save_model=True", "--runner.run_name=c1"]
+    r = Runner(argv=argv)
+    model, env, eval_env = r._build_model(str(tmp_path / "run"), None)
+    assert model.nr_envs == 4 and not model.is_torch_data_interface
+    logged = []
+    model.log = lambda name, value, step: logged.append((name, float(value), int(step)))
+    model.train()
+    names = [n for n, _, _ in logged]
+    for n in ("rollout/episode_return", "rollout/episode_length", "eval/episode_return", "eval/episode_length", "loss/critic_loss", "time/sps"):
+        assert n in names, n
+    ev = [v for n, v, _ in logged if n == "eval/episode_length"]
+    assert len(ev) == 3 and all(v == 200.0 for v in ev)             # every evaluation: 3 episodes of TimeLimit(200)
+    rets = [v for n, v, _ in logged if n == "rollout/episode_return"]
+    assert all(-2000.0 < v < 0.0 for v in rets)                       # Pendulum-v1 returns: 200 steps of cost in [0, 16.3]
+    assert [v for n, v, _ in logged if n == "rollout/episode_length"] == [200.0] * len(rets)
+    assert (tmp_path / "run" / "models" / "best.model").exists()    # episodes finished -> save-best fired (ppo.py:353-357)
+    assert model.nr_episodes == 4 * (3 * 256 // 200)
+
+
+def test_device_episode_statistics_match_a_host_recomputation(gemm_engine):
+    """for TORCH-interface envs episode return / length are tracked on the device inside the rollout-store kernel and
+    read back once per iteration.  Check against a host replay of the stored rewards / terminations / truncations with the semantics
+    of the reference env + wrapper (warp_torch/environment.py:159-178, wrappers.py:15-33)."""
+    from rl_x_b200.runner.runner import Runner
+    N, T, horizon, iters = 64, 40, 13, 3
+    argv = [f"--environment.nr_envs={N}", "--environment.obs_dim=24", "--environment.act_dim=5", f"--environment.horizon={horizon}",
+            "--environment.termination_probability=0.03", f"--algorithm.nr_steps={T}", "--algorithm.minibatch_size=256", "--algorithm.nr_epochs=1",
+            "--algorithm.nr_hidden_units=64", f"--algorithm.total_timesteps={iters * N * T}", f"--algorithm.gemm_engine={gemm_engine}"]
+    r = Runner(argv=argv)
+    model, env, _ = r._build_model("/tmp/rlx_epstats", None)
+    assert model.is_torch_data_interface
+    logged, per_iter = [], []
+    model.log = lambda name, value, step: logged.append((name, float(value), int(step)))
+    orig = model.start_logging
+
+    def start_logging(step):
+        b = model.batch
+        per_iter.append((b.rewards.cpu().numpy().copy(), b.terminations.cpu().numpy().copy()))
+        orig(step)
+
+    model.start_logging = start_logging
+    model.train()
+    ep_ret, ep_len, t_global = np.zeros(N, np.float32), np.zeros(N, np.float32), 0
+    want_ret, want_len, episodes = [], [], 0
+    for rew, term in per_iter:
+        rets, lens = [], []
+        for t in range(T):
+            t_global += 1
+            done = (term[t] > 0.5) | (t_global % horizon == 0)  # the synthetic env truncates every `horizon` steps
+            ep_ret += rew[t]
+            ep_len += 1
+            rets += ep_ret[done].tolist()
+            lens += ep_len[done].tolist()
+            ep_ret[done], ep_len[done] = 0, 0
+        episodes += len(rets)
+        want_ret.append(np.mean(rets))
+        want_len.append(np.mean(lens))
+    got_ret = [v for n, v, _ in logged if n == "rollout/episode_return"]
+    got_len = [v for n, v, _ in logged if n == "rollout/episode_length"]
+    np.testing.assert_allclose(got_ret, want_ret, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(got_len, want_len, rtol=1e-7)
+    assert [v for n, v, _ in logged if n == "steps/nr_episodes"][-1] == episodes
+    assert len(model.saving_return_buffer) == episodes
+
+
 def test_load_checkpoint_written_by_the_reference(tmp_path, monkeypatch):
     """PPO.load() on a best.model written by the executed reference's own save() (tests/golden/make_golden_ppo_ckpt.py): weights and both
     Adam states arrive where the reference had them (its optimizer numbers policy_logstd as parameter 0), training continues from it, and

@@ -356,3 +356,43 @@ def test_checkpoint_written_here_loads_into_the_reference_modules():
             assert torch.equal(p.detach(), fp.view(fp.flat, seg)), name
             assert torch.equal(opt.state[p]["exp_avg"], fp.view(m1, seg)) and torch.equal(opt.state[p]["exp_avg_sq"], fp.view(m2, seg)), name
             assert float(opt.state[p]["step"]) == 5.0
+
+
+# ------------------------------------------------------------------------------------------------- config 1: Pendulum-v1
+def test_pendulum_restates_the_published_dynamics_and_the_autoreset_convention():
+    """BASELINE.json configs[0].  Known answers computed by hand from the published Pendulum-v1 update rule (see environment.py), plus the
+    gymnasium-0.29 vector autoreset convention the reference's wrapper reads (gym/mujoco/humanoid_v4/wrappers.py:9-32)."""
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.environments.synthetic.pendulum import create_train_and_eval_env, get_config
+    from rl_x_b200.environments.synthetic.pendulum.environment import angle_normalize
+    cfg = ConfigDict(environment=get_config("synthetic.pendulum"))
+    env, eval_env = create_train_and_eval_env(cfg)
+    assert env is eval_env and env.nr_envs == 4 and env.general_properties.data_interface_type.name == "NUMPY"
+    assert env.single_observation_space.shape == (3,) and env.single_action_space.shape == (1,)
+    assert float(env.single_action_space.low[0]) == -2.0 and float(env.single_action_space.high[0]) == 2.0
+    assert abs(angle_normalize(3 * np.pi / 2) + np.pi / 2) < 1e-12 and abs(angle_normalize(-np.pi) + np.pi) < 1e-12
+    obs, info = env.reset(seed=5)
+    rng = np.random.default_rng(5)  # sub-env 0 owns default_rng(seed + 0)
+    th, thdot = rng.uniform(low=[-np.pi, -1.0], high=[np.pi, 1.0])
+    np.testing.assert_allclose(obs[0], [np.cos(th), np.sin(th), thdot], rtol=1e-6)
+    u = 3.5  # clipped to max_torque 2
+    obs1, rew, term, trunc, info = env.step(np.full((4, 1), u))
+    cost = angle_normalize(th) ** 2 + 0.1 * thdot ** 2 + 0.001 * 2.0 ** 2
+    thdot1 = np.clip(thdot + (15.0 * np.sin(th) + 3.0 * 2.0) * 0.05, -8, 8)
+    th1 = th + thdot1 * 0.05
+    assert abs(rew[0] + cost) < 1e-12 and not term.any() and not trunc.any() and info == {}
+    np.testing.assert_allclose(obs1[0], [np.cos(th1), np.sin(th1), thdot1], rtol=1e-6)
+    total = rew.copy()
+    for t in range(2, 201):
+        obs_t, rew, term, trunc, info = env.step(np.zeros((4, 1)))
+        total += rew
+        if t < 200:
+            assert not trunc.any() and info == {}
+    assert trunc.all() and not term.any()  # TimeLimit(200)
+    log = env.get_logging_info_dict(info)
+    np.testing.assert_allclose(log["episode_return"], total, rtol=1e-12)
+    assert log["episode_length"] == [200.0] * 4
+    final0 = env.get_final_observation_at_index(info, 0)
+    assert final0.shape == (3,) and not np.array_equal(final0, obs_t[0])  # obs_t is already the next episode's first observation
+    assert env.get_final_info_value_at_index(info, "episode_return", 2) == log["episode_return"][2]
+    assert abs(np.hypot(obs_t[:, 0], obs_t[:, 1]) - 1).max() < 1e-6 and np.abs(obs_t[:, 2]).max() <= 1.0  # fresh reset states
