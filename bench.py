@@ -116,19 +116,19 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------- GPU arm
-def build_model(args, rank, world, interface):
+def build_model(args, rank, world, interface, global_minibatch=None):
     from rl_x_b200.runner.runner import Runner
     argv = [f"--environment.nr_envs={args.envs}", f"--environment.obs_dim={C2['obs_dim']}", f"--environment.act_dim={C2['act_dim']}",
             f"--environment.seed={1 + rank}", f"--environment.data_interface={interface}", "--environment.horizon=1000",
             f"--environment.stream={'ring' if interface == 'numpy' else 'fresh'}",
             f"--algorithm.nr_steps={C2['nr_steps']}", f"--algorithm.nr_epochs={args.epochs}",
-            f"--algorithm.minibatch_size={args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
+            f"--algorithm.minibatch_size={global_minibatch if global_minibatch else args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
             f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15",
             f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}",
             f"--algorithm.gradient_exchange={args.exchange}"]
     r = Runner(argv=argv)
     train_env, eval_env = r._create_train_and_eval_env(r._config)
-    r._config.environment.seed = 1  # identical policy init / permutation stream on every rank; env streams differ via the env seed above
+    # weights and the permutation stream follow RANK 0's seed inside PPO.__init__ (broadcast); env streams differ via the env seed above
     model = r._model_class(r._config, train_env, eval_env, "/tmp/rlx_bench", None)
     return model
 
@@ -223,24 +223,80 @@ def cpu_baseline_sample(args, threads, minibatches=8, rollout_steps=8):
     return N * T / t_iter, t_iter, sample
 
 
+def reference_class_run(args, threads, warmup, steps, max_seconds, eager, timeout):
+    """The UNMODIFIED reference PPO class (oracle/_ref, staged by oracle/make_ref.py) for `warmup` + `steps` REAL iterations of this
+    workload on the host cores, in a child process (CXX / TORCHDYNAMO_DISABLE must be set before torch is imported).  Returns the
+    child's record or raises."""
+    env = dict(os.environ)
+    env["CXX"], env["CC"], env["WANDB_MODE"] = "/usr/bin/g++", "/usr/bin/gcc", "disabled"
+    env["CUDA_VISIBLE_DEVICES"] = ""  # the reference arm is the reference's CPU path
+    if eager:
+        env["TORCHDYNAMO_DISABLE"] = "1"
+    else:
+        env.pop("TORCHDYNAMO_DISABLE", None)
+    cmd = [sys.executable, "-m", "oracle.ref_arm", "--envs", str(args.envs), "--nr-steps", str(C2["nr_steps"]), "--obs", str(C2["obs_dim"]),
+           "--act", str(C2["act_dim"]), "--hidden", str(C2["hidden"]), "--minibatch", str(args.minibatch), "--epochs", str(args.epochs),
+           "--warmup", str(warmup), "--steps", str(steps), "--threads", str(threads), "--min-steps", str(min(3, steps))]
+    if max_seconds:
+        cmd += ["--max-seconds", str(max_seconds)]
+    out = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    for line in out.stdout.splitlines():
+        if line.startswith("REF_ARM_JSON "):
+            return json.loads(line[len("REF_ARM_JSON "):])
+    raise RuntimeError(f"oracle.ref_arm failed (rc {out.returncode}): {out.stderr.strip().splitlines()[-1] if out.stderr.strip() else 'no output'}")
+
+
 def run_reference_arm(args, rank, world):
+    """--impl reference: REAL iterations of the reference's own PPO class on the host cores (compile_mode="default",
+    CXX=/usr/bin/g++), all threads the box schedules best.  One compile iteration + `warmup` (capped at 1: every extra one costs ~25 s of
+    CPU) untimed, then up to `steps` timed iterations, bounded to ~5 minutes of timed work (never fewer than 3); `steps` in the line is
+    the number actually timed.  The composed port sample (the previous rounds' figure) is kept as a cross-check field."""
     if rank != 0:
         return
+    from oracle import make_ref
     threads = calibrate_threads(available_cores())
-    per_step = []
-    sample = ""
-    for i in range(args.warmup + args.steps):
+    line = {"impl": "reference", "metric": "env-steps/sec (PPO update incl.)", "unit": "env-steps/s", "n_gpus": args.gpus, "steps_requested": args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1)}
+    rec, err = None, None
+    t_start = time.time()
+    if make_ref.available():
+        warm = 1 + min(args.warmup, 1)
+        for eager in (False, True):
+            try:
+                rec = reference_class_run(args, threads, warm if not eager else min(args.warmup, 1), args.steps, 300.0, eager, timeout=1500)
+                break
+            except Exception as e:  # Inductor could not build on this host: say so and time the same classes eagerly
+                err = f"{'eager' if eager else 'torch.compile'} run failed: {e}"
+    else:
+        err = "oracle/_ref not staged (python oracle/make_ref.py needs /root/reference)"
+    if rec is not None:
+        secs = rec["seconds"]
+        t = float(np.mean(secs))
+        value = args.envs * C2["nr_steps"] / t
+        line.update({"value": value, "steps": len(secs), "warmup": rec["warmup_done"], "ms_per_step": t * 1e3,
+                     "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "reference",
+                                      "sample": f"{len(secs)} full iterations of {rec['class']} ({rec['file']}), device=cpu, fp32, "
+                                                f"compile_mode={'default (Inductor, CXX=/usr/bin/g++)' if rec['torch_compile'] else 'eager (TORCHDYNAMO_DISABLE=1)'}, "
+                                                f"{threads} torch threads; iteration seconds min/mean/max = {min(secs):.2f}/{t:.2f}/{max(secs):.2f}; "
+                                                f"first (compile) iteration {rec['first_iteration_s']:.1f} s excluded",
+                                      "phases_s": {k: float(np.mean(v)) for k, v in rec["phases"].items() if v}},
+                     "wall_s": time.time() - t_start})
+        if err:
+            line["note"] = err
+    else:
+        per_step = []
+        for i in range(max(args.warmup, 1) + min(args.steps, 5)):
+            v, t_iter, sample = cpu_baseline_sample(args, threads, minibatches=4, rollout_steps=4)
+            if i >= max(args.warmup, 1):
+                per_step.append(t_iter)
+        t = float(np.mean(per_step))
+        value = args.envs * C2["nr_steps"] / t
+        line.update({"value": value, "steps": len(per_step), "warmup": max(args.warmup, 1), "ms_per_step": t * 1e3, "note": err,
+                     "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample + " (EXTRAPOLATED, not a full iteration)"}})
+    if not args.no_cpu and rec is not None:
         v, t_iter, sample = cpu_baseline_sample(args, threads, minibatches=4, rollout_steps=4)
-        if i >= args.warmup:
-            per_step.append(t_iter)
-    t = float(np.mean(per_step))
-    value = args.envs * C2["nr_steps"] / t
-    line = {"impl": "reference", "metric": "env-steps/sec (PPO update incl.)", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        line["port_cross_check"] = {"value": v, "unit": "env-steps/s", "kind": "port", "sample": sample}
+    line["e2e"] = {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     print(json.dumps(line))
 
 
@@ -322,7 +378,12 @@ def run_sac(args):
             n += 1
         line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "updates/s", "cores": threads, "kind": "port",
                                 "sample": f"{n} oracle updates at batch 4096 in ~10 s (batch generation included, replay sampling excluded)"}
-    print(json.dumps(line))
+    # ~10 GFLOP of dense algebra per update; every layer is < 10 us, so the bound that matters is launch latency
+    flop = 2.0 * batch * (3 * (obs * 256 + 256 * 256 + 2 * 256 * act) + 3 * 4 * ((obs + act) * 256 + 256 * 256 + 256))
+    line["roofline"] = {"bound": "tensor", "achieved": flop * line["value"] / 1e12, "peak": measured_peaks()["tflops"], "unit": "TFLOP/s",
+                        "frac": flop * line["value"] / 1e12 / measured_peaks()["tflops"],
+                        "note": "launch/latency-bound by size (every GEMM < 10 us); algorithmic FLOPs per update ~ fwd+bwd of policy and 4 Q passes"}
+    return line
 
 
 def run_fastsac(args):
@@ -417,7 +478,70 @@ def run_fastsac(args):
             n += 1
         line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "critic updates/s", "cores": threads, "kind": "port",
                                 "sample": f"{n} oracle critic updates at batch {B} in ~10 s (policy updates and sampling excluded)"}
-    print(json.dumps(line))
+    return line
+
+
+def run_ppo_lstm(args):
+    """BASELINE config 5: PPO+LSTM, synthetic Box(obs=64, act=8), 2048 envs x 128 steps, minibatch 32768 rows (= 256 envs x 128 steps), 10
+    epochs, reference widths (encoders 128, LSTM 64, torso 256).  value = env-steps/s of full iterations through PPO_LSTM.train()."""
+    from rl_x_b200 import _native as nt
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.ppo_lstm.b200.default_config import get_config
+    from rl_x_b200.algorithms.ppo_lstm.b200.ppo_lstm import PPO_LSTM
+    from rl_x_b200.environments.synthetic.box.create_env import create_train_and_eval_env
+    from rl_x_b200.environments.synthetic.box.default_config import get_config as env_config
+    torch.cuda.set_device(0)
+    N, T, obs, act, mb, E = 2048, 128, 64, 8, 32768, 10
+    W, K = 1, max(2, min(args.steps, 3))
+    e = env_config("synthetic.box")
+    e.nr_envs, e.obs_dim, e.act_dim, e.seed = N, obs, act, 1
+    a = get_config("ppo_lstm.b200")
+    a.nr_steps, a.minibatch_size, a.nr_epochs, a.total_timesteps = T, mb, E, float(N * T * (W + K))
+    cfg = ConfigDict(algorithm=a, environment=e, runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    env, _ = create_train_and_eval_env(cfg)
+    model = PPO_LSTM(cfg, env, env, "/tmp/rlx_bench_lstm", None)
+    lib = nt.load()
+    stamps, launches = [], []
+
+    def start_logging(step):
+        torch.cuda.synchronize()
+        stamps.append(time.perf_counter())
+        launches.append(int(lib.rlx_launch_count()))
+
+    model.start_logging, model.log, model.end_logging = start_logging, (lambda *a_, **k_: None), (lambda *a_, **k_: None)
+    torch.cuda.synchronize()
+    lib.rlx_reset_launch_count()
+    stamps.append(time.perf_counter())
+    launches.append(0)
+    model.train()
+    it = np.diff(np.asarray(stamps))[W:]
+    sec = float(np.mean(it))
+    line = {"metric": "env-steps/sec (PPO+LSTM update incl.)", "value": N * T / sec, "unit": "env-steps/s", "n_gpus": 1, "steps": len(it), "warmup": W,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"PPO+LSTM synthetic Box(obs={obs}, act={act}), num_envs={N}, seq_len={T}, minibatch={mb} rows (256 envs), nr_epochs={E} "
+                                   "(BASELINE.json configs[4])"},
+            "gpu_launches": int((launches[-1] - launches[W]) / max(len(it), 1)), "timing": "host clock around synchronised iterations of PPO_LSTM.train()"}
+    if not args.no_cpu:
+        from oracle import ppo_lstm_oracle as LO
+        threads = calibrate_threads(available_cores())
+        torch.set_num_threads(threads)
+        pol, cri = LO.init_params(obs, act, hidden=256, enc=128, lstm=64, std_dev=1.0, seed=1)
+        learner = LO.Learner(pol, cri)
+        n_env = 64  # a quarter-of-a-quarter minibatch keeps the leg ~10 s; cost is linear in envs
+        g = torch.Generator().manual_seed(0)
+        rn = lambda *s_: torch.randn(*s_, generator=g)
+        mbatch = dict(states=rn(T, n_env, obs), actions=rn(T, n_env, act), log_probs=rn(T, n_env) * 0.1 - 8.0, returns=rn(T, n_env), advantages=rn(T, n_env),
+                      dones=(torch.rand(T, n_env, generator=g) < 0.01).float(), init_carry=(torch.zeros(n_env, 64), torch.zeros(n_env, 64)))
+        learner.minibatch_step(mbatch)
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 8.0:
+            learner.minibatch_step(mbatch)
+            n += 1
+        t_mb = (time.perf_counter() - t0) / n * (256 / n_env)
+        t_iter = E * (N // 256) * t_mb
+        line["cpu_baseline"] = {"value": N * T / t_iter, "unit": "env-steps/s", "cores": threads, "kind": "port (parity unpinned: the Flax reference cannot run here)",
+                                "sample": f"{n} oracle minibatch updates of {n_env} envs x {T} steps; composed as E*8*t_minibatch (update only, rollout excluded)"}
+    return line
 
 
 def workload_config(args, world):
@@ -444,9 +568,13 @@ def main():
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
     ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
-    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac"])
+    ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac", "ppo_lstm"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="N=1: skip the nested SAC / FastSAC / PPO+LSTM records")
+    ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the sharded-vs-single parity run before timing")
+    ap.add_argument("--no-strict", action="store_true", help="N>1: skip the second timed region at the contract's GLOBAL minibatch of 32768")
+    ap.add_argument("--global-minibatch", type=int, default=0, help="N>1: headline region with this GLOBAL minibatch instead of --minibatch per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -455,9 +583,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
 
-    if args.workload in ("sac", "fastsac"):
+    if args.workload in ("sac", "fastsac", "ppo_lstm"):
         if rank == 0:
-            (run_sac if args.workload == "sac" else run_fastsac)(args)
+            print(json.dumps({"sac": run_sac, "fastsac": run_fastsac, "ppo_lstm": run_ppo_lstm}[args.workload](args)))
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
@@ -471,7 +599,27 @@ def main():
     lib = nt.load()
     lib.rlx_set_head_engine(1 if args.head_engine == "gemm" else 0)
 
-    model = build_model(args, rank, world, "torch")
+    # ---- multi-GPU parity, visible to whoever runs the bench: the env-sharded run (reference-exact global permutation, this exchange, this
+    # GEMM engine) against the same global problem on ONE GPU (tests/dist_check_ppo.py: 64 envs x 16 steps, obs 376 / act 17 / hidden 256,
+    # 2 iterations x 2 epochs of 6 minibatches), before anything is timed
+    parity_check = None
+    if world > 1 and not args.no_parity_check:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("dist_check_ppo", os.path.join(ROOT, "tests", "dist_check_ppo.py"))
+        chk = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(chk)
+        sharded = chk.run_model(world, rank, local_rank, args.engine, args.exchange)
+        dist.barrier()
+        if rank == 0:
+            single = chk.run_model(world, rank, local_rank, args.engine, args.exchange, single=True)
+            wrel, mrel = chk.weight_and_metric_distance(sharded, single)
+            parity_check = {"max_rel": wrel, "metrics_max_rel": mrel, "mode": "exact_global_permutation", "exchange": args.exchange, "world": world,
+                            "problem": f"{chk.NG} envs x {chk.T} steps, obs {chk.OBS} act {chk.ACT} hidden {chk.HID}, minibatch {chk.MB}, "
+                                       f"{chk.ITERS} iterations x {chk.EPOCHS} epochs", "passed": bool(wrel < 2e-5 and mrel < 2e-4),
+                            "bar": "weights 2e-5 of the norm, logged metrics 2e-4 (tests/dist_check_ppo.py)"}
+        dist.barrier()
+
+    model = build_model(args, rank, world, "torch", global_minibatch=args.global_minibatch or None)
     model._begin_training()
     for _ in range(args.warmup):
         model._train_iteration()
@@ -552,9 +700,35 @@ def main():
             "gradient_exchange": (model.gradient_exchange if world > 1 else None),
             "train_tflops_per_step": FLOP_PER_SAMPLE_TRAIN * args.envs * C2["nr_steps"] * args.epochs / 1e12}
 
+    if parity_check is not None:
+        line["parity_check"] = parity_check
     # end-to-end through the host-buffer path (NUMPY-interface env: pinned host observations, H2D/D2H every step)
     model._end_training()
+    if world > 1 and not args.no_strict and not args.global_minibatch:
+        # SURVEY.md §8(d) C3 as the contract wrote it: the GLOBAL minibatch stays 32768 (4096 rows per rank at 8 GPUs, 128 exchanges per
+        # epoch instead of 16): strong-scaled minibatches, reported next to the weak-scaling headline
+        torch.cuda.synchronize()
+        dist.barrier()  # peers may still be reading this rank's exchange slots
+        del model
+        torch.cuda.empty_cache()
+        m3 = build_model(args, rank, world, "torch", global_minibatch=C2["minibatch_size"])
+        m3._begin_training()
+        for _ in range(args.warmup):
+            m3._train_iteration()
+        s3, _, _ = timed_iterations(m3, args.steps, dist)
+        tt = torch.tensor([s3], device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        s3 = float(tt.item())
+        line["strict_c3"] = {"value": steps_per_iter * args.steps / s3, "unit": "env-steps/s", "ms_per_step": s3 / args.steps * 1e3,
+                             "minibatch_size_global": C2["minibatch_size"], "rows_per_rank_per_minibatch": C2["minibatch_size"] // world,
+                             "exchanges_per_step": args.epochs * (args.envs * world * C2["nr_steps"] // C2["minibatch_size"]),
+                             "note": "same envs per GPU; global minibatch fixed at the contract's 32768 (config C3 of SURVEY.md §8)"}
+        m3._end_training()
+        model = m3
     if not args.no_e2e:
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         del model
         torch.cuda.empty_cache()
         m2 = build_model(args, rank, world, "numpy")
@@ -575,9 +749,33 @@ def main():
         m2._end_training()
         del m2
     if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import make_ref
         threads = calibrate_threads(available_cores())
         v, t_iter, sample = cpu_baseline_sample(args, threads)
-        line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": threads, "host_cores_available": available_cores(), "kind": "port", "sample": sample, "s_per_step": t_iter}
+        port = {"value": v, "unit": "env-steps/s", "cores": threads, "host_cores_available": available_cores(), "kind": "port", "sample": sample, "s_per_step": t_iter}
+        line["cpu_baseline"] = port
+        if make_ref.available():
+            # the reference's own class on this box's host cores: ONE full iteration of this workload after one warm-up iteration, eager
+            # (Inductor's ~1 min of compilation does not fit a bounded leg; `--impl reference` times the compiled classes)
+            try:
+                rec = reference_class_run(args, threads, 1, 1, None, True, timeout=600)
+                t = float(np.mean(rec["seconds"]))
+                line["cpu_baseline"] = {"value": args.envs * C2["nr_steps"] / t, "unit": "env-steps/s", "cores": threads, "host_cores_available": available_cores(),
+                                        "kind": "reference", "s_per_step": t,
+                                        "sample": f"1 full iteration of {rec['class']} ({rec['file']}) on this workload after 1 warm-up iteration; device=cpu, fp32, "
+                                                  f"eager (TORCHDYNAMO_DISABLE=1), {threads} torch threads", "port_cross_check": port}
+            except Exception as e:
+                line["cpu_baseline"]["note"] = f"reference class run failed ({e}); port sample reported"
+    if rank == 0 and world == 1 and not args.no_workloads:
+        # the other BASELINE.json configs, each with its own value / cpu_baseline (SAC also its roofline), nested so that the one parsed
+        # line carries them (they are separate workloads, not part of `value`)
+        line["workloads"] = {}
+        for name, fn in (("sac", run_sac), ("fastsac", run_fastsac), ("ppo_lstm", run_ppo_lstm)):
+            try:
+                torch.cuda.empty_cache()
+                line["workloads"][name] = fn(args)
+            except Exception as e:
+                line["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -216,6 +216,8 @@ class PPO:
         # ---- data-parallel topology: one process per GPU, envs sharded over ranks (SURVEY §8 e)
         import torch.distributed as dist
         self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        if config.algorithm.get("ignore_process_group", False):
+            self.dist = None  # a single-GPU instance inside a multi-rank job (bench.py's sharded-vs-single parity check)
         self.world_size = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
         self.global_nr_envs = self.nr_envs * self.world_size

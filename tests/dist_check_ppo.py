@@ -61,22 +61,25 @@ class TableEnv:
         pass
 
 
-def run(out, engine, exchange="peer"):
+METRICS = ["loss/policy_gradient_loss", "loss/critic_loss", "gradients/policy_grad_norm", "gradients/critic_grad_norm", "policy_ratio/clip_fraction",
+           "steps/nr_episodes", "v_value/explained_variance"]
+
+
+def run_model(world, rank, local, engine, exchange="peer", single=False):
+    """One training run of the table problem on this rank's env slice (`single`: the whole problem on this GPU, ignoring any process
+    group).  Returns (policy dict, critic dict, {metric: series}) - the weights are replicated, any rank's copy will do."""
     from rl_x_b200.config_dict import ConfigDict
     from rl_x_b200.algorithms.ppo.b200.default_config import get_config
     from rl_x_b200.algorithms.ppo.b200.ppo import PPO
-    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if single:
+        world, rank = 1, 0
     nl = NG // world
     lo, hi = rank * nl, (rank + 1) * nl
     dev = torch.device("cuda", local)
     a = get_config("ppo.b200")
     a.nr_steps, a.minibatch_size, a.nr_epochs, a.nr_hidden_units, a.total_timesteps = T, MB, EPOCHS, HID, NG * T * ITERS
     a.entropy_coef, a.gemm_engine, a.gradient_exchange = 0.01, engine, exchange
+    a.ignore_process_group = bool(single)
     cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=5, nr_envs=nl),
                      runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
     env = TableEnv(lo, hi, dev)
@@ -92,15 +95,41 @@ def run(out, engine, exchange="peer"):
     model._draw_noise = draw
     logged = []
     model.log = lambda name, value, step: logged.append((name, float(value)))
+    model.rank = 0 if single else model.rank  # a `single` instance logs whatever its rank in the job is
     model.train()
     if world > 1:
         assert model.gradient_exchange == exchange, f"asked for the {exchange} exchange, ran {model.gradient_exchange}"
         assert (model.peer_comm is not None) == (exchange == "peer")
+    pol, cri = model.params.state_dicts()
+    if world > 1:  # peers may still be reading this rank's exchange slots: nobody frees them before everybody is done
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+    return pol, cri, {n: [v for m, v in logged if m == n] for n in METRICS}
+
+
+def weight_and_metric_distance(a, b):
+    """(worst relative weight difference, worst relative metric difference) between two run_model results."""
+    worst = 0.0
+    for x, y in ((a[0], b[0]), (a[1], b[1])):
+        for k in x:
+            worst = max(worst, float((x[k].double() - y[k].double()).norm() / y[k].double().norm()))
+    mworst = 0.0
+    for n in METRICS:
+        u, v = np.asarray(a[2][n], dtype=np.float64), np.asarray(b[2][n], dtype=np.float64)
+        if u.shape == v.shape and u.size:
+            mworst = max(mworst, float(np.max(np.abs(u - v) / np.maximum(np.abs(v), 1.0))))
+    return worst, mworst
+
+
+def run(out, engine, exchange="peer"):
+    world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pol, cri, metrics = run_model(world, rank, local, engine, exchange)
     if rank == 0:
-        pol, cri = model.params.state_dicts()
-        metrics = {n: [v for m, v in logged if m == n] for n in ["loss/policy_gradient_loss", "loss/critic_loss", "gradients/policy_grad_norm",
-                                                                   "gradients/critic_grad_norm", "policy_ratio/clip_fraction", "steps/nr_episodes",
-                                                                   "v_value/explained_variance"]}
         torch.save({"pol": pol, "cri": cri, "metrics": metrics, "world": world}, out)
         print(f"world={world} saved {out}")
     if world > 1:

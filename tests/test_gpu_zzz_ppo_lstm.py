@@ -24,7 +24,10 @@ def _perturbed(obs, act, hid, enc, lstm, seed):
     return pol, cri
 
 
-@pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm", [(7, 5, 6, 2, 12, 8, 4), (33, 40, 5, 2, 8, 8, 4), (16, 24, 64, 8, 256, 128, 64)])
+# last case: BASELINE.json configs[4] shapes — obs 64, act 8, seq_len 128, one minibatch of 32768 rows = 256 envs, reference widths
+# (ppo_lstm/flax/default_config.py: lstm_hidden_dim 64, obs_encoding_dim 128, nr_hidden_units 256)
+@pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm", [(7, 5, 6, 2, 12, 8, 4), (33, 40, 5, 2, 8, 8, 4), (16, 24, 64, 8, 256, 128, 64),
+                                                      (128, 256, 64, 8, 256, 128, 64)])
 def test_lstm_fwdbwd_matches_oracle_autograd(T, n, obs, act, hid, enc, lstm):
     from rl_x_b200 import _native as nt
     lib = nt.load()
