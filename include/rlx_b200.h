@@ -266,6 +266,9 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
 /* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused kernel (default), 1 = the GEMM formulation of csrc/ppo_head_gemm.cu
  * (logits and dZ2 as GEMMs around one flat loss kernel; emulation-validated, first hardware run pending).  Returns the engine in effect. */
 int rlx_set_head_engine(int engine);
+/* 1 (default): rlx_ppo_update_epoch_f32 runs gradient assembly + both grad norms + clip + Adam of a minibatch as ONE kernel (grid barrier
+ * in the caller's workspace); 0: the three separate kernels of rlx_ppo_minibatch_fwdbwd_f32 / rlx_gradnorm_clip_adam_f32.  Returns the setting. */
+int rlx_set_fused_tail(int on);
 /* bring-up / test entry of the GEMM head on caller buffers: H2 [m, 2*hidden] (policy | critic halves), torch-layout head weights; outputs
  * dZ2 [m, 2*hidden], dhead [m, round_up(act+1, 4)] (dMean | dV | 0) and ONE partial block headpart [2*act + 5 + 2*hidden] =
  * db3p | db3c | dlogstd | pg vl kl cf sums | db2p | db2c.  scratch: >= m * (2*act + 8) + (m / 256 + 2) * max(2*hidden, 8) floats. */

@@ -66,7 +66,7 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
 constexpr int kHeadWgradRows = 64;
 
 struct TrainPlan {
-  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, total;
+  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, off_barrier, total;
   int max_s1, max_s2, max_s3;
   int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
@@ -80,7 +80,7 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   P.head_blocks = head_grid(m);
   P.head_npart = (int)(2 * A + 5 + 2 * H);
   P.wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
-  P.norm_blocks = 64;
+  P.norm_blocks = std::max(64, sm_count());  // the fused optimiser tail writes one partial pair per CTA of its (<= SM count) grid
   size_t o = 0;
   auto take = [&](size_t& off, size_t nfloats) {
     off = o;
@@ -99,6 +99,7 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   P.max_s3 = choose_splits(m, (int)dh_ld_plan, (int)H, 2, true).splits;
   take(P.off_part3, std::max<size_t>((size_t)P.wgrad_chunks * (A + 1) * H, (size_t)P.max_s3 * 2 * dh_ld_plan * H));
   take(P.off_norm, (size_t)P.norm_blocks * 2);
+  take(P.off_barrier, 64);
   P.total = o;
   return P;
 }
@@ -151,6 +152,7 @@ static bool head_dims_ok(const rlx_ppo_dims& d) {
 
 int ppo_head_gemm_path(const HeadGemmArgs& a, cudaStream_t st);  // ppo_head_gemm.cu
 static int g_head_engine = 0;                                       // 0 fused kernel, 1 GEMM formulation (rlx_set_head_engine)
+static int g_fused_tail = 1;                                        // rlx_set_fused_tail: 1 = one-launch optimiser tail inside the epoch call
 
 static void fill_head_common(HeadP& h, const PpoLayout& L, const float* params, const float* H2, long long rows) {
   h.M = (int)rows; h.H = L.H; h.act = L.act;
@@ -231,7 +233,30 @@ static int check_mb_args(const rlx_ppo_minibatch_args* a, bool need_data) {
   return RLX_OK;
 }
 
-extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, void* stream) {
+static long long tall_elements(const GradReduceP& r) {
+  long long tall = 0;
+  for (int gi = 0; gi < kNumGroups; ++gi)
+    if (r.g[gi].nsplit > kTallSplit) tall += r.g[gi].len;
+  return tall;
+}
+static double partial_bytes(const GradReduceP& r) {
+  double b = 0;
+  for (int gi = 0; gi < kNumGroups; ++gi) b += 4.0 * r.g[gi].nsplit * r.g[gi].len;
+  return b;
+}
+static int launch_grad_reduce(const GradReduceP& r, cudaStream_t st) {
+  const int flat_blocks = (int)ceil_div(r.total, 256);
+  const int tall_blocks = (int)ceil_div(tall_elements(r), 8);  // 8 warps per CTA, one element per warp
+  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, partial_bytes(r) + 4.0 * r.total, ppo_grad_reduce_kernel, (unsigned)(flat_blocks + tall_blocks), 256, 0, st, r, flat_blocks);
+  return RLX_OK;
+}
+
+// `deferred`: when non-null the flat-gradient assembly is NOT launched; its parameters are returned for the fused optimiser tail.
+static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred);
+
+extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, void* stream) { return minibatch_fwdbwd(a, stream, nullptr); }
+
+static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred) {
   int rc = check_mb_args(a, true);
   if (rc) return rc;
   const rlx_ppo_dims& d = a->dims;
@@ -454,23 +479,14 @@ extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, voi
   r.head_partials = headpart; r.nblk = head_blocks; r.npart = npart; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
-  const int flat_blocks = (int)ceil_div(L.total(), 256);
-  long long tall = 0;
-  for (int gi = 0; gi < kNumGroups; ++gi)
-    if (r.g[gi].nsplit > kTallSplit) tall += r.g[gi].len;
-  const int tall_blocks = (int)ceil_div(tall, 8);  // 8 warps per CTA, one element per warp
-  RLX_LAUNCH_C(KC_GRAD_REDUCE, 0, 4.0 * ((double)s1 * 2 * H * (O + 1) + (double)s2 * 2 * H * H + (double)w3_nsplit * (A + 1) * H + L.total()),
-               ppo_grad_reduce_kernel, (unsigned)(flat_blocks + tall_blocks), 256, 0, st, r, flat_blocks);
-  return RLX_OK;
+  if (deferred != nullptr) {
+    *deferred = r;
+    return RLX_OK;
+  }
+  return launch_grad_reduce(r, st);
 }
 
-extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void* stream) {
-  int rc = check_mb_args(a, false);
-  if (rc) return rc;
-  RLX_CHECK_ARG(a->exp_avg && a->exp_avg_sq && a->lr && a->step_count, "optimizer state is null");
-  const PpoLayout L = make_layout(a->dims);
-  const TrainPlan P = plan_train(a->dims, std::max<int64_t>(a->m, 1));
-  cudaStream_t st = (cudaStream_t)stream;
+static AdamP make_adam_params(const rlx_ppo_minibatch_args* a, const PpoLayout& L, const TrainPlan& P) {
   AdamP p{};
   p.total = L.total();
   for (int i = 0; i <= RLX_PPO_NSEG; ++i) p.seg_off[i] = L.off[i];
@@ -483,7 +499,19 @@ extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void*
   p.norm_partials = ws_ptr<float>(a->workspace, P.off_norm);
   p.nblk_norm = P.norm_blocks;
   p.metrics = a->metrics;
-  RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 4.0 * L.total(), ppo_grad_sumsq_kernel, (unsigned)P.norm_blocks, 256, 0, st, p);
+  return p;
+}
+
+extern "C" int rlx_gradnorm_clip_adam_f32(const rlx_ppo_minibatch_args* a, void* stream) {
+  int rc = check_mb_args(a, false);
+  if (rc) return rc;
+  RLX_CHECK_ARG(a->exp_avg && a->exp_avg_sq && a->lr && a->step_count, "optimizer state is null");
+  const PpoLayout L = make_layout(a->dims);
+  const TrainPlan P = plan_train(a->dims, std::max<int64_t>(a->m, 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  AdamP p = make_adam_params(a, L, P);
+  p.nblk_norm = 64;
+  RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 4.0 * L.total(), ppo_grad_sumsq_kernel, (unsigned)p.nblk_norm, 256, 0, st, p);
   RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 28.0 * L.total(), ppo_clip_adam_kernel, (unsigned)ceil_div(L.total(), 256), 256, 0, st, p);
   return RLX_OK;
 }
@@ -493,6 +521,22 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
   const int64_t nmb = ceil_div(count, mb);
   const int A = first->dims.act_dim;
   const int64_t O = first->states_ld > 0 ? first->states_ld : first->dims.obs_dim;  // row pitch of the gathered states
+  // fused optimiser tail (ppo_optim.cuh): every thread of a <= SM-count grid keeps its gradient elements in registers across a grid
+  // barrier.  Needs the whole flat gradient to fit (kTailPerThread elements per thread) and the tall groups (head bias partials: 2H +
+  // 2A + 1 elements, W3 when it comes from the SIMT head) to fit two per warp; otherwise the three separate kernels run.
+  cudaStream_t st = (cudaStream_t)stream;
+  bool fused = g_fused_tail && dims_ok(first->dims) && first->exp_avg && first->exp_avg_sq && first->lr && first->step_count && first->workspace;
+  const PpoLayout L = fused ? make_layout(first->dims) : PpoLayout{};
+  unsigned tail_grid = 0;
+  if (fused) {
+    tail_grid = (unsigned)std::min<int64_t>(sm_count(), ceil_div(L.total(), kTailThreads));
+    fused = (int64_t)tail_grid * kTailThreads * kTailPerThread >= L.total();
+    if (fused) {
+      const TrainPlan P0 = plan_train(first->dims, std::max<int64_t>(std::min<int64_t>(mb, count), 1));
+      if (first->workspace_bytes < P0.total) fused = false;  // the per-minibatch checks below will report it
+      else RLX_CHECK_CUDA(cudaMemsetAsync(ws_ptr<unsigned int>(first->workspace, P0.off_barrier), 0, 64, st));
+    }
+  }
   for (int64_t k = 0; k < nmb; ++k) {
     rlx_ppo_minibatch_args a = *first;
     const int64_t r0 = k * mb;
@@ -505,10 +549,28 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
     a.returns = first->returns + r0;
     a.adv_stats = first->adv_stats + 2 * k;
     a.metrics = first->metrics ? first->metrics + RLX_PPO_NMETRIC * k : nullptr;
-    int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
+    if (!fused || a.m != std::min<int64_t>(mb, count)) {  // a short last minibatch has its own workspace plan: separate kernels
+      int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
+      if (rc) return rc;
+      rc = rlx_gradnorm_clip_adam_f32(&a, stream);
+      if (rc) return rc;
+      continue;
+    }
+    TailP t{};
+    int rc = minibatch_fwdbwd(&a, stream, &t.r);
     if (rc) return rc;
-    rc = rlx_gradnorm_clip_adam_f32(&a, stream);
-    if (rc) return rc;
+    if (tall_elements(t.r) > 2LL * tail_grid * (kTailThreads / 32)) {  // more per-CTA partial columns than two per warp: separate kernels
+      rc = launch_grad_reduce(t.r, st);
+      if (rc) return rc;
+      rc = rlx_gradnorm_clip_adam_f32(&a, stream);
+      if (rc) return rc;
+      continue;
+    }
+    const TrainPlan P = plan_train(a.dims, std::max<int64_t>(a.m, 1));
+    t.a = make_adam_params(&a, L, P);
+    t.a.nblk_norm = (int)tail_grid;
+    t.barrier = ws_ptr<unsigned int>(a.workspace, P.off_barrier);
+    RLX_LAUNCH_C(KC_CLIP_ADAM, 0, partial_bytes(t.r) + 28.0 * L.total(), ppo_fused_tail_kernel, tail_grid, kTailThreads, 0, st, t);
   }
   return RLX_OK;
 }
@@ -582,6 +644,11 @@ extern "C" int rlx_set_head_engine(int engine) {
   if (engine == 0 || engine == 1) g_head_engine = engine;
   else set_error("rlx_set_head_engine: unknown engine %d", engine);
   return g_head_engine;
+}
+
+extern "C" int rlx_set_fused_tail(int on) {
+  g_fused_tail = on ? 1 : 0;
+  return g_fused_tail;
 }
 
 extern "C" int rlx_set_gemm_engine(int engine) {

@@ -145,11 +145,11 @@ def test_train_reproduces_reference_run(golden, interface, gemm_engine):
     # FIRST iteration, where both sides act with identical weights.  From the second iteration on the run follows its own weights, which
     # Adam's eps-regime components have moved ~1e-5 of their norm away from the reference's (see test_one_epoch_at_bench_shape_vs_oracle):
     # there the bound is 1e-4 of the norm.  The elementwise allclose is the coarse guard against single outliers.
-    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+    relnorm = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
     for it, s in enumerate(snaps):
         bar = 1e-5 if it == 0 else 1e-4
         for key, name in (("val", "values"), ("lp", "log_probs"), ("adv", "advantages"), ("ret", "returns")):
-            assert rel(s[key], g[f"iter{it}/{name}"]) <= bar, (it, name, rel(s[key], g[f"iter{it}/{name}"]))
+            assert relnorm(s[key], g[f"iter{it}/{name}"]) <= bar, (it, name, relnorm(s[key], g[f"iter{it}/{name}"]))
         np.testing.assert_allclose(s["val"], g[f"iter{it}/values"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(s["lp"], g[f"iter{it}/log_probs"], rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(s["adv"], g[f"iter{it}/advantages"], rtol=1e-4, atol=2e-5)
