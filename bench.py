@@ -569,6 +569,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
     ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac", "ppo_lstm"])
+    ap.add_argument("--tc-pair", default="", help="tcgen05 CTA-pair engine: MODE[:FWD_BN], MODE 0 off / 1 weight gradients (default) / 2 all GEMMs, FWD_BN 128|256")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-workloads", action="store_true", help="N=1: skip the nested SAC / FastSAC / PPO+LSTM records")
@@ -598,6 +599,9 @@ def main():
     from rl_x_b200 import _native as nt
     lib = nt.load()
     lib.rlx_set_head_engine(1 if args.head_engine == "gemm" else 0)
+    if args.tc_pair:
+        mode, _, bn = args.tc_pair.partition(":")
+        lib.rlx_set_tc_pair(int(mode), int(bn or 0))
 
     # ---- multi-GPU parity, visible to whoever runs the bench: the env-sharded run (reference-exact global permutation, this exchange, this
     # GEMM engine) against the same global problem on ONE GPU (tests/dist_check_ppo.py: 64 envs x 16 steps, obs 376 / act 17 / hidden 256,

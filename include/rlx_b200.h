@@ -266,8 +266,13 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
 /* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused kernel (default), 1 = the GEMM formulation of csrc/ppo_head_gemm.cu
  * (logits and dZ2 as GEMMs around one flat loss kernel; emulation-validated, first hardware run pending).  Returns the engine in effect. */
 int rlx_set_head_engine(int engine);
-/* 1 (default): rlx_ppo_update_epoch_f32 runs gradient assembly + both grad norms + clip + Adam of a minibatch as ONE kernel (grid barrier
- * in the caller's workspace); 0: the three separate kernels of rlx_ppo_minibatch_fwdbwd_f32 / rlx_gradnorm_clip_adam_f32.  Returns the setting. */
+/* tcgen05 engine on CTA pairs (cta_group::2, csrc/gemm_tc2.cu).  mode 0: single-CTA kernels only; 1 (default): the weight-gradient GEMMs
+ * of the PPO update run on pairs (256 x 256 / 256 x 192 tiles); 2: the forward / dX GEMMs too, with fwd_bn-wide pair tiles (128: double-
+ * buffered accumulators, 256: single; other values keep the current setting).  Returns the mode. */
+int rlx_set_tc_pair(int mode, int fwd_bn);
+/* 1: rlx_ppo_update_epoch_f32 runs gradient assembly + both grad norms + clip + Adam of a minibatch as ONE kernel (grid barrier in the
+ * caller's workspace); 0 (default; measured faster on B200): the three separate kernels of rlx_ppo_minibatch_fwdbwd_f32 /
+ * rlx_gradnorm_clip_adam_f32.  Returns the setting. */
 int rlx_set_fused_tail(int on);
 /* bring-up / test entry of the GEMM head on caller buffers: H2 [m, 2*hidden] (policy | critic halves), torch-layout head weights; outputs
  * dZ2 [m, 2*hidden], dhead [m, round_up(act+1, 4)] (dMean | dV | 0) and ONE partial block headpart [2*act + 5 + 2*hidden] =

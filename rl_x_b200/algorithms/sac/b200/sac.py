@@ -437,14 +437,14 @@ class SAC:
         Pq = self.k.Pq
 
         def q_pair(flat):
-            out, o = [], 0
+            out = []
             for net in range(2):
+                o = net * Pq  # per-net stride (padded to 256 bytes in the flat layout)
                 for key, spec in Q_SEGMENTS:
                     shp = _shape(spec, self.k.O, self.k.A, self.k.H)
                     n = int(np.prod(shp))
                     out.append(flat[o:o + n].view(shp))
                     o += n
-            assert o == 2 * Pq
             return out
 
         return {"policy": ([pm[k] for k in POLICY_PARAM_ORDER], [pv[k] for k in POLICY_PARAM_ORDER]),

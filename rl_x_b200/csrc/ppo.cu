@@ -17,21 +17,23 @@
 namespace rlx {
 
 static bool use_tc(const rlx_ppo_dims& d) { return g_gemm_engine == 1 && tc_supported(d); }
+extern bool g_tc_pair_force;  // gemm_tc.cu
 
 struct Splits {
   int splits, kchunk;
 };
 // choose a split-K factor for a [M' x N'] output reduced over `rows`: ~2 CTAs per SM for the SIMT engine, one persistent
 // CTA per SM for the tcgen05 engine (k-chunks are multiples of 32 there: one 128-byte swizzle row of fp32)
-static Splits choose_splits(long long rows, int out_m, int out_n, int batch, bool tc) {
+// pair_bn > 0: the GEMM runs on CTA pairs (256 x pair_bn tiles, sm_count / 2 pairs)
+static Splits choose_splits(long long rows, int out_m, int out_n, int batch, bool tc, int pair_bn = 0) {
   if (tc) {
     // persistent kernel, one CTA per SM: pick the split count whose tile total fills whole waves of SMs.  The tensor core accumulates
     // with round-toward-zero, so each TMEM accumulation chain is also kept <= 1024 rows (128 MMAs); the long part of the
     // reduction happens in the fp32 grad_reduce kernel (profiles/tc_accuracy_probe.py).
-    const int bn = (out_n % 256 == 0) ? 256 : 128;
-    const long long tiles = ceil_div(out_m, 128) * ceil_div(out_n, bn) * batch;
+    const int bn = pair_bn > 0 ? pair_bn : ((out_n % 256 == 0) ? 256 : 128);
+    const long long tiles = ceil_div(out_m, pair_bn > 0 ? 256 : 128) * ceil_div(out_n, bn) * batch;
     const long long smin = std::max<long long>(1, ceil_div(rows, 1024)), smax = std::max<long long>(smin, std::min<long long>(smin + 64, rows / 64));
-    const long long sms = sm_count();
+    const long long sms = pair_bn > 0 ? sm_count() / 2 : sm_count();
     long long best = smin;
     double best_fill = -1.0;
     for (long long s = smin; s <= smax; ++s) {
@@ -76,7 +78,9 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   TrainPlan P;
   const long long H = d.hidden, O = d.obs_dim, A = d.act_dim;
   P.max_s1 = std::max(choose_splits(m, (int)(2 * H), (int)O, 1, false).splits, choose_splits(m, (int)O + 1, (int)(2 * H), 1, true).splits);
+  P.max_s1 = std::max(P.max_s1, choose_splits(m, (int)(2 * H), (int)O + 1, 1, true, 192).splits);  // CTA-pair orientation of dW1
   P.max_s2 = std::max(choose_splits(m, (int)H, (int)H, 2, false).splits, choose_splits(m, (int)H, (int)H, 2, true).splits);
+  P.max_s2 = std::max(P.max_s2, choose_splits(m, (int)H, (int)H, 2, true, 256).splits);
   P.head_blocks = head_grid(m);
   P.head_npart = (int)(2 * A + 5 + 2 * H);
   P.wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
@@ -125,7 +129,8 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   g.M = (int)rows; g.N = 2 * H; g.K = L.obs;
   g.lda = (int)ldx; g.ldb = L.obs; g.ldc = 2 * H;
   g.splits = 1; g.kchunk = (int)(ceil_div(L.obs, 8) * 8);
-  int rc = run_gemm<true, true, EPI_BIAS_TANH>(tc, g, 1, stream, KC_GEMM_FWD, rows, 2 * H);
+  const int pair_fwd = tc ? tc_pair_fwd_bn() : 0;
+  int rc = run_gemm<true, true, EPI_BIAS_TANH>(tc, g, 1, stream, KC_GEMM_FWD, rows, 2 * H, pair_fwd);
   if (rc) return rc;
   GemmP g2{};
   g2.A = H1; g2.B = params + L.off[W2P]; g2.C = H2; g2.bias = params + L.off[B2P];
@@ -133,7 +138,7 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
   g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
   g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
-  return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, H);
+  return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, H, pair_fwd);
 }
 
 #define RLX_DISPATCH_NCH(CLS, FLOPS, BYTES, H, KERNEL, grid, block, smem, stream, arg)                                              \
@@ -152,7 +157,10 @@ static bool head_dims_ok(const rlx_ppo_dims& d) {
 
 int ppo_head_gemm_path(const HeadGemmArgs& a, cudaStream_t st);  // ppo_head_gemm.cu
 static int g_head_engine = 0;                                       // 0 fused kernel, 1 GEMM formulation (rlx_set_head_engine)
-static int g_fused_tail = 1;                                        // rlx_set_fused_tail: 1 = one-launch optimiser tail inside the epoch call
+// rlx_set_fused_tail(1): one-launch optimiser tail inside the epoch call.  Measured on B200 (round 2, gpurun_out/r2_bench3.json): SLOWER than the
+// three separate kernels (57 us vs 20 + 9 + 8 us per minibatch) - the <= SM-count grid that the grid barrier needs leaves too few threads
+// in flight for the split-K partial reads (25 MB per minibatch), which the 1287-CTA grad_reduce grid hides.  Kept as an opt-in.
+static int g_fused_tail = 0;
 
 static void fill_head_common(HeadP& h, const PpoLayout& L, const float* params, const float* H2, long long rows) {
   h.M = (int)rows; h.H = L.H; h.act = L.act;
@@ -411,7 +419,8 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
       w3_nsplit = wgrad_chunks;
     }
     // ---- dW2 : part2[split][net][o][i] = sum_rows dZ2[r, net*H+o] * H1[r, net*H+i]   (db2 comes from the head kernel)
-    const Splits S2 = choose_splits(m, H, H, 2, tc);
+    const int pair_dw = (tc && tc_pair_mode() >= 1 && H % 256 == 0) ? 256 : 0;
+    const Splits S2 = choose_splits(m, H, H, 2, tc, pair_dw);
     s2 = S2.splits;
     GemmP g{};
     g.A = dZ2; g.B = H1; g.C = part2;
@@ -419,7 +428,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     g.lda = 2 * H; g.ldb = 2 * H; g.ldc = H;
     g.sA = H; g.sB = H; g.sC = (long long)H * H;
     g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H;
-    rc = run_gemm<false, false, EPI_NONE>(tc, g, 2, st, KC_GEMM_DW, m, m);
+    rc = run_gemm<false, false, EPI_NONE>(tc, g, 2, st, KC_GEMM_DW, m, m, pair_dw);
     if (rc) return rc;
     // ---- dZ1 = (dZ2 @ W2) * (1 - H1^2)   per net
     GemmP gd{};
@@ -428,7 +437,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
     gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
     gd.splits = 1; gd.kchunk = (int)(ceil_div(H, 8) * 8);
-    rc = run_gemm<true, false, EPI_DTANH>(tc, gd, 2, st, KC_GEMM_DX, m, H);
+    rc = run_gemm<true, false, EPI_DTANH>(tc, gd, 2, st, KC_GEMM_DX, m, H, tc ? tc_pair_fwd_bn() : 0);
     if (rc) return rc;
     // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i];  db1[o] = sum_rows dZ1[r, o]
     GemmP g1{};
@@ -436,7 +445,22 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     g1.M = 2 * H; g1.N = O; g1.K = (int)m;
     g1.lda = 2 * H; g1.ldb = (int)ldx; g1.ldc = O;
     bool done = false;
-    if (tc && a->states_ones_col) {
+    if (tc && a->states_ones_col && tc_pair_mode() >= 1 && (2 * H) % 256 == 0) {
+      // CTA pairs, NOT transposed: M = 2H (whole 256-row pair tiles), N = O + 1 in 192-wide tiles (377 -> 2 x 192); the constant-one
+      // column of X lands in output column O, which the epilogue diverts into rs1 (= db1)
+      const Splits S1 = choose_splits(m, 2 * H, O + 1, 1, true, 192);
+      GemmP gp = g1;
+      gp.N = O + 1;
+      gp.splits = S1.splits; gp.kchunk = S1.kchunk; gp.sSplitC = 2LL * H * O;
+      rc = tc_gemm(gp, false, false, TC_NONE, 1, KC_GEMM_DW, m, m, O, rs1, 0, 2LL * H, st, 192);
+      if (rc == RLX_OK) {
+        done = true;
+        s1 = S1.splits;
+      } else if (rc != RLX_ERR_UNSUPPORTED) {
+        return rc;
+      }
+    }
+    if (!done && tc && a->states_ones_col) {
       // tensor-core path, computed TRANSPOSED: C^T[i, o] = sum_r X_aug[r, i] dZ1[r, o] with M = O+1 (the constant-one column of X
       // makes db1 the last output row) and N = 2H = full 256-wide tiles; the epilogue stores C^T transposed back into [o][i].
       const Splits S1 = choose_splits(m, O + 1, 2 * H, 1, true);
@@ -628,8 +652,12 @@ extern "C" int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   const bool a_k = layout != 2, b_k = layout == 0;
   const long long a_rows = a_k ? M : K, b_rows = b_k ? N : K;
-  if (engine == 1) {
-    const int rc = tc_gemm(g, a_k, b_k, epilogue, 1, KC_OTHER, a_rows, b_rows, 0, nullptr, 0, 0, st);
+  if (engine >= 1 && engine <= 4) {
+    // 1: single-CTA tcgen05 kernels; 2 / 3 / 4: CTA-pair kernels (cta_group::2) with 128 / 256 / 192-wide tiles
+    const int pair_bn = engine == 2 ? 128 : engine == 3 ? 256 : engine == 4 ? 192 : 0;
+    g_tc_pair_force = pair_bn != 0;
+    const int rc = tc_gemm(g, a_k, b_k, epilogue, 1, KC_OTHER, a_rows, b_rows, 0, nullptr, 0, 0, st, pair_bn);
+    g_tc_pair_force = false;
     if (rc == RLX_ERR_UNSUPPORTED) set_error("rlx_debug_gemm_f32: shape/alignment not supported by the tcgen05 engine");
     return rc;
   }

@@ -427,14 +427,16 @@ def test_one_epoch_at_bench_shape_vs_oracle():
     mom2.flat.copy_(exp_avg_sq)
     m1p, m1c = mom1.state_dicts()
     m2p, m2c = mom2.state_dicts()
+    report = {}
     for keys, opt, cur, params, m1, m2 in ((O.POLICY_KEYS, L.popt, pol_now, L.pol, m1p, m2p), (O.CRITIC_KEYS, L.copt, cri_now, L.cri, m1c, m2c)):
         for i, name in enumerate(keys):
             st = opt.state[opt.param_groups[0]["params"][i]]
-            assert _rel(m1[name].numpy(), st["exp_avg"].numpy()) <= 1e-5, (name, "exp_avg", _rel(m1[name].numpy(), st["exp_avg"].numpy()))
-            assert _rel(m2[name].numpy(), st["exp_avg_sq"].numpy()) <= 2e-5, (name, "exp_avg_sq", _rel(m2[name].numpy(), st["exp_avg_sq"].numpy()))
             ours, ref = cur[name].numpy(), params[name].detach().numpy()
-            assert _rel(ours, ref) <= 1e-4, (name, _rel(ours, ref))
-            assert float(np.abs(ours - ref).max()) <= 0.1 * nmb * 3e-4, (name, float(np.abs(ours - ref).max()))
+            report[name] = (_rel(m1[name].numpy(), st["exp_avg"].numpy()), _rel(m2[name].numpy(), st["exp_avg_sq"].numpy()), _rel(ours, ref),
+                            float(np.abs(ours - ref).max()) / 3e-4)
+    print("bench-shape epoch: name -> (rel exp_avg, rel exp_avg_sq, rel weights, max |dw| in lr steps)", report)
+    for name, (r1, r2, rw, steps) in report.items():
+        assert r1 <= 1e-5 and r2 <= 2e-5 and rw <= 1e-4 and steps <= 0.1 * nmb, (name, report)
     m = metrics.cpu().numpy()
     for i, r in enumerate(ref_metrics):
         assert abs(m[i, 0] - r["pg_loss"]) <= 1e-5 * max(abs(r["pg_loss"]), 0.5), (i, m[i, 0], r["pg_loss"])
