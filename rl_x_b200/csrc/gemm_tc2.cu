@@ -39,8 +39,13 @@ __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_smem_addr, uint32
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive WITHOUT a cluster-scope release: ptxas turns `.release.cluster` into MEMBAR.ALL.GPU + error barriers in front of the arrive,
+// i.e. the arriving thread drains every outstanding global access first (measured: the pair kernel ran 1.5x slower than the single-CTA
+// one with it, gpurun_out/r2_bench4_*).  Nothing here needs it: what the arrival publishes is shared memory already fenced towards the
+// async proxy (splitter) or tensor-memory reads ordered by tcgen05.fence::before_thread_sync (epilogue) - the form CUTLASS' ClusterBarrier
+// uses for the same hand-offs.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Waits of the pair kernel carry a watchdog: a protocol error between the two CTAs must end in a trap (reported as a launch failure),
 // never in a hung device.  try_wait suspends the thread for a hardware-defined time slice, so the loop is not a hot spin.
@@ -55,8 +60,8 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   unsigned long long t0 = 0;
   for (uint32_t it = 0;; ++it) {
     uint32_t ok;
-    if (CLUSTER) {
-      // cluster-scope acquire: the arrivals come from the peer CTA
+    if (false && CLUSTER) {
+      // (an explicit cluster-scope acquire makes ptxas invalidate L1 after every successful wait; the default form is what CUTLASS uses)
       asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
                    : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
     } else {
@@ -76,7 +81,9 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait_wd<true>(bar, parity); }
 __device__ __forceinline__ void mbar_wait_local(uint64_t* bar, uint32_t parity) { mbar_wait_wd<false>(bar, parity); }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to this CTA's shared memory -> visible to async-proxy reads (the tensor cores of both CTAs read it through the async
+// proxy); the unqualified `fence.proxy.async` also compiles to MEMBAR.ALL.GPU
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");

@@ -252,5 +252,13 @@ def test_sac_checkpoint_has_the_reference_optimizer_layout(tmp_path):
     cfg = model.config
     cfg.runner.load_model = str(tmp_path / "best.model")
     m2 = SAC.load(cfg, env, env, "/tmp/rlx_sac_test2", None, [])
-    for name in ("policy", "q", "log_alpha", "m_policy", "v_policy", "m_q", "v_q", "m_la", "v_la", "steps"):
+    for name in ("policy", "log_alpha", "m_policy", "v_policy", "m_la", "v_la", "steps"):
         assert torch.equal(getattr(m2, name), getattr(model, name)), name
+    # q-net tensors by name (the flat buffers pad every net to a 256-byte stride; the padding is not part of a checkpoint)
+    (_, qs1), (_, qs2) = model.state_dicts(), m2.state_dicts()
+    for net in qs1:
+        for key in qs1[net]:
+            assert torch.equal(qs1[net][key], qs2[net][key]), (net, key)
+    ov1, ov2 = model._optimizer_views(), m2._optimizer_views()
+    for a, b in zip(ov1["q"][0] + ov1["q"][1], ov2["q"][0] + ov2["q"][1]):
+        assert torch.equal(a, b)
