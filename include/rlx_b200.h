@@ -266,9 +266,17 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
 /* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused kernel (default), 1 = the GEMM formulation of csrc/ppo_head_gemm.cu
  * (logits and dZ2 as GEMMs around one flat loss kernel; emulation-validated, first hardware run pending).  Returns the engine in effect. */
 int rlx_set_head_engine(int engine);
-/* tcgen05 engine on CTA pairs (cta_group::2, csrc/gemm_tc2.cu).  mode 0: single-CTA kernels only; 1 (default): the weight-gradient GEMMs
- * of the PPO update run on pairs (256 x 256 / 256 x 192 tiles); 2: the forward / dX GEMMs too, with fwd_bn-wide pair tiles (128: double-
- * buffered accumulators, 256: single; other values keep the current setting).  Returns the mode. */
+/* bf16-autocast mode of the PPO entry points (the reference's `bf16_mixed_precision_training`, ppo.py:98-107,123,155,208,253; its default).
+ * on != 0: rlx_ppo_forward_f32 / rlx_critic_forward_f32 / rlx_ppo_minibatch_fwdbwd_f32 / rlx_gae_f32 round every value that torch's autocast
+ * holds in a bf16 tensor to bf16 where torch rounds it - Linear inputs, weights and biases, Linear outputs, tanh outputs, the sampled action
+ * and the bf16 subtraction / square inside its log-prob, gamma * next_values, and on the way back the gradients of those bf16 tensors and the
+ * weight / bias gradients (one rounding of the complete fp32-accumulated sum) - while storage, losses, clipping and Adam stay fp32 as in
+ * the reference.  bf16 values are exact TF32 operands, so the tensor-core GEMMs run ONE kind::tf32 MMA per product in this mode (fp32
+ * accumulation in TMEM, as a bf16 tensor-core GEMM accumulates) instead of the three of the fp32-equivalent split.  Returns the setting. */
+int rlx_set_autocast_bf16(int on);
+/* tcgen05 engine on CTA pairs (cta_group::2, csrc/gemm_tc2.cu).  mode 0: single-CTA kernels only; 1: the weight-gradient GEMMs of the PPO
+ * update run on pairs (256 x 256 / 256 x 192 tiles); 2 (default, with fwd_bn = 128): the forward / dX GEMMs too, with fwd_bn-wide pair tiles
+ * (128: double-buffered accumulators, 256: single; other values keep the current setting).  Returns the mode. */
 int rlx_set_tc_pair(int mode, int fwd_bn);
 /* 1: rlx_ppo_update_epoch_f32 runs gradient assembly + both grad norms + clip + Adam of a minibatch as ONE kernel (grid barrier in the
  * caller's workspace); 0 (default; measured faster on B200): the three separate kernels of rlx_ppo_minibatch_fwdbwd_f32 /

@@ -233,8 +233,12 @@ class PPO:
 
         if self.evaluation_frequency % (self.nr_steps * self.nr_envs) != 0 and self.evaluation_frequency != -1:
             raise ValueError("Evaluation frequency must be a multiple of the number of steps and environments.")
-        if config.algorithm.get("bf16_mixed_precision_training", False):
-            raise ValueError("rl_x_b200 PPO implements the reference's fp32 path; set algorithm.bf16_mixed_precision_training=False.")
+        # the reference's mixed-precision mode (ppo.py:98-107,123,155,208,253): autocast(bf16) around acting, next-values and both loss
+        # functions.  Here: the same roundings inside the kernels, bf16 values carried in fp32 storage, one tensor-core pass per product
+        # (rlx_set_autocast_bf16).  Single GPU for now: the sharded update would round every rank's partial gradient instead of the sum.
+        self.bf16_mixed_precision_training = bool(config.algorithm.get("bf16_mixed_precision_training", False))
+        if self.bf16_mixed_precision_training and self.world_size > 1:
+            raise NotImplementedError("rl_x_b200 PPO: bf16_mixed_precision_training is single-GPU in this build.")
         if config.algorithm.device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("rl_x_b200 PPO needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -594,6 +598,7 @@ class PPO:
     def _begin_training(self):
         """Everything PPO.train() does before its while loop (ppo.py:169-193)."""
         self._allocate()
+        self._select_precision()
         b, k = self.batch, self.kernels
         self.set_train_mode()
         self.saving_return_buffer = deque(maxlen=100 * self.nr_envs)
@@ -650,8 +655,13 @@ class PPO:
             return PermutationStream(self.local_rng, self.local_batch_size, self.nr_epochs, self.local_batch_size, None)
         return PermutationStream(self.rng, self.batch_size, self.nr_epochs, self.local_batch_size, None)
 
+    def _select_precision(self):
+        """The precision mode is a library-wide switch: select this instance's before every pass through the kernels."""
+        self.kernels.lib.rlx_set_autocast_bf16(1 if self.bf16_mixed_precision_training else 0)
+
     def _train_iteration(self):
         """One pass of the reference's while-loop body (ppo.py:195-393): acting, advantages, optimising, eval, save, log."""
+        self._select_precision()
         b, k = self.batch, self.kernels
         start_time = time.time()
         time_metrics = {}
@@ -757,6 +767,7 @@ class PPO:
     # ------------------------------------------------------------------------------------------ eval / test
     def _deterministic_action(self, state):
         """ref: policy.get_deterministic_action (policy.py:85-93)."""
+        self._select_precision()
         self.kernels.forward(self.params.flat, state, self._eval_ws(state.shape[0]), act_low=self.env_as_low, act_high=self.env_as_high,
                              clip_rescale=self.action_clipping_and_rescaling, deterministic=True, env_action=self._eval_action(state.shape[0]))
         return self._eval_action(state.shape[0])
@@ -873,7 +884,7 @@ class PPO:
         checkpoint = torch.load(config.runner.load_model, weights_only=False)
         loaded_algorithm_config = checkpoint["config_algorithm"]
         for key, value in loaded_algorithm_config.items():
-            if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device", "bf16_mixed_precision_training", "compile_mode"):
+            if f"algorithm.{key}" not in explicitly_set_algorithm_params and key in config.algorithm and key not in ("name", "device", "compile_mode"):
                 config.algorithm[key] = value
         model = cls(config, train_env, eval_env, run_path, writer)
         named = {**checkpoint["policy_state_dict"], **checkpoint["critic_state_dict"]}

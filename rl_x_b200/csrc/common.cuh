@@ -14,6 +14,11 @@ namespace rlx {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launch_count;
 extern int g_gemm_engine;
+// bf16-autocast mode of the PPO path (rlx_set_autocast_bf16; the reference's `bf16_mixed_precision_training`, ppo.py:98-107,123,155,208,253):
+// every value torch's autocast would hold in a bf16 tensor is rounded to bf16 (round-to-nearest-even) where torch rounds it, and kept in
+// fp32 storage.  bf16 values are exact TF32 operands, so ONE kind::tf32 MMA per product gives exactly the bf16 x bf16 -> fp32 products of a
+// bf16 tensor-core GEMM: the 3-way split (and the splitter warps' work) is switched off in this mode.
+extern int g_autocast_bf16;
 
 inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
@@ -59,6 +64,14 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int sm_count();
+
+// round-to-nearest-even to bfloat16, returned as fp32 (what `x.to(torch.bfloat16).float()` gives; NaN stays NaN)
+__device__ __forceinline__ float bf16r(float x) {
+  const unsigned u = __float_as_uint(x);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;  // inf / nan
+  return __uint_as_float((u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u);
+}
+__device__ __forceinline__ float bf16r_if(float x, int on) { return on ? bf16r(x) : x; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

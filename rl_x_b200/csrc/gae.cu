@@ -26,6 +26,7 @@ struct GaeP {
   long long T, N;
   float gamma_f;        // (float)gamma
   float gl_f;           // (float)(gamma * lambda), product taken in double as TorchScript does
+  int bf16;             // bf16-autocast mode (ppo.py:98-107): next_values is a bf16 tensor there, so `gamma * next_values` is a bf16 product
 };
 
 // GAE_TT: time steps per shared-memory tile.  128 = the whole config-2 rollout in one DRAM round trip (few CTAs, latency matters);
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(256) gae_kernel(const GaeP p) {
         const float nv = has_nv ? s_x[tt][lane] : (tt + 1 < nt ? s_v[tt + 1][lane] : v_after_tile);
         const float nonterm = __fsub_rn(1.f, tm);
         // delta = rewards + gamma * next_values * (1 - terminations) - values
-        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma_f, nv), nonterm)), v);
+        const float gnv = p.bf16 ? bf16r(__fmul_rn(p.gamma_f, nv)) : __fmul_rn(p.gamma_f, nv);
+        const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(gnv, nonterm)), v);
         s_r[tt][lane] = delta;
         s_t[tt][lane] = __fmul_rn(p.gl_f, nonterm);
       }
@@ -135,7 +137,7 @@ extern "C" int rlx_gae_f32(const float* rewards, const float* terminations, cons
   RLX_CHECK_ARG(rewards && terminations && values && advantages && returns, "null tensor");
   RLX_CHECK_ARG(next_values || last_value, "either next_values or last_value is required");
   GaeP p{rewards, terminations, values, next_values, last_value, advantages, returns, T, N, (float)gamma,
-         (float)(gamma * gae_lambda)};
+         (float)(gamma * gae_lambda), g_autocast_bf16};
   const unsigned grid = (unsigned)ceil_div(N, GAE_ENVS);
   const double bytes = (next_values ? 24.0 : 20.0) * (double)T * (double)N;
   static bool attr_set = false;

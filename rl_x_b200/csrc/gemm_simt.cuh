@@ -24,6 +24,9 @@ struct GemmP {
   int splits;         // split-K factor (grid.z = batch * splits)
   int kchunk;         // rows of K per split (multiple of 8)
   long long sSplitC, sSplitRowsum;             // per-split output strides
+  int bf16;           // bf16-autocast mode: operands are bf16 values; Linear outputs / activations / their gradients are rounded to bf16
+                      // where torch's autocast rounds them (EPI_NONE outputs - split-K partials of weight gradients - stay fp32: they
+                      // are rounded once after the full reduction)
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 8, GPAD = 4;
@@ -157,12 +160,12 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmP p) {
         const int n = nb + j;
         float x = acc[i][jh * 4 + j];
         if (n < p.N) {
-          if (EPI == EPI_BIAS) x += bias[n];
-          if (EPI == EPI_BIAS_TANH) x = tanhf(x + bias[n]);
+          if (EPI == EPI_BIAS) x = bf16r_if(x + bias[n], p.bf16);
+          if (EPI == EPI_BIAS_TANH) x = bf16r_if(tanhf(bf16r_if(x + bias[n], p.bf16)), p.bf16);  // Linear output bf16, tanh output bf16
           if (EPI == EPI_BIAS_RELU) x = fmaxf(x + bias[n], 0.f);
           if (EPI == EPI_DTANH) {
             const float h = aux[(long long)m * p.ldaux + n];
-            x = x * (1.f - h * h);
+            x = bf16r_if(bf16r_if(x, p.bf16) * (1.f - h * h), p.bf16);  // linear-backward output bf16, then tanh_backward in bf16
           }
           if (EPI == EPI_DRELU) {
             const float h = aux[(long long)m * p.ldaux + n];

@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
             const uint64_t da_lo = da + LO_OFF;
             const uint64_t db_lo = db + LO_OFF;
             const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-            umma_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
-            umma_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
-            umma_tf32(d_main, da, db, idesc, accum);     // hi * hi
+            if (!p.single) {
+              umma_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
+              umma_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
+            }
+            umma_tf32(d_main, da, db, idesc, accum);       // hi * hi  (bf16-valued operands: the whole product)
           }
           umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C_::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * C_::STAGE_BYTES + C_::A_BYTES + C_::B_BYTES);
 #pragma unroll 8
-        for (int i = t; i < NV; i += 128) {
+        for (int i = t; i < (p.single ? 0 : NV); i += 128) {
           const uint4 v = raw[i];
           float4 o;
           o.x = __uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u);
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = nb + j;
-              const float v = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+              const float v = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
               if (n < p.N) {
                 if (m < p.m_main) cbase[(long long)n * p.ldc + m] = v;
                 else if (m == p.m_main && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + n] = v;
@@ -265,7 +267,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
         }
         if (rows_valid > 0 && nb < p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);  // main + correction (fp32 RN)
+          for (int j = 0; j < 32; ++j)  // main + correction (fp32 RN); single-pass mode never wrote the correction accumulator
+            tile[lane * 33 + j] = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
           __syncwarp();
           const int n = nb + lane;
           const bool n_ok = n < p.N;
@@ -281,13 +284,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_gemm_kernel(const __grid_co
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) x[rr] = (EPI == TC_EPI_DTANH) ? x[rr] * (1.f - hv[rr] * hv[rr]) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
+            for (int rr = 0; rr < 32; ++rr)  // bf16 mode: linear-backward output rounded to bf16, then tanh_backward rounded to bf16
+              x[rr] = (EPI == TC_EPI_DTANH) ? bf16r_if(bf16r_if(x[rr], p.bf16) * (1.f - hv[rr] * hv[rr]), p.bf16) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
           }
           if (HAS_BIAS) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
-              const float z = x[rr] + bv;
-              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? tanhf(z) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
+              const float z = (EPI == TC_EPI_BIAS_RELU) ? x[rr] + bv : bf16r_if(x[rr] + bv, p.bf16);  // bf16 mode: Linear output is a bf16 tensor
+              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanhf(z), p.bf16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
             }
           }
           if (n < p.n_main) {
@@ -362,7 +366,7 @@ namespace tc {
 int tc2_launch(int bn, bool a_kmaj, bool b_kmaj, int epi, const TcOperand& A, const TcOperand& B, const TcParams& p, int kclass, cudaStream_t stream);  // gemm_tc2.cu
 }
 // CTA-pair engine selection (rlx_set_tc_pair): 0 = single-CTA kernels only; 1 = weight-gradient GEMMs on CTA pairs; 2 = every large GEMM.
-static int g_tc_pair = 1;
+static int g_tc_pair = 2;  // measured (gpurun_out/r2_bench5_*): ms/step 98.7 (0) / 94.3 (1) / 93.3 (2, 128-wide) / 94.7 (2, 256-wide)
 bool g_tc_pair_force = false;        // test hook (rlx_debug_gemm_f32): run the pair kernel even when the problem is smaller than the machine
 static int g_tc_pair_fwd_bn = 128;  // pair tile width for the forward / dX GEMMs in mode 2 (128: double-buffered accumulators, 256: single)
 int tc_pair_mode() { return g_tc_pair; }
@@ -419,6 +423,8 @@ int tc_gemm_t(const GemmP& g, bool a_kmaj, bool b_kmaj, int epi, int batch, int 
   p.extra_col = extra_col; p.extra_batch_off = extra_batch_off; p.extra_split_off = extra_split_off;
   p.bias = g.bias; p.bias_batch_off = g.sBias;
   p.aux = g.aux; p.ldaux = g.ldaux; p.aux_batch_off = g.sAux;
+  p.single = g.bf16 ? 1 : 0;
+  p.bf16 = g.bf16;
   // global tensors: K-major [mn_rows, k_cols]; MN-major [k_rows, mn_cols].  a_rows / b_rows are the VALID rows of one batch entry
   // (TMA zero-fills beyond them); batch entries that sit at row offsets extend the tensor accordingly.
   TcOperand A{g.A, (a_kmaj ? (long long)p.a_mn_off : (long long)p.a_k_off) * (batch - 1) + a_rows,

@@ -260,9 +260,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const uint64_t da_lo = da + LO_OFF;
             const uint64_t db_lo = db + LO_OFF;
             const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-            umma2_tf32(d_corr, da_lo, db, idesc, accum);
-            umma2_tf32(d_corr, da, db_lo, idesc, 1u);
-            umma2_tf32(d_main, da, db, idesc, accum);
+            if (!p.single) {
+              umma2_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
+              umma2_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
+            }
+            umma2_tf32(d_main, da, db, idesc, accum);       // hi * hi  (bf16-valued operands: the whole product)
           }
           umma_commit2(&empty_bar[s], 3);  // ring slot free in both CTAs
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -285,7 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C_::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * C_::STAGE_BYTES + C_::A_BYTES + C_::B_BYTES);
 #pragma unroll 8
-        for (int i = t; i < NV; i += 128) {
+        for (int i = t; i < (p.single ? 0 : NV); i += 128) {
           const uint4 v = raw[i];
           float4 o;
           o.x = __uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u);
@@ -333,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = nb + j;
-              const float v = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+              const float v = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
               if (n < p.N) {
                 if (m < p.m_main) cbase[(long long)n * p.ldc + m] = v;
                 else if (m == p.m_main && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + n] = v;
@@ -344,7 +346,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         }
         if (rows_valid > 0 && nb < p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+          for (int j = 0; j < 32; ++j)  // main + correction (fp32 RN); single-pass mode never wrote the correction accumulator
+            tile[lane * 33 + j] = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
           __syncwarp();
           const int n = nb + lane;
           const bool n_ok = n < p.N;
@@ -358,13 +361,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
 #pragma unroll
-            for (int rr = 0; rr < 32; ++rr) x[rr] = (EPI == TC_EPI_DTANH) ? x[rr] * (1.f - hv[rr] * hv[rr]) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
+            for (int rr = 0; rr < 32; ++rr)  // bf16 mode: linear-backward output rounded to bf16, then tanh_backward rounded to bf16
+              x[rr] = (EPI == TC_EPI_DTANH) ? bf16r_if(bf16r_if(x[rr], p.bf16) * (1.f - hv[rr] * hv[rr]), p.bf16) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
           }
           if (HAS_BIAS) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
-              const float z = x[rr] + bv;
-              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? tanhf(z) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
+              const float z = (EPI == TC_EPI_BIAS_RELU) ? x[rr] + bv : bf16r_if(x[rr] + bv, p.bf16);  // bf16 mode: Linear output is a bf16 tensor
+              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanhf(z), p.bf16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
             }
           }
           if (n < p.n_main) {

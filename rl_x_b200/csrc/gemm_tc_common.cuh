@@ -34,6 +34,8 @@ struct TcParams {
   long long bias_batch_off;
   const float* aux;          // TC_EPI_DTANH: activation values, same indexing as C
   long long ldaux, aux_batch_off;
+  int single;                // bf16-autocast mode: operands are bf16 values = exact TF32 operands -> ONE MMA per k-slice, no lo tiles
+  int bf16;                  // round Linear outputs / activations / activation gradients to bf16 in the epilogue (see GemmP::bf16)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers

@@ -7,6 +7,7 @@ namespace rlx {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launch_count{0};
 int g_gemm_engine = 0;
+int g_autocast_bf16 = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -56,6 +57,10 @@ extern "C" uint64_t rlx_launch_count(void) { return rlx::g_launch_count.load(); 
 extern "C" void rlx_reset_launch_count(void) { rlx::g_launch_count.store(0); }
 extern "C" void rlx_add_launch_count(uint64_t n) { rlx::g_launch_count.fetch_add(n); }
 extern "C" int rlx_get_gemm_engine(void) { return rlx::g_gemm_engine; }
+extern "C" int rlx_set_autocast_bf16(int on) {
+  rlx::g_autocast_bf16 = on ? 1 : 0;
+  return rlx::g_autocast_bf16;
+}
 
 extern "C" int64_t rlx_ppo_param_count(const rlx_ppo_dims* d) {
   if (d == nullptr || !rlx::dims_ok(*d)) {

@@ -52,8 +52,25 @@ static Splits choose_splits(long long rows, int out_m, int out_n, int batch, boo
   return Splits{(int)ceil_div(rows, kchunk), (int)kchunk};
 }
 
+// bf16-autocast mode: dst = bf16-rounded copy of src (what `.to(torch.bfloat16)` of autocast's Linear does to the input and to the
+// weights), except the [keep_lo, keep_hi) range, which is copied as is (logstd: an fp32 parameter no autocast op touches)
+__global__ void __launch_bounds__(256) round_bf16_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, long long keep_lo,
+                                                         long long keep_hi) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float x = src[i];
+    dst[i] = (i >= keep_lo && i < keep_hi) ? x : bf16r(x);
+  }
+}
+static int launch_round_bf16(const float* src, float* dst, long long n, long long keep_lo, long long keep_hi, cudaStream_t st) {
+  if (n <= 0) return RLX_OK;
+  const unsigned grid = (unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 8);
+  RLX_LAUNCH_C(KC_OTHER, 0, 8.0 * n, round_bf16_kernel, grid, 256, 0, st, src, dst, n, keep_lo, keep_hi);
+  return RLX_OK;
+}
+
 struct FwdPlan {
-  size_t off_H1, off_H2, total;
+  size_t off_H1, off_H2, off_P, off_X, total;
 };
 static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
   FwdPlan P;
@@ -61,6 +78,9 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
   const size_t act_bytes = align_up((size_t)n * 2 * d.hidden * sizeof(float), 256);
   P.off_H1 = o; o += act_bytes;
   P.off_H2 = o; o += act_bytes;
+  // bf16-autocast mode: rounded copies of the parameters and of the observations (always planned: the mode is a run-time switch)
+  P.off_P = o; o += align_up((size_t)make_layout(d).total() * sizeof(float), 256);
+  P.off_X = o; o += align_up((size_t)n * d.obs_dim * sizeof(float), 256);
   P.total = o;
   return P;
 }
@@ -68,7 +88,7 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
 constexpr int kHeadWgradRows = 64;
 
 struct TrainPlan {
-  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, off_barrier, total;
+  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, off_barrier, off_P, off_X, total;
   int max_s1, max_s2, max_s3;
   int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
@@ -104,6 +124,8 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   take(P.off_part3, std::max<size_t>((size_t)P.wgrad_chunks * (A + 1) * H, (size_t)P.max_s3 * 2 * dh_ld_plan * H));
   take(P.off_norm, (size_t)P.norm_blocks * 2);
   take(P.off_barrier, 64);
+  take(P.off_P, (size_t)make_layout(d).total());                          // bf16-autocast mode: rounded parameter copy
+  take(P.off_X, (size_t)m * (size_t)(ceil_div(O + 1, 4) * 4));             // ... and rounded copy of the minibatch states (pitch <= obs + 4)
   P.total = o;
   return P;
 }
@@ -121,7 +143,7 @@ static size_t head_smem_bytes(const rlx_ppo_dims& d, bool train) {
 
 // hidden layers: H1 = tanh(X W1cat^T + b1cat), H2 = tanh(H1 (blockdiag W2)^T + b2cat).  ldx = row pitch of X.
 static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const float* params, const float* X, long long ldx, long long rows,
-                              float* H1, float* H2, cudaStream_t stream) {
+                              float* H1, float* H2, cudaStream_t stream, int bf16 = 0) {
   const int H = L.H;
   const bool tc = use_tc(d);
   GemmP g{};
@@ -129,6 +151,7 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   g.M = (int)rows; g.N = 2 * H; g.K = L.obs;
   g.lda = (int)ldx; g.ldb = L.obs; g.ldc = 2 * H;
   g.splits = 1; g.kchunk = (int)(ceil_div(L.obs, 8) * 8);
+  g.bf16 = bf16;
   const int pair_fwd = tc ? tc_pair_fwd_bn() : 0;
   int rc = run_gemm<true, true, EPI_BIAS_TANH>(tc, g, 1, stream, KC_GEMM_FWD, rows, 2 * H, pair_fwd);
   if (rc) return rc;
@@ -138,6 +161,7 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   g2.lda = 2 * H; g2.ldb = H; g2.ldc = 2 * H;
   g2.sA = H; g2.sB = (long long)H * H; g2.sC = H; g2.sBias = H;
   g2.splits = 1; g2.kchunk = (int)(ceil_div(H, 8) * 8);
+  g2.bf16 = bf16;
   return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, H, pair_fwd);
 }
 
@@ -196,10 +220,25 @@ extern "C" int rlx_ppo_forward_f32(const rlx_ppo_forward_args* a, void* stream) 
   float* H1 = ws_ptr<float>(a->workspace, P.off_H1);
   float* H2 = ws_ptr<float>(a->workspace, P.off_H2);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = mlp_hidden_forward(a->dims, L, a->params, a->obs, a->dims.obs_dim, a->n, H1, H2, st);
+  const int bf16 = g_autocast_bf16;
+  const float* params = a->params;
+  const float* obs = a->obs;
+  int rc;
+  if (bf16) {
+    float* pr = ws_ptr<float>(a->workspace, P.off_P);
+    float* xr = ws_ptr<float>(a->workspace, P.off_X);
+    rc = launch_round_bf16(a->params, pr, L.total(), L.off[LOGSTD], L.off[LOGSTD + 1], st);
+    if (rc) return rc;
+    rc = launch_round_bf16(a->obs, xr, a->n * (long long)L.obs, 0, 0, st);
+    if (rc) return rc;
+    params = pr;
+    obs = xr;
+  }
+  rc = mlp_hidden_forward(a->dims, L, params, obs, a->dims.obs_dim, a->n, H1, H2, st, bf16);
   if (rc) return rc;
   HeadP h{};
-  fill_head_common(h, L, a->params, H2, a->n);
+  fill_head_common(h, L, params, H2, a->n);
+  h.bf16 = bf16;
   h.noise = a->noise; h.seed = a->rng_seed; h.offset = a->rng_offset;
   h.act_low = a->act_low; h.act_high = a->act_high;
   h.clip_rescale = a->clip_rescale; h.deterministic = a->deterministic;
@@ -293,13 +332,28 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
 
   int head_blocks = 0, wgrad_chunks = 0, s1 = 0, s2 = 0, w3_nsplit = 0;
   long long w3_stride = (long long)(A + 1) * H, w3c_off = (long long)A * H;
+  const int bf16 = g_autocast_bf16;
+  const float* params = a->params;   // bf16 mode: the rounded copies below (what autocast's casts hand to every Linear)
+  const float* states = a->states;
   if (m > 0) {
+    if (bf16) {
+      RLX_CHECK_ARG(ldx <= (long long)(ceil_div(O + 1, 4) * 4), "bf16 mode: states_ld larger than the planned rounded copy");
+      float* pr = ws_ptr<float>(ws, P.off_P);
+      float* xr = ws_ptr<float>(ws, P.off_X);
+      rc = launch_round_bf16(a->params, pr, L.total(), L.off[LOGSTD], L.off[LOGSTD + 1], st);
+      if (rc) return rc;
+      rc = launch_round_bf16(a->states, xr, m * ldx, 0, 0, st);
+      if (rc) return rc;
+      params = pr;
+      states = xr;
+    }
     // ---- forward hidden layers
-    rc = mlp_hidden_forward(d, L, a->params, a->states, ldx, m, H1, H2, st);
+    rc = mlp_hidden_forward(d, L, params, states, ldx, m, H1, H2, st, bf16);
     if (rc) return rc;
     // ---- head: loss + dZ2 + dhead + block partials (incl. db2 = column sums of dZ2)
     HeadP h{};
-    fill_head_common(h, L, a->params, H2, m);
+    fill_head_common(h, L, params, H2, m);
+    h.bf16 = bf16;
     h.actions = a->actions; h.logp_old = a->log_probs; h.adv = a->advantages; h.ret = a->returns; h.adv_stats = a->adv_stats;
     h.inv_mg = inv_mg; h.clip_range = a->hp.clip_range; h.critic_coef = a->hp.critic_coef;
     h.ratio_delta_metric = a->hp.ratio_delta_metric != 0.f ? 1 : 0;
@@ -310,7 +364,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     const bool fast_head = (A <= 31) && (H % 2 == 0) && (H <= 1024);
     const double head_flops = 4.0 * m * H * (A + 1), head_bytes = 4.0 * m * (4.0 * H + 2.0 * A + 5);
     // opt-in GEMM formulation of the head (ppo_head_gemm.cu); dZ1 is free until the dX GEMM and serves as its scratch
-    const bool gemm_head = fast_head && g_head_engine == 1 && head_gemm_scratch_floats(m, H, A) <= m * 2LL * H;
+    const bool gemm_head = fast_head && g_head_engine == 1 && !bf16 && head_gemm_scratch_floats(m, H, A) <= m * 2LL * H;
     if (gemm_head) {
       HeadGemmArgs ha{m, H, A, dh_ld, H2, a->params + L.off[W3P], a->params + L.off[W3C], a->params + L.off[B3P], a->params + L.off[B3C],
                       a->params + L.off[LOGSTD], a->actions, a->log_probs, a->advantages, a->returns, a->adv_stats, inv_mg, a->hp.clip_range,
@@ -375,6 +429,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
         g3.lda = dh_ld; g3.ldb = 2 * H; g3.ldc = H;
         g3.sA = 0; g3.sB = H; g3.sC = (long long)dh_ld * H;
         g3.splits = S3.splits; g3.kchunk = S3.kchunk; g3.sSplitC = 2LL * dh_ld * H;
+        g3.bf16 = bf16;
         rc = tc_gemm(g3, false, false, TC_NONE, 2, KC_HEAD_WGRAD, m, m, 0, nullptr, 0, 0, st);
         if (rc == RLX_OK) {
           w3_done = true;
@@ -428,11 +483,13 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     g.lda = 2 * H; g.ldb = 2 * H; g.ldc = H;
     g.sA = H; g.sB = H; g.sC = (long long)H * H;
     g.splits = S2.splits; g.kchunk = S2.kchunk; g.sSplitC = 2LL * H * H;
+    g.bf16 = bf16;
     rc = run_gemm<false, false, EPI_NONE>(tc, g, 2, st, KC_GEMM_DW, m, m, pair_dw);
     if (rc) return rc;
     // ---- dZ1 = (dZ2 @ W2) * (1 - H1^2)   per net
     GemmP gd{};
-    gd.A = dZ2; gd.B = a->params + L.off[W2P]; gd.C = dZ1; gd.aux = H1;
+    gd.A = dZ2; gd.B = params + L.off[W2P]; gd.C = dZ1; gd.aux = H1;
+    gd.bf16 = bf16;
     gd.M = (int)m; gd.N = H; gd.K = H;
     gd.lda = 2 * H; gd.ldb = H; gd.ldc = 2 * H; gd.ldaux = 2 * H;
     gd.sA = H; gd.sB = (long long)H * H; gd.sC = H; gd.sAux = H;
@@ -441,7 +498,8 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     if (rc) return rc;
     // ---- dW1cat | db1cat : part1[split][o][i] = sum_rows dZ1[r, o] * X[r, i];  db1[o] = sum_rows dZ1[r, o]
     GemmP g1{};
-    g1.A = dZ1; g1.B = a->states; g1.C = part1;
+    g1.A = dZ1; g1.B = states; g1.C = part1;
+    g1.bf16 = bf16;
     g1.M = 2 * H; g1.N = O; g1.K = (int)m;
     g1.lda = 2 * H; g1.ldb = (int)ldx; g1.ldc = O;
     bool done = false;
@@ -465,7 +523,8 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
       // makes db1 the last output row) and N = 2H = full 256-wide tiles; the epilogue stores C^T transposed back into [o][i].
       const Splits S1 = choose_splits(m, O + 1, 2 * H, 1, true);
       GemmP gt{};
-      gt.A = a->states; gt.B = dZ1; gt.C = part1;
+      gt.A = states; gt.B = dZ1; gt.C = part1;
+      gt.bf16 = bf16;
       gt.M = O + 1; gt.N = 2 * H; gt.K = (int)m;
       gt.lda = (int)ldx; gt.ldb = 2 * H; gt.ldc = O;
       gt.splits = S1.splits; gt.kchunk = S1.kchunk; gt.sSplitC = 2LL * H * O;
@@ -503,6 +562,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
   r.head_partials = headpart; r.nblk = head_blocks; r.npart = npart; r.inv_mg = inv_mg; r.critic_coef = a->hp.critic_coef;
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
+  r.bf16 = bf16;
   if (deferred != nullptr) {
     *deferred = r;
     return RLX_OK;

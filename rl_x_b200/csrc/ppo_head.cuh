@@ -67,6 +67,8 @@ struct HeadP {
   float* dZ2;              // [M, 2H]
   float* dhead;            // [M, act+1]   (dmean | dv)
   float* block_partials;   // [gridDim.x, 2*act+5+2H]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac | db2p[H] | db2c[H])
+  int bf16;                // bf16-autocast mode: the mean / value (outputs of the last Linear) are bf16 tensors, and so are the gradients that
+                           // flow back into them and through them (d mean, d value, the linear-backward output and tanh_backward's output)
 };
 
 // Loads the row's H2 slices and returns the act means (lane a holds mean a; a+32 in mean_hi) and the value (all lanes).
@@ -90,7 +92,7 @@ __device__ __forceinline__ void head_row_forward(const HeadP& p, const float* __
       const int j = lane + 32 * c;
       if (j < p.H) s = fmaf(hp[c], sW3p[a * p.H + j], s);
     }
-    s = warp_sum(s) + p.b3p[a];
+    s = bf16r_if(warp_sum(s) + p.b3p[a], p.bf16);
     if (lane == (a & 31)) {
       if (a < 32) mean_lo = s; else mean_hi = s;
     }
@@ -101,7 +103,7 @@ __device__ __forceinline__ void head_row_forward(const HeadP& p, const float* __
     const int j = lane + 32 * c;
     if (j < p.H) s = fmaf(hc[c], sW3c[j], s);
   }
-  value = warp_sum(s) + p.b3c[0];
+  value = bf16r_if(warp_sum(s) + p.b3c[0], p.bf16);
 }
 
 __device__ __forceinline__ void head_stage_weights(const HeadP& p, float* sW3p, float* sW3c) {
@@ -133,11 +135,19 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
           const float ls = p.logstd[a];
           const float sd = expf(ls);
           const float eps = p.noise ? p.noise[row * p.act + a] : philox_normal(p.seed, p.offset, (uint32_t)row, (uint32_t)a);
-          x = __fadd_rn(mean, __fmul_rn(sd, eps));  // Normal.sample(): loc + scale * eps  (no FMA contraction)
-          // Normal.log_prob (torch/distributions/normal.py:87-103)
           const float var = sd * sd;
-          const float d = x - mean;
-          lp_sum += -(d * d) / (2.f * var) - logf(sd) - kLogSqrt2Pi;
+          if (p.bf16) {
+            // Normal(bf16 loc, fp32 scale).sample() = at::normal(loc, scale): a tensor of loc's dtype filled with N(0,1) draws, then
+            // .mul_(scale).add_(loc) in place - three bf16 roundings; log_prob sees (value - loc) and its square as bf16 tensors
+            x = bf16r(__fadd_rn(bf16r(__fmul_rn(bf16r(eps), sd)), mean));
+            const float d2 = bf16r(bf16r(x - mean) * bf16r(x - mean));
+            lp_sum += -d2 / (2.f * var) - logf(sd) - kLogSqrt2Pi;
+          } else {
+            x = __fadd_rn(mean, __fmul_rn(sd, eps));  // Normal.sample(): loc + scale * eps  (no FMA contraction)
+            // Normal.log_prob (torch/distributions/normal.py:87-103)
+            const float d = x - mean;
+            lp_sum += -(d * d) / (2.f * var) - logf(sd) - kLogSqrt2Pi;
+          }
         }
         if (p.action) p.action[row * p.act + a] = x;
         if (p.env_action) {
@@ -145,7 +155,7 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
           if (p.clip_rescale) {  // policy.py:68-70
             const float c = fminf(fmaxf(x, -1.f), 1.f);
             const float lo = p.act_low[a], hi = p.act_high[a];
-            e = lo + (0.5f * (c + 1.f)) * (hi - lo);
+            e = lo + bf16r_if(0.5f * bf16r_if(c + 1.f, p.bf16), p.bf16) * (hi - lo);  // bf16 mode: clipped + 1.0 and 0.5 * (...) stay bf16 tensors
           }
           p.env_action[row * p.act + a] = e;
         }
@@ -213,7 +223,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     const float dratio = -A * (w1 + (1.f - w1) * inr);
     const float dlogp = dratio * ratio * p.inv_mg;
     const float verr = value - p.ret[row];
-    const float dv = p.critic_coef * verr * p.inv_mg;
+    const float dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);
 
     acc_pg += pg;
     acc_vl += 0.5f * verr * verr;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     float dmean[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      dmean[half] = dlogp * dmu[half];
+      dmean[half] = bf16r_if(dlogp * dmu[half], p.bf16);
       acc_db3p[half] += dmean[half];
       acc_dls[half] += dlogp * (zz[half] - 1.f);  // d logp / d logstd = (x-mean)^2/var - 1
       const int a = lane + 32 * half;
@@ -249,8 +259,8 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     for (int c = 0; c < NCH; ++c) {
       const int j = lane + 32 * c;
       if (j < p.H) {
-        const float zp = dz[c] * (1.f - hp[c] * hp[c]);
-        const float zc = dv * sW3c[j] * (1.f - hc[c] * hc[c]);
+        const float zp = bf16r_if(bf16r_if(dz[c], p.bf16) * (1.f - hp[c] * hp[c]), p.bf16);
+        const float zc = bf16r_if(bf16r_if(dv * sW3c[j], p.bf16) * (1.f - hc[c] * hc[c]), p.bf16);
         out[j] = zp;
         out[p.H + j] = zc;
         acc_db2p[c] += zp;
@@ -398,8 +408,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
       for (int a = 0; a < 32; ++a)
         if (a == act) { v0[a] = s0; v1[a] = s1; }
     }
-    const float out0 = butterfly_reduce32(v0, lane) + my_b3;  // lane a < act: mean_a; lane act: value
-    const float out1 = butterfly_reduce32(v1, lane) + my_b3;
+    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, p.bf16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
+    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, p.bf16);
 
     float dmean[2], dvv[2];
 #pragma unroll
@@ -427,12 +437,12 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
         const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
         const float verr = value - p.ret[row];
-        dv = p.critic_coef * verr * p.inv_mg;
+        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);  // gradient of a bf16 tensor is a bf16 tensor
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
-        dm = dlogp * dmu;
+        dm = bf16r_if(dlogp * dmu, p.bf16);
         if (own) {
           acc_db3 += dm;
           acc_dls += dlogp * (zz - 1.f);
@@ -474,8 +484,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         const int j = lane + 32 * c;
         if (j < H) {
           const float hpv = hp[r][c], hcv = hc[r][c];
-          const float zp = (r ? dz1[c] : dz0[c]) * (1.f - hpv * hpv);
-          const float zc = dvv[r] * sW3c[j] * (1.f - hcv * hcv);
+          const float zp = bf16r_if(bf16r_if(r ? dz1[c] : dz0[c], p.bf16) * (1.f - hpv * hpv), p.bf16);  // linear-backward output, then tanh_backward
+          const float zc = bf16r_if(bf16r_if(dvv[r] * sW3c[j], p.bf16) * (1.f - hcv * hcv), p.bf16);
           out[j] = zp;
           out[H + j] = zc;
           acc_db2p[c] += zp;
@@ -657,8 +667,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
       for (int a = 0; a < 32; ++a)
         if (a == act) { v0[a] = s0; v1[a] = s1; }
     }
-    const float out0 = butterfly_reduce32(v0, lane) + my_b3;  // lane a < act: mean_a; lane act: value
-    const float out1 = butterfly_reduce32(v1, lane) + my_b3;
+    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, p.bf16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
+    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, p.bf16);
 
     float dmean[2], dvv[2];
 #pragma unroll
@@ -686,12 +696,12 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
         const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
         const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
         const float verr = value - p.ret[row];
-        dv = p.critic_coef * verr * p.inv_mg;
+        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);  // gradient of a bf16 tensor is a bf16 tensor
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
-        dm = dlogp * dmu;
+        dm = bf16r_if(dlogp * dmu, p.bf16);
         if (own) {
           acc_db3 += dm;
           acc_dls += dlogp * (zz - 1.f);
@@ -731,9 +741,11 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
       for (int g = 0; g < NG; ++g) {
         const float4 a4 = hp[r][g], c4 = hc[r][g], d4 = r ? dz1[g] : dz0[g], wc = sW3c4[g * 32 + lane];
         float4 zp, zc;
-        zp.x = d4.x * (1.f - a4.x * a4.x); zp.y = d4.y * (1.f - a4.y * a4.y); zp.z = d4.z * (1.f - a4.z * a4.z); zp.w = d4.w * (1.f - a4.w * a4.w);
-        zc.x = dvv[r] * wc.x * (1.f - c4.x * c4.x); zc.y = dvv[r] * wc.y * (1.f - c4.y * c4.y);
-        zc.z = dvv[r] * wc.z * (1.f - c4.z * c4.z); zc.w = dvv[r] * wc.w * (1.f - c4.w * c4.w);
+        const int bf = p.bf16;  // bf16 mode: the linear-backward output and tanh_backward's output are bf16 tensors
+        zp.x = bf16r_if(bf16r_if(d4.x, bf) * (1.f - a4.x * a4.x), bf); zp.y = bf16r_if(bf16r_if(d4.y, bf) * (1.f - a4.y * a4.y), bf);
+        zp.z = bf16r_if(bf16r_if(d4.z, bf) * (1.f - a4.z * a4.z), bf); zp.w = bf16r_if(bf16r_if(d4.w, bf) * (1.f - a4.w * a4.w), bf);
+        zc.x = bf16r_if(bf16r_if(dvv[r] * wc.x, bf) * (1.f - c4.x * c4.x), bf); zc.y = bf16r_if(bf16r_if(dvv[r] * wc.y, bf) * (1.f - c4.y * c4.y), bf);
+        zc.z = bf16r_if(bf16r_if(dvv[r] * wc.z, bf) * (1.f - c4.z * c4.z), bf); zc.w = bf16r_if(bf16r_if(dvv[r] * wc.w, bf) * (1.f - c4.w * c4.w), bf);
         out[g * 32 + lane] = zp;
         out[H4 + g * 32 + lane] = zc;
         acc_db2p[g].x += zp.x; acc_db2p[g].y += zp.y; acc_db2p[g].z += zp.z; acc_db2p[g].w += zp.w;

@@ -30,6 +30,8 @@ struct GradReduceP {
   const float* logstd;
   float* metrics;              // [RLX_PPO_NMETRIC]
   float m_local;
+  int bf16;                    // bf16-autocast mode: weight / bias gradients come out of bf16 GEMMs / reductions (fp32 accumulation, one rounding
+                               // of the complete sum); logstd is an fp32 parameter outside every autocast op and is not rounded
 };
 
 // Groups with few partials per element (split-K GEMM outputs) are summed by one thread per element with 8 loads in flight;
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
       }
       if (mine) {
         if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
+        else s = bf16r_if(s, p.bf16);
         p.grads[i] = s;
       }
     }
@@ -86,6 +89,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
         float s = grad_sum_warp(g.src + w, g.nsplit, g.stride, lane);
         const long long i = g.off + w;
         if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
+        else s = bf16r_if(s, p.bf16);
         if (lane == 0) p.grads[i] = s;
         w = -1;
       } else if (w >= g.len) {
@@ -253,6 +257,7 @@ __global__ void __launch_bounds__(kTailThreads) ppo_fused_tail_kernel(const Tail
       }
       if (own) {
         if (i >= r.logstd_off && i < r.logstd_off + r.act) s += r.entropy_grad;
+        else s = bf16r_if(s, r.bf16);
         g[k] = s;
         mine[k] = true;
         r.grads[i] = s;
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(kTailThreads) ppo_fused_tail_kernel(const Tail
         float s = grad_sum_warp(gg.src + w, gg.nsplit, gg.stride, lane);
         const long long i = gg.off + w;
         if (i >= r.logstd_off && i < r.logstd_off + r.act) s += r.entropy_grad;
+        else s = bf16r_if(s, r.bf16);
         if (lane == 0) {
           tg[k] = s;
           ti[k] = i;
