@@ -116,7 +116,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------- GPU arm
-def build_model(args, rank, world, interface, global_minibatch=None):
+def build_model(args, rank, world, interface, global_minibatch=None, bf16=False):
     from rl_x_b200.runner.runner import Runner
     argv = [f"--environment.nr_envs={args.envs}", f"--environment.obs_dim={C2['obs_dim']}", f"--environment.act_dim={C2['act_dim']}",
             f"--environment.seed={1 + rank}", f"--environment.data_interface={interface}", "--environment.horizon=1000",
@@ -125,7 +125,7 @@ def build_model(args, rank, world, interface, global_minibatch=None):
             f"--algorithm.minibatch_size={global_minibatch if global_minibatch else args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
             f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15",
             f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}",
-            f"--algorithm.gradient_exchange={args.exchange}"]
+            f"--algorithm.gradient_exchange={args.exchange}", f"--algorithm.bf16_mixed_precision_training={'True' if bf16 else 'False'}"]
     r = Runner(argv=argv)
     train_env, eval_env = r._create_train_and_eval_env(r._config)
     # weights and the permutation stream follow RANK 0's seed inside PPO.__init__ (broadcast); env streams differ via the env seed above
@@ -572,6 +572,7 @@ def main():
     ap.add_argument("--tc-pair", default="", help="tcgen05 CTA-pair engine: MODE[:FWD_BN], MODE 0 off / 1 weight gradients (default) / 2 all GEMMs, FWD_BN 128|256")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true", help="N=1: skip the bf16-autocast sub-line")
     ap.add_argument("--no-workloads", action="store_true", help="N=1: skip the nested SAC / FastSAC / PPO+LSTM records")
     ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the sharded-vs-single parity run before timing")
     ap.add_argument("--no-strict", action="store_true", help="N>1: skip the second timed region at the contract's GLOBAL minibatch of 32768")
@@ -770,6 +771,34 @@ def main():
                                                   f"eager (TORCHDYNAMO_DISABLE=1), {threads} torch threads", "port_cross_check": port}
             except Exception as e:
                 line["cpu_baseline"]["note"] = f"reference class run failed ({e}); port sample reported"
+    if rank == 0 and world == 1 and not args.no_bf16:
+        # the reference's DEFAULT precision mode (bf16 autocast, ppo/pytorch/default_config.py:11) as a separate sub-line: same workload, same
+        # timing rules, kept apart from the fp32 headline (BASELINE.md's CPU numbers and the parity bar of 1e-5 are fp32)
+        try:
+            torch.cuda.empty_cache()
+            mb16 = build_model(args, rank, world, "torch", bf16=True)
+            mb16._begin_training()
+            for _ in range(args.warmup):
+                mb16._train_iteration()
+            sb, _, _ = timed_iterations(mb16, args.steps, None)
+            nt.timing_begin()
+            for _ in range(2):
+                mb16._train_iteration()
+            cls16 = nt.timing_end()
+            g16 = {k: cls16[k] for k in ("gemm_fwd", "gemm_dx", "gemm_dw")}
+            tf16 = sum(v["flops"] for v in g16.values()) / (sum(v["ms"] for v in g16.values()) * 1e-3) / 1e12
+            line["bf16_autocast"] = {"value": steps_per_iter * args.steps / sb, "unit": "env-steps/s", "ms_per_step": sb / args.steps * 1e3, "dtype": "bf16-autocast",
+                                     "note": "bf16_mixed_precision_training=True: bf16 values in fp32 storage, ONE tcgen05 kind::tf32 MMA per product (exact for bf16 operands), "
+                                             "fp32 accumulation, losses / clipping / Adam in fp32 as in the reference",
+                                     "kernel_ms": {k: round(v["ms"] / 2, 4) for k, v in cls16.items() if v["launches"]},
+                                     "roofline": {"bound": "tensor", "achieved": tf16, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf16 / peaks["tflops"],
+                                                  "note": "algorithmic FLOPs of the MLP GEMMs against the measured dense bf16 peak; the tf32 pipe this mode runs on peaks at half of it"}}
+            mb16._end_training()
+            del mb16
+            lib.rlx_set_autocast_bf16(0)
+        except Exception as e:
+            line["bf16_autocast"] = {"error": f"{type(e).__name__}: {e}"}
+            lib.rlx_set_autocast_bf16(0)
     if rank == 0 and world == 1 and not args.no_workloads:
         # the other BASELINE.json configs, each with its own value / cpu_baseline (SAC also its roofline), nested so that the one parsed
         # line carries them (they are separate workloads, not part of `value`)

@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-shared",
+    "--threads", "8",   # one compilation per source file in parallel
 ]
 
 

@@ -123,7 +123,9 @@ struct Cfg2 {
   static_assert(ACC_STAGES * 2 * BN <= 512, "TMEM columns");
 };
 
-template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI>
+// BF16: the bf16-autocast variant (single-pass MMAs on bf16-valued operands, bf16 roundings in the epilogue), a compile-time switch so that
+// the fp32-equivalent kernels carry none of it
+template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI, bool BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
     tc_gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
   using C_ = Cfg2<BN>;
@@ -260,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             const uint64_t da_lo = da + LO_OFF;
             const uint64_t db_lo = db + LO_OFF;
             const uint32_t accum = (kb | kk) != 0 ? 1u : 0u;
-            if (!p.single) {
+            if (!BF16) {
               umma2_tf32(d_corr, da_lo, db, idesc, accum);  // lo * hi   } small terms, own accumulator
               umma2_tf32(d_corr, da, db_lo, idesc, 1u);     // hi * lo   }
             }
@@ -287,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         const uint4* raw = reinterpret_cast<const uint4*>(smem + s * C_::STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + s * C_::STAGE_BYTES + C_::A_BYTES + C_::B_BYTES);
 #pragma unroll 8
-        for (int i = t; i < (p.single ? 0 : NV); i += 128) {
+        for (int i = t; i < (BF16 ? 0 : NV); i += 128) {
           const uint4 v = raw[i];
           float4 o;
           o.x = __uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u);
@@ -335,7 +337,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = nb + j;
-              const float v = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+              const float v = BF16 ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
               if (n < p.N) {
                 if (m < p.m_main) cbase[(long long)n * p.ldc + m] = v;
                 else if (m == p.m_main && p.extra_col != nullptr) p.extra_col[p.extra_batch_off * zb + p.extra_split_off * zs + n] = v;
@@ -347,7 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
         if (rows_valid > 0 && nb < p.N) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)  // main + correction (fp32 RN); single-pass mode never wrote the correction accumulator
-            tile[lane * 33 + j] = p.single ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            tile[lane * 33 + j] = BF16 ? __uint_as_float(r[j]) : __uint_as_float(r[j]) + __uint_as_float(rc[j]);
           __syncwarp();
           const int n = nb + lane;
           const bool n_ok = n < p.N;
@@ -362,13 +364,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
             for (int rr = 0; rr < 32; ++rr) hv[rr] = (rr < rows_valid && n_ok) ? abase[(long long)(row0 + rr) * p.ldaux + n] : 0.f;
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr)  // bf16 mode: linear-backward output rounded to bf16, then tanh_backward rounded to bf16
-              x[rr] = (EPI == TC_EPI_DTANH) ? bf16r_if(bf16r_if(x[rr], p.bf16) * (1.f - hv[rr] * hv[rr]), p.bf16) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
+              x[rr] = (EPI == TC_EPI_DTANH) ? bf16r_if(bf16r_if(x[rr], BF16) * (1.f - hv[rr] * hv[rr]), BF16) : ((hv[rr] > 0.f) ? x[rr] : 0.f);
           }
           if (HAS_BIAS) {
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
-              const float z = (EPI == TC_EPI_BIAS_RELU) ? x[rr] + bv : bf16r_if(x[rr] + bv, p.bf16);  // bf16 mode: Linear output is a bf16 tensor
-              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanhf(z), p.bf16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
+              const float z = (EPI == TC_EPI_BIAS_RELU) ? x[rr] + bv : bf16r_if(x[rr] + bv, BF16);  // bf16 mode: Linear output is a bf16 tensor
+              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanhf(z), BF16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
             }
           }
           if (n < p.n_main) {
@@ -401,7 +403,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
   }
 }
 
-template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI>
+template <int BN, bool A_KMAJ, bool B_KMAJ, int EPI, bool BF16 = false>
 static int launch_cfg2(const TcOperand& A, const TcOperand& B, TcParams p, int kclass, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, A.base, A.rows, A.cols, A.ld, 32, A_KMAJ ? BM : BK, A_KMAJ);
@@ -412,7 +414,7 @@ static int launch_cfg2(const TcOperand& A, const TcOperand& B, TcParams p, int k
   p.tiles_n = (int)ceil_div(p.N, BN);
   const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch * p.splits;
   if (tiles <= 0) return RLX_OK;
-  auto kern = tc_gemm2_kernel<BN, A_KMAJ, B_KMAJ, EPI>;
+  auto kern = tc_gemm2_kernel<BN, A_KMAJ, B_KMAJ, EPI, BF16>;
   static bool attr_done = false;
   if (!attr_done) {
     RLX_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM_BYTES));
@@ -429,6 +431,10 @@ static int launch_cfg2(const TcOperand& A, const TcOperand& B, TcParams p, int k
 int tc2_launch(int bn, bool a_kmaj, bool b_kmaj, int epi, const TcOperand& A, const TcOperand& B, const TcParams& p, int kclass, cudaStream_t stream) {
 #define RLX_TC2_DISPATCH(BN_)                                                                                                    \
   do {                                                                                                                          \
+    if (p.bf16 && a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg2<BN_, true, true, TC_EPI_BIAS_TANH, true>(A, B, p, kclass, stream); \
+    if (p.bf16 && a_kmaj && !b_kmaj && epi == TC_EPI_DTANH) return launch_cfg2<BN_, true, false, TC_EPI_DTANH, true>(A, B, p, kclass, stream);     \
+    if (p.bf16 && !a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg2<BN_, false, false, TC_EPI_NONE, true>(A, B, p, kclass, stream);     \
+    if (p.bf16) return RLX_ERR_UNSUPPORTED;                                                                                     \
     if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_TANH) return launch_cfg2<BN_, true, true, TC_EPI_BIAS_TANH>(A, B, p, kclass, stream); \
     if (a_kmaj && b_kmaj && epi == TC_EPI_NONE) return launch_cfg2<BN_, true, true, TC_EPI_NONE>(A, B, p, kclass, stream);       \
     if (a_kmaj && b_kmaj && epi == TC_EPI_BIAS_RELU) return launch_cfg2<BN_, true, true, TC_EPI_BIAS_RELU>(A, B, p, kclass, stream); \
@@ -439,6 +445,7 @@ int tc2_launch(int bn, bool a_kmaj, bool b_kmaj, int epi, const TcOperand& A, co
     if (!a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg2<BN_, false, false, TC_EPI_NONE>(A, B, p, kclass, stream);   \
   } while (0)
   if (bn == 192) {  // N = 377 (obs + 1) = 2 x 192: the layer-1 weight gradient, both operands MN-major
+    if (!a_kmaj && !b_kmaj && epi == TC_EPI_NONE && p.bf16) return launch_cfg2<192, false, false, TC_EPI_NONE, true>(A, B, p, kclass, stream);
     if (!a_kmaj && !b_kmaj && epi == TC_EPI_NONE) return launch_cfg2<192, false, false, TC_EPI_NONE>(A, B, p, kclass, stream);
     return RLX_ERR_UNSUPPORTED;
   }

@@ -165,14 +165,25 @@ static int mlp_hidden_forward(const rlx_ppo_dims& d, const PpoLayout& L, const f
   return run_gemm<true, true, EPI_BIAS_TANH>(tc, g2, 2, stream, KC_GEMM_FWD, rows, H, pair_fwd);
 }
 
+#define RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, NCH_, BF_, grid, block, smem, stream, arg)                                    \
+  do {                                                                                                                              \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<NCH_, BF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem)));              \
+    RLX_LAUNCH_C(CLS, FLOPS, BYTES, (KERNEL<NCH_, BF_>), grid, block, smem, stream, arg);                                           \
+  } while (0)
+#define RLX_DISPATCH_NCH_B(CLS, FLOPS, BYTES, H, KERNEL, BF_, grid, block, smem, stream, arg)                                       \
+  do {                                                                                                                              \
+    const int _nch = (int)ceil_div((H), 32);                                                                                        \
+    if (_nch <= 2) RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, 2, BF_, grid, block, smem, stream, arg);                           \
+    else if (_nch <= 4) RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, 4, BF_, grid, block, smem, stream, arg);                      \
+    else if (_nch <= 8) RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, 8, BF_, grid, block, smem, stream, arg);                      \
+    else if (_nch <= 16) RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, 16, BF_, grid, block, smem, stream, arg);                    \
+    else RLX_DISPATCH_NCH_1(CLS, FLOPS, BYTES, KERNEL, 32, BF_, grid, block, smem, stream, arg);                                    \
+  } while (0)
+// bf16-autocast mode selects the kernels compiled with the bf16 roundings (h.bf16 is set by the callers)
 #define RLX_DISPATCH_NCH(CLS, FLOPS, BYTES, H, KERNEL, grid, block, smem, stream, arg)                                              \
-  do {                                                                                                            \
-    const int _nch = (int)ceil_div((H), 32);                                                                      \
-    if (_nch <= 2) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<2>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 4) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<4>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 8) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<8>, grid, block, smem, stream, arg); } \
-    else if (_nch <= 16) { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<16>, grid, block, smem, stream, arg); } \
-    else { RLX_CHECK_CUDA(cudaFuncSetAttribute(KERNEL<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); RLX_LAUNCH_C(CLS, FLOPS, BYTES, KERNEL<32>, grid, block, smem, stream, arg); } \
+  do {                                                                                                                              \
+    if ((arg).bf16) RLX_DISPATCH_NCH_B(CLS, FLOPS, BYTES, H, KERNEL, true, grid, block, smem, stream, arg);                         \
+    else RLX_DISPATCH_NCH_B(CLS, FLOPS, BYTES, H, KERNEL, false, grid, block, smem, stream, arg);                                   \
   } while (0)
 
 static bool head_dims_ok(const rlx_ppo_dims& d) {
@@ -379,10 +390,15 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
       if (gemm_head) {
         // loss, dZ2, dhead and the partial block are done
       } else if (vec_head) {
-#define RLX_HEAD3(H_, AM_)                                                                                                       \
-  do {                                                                                                                           \
-    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train3_kernel<H_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train3_kernel<H_, AM_>), head_blocks, 256, smem, st, h, ex);    \
+#define RLX_HEAD3_B(H_, AM_, BF_)                                                                                                     \
+  do {                                                                                                                                \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train3_kernel<H_, AM_, BF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train3_kernel<H_, AM_, BF_>), head_blocks, 256, smem, st, h, ex);    \
+  } while (0)
+#define RLX_HEAD3(H_, AM_)                          \
+  do {                                              \
+    if (bf16) RLX_HEAD3_B(H_, AM_, true);           \
+    else RLX_HEAD3_B(H_, AM_, false);               \
   } while (0)
 #define RLX_HEAD3_ACT(H_)                      \
   do {                                         \
@@ -396,12 +412,18 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
         else RLX_HEAD3_ACT(512);
 #undef RLX_HEAD3_ACT
 #undef RLX_HEAD3
+#undef RLX_HEAD3_B
       } else {
         const int nch = (int)ceil_div(H, 32);
-#define RLX_HEAD2(NCH_, AM_)                                                                                                     \
-  do {                                                                                                                           \
-    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train2_kernel<NCH_, AM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train2_kernel<NCH_, AM_>), head_blocks, 256, smem, st, h, ex);  \
+#define RLX_HEAD2_B(NCH_, AM_, BF_)                                                                                                   \
+  do {                                                                                                                                \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train2_kernel<NCH_, AM_, BF_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train2_kernel<NCH_, AM_, BF_>), head_blocks, 256, smem, st, h, ex);  \
+  } while (0)
+#define RLX_HEAD2(NCH_, AM_)                        \
+  do {                                              \
+    if (bf16) RLX_HEAD2_B(NCH_, AM_, true);         \
+    else RLX_HEAD2_B(NCH_, AM_, false);             \
   } while (0)
 #define RLX_HEAD2_ACT(NCH_)                         \
   do {                                              \
@@ -417,6 +439,7 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
         else RLX_HEAD2_ACT(32);
 #undef RLX_HEAD2_ACT
 #undef RLX_HEAD2
+#undef RLX_HEAD2_B
       }
       // ---- dW3 = dhead^T [act+1, m] . H2 [m, 2H]
       bool w3_done = false;

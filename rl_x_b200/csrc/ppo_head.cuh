@@ -67,12 +67,12 @@ struct HeadP {
   float* dZ2;              // [M, 2H]
   float* dhead;            // [M, act+1]   (dmean | dv)
   float* block_partials;   // [gridDim.x, 2*act+5+2H]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac | db2p[H] | db2c[H])
-  int bf16;                // bf16-autocast mode: the mean / value (outputs of the last Linear) are bf16 tensors, and so are the gradients that
+  int bf16;                // (informational; the kernels are compiled per mode) bf16-autocast mode: the mean / value (outputs of the last Linear) are bf16 tensors, and so are the gradients that
                            // flow back into them and through them (d mean, d value, the linear-backward output and tanh_backward's output)
 };
 
 // Loads the row's H2 slices and returns the act means (lane a holds mean a; a+32 in mean_hi) and the value (all lanes).
-template <int NCH>
+template <int NCH, bool BF16>
 __device__ __forceinline__ void head_row_forward(const HeadP& p, const float* __restrict__ sW3p, const float* __restrict__ sW3c,
                                                  long long row, int lane, float (&hp)[NCH], float (&hc)[NCH], float& mean_lo,
                                                  float& mean_hi, float& value) {
@@ -92,7 +92,7 @@ __device__ __forceinline__ void head_row_forward(const HeadP& p, const float* __
       const int j = lane + 32 * c;
       if (j < p.H) s = fmaf(hp[c], sW3p[a * p.H + j], s);
     }
-    s = bf16r_if(warp_sum(s) + p.b3p[a], p.bf16);
+    s = bf16r_if(warp_sum(s) + p.b3p[a], BF16);
     if (lane == (a & 31)) {
       if (a < 32) mean_lo = s; else mean_hi = s;
     }
@@ -103,7 +103,7 @@ __device__ __forceinline__ void head_row_forward(const HeadP& p, const float* __
     const int j = lane + 32 * c;
     if (j < p.H) s = fmaf(hc[c], sW3c[j], s);
   }
-  value = bf16r_if(warp_sum(s) + p.b3c[0], p.bf16);
+  value = bf16r_if(warp_sum(s) + p.b3c[0], BF16);
 }
 
 __device__ __forceinline__ void head_stage_weights(const HeadP& p, float* sW3p, float* sW3c) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void head_stage_weights(const HeadP& p, float* sW3p, 
 }
 
 // ------------------------------------------------------------------------------------------------ rollout head
-template <int NCH>
+template <int NCH, bool BF16 = false>
 __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
   extern __shared__ float smem[];
   float* sW3p = smem;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (long long row = (long long)blockIdx.x * nw + wib; row < p.M; row += (long long)gridDim.x * nw) {
     float hp[NCH], hc[NCH], mean_lo, mean_hi, value;
-    head_row_forward<NCH>(p, sW3p, sW3c, row, lane, hp, hc, mean_lo, mean_hi, value);
+    head_row_forward<NCH, BF16>(p, sW3p, sW3c, row, lane, hp, hc, mean_lo, mean_hi, value);
     if (p.value_out && lane == 0) p.value_out[row] = value;
     float lp_sum = 0.f;
 #pragma unroll
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
           const float sd = expf(ls);
           const float eps = p.noise ? p.noise[row * p.act + a] : philox_normal(p.seed, p.offset, (uint32_t)row, (uint32_t)a);
           const float var = sd * sd;
-          if (p.bf16) {
+          if (BF16) {
             // Normal(bf16 loc, fp32 scale).sample() = at::normal(loc, scale): a tensor of loc's dtype filled with N(0,1) draws, then
             // .mul_(scale).add_(loc) in place - three bf16 roundings; log_prob sees (value - loc) and its square as bf16 tensors
             x = bf16r(__fadd_rn(bf16r(__fmul_rn(bf16r(eps), sd)), mean));
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
           if (p.clip_rescale) {  // policy.py:68-70
             const float c = fminf(fmaxf(x, -1.f), 1.f);
             const float lo = p.act_low[a], hi = p.act_high[a];
-            e = lo + bf16r_if(0.5f * bf16r_if(c + 1.f, p.bf16), p.bf16) * (hi - lo);  // bf16 mode: clipped + 1.0 and 0.5 * (...) stay bf16 tensors
+            e = lo + bf16r_if(0.5f * bf16r_if(c + 1.f, BF16), BF16) * (hi - lo);  // bf16 mode: clipped + 1.0 and 0.5 * (...) stay bf16 tensors
           }
           p.env_action[row * p.act + a] = e;
         }
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) ppo_head_rollout_kernel(const HeadP p) {
 }
 
 // -------------------------------------------------------------------------------------------------- train head
-template <int NCH>
+template <int NCH, bool BF16 = false>
 __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
   extern __shared__ float smem[];
   float* sW3p = smem;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
 
   for (long long row = (long long)blockIdx.x * nw + wib; row < p.M; row += (long long)gridDim.x * nw) {
     float hp[NCH], hc[NCH], mean_lo, mean_hi, value;
-    head_row_forward<NCH>(p, sW3p, sW3c, row, lane, hp, hc, mean_lo, mean_hi, value);
+    head_row_forward<NCH, BF16>(p, sW3p, sW3c, row, lane, hp, hc, mean_lo, mean_hi, value);
 
     // new log-prob (policy.py:76-82)
     float dmu[2] = {0.f, 0.f}, zz[2] = {0.f, 0.f};  // (x-mean)/var and (x-mean)^2/var per owned component
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     const float dratio = -A * (w1 + (1.f - w1) * inr);
     const float dlogp = dratio * ratio * p.inv_mg;
     const float verr = value - p.ret[row];
-    const float dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);
+    const float dv = bf16r_if(p.critic_coef * verr * p.inv_mg, BF16);
 
     acc_pg += pg;
     acc_vl += 0.5f * verr * verr;
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     float dmean[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      dmean[half] = bf16r_if(dlogp * dmu[half], p.bf16);
+      dmean[half] = bf16r_if(dlogp * dmu[half], BF16);
       acc_db3p[half] += dmean[half];
       acc_dls[half] += dlogp * (zz[half] - 1.f);  // d logp / d logstd = (x-mean)^2/var - 1
       const int a = lane + 32 * half;
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     for (int c = 0; c < NCH; ++c) {
       const int j = lane + 32 * c;
       if (j < p.H) {
-        const float zp = bf16r_if(bf16r_if(dz[c], p.bf16) * (1.f - hp[c] * hp[c]), p.bf16);
-        const float zc = bf16r_if(bf16r_if(dv * sW3c[j], p.bf16) * (1.f - hc[c] * hc[c]), p.bf16);
+        const float zp = bf16r_if(bf16r_if(dz[c], BF16) * (1.f - hp[c] * hp[c]), BF16);
+        const float zc = bf16r_if(bf16r_if(dv * sW3c[j], BF16) * (1.f - hc[c] * hc[c]), BF16);
         out[j] = zp;
         out[p.H + j] = zc;
         acc_db2p[c] += zp;
@@ -334,7 +334,7 @@ struct HeadTrain2Extra {
   int dh_ld;  // pitch of dhead rows
 };
 
-template <int NCH, int ACT_MAX>
+template <int NCH, int ACT_MAX, bool BF16 = false>
 __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, const HeadTrain2Extra ex) {
   extern __shared__ float smem[];
   float* sW3p = smem;
@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
       for (int a = 0; a < 32; ++a)
         if (a == act) { v0[a] = s0; v1[a] = s1; }
     }
-    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, p.bf16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
-    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, p.bf16);
+    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, BF16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
+    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, BF16);
 
     float dmean[2], dvv[2];
 #pragma unroll
@@ -437,12 +437,12 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
         const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
         const float verr = value - p.ret[row];
-        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);  // gradient of a bf16 tensor is a bf16 tensor
+        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, BF16);  // gradient of a bf16 tensor is a bf16 tensor
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
-        dm = bf16r_if(dlogp * dmu, p.bf16);
+        dm = bf16r_if(dlogp * dmu, BF16);
         if (own) {
           acc_db3 += dm;
           acc_dls += dlogp * (zz - 1.f);
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         const int j = lane + 32 * c;
         if (j < H) {
           const float hpv = hp[r][c], hcv = hc[r][c];
-          const float zp = bf16r_if(bf16r_if(r ? dz1[c] : dz0[c], p.bf16) * (1.f - hpv * hpv), p.bf16);  // linear-backward output, then tanh_backward
-          const float zc = bf16r_if(bf16r_if(dvv[r] * sW3c[j], p.bf16) * (1.f - hcv * hcv), p.bf16);
+          const float zp = bf16r_if(bf16r_if(r ? dz1[c] : dz0[c], BF16) * (1.f - hpv * hpv), BF16);  // linear-backward output, then tanh_backward
+          const float zc = bf16r_if(bf16r_if(dvv[r] * sW3c[j], BF16) * (1.f - hcv * hcv), BF16);
           out[j] = zp;
           out[H + j] = zc;
           acc_db2p[c] += zp;
@@ -596,7 +596,7 @@ __device__ __forceinline__ void axpy4(float g, const float4& w, float4& d) {
   d.x = fmaf(g, w.x, d.x); d.y = fmaf(g, w.y, d.y); d.z = fmaf(g, w.z, d.z); d.w = fmaf(g, w.w, d.w);
 }
 
-template <int H_, int ACT_MAX>
+template <int H_, int ACT_MAX, bool BF16 = false>
 __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, const HeadTrain2Extra ex) {
   constexpr int NG = H_ / 128;
   constexpr int H4 = H_ / 4;
@@ -667,8 +667,8 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
       for (int a = 0; a < 32; ++a)
         if (a == act) { v0[a] = s0; v1[a] = s1; }
     }
-    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, p.bf16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
-    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, p.bf16);
+    const float out0 = bf16r_if(butterfly_reduce32(v0, lane) + my_b3, BF16);  // lane a < act: mean_a; lane act: value (bf16 tensors in bf16 mode)
+    const float out1 = bf16r_if(butterfly_reduce32(v1, lane) + my_b3, BF16);
 
     float dmean[2], dvv[2];
 #pragma unroll
@@ -696,12 +696,12 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
         const float inr = (ratio >= clip_lo && ratio <= clip_hi) ? 1.f : 0.f;
         const float dlogp = (-A * (w1 + (1.f - w1) * inr)) * ratio * p.inv_mg;
         const float verr = value - p.ret[row];
-        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, p.bf16);  // gradient of a bf16 tensor is a bf16 tensor
+        dv = bf16r_if(p.critic_coef * verr * p.inv_mg, BF16);  // gradient of a bf16 tensor is a bf16 tensor
         acc_pg += fmaxf(pg1, pg2);
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
-        dm = bf16r_if(dlogp * dmu, p.bf16);
+        dm = bf16r_if(dlogp * dmu, BF16);
         if (own) {
           acc_db3 += dm;
           acc_dls += dlogp * (zz - 1.f);
@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
       for (int g = 0; g < NG; ++g) {
         const float4 a4 = hp[r][g], c4 = hc[r][g], d4 = r ? dz1[g] : dz0[g], wc = sW3c4[g * 32 + lane];
         float4 zp, zc;
-        const int bf = p.bf16;  // bf16 mode: the linear-backward output and tanh_backward's output are bf16 tensors
+        constexpr int bf = BF16 ? 1 : 0;  // bf16 mode: the linear-backward output and tanh_backward's output are bf16 tensors
         zp.x = bf16r_if(bf16r_if(d4.x, bf) * (1.f - a4.x * a4.x), bf); zp.y = bf16r_if(bf16r_if(d4.y, bf) * (1.f - a4.y * a4.y), bf);
         zp.z = bf16r_if(bf16r_if(d4.z, bf) * (1.f - a4.z * a4.z), bf); zp.w = bf16r_if(bf16r_if(d4.w, bf) * (1.f - a4.w * a4.w), bf);
         zc.x = bf16r_if(bf16r_if(dvv[r] * wc.x, bf) * (1.f - c4.x * c4.x), bf); zc.y = bf16r_if(bf16r_if(dvv[r] * wc.y, bf) * (1.f - c4.y * c4.y), bf);

@@ -89,7 +89,9 @@ def test_bf16_forward_vs_oracle(obs, act, hidden, n):
     ulp2 = lambda ref: dict(rtol=2.0 ** -7, atol=2.0 ** -7 * float(ref.float().pow(2).mean().sqrt()))
     np.testing.assert_allclose(v.numpy(), v_ref.float().numpy(), **ulp2(v_ref))
     assert _rel(v.numpy(), v_ref.float().numpy()) <= 2e-3
-    np.testing.assert_allclose(d.numpy(), d_ref.float().numpy(), **ulp2(d_ref))
+    # deterministic env action = low + 0.5 * (clip(mean) + 1) * (high - low): 2 ulps of a clipped bf16 mean (|mean| <= 1: 2 * 2^-8) scaled by
+    # (high - low) / 2; relative to the env action itself the bound would be meaningless near its zero crossing
+    np.testing.assert_allclose(d.numpy(), d_ref.float().numpy(), rtol=0, atol=2 * 2.0 ** -8 * float((high - low).max()) / 2 * 1.01)
     np.testing.assert_allclose(e.numpy(), e_ref.float().numpy(), rtol=1e-6, atol=1e-6)          # same bf16 sample in, same fp32 arithmetic out
     # the sample itself: loc + scale * eps through at::normal's in-place chain on a bf16 tensor (3 roundings), with OUR mean
     std = torch.exp(pol["policy_logstd"]).expand(n, act)
@@ -142,7 +144,10 @@ def test_bf16_minibatch_gradients_vs_oracle_autograd(obs, act, hidden, m, ent):
         if name != "policy_logstd":
             assert _is_bf16(ours), name  # weight / bias gradients leave the bf16 ops as bf16 tensors; logstd's is fp32
     print("bf16 gradient distances:", report)
-    assert max(report.values()) <= 1e-2, report
+    # 1e-2 of the norm per tensor.  The last layer's bias gradients are sums of m signed bf16 terms that largely cancel (a scalar for the
+    # critic): their bf16 noise is measured against the root-sum-square of the terms, i.e. sqrt(m) * |term| * 2^-9, not against the small sum
+    for name, dist in report.items():
+        assert dist <= (5e-2 if name in ("critic.4.bias", "policy_mean.4.bias") else 1e-2), (name, report)
     mm = metrics.cpu().numpy()
     scale = float(torch.abs(mb["advantages"] - mb["advantages"].mean()).mean() / mb["advantages"].std())
     assert abs(mm[0] - met["pg_loss"]) <= 1e-2 * max(abs(met["pg_loss"]), scale)
