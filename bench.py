@@ -125,7 +125,7 @@ def build_model(args, rank, world, interface, global_minibatch=None, bf16=False)
             f"--algorithm.minibatch_size={global_minibatch if global_minibatch else args.minibatch * world}", f"--algorithm.nr_hidden_units={C2['hidden']}",
             f"--algorithm.gemm_engine={args.engine}", "--algorithm.total_timesteps=1e15",
             f"--algorithm.exact_global_permutation={'True' if args.exact_permutation else 'False'}",
-            f"--algorithm.gradient_exchange={args.exchange}", f"--algorithm.bf16_mixed_precision_training={'True' if bf16 else 'False'}"]
+            f"--algorithm.gradient_exchange={args.exchange}", f"--algorithm.peer_exchange_algorithm={args.exchange_algo}", f"--algorithm.bf16_mixed_precision_training={'True' if bf16 else 'False'}"]
     r = Runner(argv=argv)
     train_env, eval_env = r._create_train_and_eval_env(r._config)
     # weights and the permutation stream follow RANK 0's seed inside PPO.__init__ (broadcast); env streams differ via the env seed above
@@ -567,6 +567,7 @@ def main():
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
+    ap.add_argument("--exchange-algo", default="auto", choices=["auto", "one_shot", "two_shot"], help="peer exchange kernel: one-shot / two-shot (auto: two-shot from 4 GPUs)")
     ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac", "ppo_lstm"])
     ap.add_argument("--tc-pair", default="", help="tcgen05 CTA-pair engine: MODE[:FWD_BN], MODE 0 off / 1 weight gradients (default) / 2 all GEMMs, FWD_BN 128|256")

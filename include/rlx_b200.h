@@ -180,8 +180,9 @@ typedef struct rlx_ppo_hparams {
   float critic_coef;     /* ppo.py:48 */
   float max_grad_norm;   /* ppo.py:49 */
   float adam_beta1, adam_beta2, adam_eps;
-  float ratio_delta_metric; /* 0: metrics[4] = clip fraction (ppo.py:131).  != 0 (ESPO): metrics[4] = mean |ratio - 1| (espo.py:133, operator
-                               "mean"); ESPO's unclipped surrogate (espo.py:138) is clip_range = +inf */
+  float ratio_delta_metric; /* 0: metrics[4] = clip fraction (ppo.py:131).  1 (ESPO): metrics[4] = mean |ratio - 1| (espo.py:133, operator
+                               "mean"); 2 (ESPO, operator "median", espo.py:59-60): torch.median(|ratio - 1|) = the lower median, by a
+                               radix-select kernel (single-GPU minibatches).  ESPO's unclipped surrogate (espo.py:138) is clip_range = +inf */
 } rlx_ppo_hparams;
 
 /* Per-minibatch metric record written by the update (ref: ppo.py:285-294 .item() calls, kept on device instead). */
@@ -254,6 +255,10 @@ int rlx_comm_stage_f32(rlx_comm* c, const float* src, int64_t n, void* stream);
 /* out[i] = sum over ranks r = 0..world-1 (in that order) of rank r's send buffer [i], i < n <= nfloats.  Every rank must call
  * it the same number of times; the kernel spins on peer flags (and traps after ~20 s if a peer never arrives). */
 int rlx_comm_allreduce_sum_f32(rlx_comm* c, float* out, int64_t n, void* stream);
+/* 0 (default): one-shot kernel for 2 ranks, two-shot from 4 ranks up; 1: always one-shot; 2: always two-shot (2, 4 or 8 ranks).  Two-shot =
+ * reduce-scatter by peer loads (rank r sums chunk r of every send slot) + all-gather by peer stores into every rank's result buffer:
+ * 2 (W-1)/W n floats per rank over NVLink instead of (W-1) n, at the price of a second flag round.  Same result bits as one-shot. */
+int rlx_comm_set_algorithm(rlx_comm* c, int algo);
 int rlx_comm_destroy(rlx_comm* c);
 
 /* Sharded form of rlx_ppo_update_epoch_f32: minibatch k covers this rank's counts[k] consecutive gathered rows and is divided by

@@ -213,6 +213,7 @@ _SIGNATURES = {
     "rlx_comm_send_buffer": (C.c_void_p, [C.c_void_p]),
     "rlx_comm_stage_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rlx_comm_allreduce_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "rlx_comm_set_algorithm": (C.c_int, [C.c_void_p, C.c_int]),
     "rlx_comm_destroy": (C.c_int, [C.c_void_p]),
     "rlx_ppo_update_epoch_sharded_f32": (C.c_int, [C.POINTER(PpoMinibatchArgs), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rlx_replay_sample_gather_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64] + [C.c_void_p] * 10 + [C.c_void_p]),

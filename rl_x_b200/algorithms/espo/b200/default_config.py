@@ -15,7 +15,7 @@ _DEFAULTS = (
     ('gamma', 0.99),
     ('gae_lambda', 0.95),
     ('max_ratio_delta', 0.25),
-    ('delta_calc_operator', "mean"),  # mean (in-kernel) | median (torch.median over a per-row device buffer is not built: rejected)
+    ('delta_calc_operator', "mean"),  # mean (accumulated inside the loss kernel) | median (torch.median's lower median, radix-select kernel)
     ('entropy_coef', 0.0),
     ('critic_coef', 0.5),
     ('max_grad_norm', 0.5),

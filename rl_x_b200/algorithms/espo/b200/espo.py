@@ -53,10 +53,9 @@ class ESPO(PPO):
         a = config.algorithm
         self.max_epochs = int(a.max_epochs)              # espo.py:40
         self.max_ratio_delta = float(a.max_ratio_delta)  # espo.py:44
-        if a.delta_calc_operator == "median":
-            raise NotImplementedError("rl_x_b200 ESPO implements delta_calc_operator='mean' (in-kernel); 'median' is not built.")
-        if a.delta_calc_operator != "mean":
+        if a.delta_calc_operator not in ("mean", "median"):
             raise ValueError("Unknown delta_calc_operator")  # espo.py:57-63
+        self.delta_calc_operator = a.delta_calc_operator  # mean: accumulated inside the loss kernel; median: radix-select kernel (torch.median = lower median)
         view = _ConfigView(config, _AlgorithmView(a, nr_epochs=self.max_epochs, clip_range=float("inf")))
         super().__init__(view, train_env, eval_env, run_path, writer)
         self.config = config  # what save() stores (espo.py:396-404)
@@ -69,7 +68,7 @@ class ESPO(PPO):
 
     # ------------------------------------------------------------------------------------------------ hooks of the shared class
     def _make_hparams(self):
-        return make_hparams(float("inf"), self.entropy_coef, self.critic_coef, self.max_grad_norm, ratio_delta_metric=True)
+        return make_hparams(float("inf"), self.entropy_coef, self.critic_coef, self.max_grad_norm, ratio_delta_metric=self.delta_calc_operator)
 
     def _make_index_stream(self):
         return None  # indices are drawn step by step: whether another draw happens depends on the data (the stop rule)

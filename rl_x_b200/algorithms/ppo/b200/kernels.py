@@ -164,8 +164,10 @@ class PpoKernels:
 
 
 def make_hparams(clip_range, entropy_coef, critic_coef, max_grad_norm, beta1=0.9, beta2=0.999, eps=1e-8, ratio_delta_metric=False):
+    """ratio_delta_metric: False = metrics[4] is the clip fraction (PPO); True / "mean" = mean |ratio - 1|; "median" = torch.median(|ratio - 1|) (ESPO)."""
+    code = 2.0 if ratio_delta_metric == "median" else (1.0 if ratio_delta_metric else 0.0)
     return nt.PpoHparams(float(clip_range), float(entropy_coef), float(critic_coef), float(max_grad_norm), float(beta1), float(beta2),
-                         float(eps), 1.0 if ratio_delta_metric else 0.0)
+                         float(eps), code)
 
 
 class PeerComm:
@@ -205,6 +207,10 @@ class PeerComm:
     def allreduce_sum(self, out, n=None):
         n = out.numel() if n is None else int(n)
         nt.check(self.lib.rlx_comm_allreduce_sum_f32(self.handle, _f32(out, "out"), n, _stream()), "rlx_comm_allreduce_sum_f32")
+
+    def set_algorithm(self, algo):
+        """0: by world size (one-shot at 2 ranks, two-shot from 4); 1: one-shot; 2: two-shot."""
+        nt.check(self.lib.rlx_comm_set_algorithm(self.handle, int(algo)), "rlx_comm_set_algorithm")
 
     def close(self):
         if self.handle:

@@ -278,6 +278,7 @@ class PPO:
         if self.world_size > 1 and self.gradient_exchange == "peer" and self.peer_comm is None:
             try:
                 self.peer_comm = PeerComm(self.dist, P + nt.RLX_PPO_NMETRIC, self.device)
+                self.peer_comm.set_algorithm({"auto": 0, "one_shot": 1, "two_shot": 2}[str(config.algorithm.get("peer_exchange_algorithm", "auto"))])
             except RuntimeError as err:  # GPUs without peer access: NCCL carries the gradient instead (slower, same numbers up to sum order)
                 rlx_logger.warning(f"{err}; falling back to gradient_exchange='nccl'")
                 self.gradient_exchange = "nccl"

@@ -18,6 +18,10 @@ namespace rlx {
 
 static bool use_tc(const rlx_ppo_dims& d) { return g_gemm_engine == 1 && tc_supported(d); }
 extern bool g_tc_pair_force;  // gemm_tc.cu
+}  // namespace rlx
+// comm.cu: all-reduce of [gradient | metrics]; *nblk_out > 0 when the kernel also wrote that many (policy, critic) sum-of-squares partial pairs
+int comm_allreduce_ppo(rlx_comm* c, float* out, int64_t n, const rlx_ppo_dims& d, float* norm_partials, long long* step_count, void* stream, int* nblk_out);
+namespace rlx {
 
 struct Splits {
   int splits, kchunk;
@@ -88,7 +92,7 @@ static FwdPlan plan_forward(const rlx_ppo_dims& d, long long n) {
 constexpr int kHeadWgradRows = 64;
 
 struct TrainPlan {
-  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, off_barrier, off_P, off_X, total;
+  size_t off_H1, off_H2, off_dZ2, off_dZ1, off_dhead, off_headpart, off_part1, off_rs1, off_part2, off_part3, off_norm, off_barrier, off_P, off_X, off_ratio, total;
   int max_s1, max_s2, max_s3;
   int head_blocks, wgrad_chunks, norm_blocks, head_npart;
 };
@@ -126,6 +130,7 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   take(P.off_barrier, 64);
   take(P.off_P, (size_t)make_layout(d).total());                          // bf16-autocast mode: rounded parameter copy
   take(P.off_X, (size_t)m * (size_t)(ceil_div(O + 1, 4) * 4));             // ... and rounded copy of the minibatch states (pitch <= obs + 4)
+  take(P.off_ratio, (size_t)m);                                           // ESPO median: |ratio - 1| per row
   P.total = o;
   return P;
 }
@@ -368,6 +373,8 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     h.actions = a->actions; h.logp_old = a->log_probs; h.adv = a->advantages; h.ret = a->returns; h.adv_stats = a->adv_stats;
     h.inv_mg = inv_mg; h.clip_range = a->hp.clip_range; h.critic_coef = a->hp.critic_coef;
     h.ratio_delta_metric = a->hp.ratio_delta_metric != 0.f ? 1 : 0;
+    const bool want_median = a->hp.ratio_delta_metric == 2.f;  // ESPO delta_calc_operator = median (espo.py:59-60)
+    h.ratio_abs = want_median ? ws_ptr<float>(ws, P.off_ratio) : nullptr;
     h.dZ2 = dZ2; h.dhead = dhead; h.block_partials = headpart;
     head_blocks = P.head_blocks;
     const size_t smem = head_smem_bytes(d, true);
@@ -590,7 +597,13 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     *deferred = r;
     return RLX_OK;
   }
-  return launch_grad_reduce(r, st);
+  rc = launch_grad_reduce(r, st);
+  if (rc) return rc;
+  if (a->hp.ratio_delta_metric == 2.f && m > 0 && a->metrics != nullptr) {
+    // metrics[4] <- torch.median(|ratio - 1|) of this minibatch, overwriting the mean the assembly kernel has just put there
+    RLX_LAUNCH_C(KC_OTHER, 0, 16.0 * m, median_lower_kernel, 1, 1024, 0, st, ws_ptr<float>(ws, P.off_ratio), (long long)m, a->metrics + 4);
+  }
+  return RLX_OK;
 }
 
 static AdamP make_adam_params(const rlx_ppo_minibatch_args* a, const PpoLayout& L, const TrainPlan& P) {
@@ -707,12 +720,23 @@ extern "C" int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* fi
     a.metrics = send + P;
     int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
     if (rc) return rc;
-    rc = rlx_comm_allreduce_sum_f32(comm, first->grads, P + RLX_PPO_NMETRIC, stream);
+    // the two-shot exchange kernel leaves the per-net squared norms of the reduced gradient behind (and bumps Adam's step counter):
+    // clip + Adam follow directly, without a separate pass over the gradient
+    const TrainPlan TP = plan_train(a.dims, std::max<int64_t>(a.m, 1));
+    int nblk = 0;
+    rc = comm_allreduce_ppo(comm, first->grads, P + RLX_PPO_NMETRIC, a.dims, ws_ptr<float>(a.workspace, TP.off_norm), (long long*)a.step_count, stream, &nblk);
     if (rc) return rc;
     a.grads = first->grads;
     a.metrics = first->grads + P;
-    rc = rlx_gradnorm_clip_adam_f32(&a, stream);  // writes the two pre-clip norms next to the summed metrics
-    if (rc) return rc;
+    if (nblk > 0) {
+      RLX_CHECK_ARG(a.exp_avg && a.exp_avg_sq && a.lr && a.step_count, "optimizer state is null");
+      AdamP ap = make_adam_params(&a, make_layout(a.dims), TP);
+      ap.nblk_norm = nblk;
+      RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 28.0 * P, ppo_clip_adam_kernel, (unsigned)ceil_div(P, 256), 256, 0, st, ap);
+    } else {
+      rc = rlx_gradnorm_clip_adam_f32(&a, stream);  // writes the two pre-clip norms next to the summed metrics
+      if (rc) return rc;
+    }
     RLX_CHECK_CUDA(cudaMemcpyAsync(first->metrics + RLX_PPO_NMETRIC * k, first->grads + P, RLX_PPO_NMETRIC * sizeof(float),
                                    cudaMemcpyDeviceToDevice, st));
     r0 += counts[k];

@@ -64,6 +64,7 @@ struct HeadP {
   float inv_mg;            // 1 / m_global
   float clip_range, critic_coef;
   int ratio_delta_metric;  // != 0: the clip-fraction slot accumulates |ratio - 1| instead (ESPO, espo.py:133)
+  float* ratio_abs;        // optional [M]: |ratio - 1| of every row (ESPO's delta_calc_operator = median needs the individual values)
   float* dZ2;              // [M, 2H]
   float* dhead;            // [M, act+1]   (dmean | dv)
   float* block_partials;   // [gridDim.x, 2*act+5+2H]  (db3p | db3c | dlogstd | pg | vloss | kl | clipfrac | db2p[H] | db2c[H])
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(256) ppo_head_train_kernel(const HeadP p) {
     acc_vl += 0.5f * verr * verr;
     acc_kl += (ratio - 1.f) - logratio;
     acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
+    if (p.ratio_abs != nullptr && lane == 0) p.ratio_abs[row] = fabsf(ratio - 1.f);
     acc_db3c += dv;
 
     float dmean[2];
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train2_kernel(const HeadP p, 
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
+        if (p.ratio_abs != nullptr && lane == 0) p.ratio_abs[row] = fabsf(ratio - 1.f);
         dm = bf16r_if(dlogp * dmu, BF16);
         if (own) {
           acc_db3 += dm;
@@ -701,6 +704,7 @@ __global__ void __launch_bounds__(256, 2) ppo_head_train3_kernel(const HeadP p, 
         acc_vl += 0.5f * verr * verr;
         acc_kl += (ratio - 1.f) - logratio;
         acc_cf += p.ratio_delta_metric ? fabsf(ratio - 1.f) : ((fabsf(ratio - 1.f) > p.clip_range) ? 1.f : 0.f);
+        if (p.ratio_abs != nullptr && lane == 0) p.ratio_abs[row] = fabsf(ratio - 1.f);
         dm = bf16r_if(dlogp * dmu, BF16);
         if (own) {
           acc_db3 += dm;

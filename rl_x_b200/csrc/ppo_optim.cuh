@@ -192,6 +192,41 @@ __global__ void __launch_bounds__(256) ppo_clip_adam_kernel(const AdamP p) {
   p.v[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------ lower median (ESPO)
+// torch.median of a 1-D tensor returns the LOWER of the two middle values: sorted(x)[(n - 1) / 2] (espo.py:57-63,133 applies it to
+// |ratio - 1| of the minibatch).  Radix select on the bit patterns of the non-negative floats (their unsigned order is their numeric
+// order): four passes of 8 bits, each a shared-memory histogram over the candidates that share the prefix found so far.  One CTA; n is a
+// minibatch (<= a few 10^5 values).  A NaN anywhere makes torch.median NaN; so does this (NaN patterns sort above +inf and are counted).
+__global__ void __launch_bounds__(1024) median_lower_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int s_prefix, s_rank;
+  __shared__ int s_nan;
+  if (threadIdx.x == 0) { s_prefix = 0u; s_rank = (unsigned int)((n - 1) / 2); s_nan = 0; }
+  __syncthreads();
+  for (long long i = threadIdx.x; i < n; i += blockDim.x)
+    if (x[i] != x[i]) s_nan = 1;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0u;
+    __syncthreads();
+    const unsigned int prefix = s_prefix;
+    const unsigned int mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int u = __float_as_uint(fabsf(x[i]));
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int r = s_rank, b = 0;
+      while (b < 255 && r >= hist[b]) { r -= hist[b]; ++b; }
+      s_rank = r;
+      s_prefix = prefix | (b << shift);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = s_nan ? __int_as_float(0x7FC00000) : __uint_as_float(s_prefix);
+}
+
 // ------------------------------------------------------------------------------------------------ fused optimiser tail
 // grad_reduce + grad_sumsq + clip_adam of one minibatch in ONE launch (they were three: 20 + 9 + 8 us, each dominated by launch and
 // DRAM round-trip latency on 1.3 MB of data).  Every thread keeps the <= kTailPerThread gradient elements it assembled in registers

@@ -455,6 +455,35 @@ def test_one_epoch_at_bench_shape_vs_oracle():
     assert max(traj.values()) <= 2e-2, traj
 
 
+@pytest.mark.parametrize("m", [1, 2, 7, 40, 4099, 32768])
+def test_ratio_delta_median_is_torch_median(m):
+    """hp.ratio_delta_metric = 2 (ESPO delta_calc_operator = "median", espo.py:59-60): metrics[4] = torch.median(|ratio - 1|), i.e. the LOWER
+    median sorted[(m - 1) // 2], selected on the device from the per-row values the loss kernel leaves behind."""
+    from rl_x_b200.algorithms.ppo.b200.kernels import make_hparams
+    obs, act, hidden = (24, 5, 128) if m < 1000 else (376, 17, 256)
+    k = _kern(obs, act, hidden)
+    pol, cri = O.init_params(obs, act, hidden, std_dev=0.9, seed=m)
+    mb = _random_minibatch(obs, act, m, seed=m + 2)
+    with torch.no_grad():
+        lp, _ = O.get_logprob_entropy(pol, mb["states"], mb["actions"])
+    mb["log_probs"] = lp + 0.15 * torch.randn(m, generator=torch.Generator().manual_seed(m))
+    fp = _flat_from_named(k, pol, cri)
+    if m == 1:
+        mb["advantages"] = torch.zeros(1)  # the advantage normalisation of a single row is NaN; the ratio is not
+    args, grads, metrics, st, keep = _run_fwdbwd(k, fp, mb, make_hparams(float("inf"), 0.0, 0.5, 0.5, ratio_delta_metric="median"))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        lp_new, _ = O.get_logprob_entropy(pol, mb["states"], mb["actions"])
+        dev = torch.abs(torch.exp(lp_new - mb["log_probs"]) - 1)
+    ref = float(torch.median(dev))
+    ours = float(metrics[4])
+    # the kernel's ratios differ from the oracle's by fp32 rounding, so the selected element may be a neighbour in the sorted order
+    srt = torch.sort(dev).values
+    kth = (m - 1) // 2
+    lo, hi = float(srt[max(kth - 2, 0)]), float(srt[min(kth + 2, m - 1)])
+    assert abs(ours - ref) <= 2e-5 * max(ref, 1e-3) or (lo - 1e-6 <= ours <= hi + 1e-6), (ours, ref, lo, hi)
+
+
 def test_library_reports_kernel_launches():
     from rl_x_b200 import _native as nt
     lib = nt.load()

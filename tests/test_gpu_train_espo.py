@@ -84,9 +84,10 @@ def test_espo_train_reproduces_reference_run(golden_espo, interface, gemm_engine
         np.testing.assert_allclose(ours, g[f"metric/{n}"], rtol=1e-3, atol=atol, err_msg=n)
 
 
-def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine):
+@pytest.mark.parametrize("operator", ["mean", "median"])
+def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine, operator):
     """One ESPO iteration on random rollout data of Humanoid-like width (376 -> 256 -> 256 -> 17) against oracle/espo_oracle.py: same stop
-    step, same weights."""
+    step, same weights, for both delta_calc_operators (espo.py:57-63; median = torch.median = the lower median)."""
     from oracle import espo_oracle as E
     from oracle import ppo_oracle as O
     from rl_x_b200.algorithms.espo.b200.espo import ESPO
@@ -96,7 +97,8 @@ def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine):
     N, T, obs, act, hid, mb = 8, 32, 376, 17, 256, 64
     a = get_config("espo.b200")
     a.nr_steps, a.minibatch_size, a.max_epochs, a.nr_hidden_units, a.total_timesteps = T, mb, 10, hid, N * T
-    a.learning_rate, a.max_ratio_delta, a.gemm_engine, a.entropy_coef = 1e-3, 0.03, gemm_engine, 0.005
+    a.learning_rate, a.max_ratio_delta, a.gemm_engine, a.entropy_coef = 1e-3, (0.03 if operator == "mean" else 0.025), gemm_engine, 0.005
+    a.delta_calc_operator = operator
     cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=11, nr_envs=N),
                      runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
 
@@ -127,11 +129,14 @@ def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine):
     b = model.batch
     batch = O.flatten({"states": b.states[:T].cpu(), "actions": b.actions.cpu(), "log_probs": b.log_probs.cpu(), "advantages": b.advantages.cpu(),
                        "returns": b.returns.cpu()})
-    L = E.Learner(pol0, cri0, lr=1e-3, entropy_coef=0.005, critic_coef=a.critic_coef, max_grad_norm=a.max_grad_norm, max_ratio_delta=0.03)
+    L = E.Learner(pol0, cri0, lr=1e-3, entropy_coef=0.005, critic_coef=a.critic_coef, max_grad_norm=a.max_grad_norm, max_ratio_delta=a.max_ratio_delta,
+                  delta_op=torch.mean if operator == "mean" else torch.median)
     rng = np.random.default_rng(11)
     torch.set_num_threads(1)
     metrics = L.update(batch, lambda: rng.choice(N * T, size=mb, replace=False), 10)
     assert len(metrics) == model._espo_steps
+    ours_rd = model.metrics_host.numpy()[:model._espo_steps, 4]
+    np.testing.assert_allclose(ours_rd, [m["ratio_delta"] for m in metrics], rtol=2e-4, atol=1e-7)
     pol, cri = model.params.state_dicts()
     for name in O.POLICY_KEYS + O.CRITIC_KEYS:
         ours, ref = (pol if name in pol else cri)[name].numpy(), (L.pol if name in L.pol else L.cri)[name].detach().numpy()
