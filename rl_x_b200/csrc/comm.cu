@@ -55,9 +55,13 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // Peer data is read with ld.cv: peer lines must not be served from this SM's L1.
 // WORLD > 0: compile-time rank count, so that the peer loads of one element are all in flight before the first add (one NVLink round
 // trip per element instead of one per rank); WORLD == 0: any rank count.
+__device__ __forceinline__ int comm_net_of(const CommSumsq& q, long long i);
+
 template <int WORLD>
 __global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, int rank, int world_rt, unsigned long long seq,
-                                                                   float* __restrict__ out, long long n) {
+                                                                   float* __restrict__ out, long long n, CommSumsq q) {
+  __shared__ float sh[34];
+  float sp = 0.f, sc = 0.f;  // optional side product: per-net sums of squares of the reduced vector (see CommSumsq)
   const int world = WORLD > 0 ? WORLD : world_rt;
   if (blockIdx.x == 0 && threadIdx.x < world) {
     __threadfence_system();
@@ -85,6 +89,14 @@ __global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, in
 #pragma unroll
       for (int r = 1; r < WORLD; ++r) { acc.x += x[r].x; acc.y += x[r].y; acc.z += x[r].z; acc.w += x[r].w; }  // rank order, as below
       reinterpret_cast<float4*>(out)[i] = acc;
+      if (q.partials != nullptr) {
+        const float e[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const long long idx = 4 * i + j;
+          if (idx < q.total) { if (comm_net_of(q, idx)) sc = fmaf(e[j], e[j], sc); else sp = fmaf(e[j], e[j], sp); }
+        }
+      }
     } else {
       float4 acc = __ldcv(reinterpret_cast<const float4*>(v.slot[0]) + i);
       for (int r = 1; r < world; ++r) {
@@ -99,6 +111,16 @@ __global__ void __launch_bounds__(kThreads) comm_allreduce_kernel(CommView v, in
       float acc = __ldcv(v.slot[0] + i);
       for (int r = 1; r < world; ++r) acc += __ldcv(v.slot[r] + i);
       out[i] = acc;
+      if (q.partials != nullptr && WORLD > 0 && i < q.total) { if (comm_net_of(q, i)) sc = fmaf(acc, acc, sc); else sp = fmaf(acc, acc, sp); }
+    }
+  }
+  if (q.partials != nullptr && WORLD > 0) {
+    sp = block_sum(sp, sh);
+    sc = block_sum(sc, sh);
+    if (threadIdx.x == 0) {
+      q.partials[2 * blockIdx.x] = sp;
+      q.partials[2 * blockIdx.x + 1] = sc;
+      if (blockIdx.x == 0 && q.step_count != nullptr) q.step_count[0] += 1;
     }
   }
 }
@@ -332,9 +354,11 @@ static int comm_allreduce(rlx_comm* c, float* out, int64_t n, void* stream, cons
   const int64_t n4 = std::max<int64_t>(n >> 2, 1);
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n4, kThreads), sm_count());
   // algorithmic bytes: every rank's slot read once + the result written once
+  CommSumsq q1{};
+  if (sumsq && (c->world == 2 || c->world == 4 || c->world == 8)) q1 = *sumsq;  // the generic-world instantiation does not compute them
 #define RLX_COMM_LAUNCH(W)                                                                                                     \
   RLX_LAUNCH_C(KC_ALLREDUCE, 0, 4.0 * n * (c->world + 1), comm_allreduce_kernel<W>, grid, kThreads, 0, stream, v, c->rank, c->world, \
-               (unsigned long long)c->seq, out, (long long)n)
+               (unsigned long long)c->seq, out, (long long)n, q1)
   switch (c->world) {
     case 2: RLX_COMM_LAUNCH(2); break;
     case 4: RLX_COMM_LAUNCH(4); break;
@@ -342,6 +366,7 @@ static int comm_allreduce(rlx_comm* c, float* out, int64_t n, void* stream, cons
     default: RLX_COMM_LAUNCH(0); break;
   }
 #undef RLX_COMM_LAUNCH
+  if (nblk_out && q1.partials) *nblk_out = (int)grid;
   return RLX_OK;
 }
 

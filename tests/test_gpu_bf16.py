@@ -97,9 +97,11 @@ def test_bf16_forward_vs_oracle(obs, act, hidden, n):
     std = torch.exp(pol["policy_logstd"]).expand(n, act)
     t = (noise.bfloat16() * std).bfloat16().float()
     chain = (t + mean.float()).bfloat16().float()
-    # 2 ulps of the LARGER summand: where loc and scale * eps cancel, an ulp of the oracle's mean is many ulps of the small sum
-    tol = 2.0 ** -7 * torch.maximum(mean.float().abs(), t.abs()) + 1e-30
-    assert bool(((a - chain).abs() <= tol).all()), float(((a - chain).abs() / tol).max())
+    # the mean may sit 2 bf16 ulps from the oracle's (as checked on v / d above) and the sum is rounded once more: 4 ulps of the LARGER
+    # summand - where loc and scale * eps cancel, an ulp of the mean is many ulps of the small sum
+    tol = 2.0 ** -6 * torch.maximum(mean.float().abs(), t.abs()) + 1e-30
+    worst = float(((a - chain).abs() / tol).max())
+    assert worst <= 1.0, worst
     # log-prob of that sample: the oracle's mean may sit one bf16 ulp from ours -> (a - mean)/sigma^2 * ulp(mean) per action dimension
     np.testing.assert_allclose(lp.numpy(), lp_ref.float().numpy(), rtol=1e-2, atol=2e-2 * act ** 0.5)
 
