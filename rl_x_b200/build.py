@@ -20,23 +20,32 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "-shared",
-    "--threads", "8",   # one compilation per source file in parallel
 ]
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
 
 
-def _digest():
+def _headers_digest():
     h = hashlib.sha256()
-    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(INCLUDE, "rlx_b200.h")]
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [os.path.join(INCLUDE, "rlx_b200.h")]
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def _digest():
+    h = hashlib.sha256()
+    h.update(_headers_digest().encode())
+    for f in _sources():
+        h.update(f.encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
     return h.hexdigest()
 
 
@@ -54,17 +63,48 @@ def is_fresh():
         return fh.read().strip() == _digest()
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into one shared library. Returns the path."""
-    os.makedirs(LIB_DIR, exist_ok=True)
-    if not force and is_fresh():
-        return LIB_PATH
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+def _compile_one(src, hdr_digest, verbose):
+    """One translation unit -> lib/obj/<name>.o, skipped when the source, every header and the flags are unchanged."""
+    name = os.path.splitext(os.path.basename(src))[0]
+    obj, stamp = os.path.join(OBJ_DIR, name + ".o"), os.path.join(OBJ_DIR, name + ".stamp")
+    h = hashlib.sha256(hdr_digest.encode())
+    with open(src, "rb") as fh:
+        h.update(fh.read())
+    want = h.hexdigest()
+    if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return obj, None
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if proc.returncode != 0:
+        return obj, "nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr
     if verbose:
         sys.stderr.write(proc.stderr)
+    with open(stamp, "w") as fh:
+        fh.write(want)
+    return obj, None
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a (one nvcc process per translation unit, in parallel, unchanged units are reused) and link
+    them into one shared library. Returns the path."""
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    if not force and is_fresh():
+        return LIB_PATH
+    if force:
+        for f in os.listdir(OBJ_DIR):
+            os.remove(os.path.join(OBJ_DIR, f))
+    from concurrent.futures import ThreadPoolExecutor
+    hdr = _headers_digest()
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda s_: _compile_one(s_, hdr, verbose), srcs))
+    errors = [e for _, e in results if e]
+    if errors:
+        raise RuntimeError("\n".join(errors))
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [o for o, _ in results]
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB_PATH

@@ -136,7 +136,9 @@ def test_espo_update_steps_match_oracle_on_fresh_data(gemm_engine, operator):
     metrics = L.update(batch, lambda: rng.choice(N * T, size=mb, replace=False), 10)
     assert len(metrics) == model._espo_steps
     ours_rd = model.metrics_host.numpy()[:model._espo_steps, 4]
-    np.testing.assert_allclose(ours_rd, [m["ratio_delta"] for m in metrics], rtol=2e-4, atol=1e-7)
+    # the first step starts from ratio == 1: this build's rollout and update log-probs are the same kernel arithmetic (exactly 0), torch's
+    # eager forward differs from its own rollout by fp32 rounding (~1e-6)
+    np.testing.assert_allclose(ours_rd, [m["ratio_delta"] for m in metrics], rtol=2e-4, atol=5e-6)
     pol, cri = model.params.state_dicts()
     for name in O.POLICY_KEYS + O.CRITIC_KEYS:
         ours, ref = (pol if name in pol else cri)[name].numpy(), (L.pol if name in L.pol else L.cri)[name].detach().numpy()
