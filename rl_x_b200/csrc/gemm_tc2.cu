@@ -370,7 +370,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int rr = 0; rr < 32; ++rr) {
               const float z = (EPI == TC_EPI_BIAS_RELU) ? x[rr] + bv : bf16r_if(x[rr] + bv, BF16);  // bf16 mode: Linear output is a bf16 tensor
-              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanhf(z), BF16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
+              x[rr] = (EPI == TC_EPI_BIAS_TANH) ? bf16r_if(tanh_fast(z), BF16) : ((EPI == TC_EPI_BIAS_RELU) ? fmaxf(z, 0.f) : z);
             }
           }
           if (n < p.n_main) {
