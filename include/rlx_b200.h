@@ -150,6 +150,9 @@ int rlx_rollout_store_stats_f32(const float* reward, const uint8_t* terminated, 
 int rlx_gae_f32(const float* rewards, const float* terminations, const float* values, const float* next_values,
                 const float* last_value, int64_t T, int64_t N, double gamma, double gae_lambda, float* advantages,
                 float* returns, void* stream);
+/* 1 (default): the GAE kernel stages its [steps x 32 envs] tiles into shared memory with TMA (cp.async.bulk.tensor.2d) whenever the arrays
+ * are 16-byte aligned and N % 4 == 0; 0: always ordinary coalesced loads (the fallback for other shapes).  Results are bit-identical. */
+int rlx_set_gae_tma(int on);
 
 /* -------------------------------------------------------------------------------- minibatch gather + stats -- */
 /* ref: batch_states[minibatch_indices], batch_actions[...], batch_log_probs[...], batch_advantages[...], batch_returns[...]

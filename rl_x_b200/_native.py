@@ -159,6 +159,7 @@ _SIGNATURES = {
     "rlx_kernel_class_name": (C.c_char_p, [C.c_int]),
     "rlx_set_gemm_engine": (C.c_int, [C.c_int]),
     "rlx_set_head_engine": (C.c_int, [C.c_int]),
+    "rlx_set_gae_tma": (C.c_int, [C.c_int]),
     "rlx_set_autocast_bf16": (C.c_int, [C.c_int]),
     "rlx_set_tc_pair": (C.c_int, [C.c_int, C.c_int]),
     "rlx_set_fused_tail": (C.c_int, [C.c_int]),

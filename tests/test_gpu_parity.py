@@ -53,8 +53,11 @@ def _rel(a, b):
 # (130, 9601) and (65, 16384): more than 2 CTAs per SM -> the 64-step-tile instantiation, with a ragged last tile
 @pytest.mark.parametrize("T,N", [(1, 1), (5, 3), (128, 4096), (129, 33), (300, 100), (64, 31), (130, 9601), (65, 16384)])
 @pytest.mark.parametrize("shortcut", [False, True])
-def test_gae_bit_exact_vs_oracle(T, N, shortcut):
+@pytest.mark.parametrize("tma", [True, False])
+def test_gae_bit_exact_vs_oracle(T, N, shortcut, tma):
+    """tma=True: tiles staged by cp.async.bulk.tensor where alignment allows (N % 4 == 0), ordinary loads elsewhere; False: ordinary loads always."""
     k = _kern(8, 2, 32)
+    k.lib.rlx_set_gae_tma(1 if tma else 0)
     g = torch.Generator().manual_seed(T * 1000 + N)
     r = torch.randn(T, N, generator=g)
     term = (torch.rand(T, N, generator=g) < 0.1).float()
@@ -69,6 +72,7 @@ def test_gae_bit_exact_vs_oracle(T, N, shortcut):
         k.gae(r.to(DEV), term.to(DEV), v.to(DEV), 0.99, 0.95, adv, ret, last_value=nv[T - 1].contiguous().to(DEV))
     else:
         k.gae(r.to(DEV), term.to(DEV), v.to(DEV), 0.99, 0.95, adv, ret, next_values=nv.to(DEV))
+    k.lib.rlx_set_gae_tma(1)
     assert np.array_equal(adv.cpu().numpy(), adv_ref.numpy())
     assert np.array_equal(ret.cpu().numpy(), ret_ref.numpy())
 
