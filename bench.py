@@ -567,7 +567,7 @@ def main():
     ap.add_argument("--exact-permutation", action="store_true",
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
-    ap.add_argument("--exchange-algo", default="auto", choices=["auto", "one_shot", "two_shot"], help="peer exchange kernel: one-shot / two-shot (auto: two-shot from 4 GPUs)")
+    ap.add_argument("--exchange-algo", default="auto", choices=["auto", "one_shot", "two_shot"], help="peer exchange kernel: one-shot (auto) / two-shot (experimental)")
     ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac", "ppo_lstm"])
     ap.add_argument("--tc-pair", default="", help="tcgen05 CTA-pair engine: MODE[:FWD_BN], MODE 0 off / 1 weight gradients (default) / 2 all GEMMs, FWD_BN 128|256")

@@ -258,9 +258,11 @@ int rlx_comm_stage_f32(rlx_comm* c, const float* src, int64_t n, void* stream);
 /* out[i] = sum over ranks r = 0..world-1 (in that order) of rank r's send buffer [i], i < n <= nfloats.  Every rank must call
  * it the same number of times; the kernel spins on peer flags (and traps after ~20 s if a peer never arrives). */
 int rlx_comm_allreduce_sum_f32(rlx_comm* c, float* out, int64_t n, void* stream);
-/* 0 (default): one-shot kernel for 2 ranks, two-shot from 4 ranks up; 1: always one-shot; 2: always two-shot (2, 4 or 8 ranks).  Two-shot =
- * reduce-scatter by peer loads (rank r sums chunk r of every send slot) + all-gather by peer stores into every rank's result buffer:
- * 2 (W-1)/W n floats per rank over NVLink instead of (W-1) n, at the price of a second flag round.  Same result bits as one-shot. */
+/* 0 (default) and 1: one-shot kernel; 2: two-shot (2, 4 or 8 ranks) = reduce-scatter by peer loads (rank r sums chunk r of every send
+ * slot) + all-gather by peer stores into every rank's result buffer: 2 (W-1)/W n floats per rank over NVLink instead of (W-1) n, at the
+ * price of a second flag round.  Same summation order.  Experimental: slower than one-shot at the PPO gradient size even on 8 GPUs
+ * (61 vs 49 us per exchange inside the epoch), verified bit-identical to one-shot at 2 ranks; on 8 ranks it passed the in-bench
+ * sharded-vs-single parity check, but a rank failed tests/dist_check_comm.py's 2000-call stress loop (not diagnosed). */
 int rlx_comm_set_algorithm(rlx_comm* c, int algo);
 int rlx_comm_destroy(rlx_comm* c);
 

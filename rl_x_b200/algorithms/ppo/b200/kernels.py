@@ -209,7 +209,7 @@ class PeerComm:
         nt.check(self.lib.rlx_comm_allreduce_sum_f32(self.handle, _f32(out, "out"), n, _stream()), "rlx_comm_allreduce_sum_f32")
 
     def set_algorithm(self, algo):
-        """0: by world size (one-shot at 2 ranks, two-shot from 4); 1: one-shot; 2: two-shot."""
+        """0 / 1: one-shot; 2: two-shot (experimental)."""
         nt.check(self.lib.rlx_comm_set_algorithm(self.handle, int(algo)), "rlx_comm_set_algorithm")
 
     def close(self):
