@@ -108,7 +108,9 @@ static TrainPlan plan_train(const rlx_ppo_dims& d, long long m) {
   P.head_blocks = head_grid(m);
   P.head_npart = (int)(2 * A + 5 + 2 * H);
   P.wgrad_chunks = (int)ceil_div(m, kHeadWgradRows);
-  P.norm_blocks = std::max(64, sm_count());  // the fused optimiser tail writes one partial pair per CTA of its (<= SM count) grid
+  // one (policy, critic) partial pair per CTA of whichever kernel leaves the squared norms behind: the <= SM-count grids of the fused tail
+  // and of the exchange kernels, or the gradient-assembly grid (one CTA per 256 flat elements + one per 8 "tall" elements)
+  P.norm_blocks = (int)std::max<long long>(std::max(64, sm_count()), ceil_div(make_layout(d).total(), 256) + ceil_div(2 * H + 2 * A + 1 + (A + 1) * H, 8) + 8);
   size_t o = 0;
   auto take = [&](size_t& off, size_t nfloats) {
     off = o;
@@ -315,11 +317,13 @@ static int launch_grad_reduce(const GradReduceP& r, cudaStream_t st) {
 }
 
 // `deferred`: when non-null the flat-gradient assembly is NOT launched; its parameters are returned for the fused optimiser tail.
-static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred);
+// `fuse_norms`: the assembly kernel also leaves the two squared clip norms in the workspace (off_barrier + 16 bytes) and bumps Adam's
+// step counter, so that clip + Adam can follow without the separate sum-of-squares launch.
+static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred, bool fuse_norms = false);
 
 extern "C" int rlx_ppo_minibatch_fwdbwd_f32(const rlx_ppo_minibatch_args* a, void* stream) { return minibatch_fwdbwd(a, stream, nullptr); }
 
-static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred) {
+static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradReduceP* deferred, bool fuse_norms) {
   int rc = check_mb_args(a, true);
   if (rc) return rc;
   const rlx_ppo_dims& d = a->dims;
@@ -593,6 +597,15 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
   r.logstd = a->params + L.off[LOGSTD];
   r.metrics = a->metrics; r.m_local = (float)m;
   r.bf16 = bf16;
+  if (fuse_norms && deferred == nullptr) {
+    r.norm_partials = ws_ptr<float>(ws, P.off_norm);
+    r.done = ws_ptr<unsigned int>(ws, P.off_barrier);
+    r.norm_out = ws_ptr<float>(ws, P.off_barrier) + 4;
+    r.step_count = (long long*)a->step_count;
+    for (int i = 0; i <= RLX_PPO_NSEG; ++i) r.seg_off[i] = L.off[i];
+    for (int i = 0; i < RLX_PPO_NSEG; ++i)
+      if (seg_is_critic(i)) r.critic_mask |= (1u << i);
+  }
   if (deferred != nullptr) {
     *deferred = r;
     return RLX_OK;
@@ -648,6 +661,13 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
   bool fused = g_fused_tail && dims_ok(first->dims) && first->exp_avg && first->exp_avg_sq && first->lr && first->step_count && first->workspace;
   const PpoLayout L = fused ? make_layout(first->dims) : PpoLayout{};
   unsigned tail_grid = 0;
+  // clip norms fused into the gradient-assembly kernel (needs the optimiser state and the ticket word in the workspace zeroed once)
+  bool norms_in_reduce = !fused && dims_ok(first->dims) && first->exp_avg && first->exp_avg_sq && first->lr && first->step_count && first->workspace;
+  if (norms_in_reduce) {
+    const TrainPlan P0 = plan_train(first->dims, std::max<int64_t>(std::min<int64_t>(mb, count), 1));
+    if (first->workspace_bytes < P0.total) norms_in_reduce = false;
+    else RLX_CHECK_CUDA(cudaMemsetAsync(ws_ptr<unsigned int>(first->workspace, P0.off_barrier), 0, 64, st));
+  }
   if (fused) {
     tail_grid = (unsigned)std::min<int64_t>(sm_count(), ceil_div(L.total(), kTailThreads));
     fused = (int64_t)tail_grid * kTailThreads * kTailPerThread >= L.total();
@@ -669,6 +689,18 @@ extern "C" int rlx_ppo_update_epoch_f32(const rlx_ppo_minibatch_args* first, int
     a.returns = first->returns + r0;
     a.adv_stats = first->adv_stats + 2 * k;
     a.metrics = first->metrics ? first->metrics + RLX_PPO_NMETRIC * k : nullptr;
+    if (!fused && norms_in_reduce && a.m == std::min<int64_t>(mb, count)) {
+      // default: the assembly kernel leaves the clip norms behind; clip + Adam read them (no separate sum-of-squares launch)
+      int rc = minibatch_fwdbwd(&a, stream, nullptr, true);
+      if (rc) return rc;
+      const PpoLayout La = make_layout(a.dims);
+      const TrainPlan Pa = plan_train(a.dims, std::max<int64_t>(a.m, 1));
+      AdamP ap = make_adam_params(&a, La, Pa);
+      ap.norm_partials = ws_ptr<float>(a.workspace, Pa.off_barrier) + 4;
+      ap.nblk_norm = 1;
+      RLX_LAUNCH_C(KC_CLIP_ADAM, 0, 28.0 * La.total(), ppo_clip_adam_kernel, (unsigned)ceil_div(La.total(), 256), 256, 0, st, ap);
+      continue;
+    }
     if (!fused || a.m != std::min<int64_t>(mb, count)) {  // a short last minibatch has its own workspace plan: separate kernels
       int rc = rlx_ppo_minibatch_fwdbwd_f32(&a, stream);
       if (rc) return rc;

@@ -32,7 +32,22 @@ struct GradReduceP {
   float m_local;
   int bf16;                    // bf16-autocast mode: weight / bias gradients come out of bf16 GEMMs / reductions (fp32 accumulation, one rounding
                                // of the complete sum); logstd is an fp32 parameter outside every autocast op and is not rounded
+  // Optional fused clip norms (rlx_ppo_update_epoch_f32): every CTA leaves the per-net sums of squares of the elements it assembled, the
+  // LAST CTA to finish (atomic ticket) adds them up in a fixed order into norm_out[0..1] and bumps Adam's step counter - the separate
+  // ppo_grad_sumsq_kernel launch (9 us of launch + latency for 1.3 MB) disappears.
+  float* norm_partials;        // [gridDim.x, 2] or null (= feature off)
+  float* norm_out;             // [2]: policy, critic sum of squares
+  unsigned int* done;          // ticket counter, zero before the first launch; reset by the last CTA
+  long long* step_count;
+  long long seg_off[RLX_PPO_NSEG + 1];
+  unsigned critic_mask;
 };
+__device__ __forceinline__ int grad_net_of(const GradReduceP& p, long long i) {
+  int seg = 0;
+#pragma unroll
+  for (int s = 1; s < RLX_PPO_NSEG; ++s) seg += (i >= p.seg_off[s]) ? 1 : 0;
+  return (p.critic_mask >> seg) & 1u;
+}
 
 // Groups with few partials per element (split-K GEMM outputs) are summed by one thread per element with 8 loads in flight;
 // groups with many partials (per-CTA partials of the head kernels: hundreds per element) get one WARP per element, lanes
@@ -58,6 +73,7 @@ __device__ __forceinline__ float grad_sum_warp(const float* __restrict__ q, int 
 constexpr int kTallSplit = 160;  // groups with more partials than this (per-CTA partials of the head kernel) use a warp per element
 
 __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP p, const int flat_blocks) {
+  float sq_p = 0.f, sq_c = 0.f;  // this thread's contribution to the two squared norms (fused-norm mode)
   if ((int)blockIdx.x < flat_blocks) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < p.total) {
@@ -75,6 +91,7 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
         if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
         else s = bf16r_if(s, p.bf16);
         p.grads[i] = s;
+        if (p.norm_partials != nullptr) { if (grad_net_of(p, i)) sq_c = s * s; else sq_p = s * s; }
       }
     }
   } else {
@@ -90,7 +107,10 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
         const long long i = g.off + w;
         if (i >= p.logstd_off && i < p.logstd_off + p.act) s += p.entropy_grad;
         else s = bf16r_if(s, p.bf16);
-        if (lane == 0) p.grads[i] = s;
+        if (lane == 0) {
+          p.grads[i] = s;
+          if (p.norm_partials != nullptr) { if (grad_net_of(p, i)) sq_c = s * s; else sq_p = s * s; }
+        }
         w = -1;
       } else if (w >= g.len) {
         w -= g.len;
@@ -117,6 +137,36 @@ __global__ void __launch_bounds__(256) ppo_grad_reduce_kernel(const GradReduceP 
       for (int a = 0; a < p.act; ++a) e += 0.5f + 0.5f * 1.8378770664093453f + logf(expf(p.logstd[a]));
       p.metrics[2] = e * (p.m_local * p.inv_mg);
       p.metrics[7] = p.m_local;
+    }
+  }
+  if (p.norm_partials != nullptr) {
+    __shared__ float sh_n[34];
+    __shared__ int s_last;
+    sq_p = block_sum(sq_p, sh_n);
+    sq_c = block_sum(sq_c, sh_n);
+    if (threadIdx.x == 0) {
+      p.norm_partials[2 * blockIdx.x] = sq_p;
+      p.norm_partials[2 * blockIdx.x + 1] = sq_c;
+      __threadfence();
+      s_last = (atomicAdd(p.done, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      // fixed order: thread t adds partials t, t + 256, ...; then the block tree (same shape every launch => reproducible bits)
+      float a = 0.f, b = 0.f;
+      for (unsigned int q = threadIdx.x; q < gridDim.x; q += blockDim.x) {
+        a += __ldcg(p.norm_partials + 2 * q);
+        b += __ldcg(p.norm_partials + 2 * q + 1);
+      }
+      a = block_sum(a, sh_n);
+      b = block_sum(b, sh_n);
+      if (threadIdx.x == 0) {
+        p.norm_out[0] = a;
+        p.norm_out[1] = b;
+        *p.done = 0u;
+        if (p.step_count != nullptr) p.step_count[0] += 1;  // read by the clip_adam kernel launched after this one
+      }
     }
   }
 }
