@@ -32,7 +32,7 @@ def _headers_digest():
     h = hashlib.sha256()
     files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))) + [os.path.join(INCLUDE, "rlx_b200.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())      # names, not absolute paths: the digest must not depend on where the tree is checked out
         with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -43,7 +43,7 @@ def _digest():
     h = hashlib.sha256()
     h.update(_headers_digest().encode())
     for f in _sources():
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())
         with open(f, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()
@@ -73,12 +73,16 @@ def _compile_one(src, hdr_digest, verbose):
     want = h.hexdigest()
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read().strip() == want:
         return obj, None
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    tmp = obj + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", tmp, src]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         return obj, "nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr
     if verbose:
         sys.stderr.write(proc.stderr)
+    os.replace(tmp, obj)
     with open(stamp, "w") as fh:
         fh.write(want)
     return obj, None
@@ -90,6 +94,20 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     if not force and is_fresh():
         return LIB_PATH
+    # One builder at a time: the ranks of a torchrun job all call load() at start-up, and a stale library must be rebuilt by exactly one of
+    # them while the others wait and then find it fresh.
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     if force:
         for f in os.listdir(OBJ_DIR):
             os.remove(os.path.join(OBJ_DIR, f))
@@ -101,10 +119,14 @@ def build(force=False, verbose=False):
     errors = [e for _, e in results if e]
     if errors:
         raise RuntimeError("\n".join(errors))
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH] + [o for o, _ in results]
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", tmp] + [o for o, _ in results]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB_PATH)           # a process that already mapped the old file keeps it; nobody ever maps a half-written one
     with open(STAMP, "w") as fh:
         fh.write(_digest())
     return LIB_PATH

@@ -430,3 +430,20 @@ def test_tanh_fast_error_model():
         rel[ref == 0] = np.abs(y[ref == 0])
         assert rel.max() < 6e-7, (worst, rel.max())
         assert np.sqrt(np.mean(rel ** 2)) < 1e-7
+
+
+def test_build_digest_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch):
+    """The freshness stamp travels with the prebuilt .so to a box where the tree lives under another path; there the library must still count
+    as fresh, or every rank of a torchrun job would start recompiling it at the same time."""
+    import shutil
+    from rl_x_b200 import build as b
+    here = b._digest()
+    other = tmp_path / "elsewhere"
+    shutil.copytree(b.CSRC, other / "csrc")
+    shutil.copytree(b.INCLUDE, other / "include")
+    monkeypatch.setattr(b, "CSRC", str(other / "csrc"))
+    monkeypatch.setattr(b, "INCLUDE", str(other / "include"))
+    assert b._digest() == here
+    with open(other / "csrc" / "gae.cu", "a") as fh:
+        fh.write("\n// changed\n")
+    assert b._digest() != here
