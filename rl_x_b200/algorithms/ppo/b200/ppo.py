@@ -343,15 +343,21 @@ class PPO:
             # pinned staging, double-buffered so that step t+1 can be staged while the copies of step t are still in flight
             self.h_action = torch.zeros(N, act).pin_memory()
             self.h_obs = [torch.zeros(N, obs).pin_memory() for _ in range(2)]
-            self.h_reward = [torch.zeros(N).pin_memory() for _ in range(2)]
-            self.h_term = [torch.zeros(N, dtype=torch.bool).pin_memory() for _ in range(2)]
-            self.h_trunc = [torch.zeros(N, dtype=torch.bool).pin_memory() for _ in range(2)]
+            # reward | terminated | truncated of one step travel as ONE packed copy (4N + N + N bytes) instead of three tiny ones
+            self.h_pack = [torch.zeros(6 * N, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self.h_pack_np = [(p.numpy()[:4 * N].view(np.float32), p.numpy()[4 * N:5 * N].view(np.bool_), p.numpy()[5 * N:].view(np.bool_))
+                              for p in self.h_pack]
+            self.h_done_idx = [torch.zeros(N, dtype=torch.int64).pin_memory() for _ in range(2)]   # finished episodes of one step:
+            self.h_finals = [torch.zeros(N, obs).pin_memory() for _ in range(2)]                   # env indices and final observations
+            self.d_done_idx = torch.zeros(N, dtype=torch.int64, device=dev)
+            self.d_finals = z(N, obs)
             self.h2d_done = [torch.cuda.Event() for _ in range(2)]
             self.h2d_pending = [False, False]
             self.action_ready = torch.cuda.Event()
-            self.d_reward = z(N)
-            self.d_term = torch.zeros(N, dtype=torch.bool, device=dev)
-            self.d_trunc = torch.zeros(N, dtype=torch.bool, device=dev)
+            self.d_pack = torch.zeros(6 * N, dtype=torch.uint8, device=dev)
+            self.d_reward = self.d_pack[:4 * N].view(torch.float32)
+            self.d_term = self.d_pack[4 * N:5 * N].view(torch.bool)
+            self.d_trunc = self.d_pack[5 * N:].view(torch.bool)
             self.d_obs = z(N, obs)
         self.noise_buf = z(N, act) if self.rollout_noise == "torch" else None
         # device-side episode statistics for TORCH-interface envs (semantics of warp_torch/environment.py:159-178 and
@@ -435,26 +441,40 @@ class PPO:
                 if self.h2d_pending[slot]:
                     self.h2d_done[slot].synchronize()  # the pinned slot of step-2 must have been consumed
                 self._h2d(next_state, np.float32, self.h_obs[slot], b.states[step + 1])
-                self._h2d(reward, np.float32, self.h_reward[slot], self.d_reward)
-                self._h2d(terminated, bool, self.h_term[slot], self.d_term)
-                self._h2d(truncated, bool, self.h_trunc[slot], self.d_trunc)
+                h_reward, h_term, h_trunc = self.h_pack_np[slot]
+                np.copyto(h_reward, reward, casting="same_kind")
+                np.copyto(h_term, terminated, casting="unsafe")
+                np.copyto(h_trunc, truncated, casting="unsafe")
+                self.d_pack.copy_(self.h_pack[slot], non_blocking=True)
                 # next_states[step] = next_state with final observations patched in for finished episodes (ppo.py:217-223)
                 self.kernels.rollout_store(self.d_reward, self.d_term, self.d_trunc, b.states[step + 1], b.rewards[step],
                                            b.terminations[step], b.next_states[step], None)
-                self.h2d_done[slot].record()
-                self.h2d_pending[slot] = True
+                # Host-side bookkeeping of finished episodes runs while the copies above are in flight; nothing below blocks the host, so
+                # the next step's kernels are queued behind the copies instead of being launched after them.
                 done = np.logical_or(terminated, truncated)
                 if done.any():
                     idx = np.nonzero(done)[0]
+                    k = len(idx)
                     batch_getter = getattr(env, "get_final_observations_batch", None)  # optional vectorised form of the per-index call
                     if batch_getter is not None:
                         finals = np.asarray(batch_getter(info, idx), dtype=np.float32)
                     else:
                         finals = np.stack([np.asarray(env.get_final_observation_at_index(info, int(i)), dtype=np.float32) for i in idx])
-                    b.next_states[step][torch.from_numpy(idx).to(self.device)] = torch.from_numpy(finals).to(self.device)
-                    for i in idx:
-                        saving_returns.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
-                    dones_host += len(idx)
+                    # next_states[step][idx] = finals, staged through this step's pinned slot (stream order keeps it after rollout_store)
+                    self.h_done_idx[slot][:k].copy_(torch.from_numpy(idx))
+                    self.h_finals[slot][:k].copy_(torch.from_numpy(np.ascontiguousarray(finals)))
+                    self.d_done_idx[:k].copy_(self.h_done_idx[slot][:k], non_blocking=True)
+                    self.d_finals[:k].copy_(self.h_finals[slot][:k], non_blocking=True)
+                    b.next_states[step].index_copy_(0, self.d_done_idx[:k], self.d_finals[:k])
+                    values_getter = getattr(env, "get_final_info_values_batch", None)
+                    if values_getter is not None:
+                        saving_returns.extend(values_getter(info, "episode_return", idx))
+                    else:
+                        for i in idx:
+                            saving_returns.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
+                    dones_host += k
+                self.h2d_done[slot].record()
+                self.h2d_pending[slot] = True
             for key, info_value in env.get_logging_info_dict(info).items():
                 step_info_collection.setdefault(key, []).extend(info_value)
         return step_info_collection, saving_returns, dones_host

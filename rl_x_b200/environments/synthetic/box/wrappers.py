@@ -20,5 +20,9 @@ class RLXInfo:
     def get_final_info_value_at_index(self, info, key, index):
         return 0.0
 
+    def get_final_info_values_batch(self, info, key, indices):
+        """Vectorised form of get_final_info_value_at_index (optional extension used by rl_x_b200's PPO)."""
+        return [0.0] * len(indices)
+
     def __getattr__(self, name):
         return getattr(self.env, name)
