@@ -568,7 +568,8 @@ def main():
                     help="multi-GPU: reference-exact global permutation on every rank (host-bound) instead of rank-local shuffles")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU gradient exchange: library peer-memory kernel or NCCL")
     ap.add_argument("--exchange-algo", default="auto", choices=["auto", "one_shot", "two_shot"], help="peer exchange kernel: one-shot (auto) / two-shot (experimental)")
-    ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm"], help="PPO loss head: fused kernel (default) or the GEMM formulation")
+    ap.add_argument("--head-engine", default="fused", choices=["fused", "gemm", "mma"],
+                    help="PPO loss head: fused SIMT kernel, the GEMM formulation, or the fused mma.sync kernel")
     ap.add_argument("--workload", default="ppo", choices=["ppo", "sac", "fastsac", "ppo_lstm"])
     ap.add_argument("--tc-pair", default="", help="tcgen05 CTA-pair engine: MODE[:FWD_BN], MODE 0 off / 1 weight gradients (default) / 2 all GEMMs, FWD_BN 128|256")
     ap.add_argument("--no-e2e", action="store_true")
@@ -600,7 +601,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from rl_x_b200 import _native as nt
     lib = nt.load()
-    lib.rlx_set_head_engine(1 if args.head_engine == "gemm" else 0)
+    lib.rlx_set_head_engine({"fused": 0, "gemm": 1, "mma": 2}[args.head_engine])
     if args.tc_pair:
         mode, _, bn = args.tc_pair.partition(":")
         lib.rlx_set_tc_pair(int(mode), int(bn or 0))

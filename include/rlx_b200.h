@@ -273,8 +273,10 @@ int rlx_ppo_update_epoch_sharded_f32(const rlx_ppo_minibatch_args* first, int64_
                                      const int64_t* global_counts, rlx_comm* comm, void* stream);
 
 
-/* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused kernel (default), 1 = the GEMM formulation of csrc/ppo_head_gemm.cu
- * (logits and dZ2 as GEMMs around one flat loss kernel; emulation-validated, first hardware run pending).  Returns the engine in effect. */
+/* Loss head of rlx_ppo_minibatch_fwdbwd_f32: 0 = the fused SIMT kernel, 1 = the GEMM formulation of csrc/ppo_head_gemm.cu (logits and
+ * dZ2 as GEMMs around one flat loss kernel; measured slower, kept as an opt-in), 2 = the fused kernel on the warp-level tensor path
+ * (csrc/ppo_head_mma.cuh: both skinny products as 3xTF32 mma.sync tiles; fp32 mode, hidden 128/256/512, act <= 31 - other shapes and the
+ * bf16 mode run engine 0).  Returns the engine in effect. */
 int rlx_set_head_engine(int engine);
 /* bf16-autocast mode of the PPO entry points (the reference's `bf16_mixed_precision_training`, ppo.py:98-107,123,155,208,253; its default).
  * on != 0: rlx_ppo_forward_f32 / rlx_critic_forward_f32 / rlx_ppo_minibatch_fwdbwd_f32 / rlx_gae_f32 round every value that torch's autocast

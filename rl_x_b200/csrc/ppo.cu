@@ -12,6 +12,7 @@
 #include "gemm_dispatch.cuh"
 #include "ppo_head.cuh"
 #include "ppo_head_gemm.cuh"
+#include "ppo_head_mma.cuh"
 #include "ppo_optim.cuh"
 
 namespace rlx {
@@ -198,7 +199,7 @@ static bool head_dims_ok(const rlx_ppo_dims& d) {
 }
 
 int ppo_head_gemm_path(const HeadGemmArgs& a, cudaStream_t st);  // ppo_head_gemm.cu
-static int g_head_engine = 0;                                       // 0 fused kernel, 1 GEMM formulation (rlx_set_head_engine)
+static int g_head_engine = 0;                                       // 0 fused SIMT kernel, 1 GEMM formulation, 2 fused mma.sync kernel (rlx_set_head_engine)
 // rlx_set_fused_tail(1): one-launch optimiser tail inside the epoch call.  Measured on B200 (round 2, gpurun_out/r2_bench3.json): SLOWER than the
 // three separate kernels (57 us vs 20 + 9 + 8 us per minibatch) - the <= SM-count grid that the grid barrier needs leaves too few threads
 // in flight for the split-K partial reads (25 MB per minibatch), which the 1287-CTA grad_reduce grid hides.  Kept as an opt-in.
@@ -398,8 +399,31 @@ static int minibatch_fwdbwd(const rlx_ppo_minibatch_args* a, void* stream, GradR
     if (fast_head) {
       HeadTrain2Extra ex{dh_ld};
       const bool vec_head = (H == 128 || H == 256 || H == 512);
+      // fused head on the warp-level tensor path (ppo_head_mma.cuh): fp32 mode, <= 4 n-tiles of 8 head columns
+      const int nt4 = (int)ceil_div(dh_ld, 8);
+      const size_t smem4 = head4_smem_floats(H, A, nt4) * sizeof(float);
+      const bool mma_head = !gemm_head && vec_head && g_head_engine == 2 && !bf16 && nt4 <= 4 && smem4 <= 220 * 1024;
       if (gemm_head) {
         // loss, dZ2, dhead and the partial block are done
+      } else if (mma_head) {
+        head_blocks = (int)std::min<long long>(ceil_div(m, 16 * kHead4RowTiles), (long long)P.head_blocks);
+#define RLX_HEAD4(H_, NT_)                                                                                                          \
+  do {                                                                                                                              \
+    RLX_CHECK_CUDA(cudaFuncSetAttribute(ppo_head_train4_kernel<H_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4)); \
+    RLX_LAUNCH_C(KC_HEAD_TRAIN, head_flops, head_bytes, (ppo_head_train4_kernel<H_, NT_>), head_blocks, 256, smem4, st, h, ex);     \
+  } while (0)
+#define RLX_HEAD4_NT(H_)              \
+  do {                                \
+    if (nt4 == 1) RLX_HEAD4(H_, 1);   \
+    else if (nt4 == 2) RLX_HEAD4(H_, 2); \
+    else if (nt4 == 3) RLX_HEAD4(H_, 3); \
+    else RLX_HEAD4(H_, 4);            \
+  } while (0)
+        if (H == 128) RLX_HEAD4_NT(128);
+        else if (H == 256) RLX_HEAD4_NT(256);
+        else RLX_HEAD4_NT(512);
+#undef RLX_HEAD4_NT
+#undef RLX_HEAD4
       } else if (vec_head) {
 #define RLX_HEAD3_B(H_, AM_, BF_)                                                                                                     \
   do {                                                                                                                                \
@@ -808,7 +832,7 @@ extern "C" int rlx_debug_gemm_f32(int engine, int layout, int epilogue, int64_t 
 }
 
 extern "C" int rlx_set_head_engine(int engine) {
-  if (engine == 0 || engine == 1) g_head_engine = engine;
+  if (engine >= 0 && engine <= 2) g_head_engine = engine;
   else set_error("rlx_set_head_engine: unknown engine %d", engine);
   return g_head_engine;
 }
