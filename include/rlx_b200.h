@@ -303,21 +303,26 @@ int rlx_debug_ppo_head_gemm_f32(int64_t m, int32_t hidden, int32_t act_dim, cons
                                 int32_t ratio_delta_metric, float* dZ2, float* dhead, float* headpart, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------ PPO + LSTM path -- */
-/* rl_x/algorithms/ppo_lstm/flax (policy.py:36-146, critic.py:18-30, ppo_lstm.py:107-231), default options
- * (lstm_obs_combine_method = "concat", share_lstm_obs_encoder = False).  STATUS: written without GPU access — numerics are checked
- * by running these very sources in a host emulation build against oracle/ppo_lstm_oracle.py (tests/test_lstm_emulation.py); first
- * hardware run pending.  Exact-fp32 SIMT GEMMs; one launch per time step for the recurrent part.
+/* rl_x/algorithms/ppo_lstm/flax (policy.py:36-146, critic.py:18-30, ppo_lstm.py:107-231), including the two policy
+ * options lstm_obs_combine_method = "concat" | "film" (policy.py:57-59, 99-105) and share_lstm_obs_encoder (policy.py:51-53, 120-123).
+ * The sources also compile for the host (g++ -DRLX_EMU) and are checked there against oracle/ppo_lstm_oracle.py
+ * (tests/test_lstm_emulation.py); the default options have run on B200 since round 1, FiLM / shared encoder and the one-launch-per-step
+ * recurrence were added after the round-2 GPU budget was spent (emulation-validated; GPU tests in tests/test_gpu_zzz_ppo_lstm.py).
+ * Exact-fp32 SIMT GEMMs; ONE launch per time step for the recurrent part in both directions (carry reset + h.Wh + cell fused).
  *
  * Flat parameter layouts (fp32).  All kernels are stored [in, out] like Flax.  Policy segments, in order:
  *   0 We1 [obs,E] 1 be1 [E] 2 g1 [E] 3 n1 [E]      lstm_obs_encoder dense kernel/bias, LayerNorm scale/bias
- *   4 We2 [obs,E] 5 be2 [E] 6 g2 [E] 7 n2 [E]      obs_encoder
+ *   4 We2 [obs,E] 5 be2 [E] 6 g2 [E] 7 n2 [E]      obs_encoder (all four EMPTY with a shared encoder)
  *   8 Wi [E,4L] 9 Wh [L,4L] 10 bh [4L]             LSTM, gate blocks ordered i|f|g|o (Flax ii,if,ig,io / hi,hf,hg,ho)
  *   11 gl [L] 12 nl [L]                            lstm_ln
- *   13 Wt1 [E+L,H] 14 bt1 [H] 15 Wt2 [H,H] 16 bt2 [H] 17 Wm [H,A] 18 bm [A] 19 logstd [A]
+ *   13 Wt1 [E+L,H] (FiLM: [E,H]) 14 bt1 [H] 15 Wt2 [H,H] 16 bt2 [H] 17 Wm [H,A] 18 bm [A] 19 logstd [A]
+ *   20 Wf [L,2E] 21 bf [2E]                        FiLM only (EMPTY otherwise): blocks gamma|beta (Flax lstm_film_gamma / lstm_film_beta)
  * Critic segments: 0 Wc1 [obs,H] 1 bc1 [H] 2 Wc2 [H,H] 3 bc2 [H] 4 Wc3 [H,1] 5 bc3 [1]. */
-#define RLX_LSTM_POLICY_NSEG 20
+#define RLX_LSTM_POLICY_NSEG 22
 #define RLX_LSTM_CRITIC_NSEG 6
-typedef struct rlx_lstm_dims { int32_t obs_dim, act_dim, hidden, enc_dim, lstm_dim; } rlx_lstm_dims;
+#define RLX_LSTM_OPT_FILM 1            /* lstm_obs_combine_method = "film" */
+#define RLX_LSTM_OPT_SHARED_ENCODER 2  /* share_lstm_obs_encoder = True */
+typedef struct rlx_lstm_dims { int32_t obs_dim, act_dim, hidden, enc_dim, lstm_dim, options /* RLX_LSTM_OPT_* bits; 0 = reference defaults */; } rlx_lstm_dims;
 int rlx_lstm_param_layout(const rlx_lstm_dims* d, int64_t* policy_offsets /*[NSEG+1]*/, int64_t* critic_offsets /*[NSEG+1]*/);
 size_t rlx_lstm_minibatch_workspace_bytes(const rlx_lstm_dims* d, int64_t T, int64_t n_env);
 

@@ -34,7 +34,7 @@ def _orthogonal(shape, gain, gen):
     return w.t().contiguous()
 
 
-def init_params(obs_dim, act_dim, hidden=256, enc=128, lstm=64, std_dev=1.0, share_encoder=False, seed=0):
+def init_params(obs_dim, act_dim, hidden=256, enc=128, lstm=64, std_dev=1.0, share_encoder=False, seed=0, combine="concat"):
     """Same shapes and initialiser families as Policy.setup / Critic (policy.py:47-70, critic.py:22-30).  The values are NOT the
     reference's: they come from torch's generator, not from jax.random (no JAX here)."""
     g = torch.Generator().manual_seed(seed)
@@ -54,7 +54,9 @@ def init_params(obs_dim, act_dim, hidden=256, enc=128, lstm=64, std_dev=1.0, sha
         cell["i" + k] = {"kernel": torch.randn(enc, lstm, generator=g) / math.sqrt(enc)}                      # lecun_normal
         cell["h" + k] = {"kernel": _orthogonal((lstm, lstm), 1.0, g), "bias": torch.zeros(lstm)}              # orthogonal, zeros
     pol["lstm"], pol["lstm_ln"] = cell, ln(lstm)
-    pol["torso_dense1"], pol["torso_dense2"] = dense(enc + lstm, hidden, s2), dense(hidden, hidden, s2)
+    if combine == "film":  # policy.py:57-59
+        pol["lstm_film_gamma"], pol["lstm_film_beta"] = dense(lstm, enc, s2), dense(lstm, enc, s2)
+    pol["torso_dense1"], pol["torso_dense2"] = dense(enc if combine == "film" else enc + lstm, hidden, s2), dense(hidden, hidden, s2)
     pol["mean_head"] = dense(hidden, act_dim, 0.01)
     pol["policy_logstd"] = torch.full((1, act_dim), math.log(std_dev))
     cri = {"Dense_0": dense(obs_dim, hidden, s2), "Dense_1": dense(hidden, hidden, s2), "Dense_2": dense(hidden, 1, 1.0)}
@@ -103,9 +105,13 @@ def encode(pol, obs, which):
 
 
 def decode(pol, obs_latent, lstm_latent):
-    """policy.py:95-112, lstm_obs_combine_method == "concat"."""
+    """policy.py:95-112; lstm_obs_combine_method is "film" iff the tree holds the FiLM layers (policy.py:57-59), else "concat"."""
     lstm_latent = torch.tanh(layer_norm(pol["lstm_ln"], lstm_latent))
-    h = torch.tanh(dense(pol["torso_dense1"], torch.cat([obs_latent, lstm_latent], dim=-1)))
+    if "lstm_film_gamma" in pol:
+        torso_in = obs_latent * dense(pol["lstm_film_gamma"], lstm_latent) + dense(pol["lstm_film_beta"], lstm_latent)
+    else:
+        torso_in = torch.cat([obs_latent, lstm_latent], dim=-1)
+    h = torch.tanh(dense(pol["torso_dense1"], torso_in))
     h = torch.tanh(dense(pol["torso_dense2"], h))
     return dense(pol["mean_head"], h), pol["policy_logstd"]
 

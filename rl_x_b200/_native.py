@@ -99,7 +99,7 @@ class SacUpdateArgs(C.Structure):
 
 
 class LstmDims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim")]
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim", "options")]
 
 
 class LstmMinibatchArgs(C.Structure):
@@ -117,8 +117,10 @@ class LstmStepArgs(C.Structure):
                 [(k, C.c_void_p) for k in ("action", "env_action", "logp", "value", "workspace")] + [("workspace_bytes", C.c_size_t)])
 
 
-RLX_LSTM_POLICY_NSEG, RLX_LSTM_CRITIC_NSEG = 20, 6
-LSTM_POLICY_SEGMENTS = ("We1", "be1", "g1", "n1", "We2", "be2", "g2", "n2", "Wi", "Wh", "bh", "gl", "nl", "Wt1", "bt1", "Wt2", "bt2", "Wm", "bm", "logstd")
+RLX_LSTM_POLICY_NSEG, RLX_LSTM_CRITIC_NSEG = 22, 6
+RLX_LSTM_OPT_FILM, RLX_LSTM_OPT_SHARED_ENCODER = 1, 2
+LSTM_POLICY_SEGMENTS = ("We1", "be1", "g1", "n1", "We2", "be2", "g2", "n2", "Wi", "Wh", "bh", "gl", "nl", "Wt1", "bt1", "Wt2", "bt2", "Wm", "bm", "logstd",
+                        "Wf", "bf")
 LSTM_CRITIC_SEGMENTS = ("Wc1", "bc1", "Wc2", "bc2", "Wc3", "bc3")
 
 

@@ -1,5 +1,5 @@
-"""Keys and default values of rl_x/algorithms/ppo_lstm/flax/default_config.py.  `lstm_obs_combine_method` must be "concat" and
-`share_lstm_obs_encoder` False (the reference defaults): the FiLM / shared-encoder variants are not built.  `device` must stay "gpu"."""
+"""Keys and default values of rl_x/algorithms/ppo_lstm/flax/default_config.py.  `lstm_obs_combine_method` is "concat" or "film" and
+`share_lstm_obs_encoder` either value, as in the reference (policy.py:51-59, 99-125).  `device` must stay "gpu"."""
 from rl_x_b200.config_dict import config_from_defaults
 
 _DEFAULTS = (
@@ -25,6 +25,7 @@ _DEFAULTS = (
     ('nr_hidden_units', 256),
     ('evaluation_frequency', -1),
     ('evaluation_episodes', 10),
+    ('use_cuda_graph', False),  # not a reference key: replay each minibatch update as one captured CUDA graph (same kernels, same order)
 )
 
 

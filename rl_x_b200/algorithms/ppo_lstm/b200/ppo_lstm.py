@@ -36,9 +36,11 @@ def _stream():
 def init_parameters(dims, std_dev, seed):
     """Initialiser families of Policy.setup / Critic (policy.py:47-70, critic.py:22-30): orthogonal(sqrt 2) dense kernels, zero biases,
     LayerNorm scale 1 / bias 0, LSTM input kernels lecun-normal and recurrent kernels orthogonal, mean head orthogonal(0.01), critic head
-    orthogonal(1), log-std = log(std_dev).  Returns {segment name: tensor} for both trees ([in, out] kernels)."""
+    orthogonal(1), log-std = log(std_dev); FiLM gamma / beta layers orthogonal(sqrt 2) (policy.py:57-59).  Returns {segment name: tensor}
+    for both trees ([in, out] kernels); segments an option removes (obs_encoder with a shared encoder, FiLM layers with "concat") are empty."""
     g = torch.Generator().manual_seed(int(seed))
     O, A, H, E, L = dims.obs_dim, dims.act_dim, dims.hidden, dims.enc_dim, dims.lstm_dim
+    film, shared = bool(dims.options & nt.RLX_LSTM_OPT_FILM), bool(dims.options & nt.RLX_LSTM_OPT_SHARED_ENCODER)
 
     def orth(i, o, gain):
         w = torch.empty(o, i)
@@ -46,12 +48,14 @@ def init_parameters(dims, std_dev, seed):
         return w.t().contiguous()
 
     s2 = math.sqrt(2.0)
+    E2 = 0 if shared else E
     pol = {"We1": orth(O, E, s2), "be1": torch.zeros(E), "g1": torch.ones(E), "n1": torch.zeros(E),
-           "We2": orth(O, E, s2), "be2": torch.zeros(E), "g2": torch.ones(E), "n2": torch.zeros(E),
+           "We2": orth(O, E, s2) if not shared else torch.zeros(0), "be2": torch.zeros(E2), "g2": torch.ones(E2), "n2": torch.zeros(E2),
            "Wi": torch.cat([torch.randn(E, L, generator=g) / math.sqrt(E) for _ in range(4)], dim=1),
            "Wh": torch.cat([orth(L, L, 1.0) for _ in range(4)], dim=1), "bh": torch.zeros(4 * L),
            "gl": torch.ones(L), "nl": torch.zeros(L),
-           "Wt1": orth(E + L, H, s2), "bt1": torch.zeros(H), "Wt2": orth(H, H, s2), "bt2": torch.zeros(H),
+           "Wf": torch.cat([orth(L, E, s2), orth(L, E, s2)], dim=1) if film else torch.zeros(0), "bf": torch.zeros(2 * E if film else 0),
+           "Wt1": orth(E if film else E + L, H, s2), "bt1": torch.zeros(H), "Wt2": orth(H, H, s2), "bt2": torch.zeros(H),
            "Wm": orth(H, A, 0.01), "bm": torch.zeros(A), "logstd": torch.full((A,), math.log(std_dev))}
     cri = {"Wc1": orth(O, H, s2), "bc1": torch.zeros(H), "Wc2": orth(H, H, s2), "bc2": torch.zeros(H), "Wc3": orth(H, 1, 1.0), "bc3": torch.zeros(1)}
     return pol, cri
@@ -89,6 +93,7 @@ class PPO_LSTM:
         self.action_clipping_and_rescaling = a.action_clipping_and_rescaling
         self.evaluation_frequency = a.evaluation_frequency
         self.evaluation_episodes = a.evaluation_episodes
+        self.use_cuda_graph = bool(a.get("use_cuda_graph", False))  # replay the minibatch update as one CUDA graph (same kernels, same order)
         self.batch_size = self.nr_envs * self.nr_steps
         self.nr_updates = int(self.total_timesteps // self.batch_size)                 # ppo_lstm.py:55
         self.nr_minibatches = self.batch_size // self.minibatch_size                  # ppo_lstm.py:56
@@ -98,8 +103,8 @@ class PPO_LSTM:
             raise ValueError("Evaluation frequency must be a multiple of the number of steps and environments.")
         if self.minibatch_size % self.nr_steps != 0:
             raise ValueError("Minibatch size must be a multiple of nr_steps for PPO_LSTM.")
-        if a.lstm_obs_combine_method != "concat" or a.share_lstm_obs_encoder:
-            raise NotImplementedError("rl_x_b200 PPO_LSTM implements lstm_obs_combine_method='concat', share_lstm_obs_encoder=False.")
+        if a.lstm_obs_combine_method not in ("concat", "film"):
+            raise ValueError("lstm_obs_combine_method must be 'concat' or 'film' (policy.py:99-105)")
         if self.nr_minibatches < 1 or self.nr_minibatch_envs * self.nr_minibatches != self.nr_envs:
             # the reference reshapes nr_epochs permutations of arange(nr_envs) to (nr_epochs * nr_minibatches, nr_minibatch_envs), ppo_lstm.py:189-191
             raise ValueError("nr_envs must equal nr_minibatches * (minibatch_size // nr_steps)")
@@ -113,7 +118,9 @@ class PPO_LSTM:
         if len(self.os_shape) != 1 or len(self.as_shape) != 1:
             raise ValueError("rl_x_b200 PPO_LSTM supports flat observations and flat continuous actions only.")
         self.lib = nt.load()
-        self.dims = nt.LstmDims(int(self.os_shape[0]), int(self.as_shape[0]), int(a.nr_hidden_units), int(a.obs_encoding_dim), int(a.lstm_hidden_dim))
+        options = (nt.RLX_LSTM_OPT_FILM if a.lstm_obs_combine_method == "film" else 0) | (nt.RLX_LSTM_OPT_SHARED_ENCODER if a.share_lstm_obs_encoder else 0)
+        self.dims = nt.LstmDims(int(self.os_shape[0]), int(self.as_shape[0]), int(a.nr_hidden_units), int(a.obs_encoding_dim), int(a.lstm_hidden_dim),
+                                options)
         poff, coff = (C.c_int64 * (nt.RLX_LSTM_POLICY_NSEG + 1))(), (C.c_int64 * (nt.RLX_LSTM_CRITIC_NSEG + 1))()
         nt.check(self.lib.rlx_lstm_param_layout(C.byref(self.dims), poff, coff), "rlx_lstm_param_layout")
         self.policy_offsets, self.critic_offsets = list(poff), list(coff)
@@ -217,6 +224,38 @@ class PPO_LSTM:
         rows_per_call = min(T * N, 32768)  # next-value pass in row blocks: the workspace is sized per call
         ws_all, ws_all_bytes = self._workspace(1, rows_per_call)
 
+        mb_args = nt.LstmMinibatchArgs()
+        mb_args.dims, mb_args.T, mb_args.n_env = self.dims, T, n_mb
+        for name in ("states", "actions", "log_probs", "advantages", "returns", "dones", "init_c", "init_h"):
+            setattr(mb_args, name, mb[name].data_ptr())
+        mb_args.adv_stats = adv_stats.data_ptr()
+        mb_args.policy_params, mb_args.critic_params = self.policy_params.data_ptr(), self.critic_params.data_ptr()
+        mb_args.policy_grads, mb_args.critic_grads = self.policy_grads.data_ptr(), self.critic_grads.data_ptr()
+        mb_args.clip_range, mb_args.entropy_coef, mb_args.critic_coef = float(self.clip_range), float(self.entropy_coef), float(self.critic_coef)
+        mb_args.workspace, mb_args.workspace_bytes = ws_mb.data_ptr(), ws_mb_bytes
+        metrics_stage, norms_stage = z(8), z(2)   # fixed targets of the captured update (copied to row k of metrics_dev / norms_dev)
+        self._graph = None
+
+        def minibatch_update(metrics_row, norms_row):
+            """minibatch_update (ppo_lstm.py:193-222) on the envs listed in idx_dev: gather their columns, advantage statistics, loss +
+            gradients, clip + Adam for both trees.  Every pointer is fixed for the life of train() except the two result rows."""
+            for name, src, width in (("states", states, obs_d), ("actions", actions, act_d), ("log_probs", log_probs, 1),
+                                     ("advantages", advantages, 1), ("returns", returns, 1), ("dones", dones, 1)):
+                nt.check(self.lib.rlx_gather_env_columns_f32(src.data_ptr(), idx_dev.data_ptr(), T, N, n_mb, width, mb[name].data_ptr(), _stream()),
+                         "rlx_gather_env_columns_f32")
+            for name, src in (("init_c", init_c), ("init_h", init_h)):
+                nt.check(self.lib.rlx_gather_env_columns_f32(src.data_ptr(), idx_dev.data_ptr(), 1, N, n_mb, L, mb[name].data_ptr(), _stream()),
+                         "rlx_gather_env_columns_f32")
+            nt.check(self.lib.rlx_mean_popstd_f32(mb["advantages"].data_ptr(), T * n_mb, adv_stats.data_ptr(), stats_ws.data_ptr(), _stream()),
+                     "rlx_mean_popstd_f32")
+            mb_args.metrics = metrics_row.data_ptr()
+            nt.check(self.lib.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(mb_args), _stream()), "rlx_lstm_ppo_minibatch_fwdbwd_f32")
+            for params, grads, mu, nu, step, col in ((self.policy_params, self.policy_grads, self.policy_mu, self.policy_nu, self.policy_step, 0),
+                                                     (self.critic_params, self.critic_grads, self.critic_mu, self.critic_nu, self.critic_step, 1)):
+                nt.check(self.lib.rlx_optax_clip_adam_f32(params.data_ptr(), grads.data_ptr(), mu.data_ptr(), nu.data_ptr(), params.numel(),
+                                                          self.lr_dev.data_ptr(), step.data_ptr(), float(self.max_grad_norm), 0.9, 0.999, 1e-8,
+                                                          norms_row[col:].data_ptr(), opt_ws.data_ptr(), _stream()), "rlx_optax_clip_adam_f32")
+
         saving_return_buffer = deque(maxlen=100 * self.nr_envs)
         state, _ = self.train_env.reset()
         state = self._to_dev(state)
@@ -288,32 +327,26 @@ class PPO_LSTM:
                 self.rng.shuffle(perm)  # one independent env permutation per epoch (ppo_lstm.py:189-191)
                 for m in range(self.nr_minibatches):
                     idx_dev.copy_(torch.from_numpy(perm[m * n_mb:(m + 1) * n_mb]))
-                    for name, src, width in (("states", states, obs_d), ("actions", actions, act_d), ("log_probs", log_probs, 1),
-                                             ("advantages", advantages, 1), ("returns", returns, 1), ("dones", dones, 1)):
-                        nt.check(self.lib.rlx_gather_env_columns_f32(src.data_ptr(), idx_dev.data_ptr(), T, N, n_mb, width, mb[name].data_ptr(), _stream()),
-                                 "rlx_gather_env_columns_f32")
-                    for name, src in (("init_c", init_c), ("init_h", init_h)):
-                        nt.check(self.lib.rlx_gather_env_columns_f32(src.data_ptr(), idx_dev.data_ptr(), 1, N, n_mb, L, mb[name].data_ptr(), _stream()),
-                                 "rlx_gather_env_columns_f32")
-                    nt.check(self.lib.rlx_mean_popstd_f32(mb["advantages"].data_ptr(), T * n_mb, adv_stats.data_ptr(), stats_ws.data_ptr(), _stream()),
-                             "rlx_mean_popstd_f32")
-                    a = nt.LstmMinibatchArgs()
-                    a.dims, a.T, a.n_env = self.dims, T, n_mb
-                    for name in ("states", "actions", "log_probs", "advantages", "returns", "dones", "init_c", "init_h"):
-                        setattr(a, name, mb[name].data_ptr())
-                    a.adv_stats = adv_stats.data_ptr()
-                    a.policy_params, a.critic_params = self.policy_params.data_ptr(), self.critic_params.data_ptr()
-                    a.policy_grads, a.critic_grads = self.policy_grads.data_ptr(), self.critic_grads.data_ptr()
-                    a.clip_range, a.entropy_coef, a.critic_coef = float(self.clip_range), float(self.entropy_coef), float(self.critic_coef)
-                    a.metrics, a.workspace, a.workspace_bytes = metrics_dev[k].data_ptr(), ws_mb.data_ptr(), ws_mb_bytes
-                    nt.check(self.lib.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), _stream()), "rlx_lstm_ppo_minibatch_fwdbwd_f32")
                     lr_used = self.current_learning_rate()
                     self.lr_dev.fill_(lr_used)
-                    for params, grads, mu, nu, step, col in ((self.policy_params, self.policy_grads, self.policy_mu, self.policy_nu, self.policy_step, 0),
-                                                             (self.critic_params, self.critic_grads, self.critic_mu, self.critic_nu, self.critic_step, 1)):
-                        nt.check(self.lib.rlx_optax_clip_adam_f32(params.data_ptr(), grads.data_ptr(), mu.data_ptr(), nu.data_ptr(), params.numel(),
-                                                                  self.lr_dev.data_ptr(), step.data_ptr(), float(self.max_grad_norm), 0.9, 0.999, 1e-8,
-                                                                  norms_dev[k, col:].data_ptr(), opt_ws.data_ptr(), _stream()), "rlx_optax_clip_adam_f32")
+                    if not self.use_cuda_graph:
+                        minibatch_update(metrics_dev[k], norms_dev[k])
+                    else:
+                        # every launch of a minibatch update works on fixed buffers (the env indices and the learning rate are device-side
+                        # inputs written just above), so the ~400 launches are captured once and replayed: the recurrence is a chain of
+                        # small dependent kernels and eager launches leave the device idle between them
+                        if self._graph is None:
+                            minibatch_update(metrics_stage, norms_stage)   # the first update runs eagerly (it also warms every kernel up) ...
+                            self._graph = torch.cuda.CUDAGraph()
+                            before = int(self.lib.rlx_launch_count())
+                            with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):   # ... then recorded (recording executes nothing)
+                                minibatch_update(metrics_stage, norms_stage)
+                            self._graph_launches = int(self.lib.rlx_launch_count()) - before
+                        else:
+                            self._graph.replay()
+                            self.lib.rlx_add_launch_count(self._graph_launches)
+                        metrics_dev[k].copy_(metrics_stage)
+                        norms_dev[k].copy_(norms_stage)
                     self.opt_count += 1
                     k += 1
             m_host, n_host = metrics_dev.cpu().numpy(), norms_dev.cpu().numpy()  # the iteration's only device->host metric transfer

@@ -21,14 +21,19 @@ constexpr int kWgradRows = 1024;            // rows per split of the weight-grad
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------------------- layouts
-enum PSeg { WE1 = 0, BE1, G1, N1, WE2, BE2, G2, N2, WI, WH, BH, GL, NL, WT1, BT1, WT2, BT2, WM, BM, P_LOGSTD };
+enum PSeg { WE1 = 0, BE1, G1, N1, WE2, BE2, G2, N2, WI, WH, BH, GL, NL, WT1, BT1, WT2, BT2, WM, BM, P_LOGSTD, WF, BF };
 enum CSeg { WC1 = 0, BC1, WC2, BC2, WC3, BC3 };
+static inline bool is_film(const rlx_lstm_dims& d) { return (d.options & RLX_LSTM_OPT_FILM) != 0; }
+static inline bool is_shared(const rlx_lstm_dims& d) { return (d.options & RLX_LSTM_OPT_SHARED_ENCODER) != 0; }
 struct Layout {
   long long p[RLX_LSTM_POLICY_NSEG + 1], c[RLX_LSTM_CRITIC_NSEG + 1];
 };
 static Layout make_layout(const rlx_lstm_dims& d) {
   const long long O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim;
-  const long long ps[RLX_LSTM_POLICY_NSEG] = {O * E, E, E, E, O * E, E, E, E, E * 4 * L, L * 4 * L, 4 * L, L, L, (E + L) * H, H, H * H, H, H * A, A, A};
+  // options (policy.py:51-59): a shared encoder has no obs_encoder segments; FiLM adds [gamma | beta] dense blocks and narrows the torso input
+  const long long E2 = is_shared(d) ? 0 : E, TIW = is_film(d) ? E : E + L, F = is_film(d) ? 2 * E : 0;
+  const long long ps[RLX_LSTM_POLICY_NSEG] = {O * E, E, E, E, O * E2, E2, E2, E2, E * 4 * L, L * 4 * L, 4 * L, L, L, TIW * H, H, H * H, H, H * A, A, A,
+                                              L * F, F};
   const long long cs[RLX_LSTM_CRITIC_NSEG] = {O * H, H, H * H, H, H, 1};
   Layout l;
   long long o = 0;
@@ -40,13 +45,14 @@ static Layout make_layout(const rlx_lstm_dims& d) {
   return l;
 }
 static bool dims_ok(const rlx_lstm_dims& d) {
-  return d.obs_dim > 0 && d.act_dim > 0 && d.act_dim <= 64 && d.hidden > 0 && d.enc_dim > 0 && d.enc_dim <= 1024 && d.lstm_dim > 0 && d.lstm_dim <= 1024;
+  return d.obs_dim > 0 && d.act_dim > 0 && d.act_dim <= 64 && d.hidden > 0 && d.enc_dim > 0 && d.enc_dim <= 1024 && d.lstm_dim > 0 && d.lstm_dim <= 1024 &&
+         (d.options & ~(RLX_LSTM_OPT_FILM | RLX_LSTM_OPT_SHARED_ENCODER)) == 0;
 }
 
 // workspace carve-up (floats); R = T * n_env rows, time-major (row = t * n_env + e)
 struct Ws {
   size_t Z1, E1, Z2, TI, Gi, Gates, Call, Hall, Hm, Cm, T1, T2, C1, C2, Mean, V, dMean, dV, Terms, dLs, dT2, dT1, dTI, dHall, dG, dE1, dZ1, dZ2,
-      dC2, dC1, Gh, dHn, dCn, Small, Stats1, Stats2, StatsL, Part, Col, total;
+      dC2, dC1, Gh, dHn, dCn, Small, Stats1, Stats2, StatsL, Part, Col, WhT, E2, LL, GB, dGB, dOL, dLL, total;
 };
 static Ws plan(const rlx_lstm_dims& d, long long T, long long n) {
   const size_t R = (size_t)(T * n), O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim;
@@ -63,12 +69,16 @@ static Ws plan(const rlx_lstm_dims& d, long long T, long long n) {
   take(w.Stats1, R * 2); take(w.Stats2, R * 2); take(w.StatsL, R * 2);
   const size_t splits = (size_t)ceil_div((long long)R, kWgradRows);
   size_t biggest = 0;  // largest weight matrix: one partial of it per row split
-  for (size_t v : {(size_t)d.obs_dim * E, E * 4 * L, L * 4 * L, (E + L) * H, H * H, H * A, (size_t)d.obs_dim * H, H}) biggest = std::max(biggest, v);
+  for (size_t v : {(size_t)d.obs_dim * E, E * 4 * L, L * 4 * L, (E + L) * H, H * H, H * A, (size_t)d.obs_dim * H, H, L * 2 * E}) biggest = std::max(biggest, v);
   take(w.Part, splits * biggest);
   const size_t chunks = (size_t)ceil_div((long long)R, kColChunk);
   size_t widest = 8;   // widest column reduction; the LayerNorm parameter gradients keep two partial sets side by side
   for (size_t v : {H, 4 * L, 2 * E, 2 * L, A}) widest = std::max(widest, v);
   take(w.Col, chunks * widest);
+  take(w.WhT, 4 * L * L);  // recurrent kernel transposed, [4L, L]: coalesced reads in the fused BPTT step
+  const size_t film = is_film(d) ? 1 : 0;  // FiLM buffers (policy.py:102-105); zero-sized otherwise
+  take(w.E2, film * R * E); take(w.LL, film * R * L); take(w.GB, film * R * 2 * E); take(w.dGB, film * R * 2 * E); take(w.dOL, film * R * E);
+  take(w.dLL, film * R * L);
   w.total = o * sizeof(float);
   return w;
 }
@@ -138,14 +148,41 @@ __global__ void ln_param_partial_kernel(const float* __restrict__ dOut, int ldd,
   part_b[id] = sb;
 }
 
-// carry reset before step t: Hm = Hprev * keep, Cm = Cprev * keep, keep = 1 - done[t-1] (keep = 1 at t = 0).  thread = (env, unit)
-__global__ void lstm_mask_kernel(const float* __restrict__ Hprev, const float* __restrict__ Cprev, const float* __restrict__ done_prev,
-                                 long long n, int L, float* __restrict__ Hm, float* __restrict__ Cm) {
+// One launch per time step of forward_sequence (policy.py:127-146): carry reset, recurrent product and cell update fused.
+//   keep = 1 - done[t-1] (1 at t = 0);  hm = hprev * keep, cm = cprev * keep  (stored: the backward pass needs both)
+//   z_g = Gi_t[e, gL + j] + bh[gL + j] + sum_k hm[e, k] Wh[k, gL + j];  c = f cm + i g;  h = o tanh(c)
+// thread = (env, unit).  Hprev / Cprev are step t-1's rows of Hall / Call (or the initial carry), never the rows written here.
+__global__ void lstm_step_fwd_kernel(const float* __restrict__ Gi, const float* __restrict__ Wh, const float* __restrict__ bh,
+                                     const float* __restrict__ Hprev, const float* __restrict__ Cprev, const float* __restrict__ done_prev,
+                                     long long n, int L, float* __restrict__ Hm, float* __restrict__ Cm, float* __restrict__ gates,
+                                     float* __restrict__ C, float* __restrict__ Hh) {
   const long long id = gtid();
   if (id >= n * L) return;
-  const float keep = done_prev ? 1.f - done_prev[id / L] : 1.f;
-  Hm[id] = Hprev[id] * keep;
-  Cm[id] = Cprev[id] * keep;
+  const long long e = id / L;
+  const int j = (int)(id % L);
+  const long long base = e * 4 * L;
+  const float keep = done_prev ? 1.f - done_prev[e] : 1.f;
+  float zi = Gi[base + j] + bh[j], zf = Gi[base + L + j] + bh[L + j], zg = Gi[base + 2 * L + j] + bh[2 * L + j], zo = Gi[base + 3 * L + j] + bh[3 * L + j];
+  const float* hp = Hprev + e * L;
+  for (int k = 0; k < L; ++k) {
+    const float hk = hp[k] * keep;
+    const float* w = Wh + (long long)k * 4 * L + j;
+    zi = fmaf(hk, w[0], zi);
+    zf = fmaf(hk, w[L], zf);
+    zg = fmaf(hk, w[2 * L], zg);
+    zo = fmaf(hk, w[3 * L], zo);
+  }
+  const float cm = Cprev[id] * keep;
+  Hm[id] = hp[j] * keep;
+  Cm[id] = cm;
+  const float i = sigmoidf_(zi), f = sigmoidf_(zf), g = tanhf(zg), o = sigmoidf_(zo);
+  const float c = f * cm + i * g;
+  gates[base + j] = i;
+  gates[base + L + j] = f;
+  gates[base + 2 * L + j] = g;
+  gates[base + 3 * L + j] = o;
+  C[id] = c;
+  Hh[id] = o * tanhf(c);
 }
 
 // gates = act(Gi_t + Gh + bh), c = f * cm + i * g, h = o * tanh(c).  thread = (env, unit)
@@ -171,19 +208,35 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ Gi, const float* 
   Hh[id] = o * tanhf(c);
 }
 
-// BPTT step t.  dH = dHall_t + dHnext * keep_next, dC = dCnext (already masked) + dH o (1 - tanh(c)^2); writes the pre-activation gate
-// gradients dG_t and dCprev = (dC f) * keep_t (keep_t = 1 - done[t-1]).  dHnext is the GEMM output dG_{t+1} . Wh^T.  thread = (env, unit)
-__global__ void lstm_cell_bwd_kernel(const float* __restrict__ dHall, const float* __restrict__ dHnext, const float* __restrict__ keep_next_done,
-                                     const float* dCnext, const float* __restrict__ gates, const float* __restrict__ C,
-                                     const float* __restrict__ Cm, const float* __restrict__ done_prev, long long n, int L,
-                                     float* __restrict__ dG, float* dCprev) {  // dCnext and dCprev are the same buffer (element-wise in place)
+// out[c, r] = in[r, c]      thread = element of `in` [rows, cols]
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  const long long id = gtid();
+  if (id >= (long long)rows * cols) return;
+  const long long r = id / cols, c = id % cols;
+  out[c * rows + r] = in[id];
+}
+
+// One launch per BPTT step t: the product with the recurrent kernel and the cell backward fused.
+//   dHm_{t+1}[e, j] = sum_q dG_{t+1}[e, q] Wh[j, q]  (gradient wrt the MASKED carry of step t+1; WhT is Wh transposed, [4L, L])
+//   dH = dHall_t + dHm_{t+1} (1 - done[t]);  dC = dCnext (already masked) + dH o (1 - tanh(c)^2)
+//   writes the pre-activation gate gradients dG_t and dCprev = (dC f) keep_t, keep_t = 1 - done[t-1].
+// thread = (env, unit).  dGnext (step t+1's rows) and dG (step t's rows) do not overlap; dCnext / dCprev are ONE buffer updated element-wise.
+__global__ void lstm_step_bwd_kernel(const float* __restrict__ dHall, const float* __restrict__ dGnext, const float* __restrict__ WhT,
+                                     const float* __restrict__ done_t, const float* dCnext, const float* __restrict__ gates,
+                                     const float* __restrict__ C, const float* __restrict__ Cm, const float* __restrict__ done_prev, long long n,
+                                     int L, float* __restrict__ dG, float* dCprev) {
   const long long id = gtid();
   if (id >= n * L) return;
   const long long e = id / L;
   const int j = (int)(id % L);
   const long long base = e * 4 * L;
   float dH = dHall[id];
-  if (dHnext) dH += dHnext[id] * (1.f - keep_next_done[e]);
+  if (dGnext) {
+    const float* dg = dGnext + base;
+    float acc = 0.f;
+    for (int q = 0; q < 4 * L; ++q) acc = fmaf(dg[q], WhT[(long long)q * L + j], acc);
+    dH += acc * (1.f - done_t[e]);
+  }
   const float i = gates[base + j], f = gates[base + L + j], g = gates[base + 2 * L + j], o = gates[base + 3 * L + j];
   const float tc = tanhf(C[id]);
   const float dC = (dCnext ? dCnext[id] : 0.f) + dH * o * (1.f - tc * tc);
@@ -193,6 +246,37 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ dHall, const floa
   dG[base + 3 * L + j] = dH * tc * o * (1.f - o);
   const float keep = done_prev ? 1.f - done_prev[e] : 1.f;
   dCprev[id] = dC * f * keep;
+}
+
+// FiLM combination (policy.py:102-105): GB = [gamma | beta] ([R, 2W]); out = OL * gamma + beta.  thread = element
+__global__ void film_fwd_kernel(const float* __restrict__ OL, int ldo, const float* __restrict__ GB, long long R, int W, float* __restrict__ out) {
+  const long long id = gtid();
+  if (id >= R * W) return;
+  const long long r = id / W;
+  const int j = (int)(id % W);
+  out[id] = OL[r * ldo + j] * GB[r * 2 * W + j] + GB[r * 2 * W + W + j];
+}
+// dGB = [dOut * OL | dOut], dOL = dOut * gamma.  thread = element
+__global__ void film_bwd_kernel(const float* __restrict__ dOut, const float* __restrict__ OL, int ldo, const float* __restrict__ GB, long long R, int W,
+                                float* __restrict__ dGB, float* __restrict__ dOL) {
+  const long long id = gtid();
+  if (id >= R * W) return;
+  const long long r = id / W;
+  const int j = (int)(id % W);
+  const float d = dOut[id];
+  dGB[r * 2 * W + j] = d * OL[r * ldo + j];
+  dGB[r * 2 * W + W + j] = d;
+  dOL[id] = d * GB[r * 2 * W + j];
+}
+// dst[r, j] = src[r, j] (ACC = false) or dst[r, j] += src[r, j] (ACC = true) over an [R, W] block with row pitches.  thread = element
+template <bool ACC>
+__global__ void cols_kernel(const float* __restrict__ src, int lds, long long R, int W, float* __restrict__ dst, int ldd) {
+  const long long id = gtid();
+  if (id >= R * W) return;
+  const long long r = id / W;
+  const int j = (int)(id % W);
+  if (ACC) dst[r * ldd + j] += src[r * lds + j];
+  else dst[r * ldd + j] = src[r * lds + j];
 }
 
 // per-row loss terms and the gradients wrt the head outputs.  terms[r] = (pg, 0.5 (v - R)^2, approx_kl, clipped?)   thread = row
@@ -404,29 +488,45 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
         *Hall = ws + w.Hall, *Hm = ws + w.Hm, *Cm = ws + w.Cm, *T1 = ws + w.T1, *T2 = ws + w.T2, *C1 = ws + w.C1, *C2 = ws + w.C2,
         *Mean = ws + w.Mean, *V = ws + w.V, *dMean = ws + w.dMean, *dV = ws + w.dV, *Terms = ws + w.Terms, *dLs = ws + w.dLs, *dT2 = ws + w.dT2,
         *dT1 = ws + w.dT1, *dTI = ws + w.dTI, *dHall = ws + w.dHall, *dG = ws + w.dG, *dE1 = ws + w.dE1, *dZ1 = ws + w.dZ1, *dZ2 = ws + w.dZ2,
-        *dC2 = ws + w.dC2, *dC1 = ws + w.dC1, *Gh = ws + w.Gh, *dHn = ws + w.dHn, *dCn = ws + w.dCn, *Small = ws + w.Small, *S1 = ws + w.Stats1,
-        *S2 = ws + w.Stats2, *SL = ws + w.StatsL, *Part = ws + w.Part, *Col = ws + w.Col;
+        *dC2 = ws + w.dC2, *dC1 = ws + w.dC1, *dCn = ws + w.dCn, *Small = ws + w.Small, *S1 = ws + w.Stats1, *S2 = ws + w.Stats2,
+        *SL = ws + w.StatsL, *Part = ws + w.Part, *Col = ws + w.Col, *WhT = ws + w.WhT;
+  // Options (policy.py:51-59, 99-125).  Where the pieces of the decoder input live:
+  //   obs latent OL: own encoder -> left E columns of TI (concat) or the E2 buffer (FiLM); shared encoder -> E1 (the LSTM's input latent)
+  //   lstm latent LLp = tanh(LN(h)): right L columns of TI (concat) or the LL buffer (FiLM)
+  //   torso input TI: [OL | LLp] (concat, width E + L) or OL * gamma + beta (FiLM, width E)
+  const bool film = is_film(d), shared = is_shared(d);
+  const int TIW = film ? E : EL;
+  float* OL = shared ? E1 : (film ? ws + w.E2 : TI);
+  const int ldOL = (shared || film) ? E : EL;
+  float* LLp = film ? ws + w.LL : TI + E;
+  const int ldLL = film ? L : EL;
 
   // ================================================================ forward
-  // encoders (policy.py:79-92): Z = X We + be; E = tanh(LN(Z)).  E2 lands in the left E columns of the torso input TI.
+  // encoders (policy.py:79-92): Z = X We + be; E = tanh(LN(Z))
   LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE1], O, E, P + l.p[BE1], Z1, E, R, st));
   LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z1, E, R, E, P + l.p[G1], P + l.p[N1], E1, E, S1);
-  LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, R, st));
-  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z2, E, R, E, P + l.p[G2], P + l.p[N2], TI, EL, S2);
-  // input-side gate pre-activations of all steps at once, then the recurrence (policy.py:115-146)
+  if (!shared) {
+    LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, R, st));
+    LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z2, E, R, E, P + l.p[G2], P + l.p[N2], OL, ldOL, S2);
+  } else if (!film) {
+    LSTM_LAUNCH(cols_kernel<false>, R * E, st, E1, E, R, E, TI, EL);
+  }
+  // input-side gate pre-activations of all steps at once, then the recurrence, one launch per step (policy.py:115-146)
   LSTM_TRY(dense_fwd<EPI_NONE>(E1, E, P + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, R, st));
   for (long long t = 0; t < T; ++t) {
     const float* hprev = t == 0 ? a->init_h : Hall + (t - 1) * n * L;
     const float* cprev = t == 0 ? a->init_c : Call + (t - 1) * n * L;
     const float* done_prev = t == 0 ? nullptr : a->dones + (t - 1) * n;
-    LSTM_LAUNCH(lstm_mask_kernel, n * L, st, hprev, cprev, done_prev, n, L, Hm + t * n * L, Cm + t * n * L);
-    LSTM_TRY(dense_fwd<EPI_NONE>(Hm + t * n * L, L, P + l.p[WH], L, 4 * L, nullptr, Gh, 4 * L, n, st));
-    LSTM_LAUNCH(lstm_cell_fwd_kernel, n * L, st, Gi + t * n * 4 * L, Gh, P + l.p[BH], Cm + t * n * L, n, L, Gates + t * n * 4 * L, Call + t * n * L,
-                Hall + t * n * L);
+    LSTM_LAUNCH(lstm_step_fwd_kernel, n * L, st, Gi + t * n * 4 * L, P + l.p[WH], P + l.p[BH], hprev, cprev, done_prev, n, L, Hm + t * n * L,
+                Cm + t * n * L, Gates + t * n * 4 * L, Call + t * n * L, Hall + t * n * L);
   }
-  // decode (policy.py:95-112): lstm latent = tanh(LN(h)) into the right L columns of TI; torso; mean head
-  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Hall, L, R, L, P + l.p[GL], P + l.p[NL], TI + E, EL, SL);
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, EL, P + l.p[WT1], EL, H, P + l.p[BT1], T1, H, R, st));
+  // decode (policy.py:95-112): lstm latent = tanh(LN(h)); combination; torso; mean head
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Hall, L, R, L, P + l.p[GL], P + l.p[NL], LLp, ldLL, SL);
+  if (film) {
+    LSTM_TRY(dense_fwd<EPI_BIAS>(LLp, L, P + l.p[WF], L, 2 * E, P + l.p[BF], ws + w.GB, 2 * E, R, st));
+    LSTM_LAUNCH(film_fwd_kernel, R * E, st, OL, ldOL, ws + w.GB, R, E, TI);
+  }
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, TIW, P + l.p[WT1], TIW, H, P + l.p[BT1], T1, H, R, st));
   LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(T1, H, P + l.p[WT2], H, H, P + l.p[BT2], T2, H, R, st));
   LSTM_TRY(dense_fwd<EPI_BIAS>(T2, H, P + l.p[WM], H, A, P + l.p[BM], Mean, A, R, st));
   // critic (critic.py:22-30)
@@ -450,30 +550,47 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   LSTM_TRY(dense_bwd_weight(T1, H, dT2, H, H, H, R, Part, gP + l.p[WT2], st));
   LSTM_TRY(colsum(dT2, H, R, H, Col, 1.f, 0.f, gP + l.p[BT2], st));
   LSTM_TRY(dense_bwd_input<EPI_DTANH>(dT2, H, P + l.p[WT2], H, H, T1, H, dT1, H, R, st));
-  LSTM_TRY(dense_bwd_weight(TI, EL, dT1, H, EL, H, R, Part, gP + l.p[WT1], st));
+  LSTM_TRY(dense_bwd_weight(TI, TIW, dT1, H, TIW, H, R, Part, gP + l.p[WT1], st));
   LSTM_TRY(colsum(dT1, H, R, H, Col, 1.f, 0.f, gP + l.p[BT1], st));
-  LSTM_TRY(dense_bwd_input<EPI_NONE>(dT1, H, P + l.p[WT1], EL, H, nullptr, 0, dTI, EL, R, st));     // [dE2 | dLstmLatent]
+  LSTM_TRY(dense_bwd_input<EPI_NONE>(dT1, H, P + l.p[WT1], TIW, H, nullptr, 0, dTI, TIW, R, st));   // concat: [dOL | dLL]; FiLM: d(OL * gamma + beta)
+  // gradients wrt the two latents
+  const float* dOL = dTI;
+  int lddOL = EL;
+  const float* dLL = dTI + E;
+  int lddLL = EL;
+  if (film) {
+    float *GB = ws + w.GB, *dGB = ws + w.dGB;
+    LSTM_LAUNCH(film_bwd_kernel, R * E, st, dTI, OL, ldOL, GB, R, E, dGB, ws + w.dOL);
+    LSTM_TRY(dense_bwd_weight(LLp, L, dGB, 2 * E, L, 2 * E, R, Part, gP + l.p[WF], st));
+    LSTM_TRY(colsum(dGB, 2 * E, R, 2 * E, Col, 1.f, 0.f, gP + l.p[BF], st));
+    LSTM_TRY(dense_bwd_input<EPI_NONE>(dGB, 2 * E, P + l.p[WF], L, 2 * E, nullptr, 0, ws + w.dLL, L, R, st));
+    dOL = ws + w.dOL; lddOL = E;
+    dLL = ws + w.dLL; lddLL = L;
+  }
   // lstm_ln (+ tanh) backward -> dHall
-  LSTM_TRY(ln_param_grads(dTI + E, EL, TI + E, EL, Hall, L, R, L, SL, Col, gP + l.p[GL], gP + l.p[NL], st));
-  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dTI + E, EL, TI + E, EL, Hall, L, R, L, P + l.p[GL], SL, dHall, L);
-  // obs_encoder backward
-  LSTM_TRY(ln_param_grads(dTI, EL, TI, EL, Z2, E, R, E, S2, Col, gP + l.p[G2], gP + l.p[N2], st));
-  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dTI, EL, TI, EL, Z2, E, R, E, P + l.p[G2], S2, dZ2, E);
-  LSTM_TRY(dense_bwd_weight(X, O, dZ2, E, O, E, R, Part, gP + l.p[WE2], st));
-  LSTM_TRY(colsum(dZ2, E, R, E, Col, 1.f, 0.f, gP + l.p[BE2], st));
+  LSTM_TRY(ln_param_grads(dLL, lddLL, LLp, ldLL, Hall, L, R, L, SL, Col, gP + l.p[GL], gP + l.p[NL], st));
+  LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dLL, lddLL, LLp, ldLL, Hall, L, R, L, P + l.p[GL], SL, dHall, L);
+  // obs_encoder backward (a shared encoder receives dOL together with the LSTM's input gradient below)
+  if (!shared) {
+    LSTM_TRY(ln_param_grads(dOL, lddOL, OL, ldOL, Z2, E, R, E, S2, Col, gP + l.p[G2], gP + l.p[N2], st));
+    LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dOL, lddOL, OL, ldOL, Z2, E, R, E, P + l.p[G2], S2, dZ2, E);
+    LSTM_TRY(dense_bwd_weight(X, O, dZ2, E, O, E, R, Part, gP + l.p[WE2], st));
+    LSTM_TRY(colsum(dZ2, E, R, E, Col, 1.f, 0.f, gP + l.p[BE2], st));
+  }
 
-  // ================================================================ back-propagation through time
+  // ================================================================ back-propagation through time, one launch per step
+  LSTM_LAUNCH(transpose_kernel, (long long)L * 4 * L, st, P + l.p[WH], L, 4 * L, WhT);
   for (long long t = T - 1; t >= 0; --t) {
     const bool last = (t == T - 1);
-    // dHn holds dG_{t+1} . Wh^T (gradient wrt the MASKED carry of step t+1); its mask is done[t]
-    LSTM_LAUNCH(lstm_cell_bwd_kernel, n * L, st, dHall + t * n * L, last ? nullptr : dHn, last ? nullptr : a->dones + t * n, last ? nullptr : dCn,
-                Gates + t * n * 4 * L, Call + t * n * L, Cm + t * n * L, t == 0 ? nullptr : a->dones + (t - 1) * n, n, L, dG + t * n * 4 * L, dCn);
-    if (t > 0) LSTM_TRY(dense_bwd_input<EPI_NONE>(dG + t * n * 4 * L, 4 * L, P + l.p[WH], L, 4 * L, nullptr, 0, dHn, L, n, st));
+    LSTM_LAUNCH(lstm_step_bwd_kernel, n * L, st, dHall + t * n * L, last ? nullptr : dG + (t + 1) * n * 4 * L, WhT, last ? nullptr : a->dones + t * n,
+                last ? nullptr : dCn, Gates + t * n * 4 * L, Call + t * n * L, Cm + t * n * L, t == 0 ? nullptr : a->dones + (t - 1) * n, n, L,
+                dG + t * n * 4 * L, dCn);
   }
   LSTM_TRY(dense_bwd_weight(Hm, L, dG, 4 * L, L, 4 * L, R, Part, gP + l.p[WH], st));
   LSTM_TRY(colsum(dG, 4 * L, R, 4 * L, Col, 1.f, 0.f, gP + l.p[BH], st));
   LSTM_TRY(dense_bwd_weight(E1, E, dG, 4 * L, E, 4 * L, R, Part, gP + l.p[WI], st));
   LSTM_TRY(dense_bwd_input<EPI_NONE>(dG, 4 * L, P + l.p[WI], E, 4 * L, nullptr, 0, dE1, E, R, st));
+  if (shared) LSTM_LAUNCH(cols_kernel<true>, R * E, st, dOL, lddOL, R, E, dE1, E);
   // lstm_obs_encoder backward
   LSTM_TRY(ln_param_grads(dE1, E, E1, E, Z1, E, R, E, S1, Col, gP + l.p[G1], gP + l.p[N1], st));
   LSTM_LAUNCH(ln_tanh_bwd_kernel, R, st, dE1, E, E1, E, Z1, E, R, E, P + l.p[G1], S1, dZ1, E);
@@ -499,15 +616,29 @@ static int policy_one_step(const rlx_lstm_dims& d, const Layout& l, const Ws& w,
   const int O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim, EL = E + L;
   float *Z1 = ws + w.Z1, *E1 = ws + w.E1, *Z2 = ws + w.Z2, *TI = ws + w.TI, *Gi = ws + w.Gi, *Gates = ws + w.Gates, *Gh = ws + w.Gh, *T1 = ws + w.T1,
         *T2 = ws + w.T2, *Mean = ws + w.Mean, *S1 = ws + w.Stats1, *S2 = ws + w.Stats2, *SL = ws + w.StatsL;
+  const bool film = is_film(d), shared = is_shared(d);  // same placement of the latents as in rlx_lstm_ppo_minibatch_fwdbwd_f32
+  const int TIW = film ? E : EL;
+  float* OL = shared ? E1 : (film ? ws + w.E2 : TI);
+  const int ldOL = (shared || film) ? E : EL;
+  float* LLp = film ? ws + w.LL : TI + E;
+  const int ldLL = film ? L : EL;
   LSTM_TRY(dense_fwd<EPI_BIAS>(obs, O, P + l.p[WE1], O, E, P + l.p[BE1], Z1, E, n, st));
   LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, Z1, E, n, E, P + l.p[G1], P + l.p[N1], E1, E, S1);
-  LSTM_TRY(dense_fwd<EPI_BIAS>(obs, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, n, st));
-  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, Z2, E, n, E, P + l.p[G2], P + l.p[N2], TI, EL, S2);
+  if (!shared) {
+    LSTM_TRY(dense_fwd<EPI_BIAS>(obs, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, n, st));
+    LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, Z2, E, n, E, P + l.p[G2], P + l.p[N2], OL, ldOL, S2);
+  } else if (!film) {
+    LSTM_LAUNCH(cols_kernel<false>, n * E, st, E1, E, n, E, TI, EL);
+  }
   LSTM_TRY(dense_fwd<EPI_NONE>(E1, E, P + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, n, st));
   LSTM_TRY(dense_fwd<EPI_NONE>(h, L, P + l.p[WH], L, 4 * L, nullptr, Gh, 4 * L, n, st));
   LSTM_LAUNCH(lstm_cell_fwd_kernel, n * L, st, Gi, Gh, P + l.p[BH], c, n, L, Gates, c, h);  // element-wise in place: thread (e, j) reads and writes c[e, j] only
-  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, h, L, n, L, P + l.p[GL], P + l.p[NL], TI + E, EL, SL);
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, EL, P + l.p[WT1], EL, H, P + l.p[BT1], T1, H, n, st));
+  LSTM_LAUNCH(ln_tanh_fwd_kernel, n, st, h, L, n, L, P + l.p[GL], P + l.p[NL], LLp, ldLL, SL);
+  if (film) {
+    LSTM_TRY(dense_fwd<EPI_BIAS>(LLp, L, P + l.p[WF], L, 2 * E, P + l.p[BF], ws + w.GB, 2 * E, n, st));
+    LSTM_LAUNCH(film_fwd_kernel, n * E, st, OL, ldOL, ws + w.GB, n, E, TI);
+  }
+  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, TIW, P + l.p[WT1], TIW, H, P + l.p[BT1], T1, H, n, st));
   LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(T1, H, P + l.p[WT2], H, H, P + l.p[BT2], T2, H, n, st));
   LSTM_TRY(dense_fwd<EPI_BIAS>(T2, H, P + l.p[WM], H, A, P + l.p[BM], Mean, A, n, st));
   return RLX_OK;

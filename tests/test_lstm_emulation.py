@@ -17,7 +17,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class Dims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim")]
+    _fields_ = [(n, C.c_int32) for n in ("obs_dim", "act_dim", "hidden", "enc_dim", "lstm_dim", "options")]
+
+
+OPT_FILM, OPT_SHARED = 1, 2   # RLX_LSTM_OPT_* (include/rlx_b200.h)
 
 
 class Args(C.Structure):
@@ -42,7 +45,7 @@ def emu(tmp_path_factory):
 POLICY_SEGS = ["lstm_obs_encoder_dense.kernel", "lstm_obs_encoder_dense.bias", "lstm_obs_encoder_ln.scale", "lstm_obs_encoder_ln.bias",
                "obs_encoder_dense.kernel", "obs_encoder_dense.bias", "obs_encoder_ln.scale", "obs_encoder_ln.bias", "Wi", "Wh", "bh",
                "lstm_ln.scale", "lstm_ln.bias", "torso_dense1.kernel", "torso_dense1.bias", "torso_dense2.kernel", "torso_dense2.bias",
-               "mean_head.kernel", "mean_head.bias", "policy_logstd"]
+               "mean_head.kernel", "mean_head.bias", "policy_logstd", "Wf", "bf"]
 CRITIC_SEGS = ["Dense_0.kernel", "Dense_0.bias", "Dense_1.kernel", "Dense_1.bias", "Dense_2.kernel", "Dense_2.bias"]
 
 
@@ -62,6 +65,11 @@ def flatten_policy(pol):
             parts.append(torch.cat([pol["lstm"]["h" + k]["kernel"] for k in L.GATES], dim=1))
         elif name == "bh":
             parts.append(torch.cat([pol["lstm"]["h" + k]["bias"] for k in L.GATES]))
+        elif name in ("Wf", "bf"):   # FiLM blocks gamma | beta side by side; empty for "concat"
+            leaf = "kernel" if name == "Wf" else "bias"
+            parts.append(torch.cat([pol["lstm_film_gamma"][leaf], pol["lstm_film_beta"][leaf]], dim=-1) if "lstm_film_gamma" in pol else torch.zeros(0))
+        elif name.startswith("obs_encoder") and "obs_encoder_dense" not in pol:
+            parts.append(torch.zeros(0))   # shared encoder: no obs_encoder segments
         else:
             parts.append(_get(pol, name))
     return [p.detach().reshape(-1) for p in parts]
@@ -75,10 +83,12 @@ def _np(t):
     return np.ascontiguousarray(t.detach().numpy(), dtype=np.float32)
 
 
+@pytest.mark.parametrize("options", [0, OPT_FILM, OPT_SHARED, OPT_FILM | OPT_SHARED])
 @pytest.mark.parametrize("T,n,obs,act,hid,enc,lstm", [(7, 5, 6, 2, 12, 8, 4), (5, 3, 9, 3, 16, 12, 8), (33, 40, 5, 2, 8, 8, 4)])
-def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, enc, lstm):
+def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, enc, lstm, options):
     torch.manual_seed(T * 100 + n)
-    pol, cri = L.init_params(obs, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.8, seed=T)
+    pol, cri = L.init_params(obs, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.8, seed=T, share_encoder=bool(options & OPT_SHARED),
+                             combine="film" if options & OPT_FILM else "concat")
     # non-trivial LayerNorm parameters and biases so that every gradient path is exercised
     for tree in (pol, cri):
         for name, v in L.tree_leaves(tree):
@@ -105,14 +115,18 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
             return torch.cat([gp_tree[f"lstm.h{k}.kernel"] for k in L.GATES], dim=1)
         if name == "bh":
             return torch.cat([gp_tree[f"lstm.h{k}.bias"] for k in L.GATES])
-        return gp_tree[name]
+        if name in ("Wf", "bf"):
+            leaf = "kernel" if name == "Wf" else "bias"
+            return (torch.cat([gp_tree[f"lstm_film_gamma.{leaf}"], gp_tree[f"lstm_film_beta.{leaf}"]], dim=-1) if options & OPT_FILM
+                    else torch.zeros(0))
+        return gp_tree.get(name, torch.zeros(0))   # obs_encoder.* are absent with a shared encoder
 
-    d = Dims(obs, act, hid, enc, lstm)
+    d = Dims(obs, act, hid, enc, lstm, options)
     P = np.concatenate([_np(x) for x in flatten_policy(pol)])
     Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
-    poff, coff = (C.c_int64 * 21)(), (C.c_int64 * 7)()
+    poff, coff = (C.c_int64 * (len(POLICY_SEGS) + 1))(), (C.c_int64 * 7)()
     assert emu.rlx_lstm_param_layout(C.byref(d), poff, coff) == 0
-    assert poff[20] == P.size and coff[6] == Cc.size
+    assert poff[len(POLICY_SEGS)] == P.size and coff[6] == Cc.size
     gP, gC = np.full_like(P, np.nan), np.full_like(Cc, np.nan)
     stats = np.array([float(adv.mean()), float(adv.std(unbiased=False))], dtype=np.float32)
     metrics = np.zeros(8, np.float32)
@@ -178,17 +192,19 @@ class StepArgs(C.Structure):
                 [(k, C.c_void_p) for k in ("action", "env_action", "logp", "value", "workspace")] + [("workspace_bytes", C.c_size_t)])
 
 
-def test_emulated_rollout_step_matches_oracle(emu):
+@pytest.mark.parametrize("options", [0, OPT_FILM, OPT_SHARED, OPT_FILM | OPT_SHARED])
+def test_emulated_rollout_step_matches_oracle(emu, options):
     """rlx_lstm_step_f32 == get_action_and_value (ppo_lstm.py:107-118) over a few consecutive steps with the carry threaded through and
     reset by rlx_lstm_mask_carry_f32; plus the critic-only forward and the population-std helper."""
     obs_d, act, hid, enc, lstm, n = 7, 3, 16, 12, 8, 6
     torch.manual_seed(4)
-    pol, cri = L.init_params(obs_d, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.6, seed=9)
+    pol, cri = L.init_params(obs_d, act, hidden=hid, enc=enc, lstm=lstm, std_dev=0.6, seed=9, share_encoder=bool(options & OPT_SHARED),
+                             combine="film" if options & OPT_FILM else "concat")
     for tree in (pol, cri):
         for name, v in L.tree_leaves(tree):
             if name.endswith("bias") or name.endswith("scale"):
                 v.add_(0.1 * torch.randn_like(v))
-    d = Dims(obs_d, act, hid, enc, lstm)
+    d = Dims(obs_d, act, hid, enc, lstm, options)
     P = np.concatenate([_np(x) for x in flatten_policy(pol)])
     Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
     low, high = np.full(act, -2.0, np.float32), np.full(act, 0.5, np.float32)
@@ -261,7 +277,17 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
     real = nt.load()
 
     class Lib:
+        """The emulation build behind the plugin's `self.lib`, plus a stand-in for CUDA-graph capture: while `capturing`, calls are
+        recorded instead of executed (as stream capture does), and FakeGraph.replay() issues the recorded calls."""
+        capturing, recorded, launches = False, None, 0
+
         def __getattr__(self, name):
+            if name == "rlx_launch_count":
+                return lambda: Lib.launches
+            if name == "rlx_add_launch_count":
+                def add(n):
+                    Lib.launches += int(n)
+                return add
             if name == "rlx_gae_f32":
                 def gae(r, term, v, nv, last, T, N, gamma, lam, adv, ret, stream):
                     t = lambda ptr: torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(T, N)))
@@ -272,7 +298,37 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
                 return gae
             f = getattr(emu, name)
             f.argtypes, f.restype = getattr(real, name).argtypes, getattr(real, name).restype
-            return f
+
+            def call(*args):
+                Lib.launches += 1
+                if Lib.capturing:
+                    Lib.recorded.append((f, args))
+                    return 0
+                return f(*args)
+            return call
+
+    class FakeGraph:
+        def replay(self):
+            for f, args in self.calls:
+                assert f(*args) == 0
+
+    class FakeGraphContext:
+        def __init__(self, g, capture_error_mode="global"):
+            self.g = g
+
+        def __enter__(self):
+            Lib.capturing, Lib.recorded = True, []
+
+        def __exit__(self, *exc):
+            Lib.capturing, self.g.calls = False, Lib.recorded
+
+    class TorchWithFakeGraphs:
+        """`torch` as the plugin module sees it on this CPU-only box: everything real except torch.cuda.CUDAGraph / torch.cuda.graph."""
+        class cuda:
+            CUDAGraph, graph = FakeGraph, FakeGraphContext
+
+        def __getattr__(self, name):
+            return getattr(torch, name)
 
     path = os.path.join(ROOT, "rl_x_b200", "algorithms", "ppo_lstm", "b200", "ppo_lstm.py")
     src = open(path).read()
@@ -284,6 +340,7 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
     mod = types.ModuleType("ppo_lstm_emulated")
     mod.LIB = Lib()
     exec(compile(src, "ppo_lstm_emulated", "exec"), mod.__dict__)
+    mod.torch = TorchWithFakeGraphs()
     N, T, obs, act = 8, 16, 12, 3
 
     class Sp:
@@ -291,7 +348,9 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
             self.shape, self.low, self.high = shape, low, high
 
     results = {}
-    for iface in ("TORCH", "NUMPY"):
+    for iface, combine, share, graph in (("TORCH", "concat", False, False), ("NUMPY", "concat", False, False), ("TORCH", "film", False, False),
+                                         ("TORCH", "concat", True, False), ("NUMPY", "film", True, False), ("TORCH", "concat", False, True),
+                                         ("NUMPY", "film", True, True)):
         class P:
             observation_space_type, action_space_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS
             data_interface_type = getattr(DataInterfaceType, iface)
@@ -332,6 +391,7 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
         a.nr_steps, a.minibatch_size, a.nr_epochs, a.total_timesteps = T, 4 * T, 2, 3 * N * T
         a.nr_hidden_units, a.obs_encoding_dim, a.lstm_hidden_dim, a.learning_rate, a.anneal_learning_rate = 32, 16, 8, 1e-3, True
         a.evaluation_frequency, a.evaluation_episodes = N * T, 2
+        a.lstm_obs_combine_method, a.share_lstm_obs_encoder, a.use_cuda_graph = combine, share, graph
         cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=5, nr_envs=N),
                          runner=ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False, load_model=""))
         env = Env()
@@ -350,8 +410,17 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
         np.testing.assert_allclose([v for nme, v in logged if nme == "lr/learning_rate"], [1e-3, 1e-3 * 2 / 3, 1e-3 / 3], rtol=1e-6)
         assert [v for nme, v in logged if nme == "steps/nr_updates"] == [4.0, 8.0, 12.0]
         assert float((model.policy_params - before).abs().max()) > 1e-4
-        results[iface] = [v for nme, v in logged if nme == "loss/critic_loss"]
-    assert results["TORCH"] == results["NUMPY"]  # the two data interfaces drive the same computation
+        results[(iface, combine, share, graph)] = ([(nme, v) for nme, v in logged if nme.split("/")[0] in ("loss", "gradients", "policy_ratio", "lr")],
+                                                   model.policy_params.clone(), model.critic_params.clone())
+        assert (model._graph is not None) == graph and (not graph or len(model._graph.calls) == 12)   # 8 gathers, stats, fwd+bwd, 2 x Adam
+        pol_named, _ = model.named_parameters()
+        assert pol_named["Wf"].numel() == (8 * 2 * 16 if combine == "film" else 0) and pol_named["We2"].numel() == (0 if share else obs * 16)
+    # the two data interfaces drive the same computation
+    assert results[("TORCH", "concat", False, False)][0] == results[("NUMPY", "concat", False, False)][0]
+    # the captured-and-replayed update (use_cuda_graph) issues the same calls on the same buffers as the eager loop: identical numbers
+    for key in (("TORCH", "concat", False), ("NUMPY", "film", True)):
+        eager, replayed = results[key + (False,)], results[key + (True,)]
+        assert eager[0] == replayed[0] and torch.equal(eager[1], replayed[1]) and torch.equal(eager[2], replayed[2])
 
 
 def test_emulated_nstep_replay_matches_reference_golden(tmp_path):
