@@ -390,8 +390,7 @@ def run_fastsac(args):
     """FastSAC at the reference's default update shape: batch 8192, 4 critic updates per policy update, 2 policy updates per
     environment step (rl_x/algorithms/fastsac/pytorch/default_config.py), 1024 x 4096 ring, synthetic Box(48) / Box(12).  One "step" =
     what the reference does after one vector-env step: sample 8 x 8192 rows (n-step gather), normalise states and next states (updating
-    the running statistics), 8 critic + entropy updates with polyak, 2 policy updates.  value = critic updates/s.
-    (Written for the first hardware run of this path; not yet executed on a GPU.)"""
+    the running statistics), 8 critic + entropy updates with polyak, 2 policy updates.  value = critic updates/s."""
     from rl_x_b200 import _native as nt
     from rl_x_b200.config_dict import ConfigDict
     from rl_x_b200.algorithms.fastsac.b200.default_config import get_config

@@ -392,7 +392,7 @@ int rlx_gather_env_columns_f32(const float* src, const int64_t* env_idx, int64_t
 /* -------------------------------------------------------------------------------------------- FastSAC update -- */
 /* SURVEY.md §8 f4 (second half): rl_x/algorithms/fastsac/pytorch, fp32 path.  STATUS: written
  * without GPU access; numerics checked by running these sources in a host emulation build against oracle/fastsac_oracle.py, which
- * is pinned to the executed reference (tests/test_fastsac_emulation.py); first hardware run pending.
+ * is pinned to the executed reference (tests/test_fastsac_emulation.py); on hardware since the round-1 driver run (tests/test_gpu_zzzz_fastsac.py).
  * Networks (fixed widths like the reference): policy Linear-LayerNorm-SiLU x3 (512, 256, 128) + mean / log_std heads (policy.py:36-48);
  * Q network Linear-LayerNorm-SiLU x3 (768, 384, 192) + nr_atoms logits on [state | action] (q_network.py:24-35).
  * Flat parameter layouts, torch [out, in] weights in state_dict order:

@@ -8,7 +8,7 @@ Host side: Python/PyTorch for device memory and the TORCH-interface environment;
                  policy_loss_fn (fastsac.py:106-138)                                             rlx_fastsac_policy_update_f32
 
 Parameters are initialised exactly like the reference (the same torch modules built in the same order under torch.manual_seed(seed),
-fastsac.py:77-84) and live in the library's flat layout; action noise is torch.randn on the device.  Not built: bf16 autocast.  STATUS: first hardware run pending (numerics validated in host emulation, tests/test_fastsac_emulation.py).
+fastsac.py:77-84) and live in the library's flat layout; action noise is torch.randn on the device.  Not built: bf16 autocast.  STATUS: on hardware since round 1 (tests/test_gpu_zzzz_fastsac.py); the same sources are checked in host emulation (tests/test_fastsac_emulation.py).
 """
 import ctypes as C
 import logging

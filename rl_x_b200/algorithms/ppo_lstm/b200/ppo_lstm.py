@@ -11,7 +11,7 @@ C-ABI library (include/rlx_b200.h, "PPO + LSTM path"):
 Differences that follow from the missing JAX runtime (all explicit): parameters are initialised with the same initialiser families
 from a torch generator (not jax.random), the action noise is torch.randn on the device, and the per-epoch env permutations come from
 the library's PCG64 stream — so runs are not seed-for-seed comparable with the reference; checkpoints are torch files with named
-tensors instead of Orbax trees.  STATUS: first hardware run pending (numerics validated in host emulation, see tests/test_lstm_emulation.py).
+tensors instead of Orbax trees.  STATUS: on hardware since round 1 (tests/test_gpu_zzz_ppo_lstm.py); the same sources are checked in host emulation (tests/test_lstm_emulation.py).
 """
 import ctypes as C
 import logging
