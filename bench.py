@@ -519,7 +519,6 @@ def run_ppo_lstm(args):
             graph_note = {"enabled": False, "check": "replayed update differs from eager launches: max |d| = %.3e" % float((pair[0][0] - pair[1][0]).abs().max())}
     except Exception as exc:  # a failed capture must not cost the workload its number
         graph_note = {"enabled": False, "check": f"capture failed: {type(exc).__name__}: {exc}"}
-        torch.cuda.synchronize()
     model = make(N, T, mb, E, W + K, graph_note["enabled"])
     lib = nt.load()
     stamps, launches = [], []
