@@ -21,6 +21,7 @@ import torch
 
 from rl_x_b200 import _native as nt
 from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer
+from rl_x_b200.environments.types import require_identity_observation_indices
 
 rlx_logger = logging.getLogger("rl_x")
 POLICY_WIDTHS, Q_WIDTHS = (512, 256, 128), (768, 384, 192)
@@ -96,6 +97,7 @@ class FastSAC:
             raise ValueError("The save frequency must be a multiple of the number of environments.")
         if a.get("bf16_mixed_precision_training", False):
             raise ValueError("rl_x_b200 FastSAC implements the reference's fp32 path; set algorithm.bf16_mixed_precision_training=False.")
+        require_identity_observation_indices(self.train_env, "FastSAC")  # policy.py:13 / q_network.py:10,42
         if a.device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("rl_x_b200 FastSAC needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device())

@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from rl_x_b200 import _native as nt
-from rl_x_b200.environments.types import DataInterfaceType, same_member
+from rl_x_b200.environments.types import DataInterfaceType, require_identity_observation_indices, same_member
 
 rlx_logger = logging.getLogger("rl_x")
 
@@ -108,6 +108,7 @@ class PPO_LSTM:
         if self.nr_minibatches < 1 or self.nr_minibatch_envs * self.nr_minibatches != self.nr_envs:
             # the reference reshapes nr_epochs permutations of arange(nr_envs) to (nr_epochs * nr_minibatches, nr_minibatch_envs), ppo_lstm.py:189-191
             raise ValueError("nr_envs must equal nr_minibatches * (minibatch_size // nr_steps)")
+        require_identity_observation_indices(self.train_env, "PPO_LSTM")  # policy.py:14,79,87 / critic.py
         if a.device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("rl_x_b200 PPO_LSTM needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device())

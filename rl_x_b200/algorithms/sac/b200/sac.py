@@ -19,7 +19,7 @@ import torch.nn as nn
 from rl_x_b200 import _native as nt
 from rl_x_b200.algorithms.sac.b200.general_properties import GeneralProperties
 from rl_x_b200.algorithms.sac.b200.replay_buffer import ReplayBuffer
-from rl_x_b200.environments.types import DataInterfaceType, same_member
+from rl_x_b200.environments.types import DataInterfaceType, require_identity_observation_indices, same_member
 
 rlx_logger = logging.getLogger("rl_x")
 
@@ -141,6 +141,7 @@ class SAC:
         self.logging_frequency, self.evaluation_frequency, self.evaluation_episodes = a.logging_frequency, a.evaluation_frequency, a.evaluation_episodes
         if a.get("bf16_mixed_precision_training", False):
             raise ValueError("rl_x_b200 SAC implements the reference's fp32 path; set algorithm.bf16_mixed_precision_training=False.")
+        require_identity_observation_indices(self.train_env, "SAC")  # policy.py:13,46 / q_network.py:10,37
         if a.device != "gpu" or not torch.cuda.is_available():
             raise RuntimeError("rl_x_b200 SAC needs a CUDA device (algorithm.device=gpu); there is no CPU fallback.")
         self.device = torch.device("cuda", torch.cuda.current_device())

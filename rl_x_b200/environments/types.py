@@ -28,6 +28,19 @@ class SimulationType(Enum):
     WARP = 4
 
 
+def require_identity_observation_indices(env, who):
+    """The reference's networks index-select their input with `env.policy_observation_indices` / `critic_observation_indices`
+    (ppo/pytorch/policy.py:14,62, critic.py:10,45; the same lines in sac, fastsac and ppo_lstm).  Every environment of the benchmark
+    configs leaves them at arange(obs_dim); this build's kernels read the whole observation row, so anything else is rejected here
+    rather than silently ignored."""
+    import numpy as np
+    obs_dim = int(env.single_observation_space.shape[0])
+    for attr in ("policy_observation_indices", "critic_observation_indices"):
+        ind = getattr(env, attr, None)
+        if ind is not None and not np.array_equal(np.asarray(ind).reshape(-1), np.arange(obs_dim)):
+            raise ValueError(f"rl_x_b200 {who} does not implement a non-identity {attr}.")
+
+
 def same_member(a, b):
     """Enum members of this package and of an unmodified reference checkout are different classes; compare by name."""
     return getattr(a, "name", a) == getattr(b, "name", b)

@@ -159,6 +159,27 @@ def test_ppo_refuses_to_run_without_cuda():
         PPO(r._config, train_env, eval_env, "/tmp/x", None)
 
 
+@pytest.mark.parametrize("algo", ["sac.b200", "fastsac.b200", "ppo_lstm.b200"])
+def test_non_identity_observation_indices_are_rejected_not_ignored(algo):
+    """the reference index-selects the network inputs with env.policy_observation_indices / critic_observation_indices
+    (sac/pytorch/policy.py:13,46, q_network.py:10,37 and the same lines in fastsac / ppo_lstm).  The kernels here read whole rows, so an
+    env that asks for a subset must be refused before anything runs (PPO / ESPO check the same thing after their device check)."""
+    from rl_x_b200.runner.runner import Runner
+    from rl_x_b200.algorithms.algorithm_manager import get_algorithm_model_class
+    r = Runner(argv=[f"--algorithm.name={algo}", "--environment.nr_envs=8"])
+    env, eval_env = r._create_train_and_eval_env(r._config)
+    cls = get_algorithm_model_class(algo)
+    obs = env.single_observation_space.shape[0]
+    env.policy_observation_indices = np.arange(obs)            # identity: accepted (the next check is the device one)
+    expected = RuntimeError if not torch.cuda.is_available() else None
+    if expected:
+        with pytest.raises(expected, match="no CPU fallback"):
+            cls(r._config, env, eval_env, "/tmp/x", None)
+    env.critic_observation_indices = np.arange(obs - 1)        # the critic sees a subset: refused
+    with pytest.raises(ValueError, match="non-identity critic_observation_indices"):
+        cls(r._config, env, eval_env, "/tmp/x", None)
+
+
 def test_synthetic_env_contract():
     from rl_x_b200.runner.runner import Runner
     r = Runner(argv=["--environment.nr_envs=8", "--environment.device=cpu", "--algorithm.device=cpu", "--environment.horizon=3"])
