@@ -93,3 +93,13 @@ def golden_small():
 @pytest.fixture(scope="session")
 def golden_humanoid():
     return Golden("humanoid")
+
+
+def emu_build_cmd(out, src):
+    """g++ command of the host-emulation builds (tests/test_*_emulation.py).  RLX_EMU_CXXFLAGS adds flags, e.g. an AddressSanitizer pass
+    over the emulated kernels:  RLX_EMU_CXXFLAGS="-g -fsanitize=address" LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_lstm_emulation.py tests/test_fastsac_emulation.py"""
+    import os
+    import shlex
+    return (["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU"] + shlex.split(os.environ.get("RLX_EMU_CXXFLAGS", ""))
+            + ["-o", str(out), str(src)])

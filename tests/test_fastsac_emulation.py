@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import emu_build_cmd
+
 from oracle import fastsac_oracle as FS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,8 +37,7 @@ class Args(C.Structure):
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = tmp_path_factory.mktemp("fastsac_emu") / "libfastsac_emu.so"
-    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
-                    os.path.join(ROOT, "rl_x_b200", "csrc", "fastsac.cu")], check=True)
+    subprocess.run(emu_build_cmd(out, os.path.join(ROOT, "rl_x_b200", "csrc", "fastsac.cu")), check=True)
     lib = C.CDLL(str(out))
     lib.rlx_fastsac_workspace_bytes.restype = C.c_size_t
     lib.rlx_fastsac_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64]
@@ -171,8 +172,7 @@ def test_plugin_class_reproduces_the_reference_run_under_emulation(tmp_path, tag
     emus = []
     for name in ("fastsac", "replay_nstep"):
         out = tmp_path / f"lib{name}_emu.so"
-        subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
-                        os.path.join(ROOT, "rl_x_b200", "csrc", f"{name}.cu")], check=True)
+        subprocess.run(emu_build_cmd(out, os.path.join(ROOT, "rl_x_b200", "csrc", f"{name}.cu")), check=True)
         emus.append(C.CDLL(str(out)))
     real = nt.load()
 

@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import emu_build_cmd
+
 from oracle import ppo_lstm_oracle as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -35,7 +37,7 @@ class Args(C.Structure):
 def emu(tmp_path_factory):
     out = tmp_path_factory.mktemp("lstm_emu") / "liblstm_emu.so"
     src = os.path.join(ROOT, "rl_x_b200", "csrc", "lstm.cu")
-    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out), src], check=True)
+    subprocess.run(emu_build_cmd(out, src), check=True)
     lib = C.CDLL(str(out))
     lib.rlx_lstm_minibatch_workspace_bytes.restype = C.c_size_t
     lib.rlx_lstm_minibatch_workspace_bytes.argtypes = [C.POINTER(Dims), C.c_int64, C.c_int64]
@@ -131,7 +133,7 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
     stats = np.array([float(adv.mean()), float(adv.std(unbiased=False))], dtype=np.float32)
     metrics = np.zeros(8, np.float32)
     nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), T, n)
-    ws = np.zeros(nbytes // 4 + 16, np.float32)
+    ws = np.zeros(nbytes // 4, np.float32)   # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun
     arrs = dict(states=_np(states), actions=_np(actions), log_probs=_np(log_probs), advantages=_np(adv), returns=_np(ret), dones=_np(dones),
                 init_c=_np(init[0]), init_h=_np(init[1]))
     a = Args()
@@ -209,7 +211,7 @@ def test_emulated_rollout_step_matches_oracle(emu, options):
     Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
     low, high = np.full(act, -2.0, np.float32), np.full(act, 0.5, np.float32)
     nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, n)
-    ws = np.zeros(nbytes // 4 + 16, np.float32)
+    ws = np.zeros(nbytes // 4, np.float32)   # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun
     c, h = np.zeros((n, lstm), np.float32), np.zeros((n, lstm), np.float32)
     carry = (torch.zeros(n, lstm), torch.zeros(n, lstm))
     emu.rlx_lstm_mask_carry_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
@@ -252,7 +254,7 @@ def test_emulated_rollout_step_matches_oracle(emu, options):
     x = torch.randn(rows, obs_d)
     xv, outv = _np(x), np.zeros(rows, np.float32)
     nb = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, rows)
-    ws2 = np.zeros(nb // 4 + 16, np.float32)
+    ws2 = np.zeros(nb // 4, np.float32)
     emu.rlx_lstm_critic_forward_f32.argtypes = [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     assert emu.rlx_lstm_critic_forward_f32(C.byref(d), Cc.ctypes.data, xv.ctypes.data, rows, outv.ctypes.data, ws2.ctypes.data, nb, None) == 0
     with torch.no_grad():
@@ -430,8 +432,7 @@ def test_emulated_nstep_replay_matches_reference_golden(tmp_path):
     from conftest import GOLDEN_DIR
     from oracle import fastsac_replay_oracle as F
     out = tmp_path / "libnstep_emu.so"
-    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
-                    os.path.join(ROOT, "rl_x_b200", "csrc", "replay_nstep.cu")], check=True)
+    subprocess.run(emu_build_cmd(out, os.path.join(ROOT, "rl_x_b200", "csrc", "replay_nstep.cu")), check=True)
     lib = C.CDLL(str(out))
     lib.rlx_replay_sample_nstep_f32.argtypes = ([C.c_void_p, C.c_void_p] + [C.c_int64] * 5 + [C.c_int32, C.c_void_p, C.c_int64, C.c_int64] +
                                                 [C.c_void_p] * 15)
@@ -464,8 +465,7 @@ def test_emulated_ppo_head_gemm_path(tmp_path, m, hid, act, rd):
     loss (ppo.py:121-160) from the layer-2 activations: dZ2, the dW3 operand dhead, and the partial block (bias / log-std gradients,
     metric sums) in the layout the rest of the update consumes."""
     out = tmp_path / "libheadgemm_emu.so"
-    subprocess.run(["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU", "-o", str(out),
-                    os.path.join(ROOT, "rl_x_b200", "csrc", "ppo_head_gemm.cu")], check=True)
+    subprocess.run(emu_build_cmd(out, os.path.join(ROOT, "rl_x_b200", "csrc", "ppo_head_gemm.cu")), check=True)
     lib = C.CDLL(str(out))
     lib.rlx_debug_ppo_head_gemm_f32.argtypes = ([C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 11 + [C.c_float] * 3 + [C.c_int32] +
                                                 [C.c_void_p] * 5)
