@@ -16,6 +16,10 @@
 namespace rlx {
 struct EmuDim { unsigned x, y, z; };
 static EmuDim threadIdx, blockIdx, blockDim, gridDim;
+// Order in which the emulated threads of a launch run: 0 = ascending (block, thread), 1 = descending.  A kernel whose threads only
+// touch their own outputs gives bit-identical results either way; one thread reading what another thread of the SAME launch writes
+// (a data race on the device) does not.  tests/test_*_emulation.py run every entry point both ways.
+static int g_emu_reverse = 0;
 typedef void* cudaStream_t;
 static char g_emu_err[512];
 static void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_emu_err, sizeof(g_emu_err), fmt, ap); va_end(ap); }
@@ -54,6 +58,7 @@ int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
   return RLX_OK;
 }
 }  // namespace rlx
+extern "C" void rlx_emu_set_thread_order(int reverse) { rlx::g_emu_reverse = reverse; }
 #define __global__
 #define __device__
 #define __forceinline__ inline
@@ -65,8 +70,10 @@ int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
     const long long _n = (nthreads_total);                                                        \
     rlx::blockDim = {256, 1, 1};                                                                  \
     rlx::gridDim = {(unsigned)rlx::ceil_div(_n, 256), 1, 1};                                      \
-    for (unsigned _b = 0; _b < rlx::gridDim.x; ++_b)                                              \
-      for (unsigned _t = 0; _t < 256; ++_t) {                                                     \
+    for (unsigned _bi = 0; _bi < rlx::gridDim.x; ++_bi)                                           \
+      for (unsigned _ti = 0; _ti < 256; ++_ti) {                                                  \
+        const unsigned _b = rlx::g_emu_reverse ? rlx::gridDim.x - 1 - _bi : _bi;                  \
+        const unsigned _t = rlx::g_emu_reverse ? 255 - _ti : _ti;                                 \
         rlx::blockIdx = {_b, 0, 0};                                                               \
         rlx::threadIdx = {_t, 0, 0};                                                              \
         kernel(__VA_ARGS__);                                                                      \

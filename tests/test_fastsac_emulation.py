@@ -91,8 +91,24 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu, tag):
         a.q_params, a.q_grads, a.q_m, a.q_v, a.q_target_params = Q.ctypes.data, gQ.ctypes.data, mQ.ctypes.data, vQ.ctypes.data, QT.ctypes.data
         a.log_alpha, a.alpha_state, a.lr, a.steps = la.ctypes.data, astate.ctypes.data, lr_a.ctypes.data, steps.ctypes.data
         a.hp, a.metrics, a.workspace, a.workspace_bytes = hp, metrics.ctypes.data, ws.ctypes.data, nbytes
+        state = dict(P=P, gP=gP, mP=mP, vP=vP, Q=Q, gQ=gQ, mQ=mQ, vQ=vQ, QT=QT, log_alpha=la, alpha_state=astate, steps=steps, metrics=metrics)
+        before = {k_: v_.copy() for k_, v_ in state.items()} if race_check[0] else None
         rc = fn(C.byref(a), None)
         assert rc == 0, rc
+        if race_check[0]:
+            # Race check (csrc/dual_build.cuh): the same update from the same state with the emulated threads of every launch run in
+            # DESCENDING order must produce the same bits; a thread reading another thread's output of the same launch would not.
+            first = {k_: v_.copy() for k_, v_ in state.items()}
+            for k_, v_ in state.items():
+                v_[...] = before[k_]
+            ws[:] = 0
+            emu.rlx_emu_set_thread_order(1)
+            try:
+                assert fn(C.byref(a), None) == 0
+            finally:
+                emu.rlx_emu_set_thread_order(0)
+            for k_, v_ in state.items():
+                assert np.array_equal(v_, first[k_]), f"{fn.__name__}: {k_} depends on the thread order"
 
     def close(ours, ref, what, rtol=3e-4, atol=3e-6):
         np.testing.assert_allclose(ours, ref, rtol=rtol, atol=atol, err_msg=what)
@@ -106,7 +122,9 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu, tag):
         assert rel <= 2e-5, (what, rel)
 
     logged = {}
+    race_check = [True]   # on for the first optimisation step (it doubles the work)
     for u in range(nopt):
+        race_check[0] = (u == 0)
         b = {k: z[f"step{u}/{k}"] for k in ["states", "next_states", "actions", "rewards", "dones", "truncations", "effective_n_steps"]}
         total = b["states"].shape[0]
         wsn = np.zeros(4 * obs * (total // 256 + 2), np.float32)

@@ -157,6 +157,17 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
     for j, key in enumerate(["loss/policy_gradient_loss", "loss/critic_loss", "loss/entropy_loss", "policy_ratio/approx_kl", "policy_ratio/clip_fraction"]):
         assert abs(float(metrics[j]) - metrics_ref[key]) <= 2e-5 * max(1.0, abs(metrics_ref[key])), (key, metrics[j], metrics_ref[key])
     assert metrics[7] == T * n
+    # Race check: the same call with the emulated threads of every launch run in DESCENDING order must give the same bits.  A thread that
+    # reads what another thread of the same launch writes (a data race on the device) would make the result depend on the order.
+    gP2, gC2, metrics2 = np.full_like(P, np.nan), np.full_like(Cc, np.nan), np.zeros(8, np.float32)
+    ws[:] = 0
+    a.policy_grads, a.critic_grads, a.metrics = gP2.ctypes.data, gC2.ctypes.data, metrics2.ctypes.data
+    emu.rlx_emu_set_thread_order(1)
+    try:
+        assert emu.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), None) == 0
+    finally:
+        emu.rlx_emu_set_thread_order(0)
+    assert np.array_equal(gP, gP2) and np.array_equal(gC, gC2) and np.array_equal(metrics, metrics2)
 
 
 def test_emulated_optax_step_and_env_gather(emu):
@@ -228,7 +239,17 @@ def test_emulated_rollout_step_matches_oracle(emu, options):
         a.clip_rescale = 1
         a.action, a.env_action, a.logp, a.value = out_a.ctypes.data, out_e.ctypes.data, out_lp.ctypes.data, out_v.ctypes.data
         a.workspace, a.workspace_bytes = ws.ctypes.data, nbytes
+        c_in, h_in = c.copy(), h.copy()
         assert emu.rlx_lstm_step_f32(C.byref(a), None) == 0
+        # race check (see the fwd/bwd test): descending thread order from the same inputs, same bits (the carry is updated in place)
+        first = [x.copy() for x in (out_a, out_e, out_lp, out_v, c, h)]
+        c[:], h[:] = c_in, h_in
+        emu.rlx_emu_set_thread_order(1)
+        try:
+            assert emu.rlx_lstm_step_f32(C.byref(a), None) == 0
+        finally:
+            emu.rlx_emu_set_thread_order(0)
+        assert all(np.array_equal(x, y) for x, y in zip(first, (out_a, out_e, out_lp, out_v, c, h)))
         np.testing.assert_allclose(out_a, _np(action), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out_e, _np(proc), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out_lp, _np(logp), rtol=1e-5, atol=1e-5)
