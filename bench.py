@@ -386,6 +386,55 @@ def run_sac(args):
     return line
 
 
+_AUX_VERDICT = None
+
+
+def aux_gemm_engine_verdict():
+    """May the FastSAC / PPO+LSTM workloads run their dense layers on the tcgen05 3xTF32 engine (rlx_set_aux_gemm_engine(1))?  That switch was
+    written after the round's GPU budget was spent, so it has to prove itself ON THIS BOX before a timed run may use it: a subprocess (a
+    tensor-core kernel that hangs ends in the watchdog trap and takes its CUDA context along - not this process's) runs, with the engine on,
+    the FastSAC golden-batch parity test, the SIMT-vs-tensor gradient agreement at batch 1024, and the PPO+LSTM oracle parity tests at the
+    config-5 shape (T=128, 256 envs) and a smaller one.  All green AND tensor GEMMs actually counted -> engine 1; anything else -> SIMT, with
+    the reason in the record.  No CPU oracle is timed here: the tests use it as the checker only."""
+    global _AUX_VERDICT
+    if _AUX_VERDICT is not None:
+        return _AUX_VERDICT
+    import subprocess
+    import tempfile
+    tests = ["tests/test_gpu_zzzz_fastsac.py::test_fastsac_updates_match_oracle_on_golden_batches",
+             "tests/test_gpu_zzzz_fastsac.py::test_fastsac_engines_agree_at_batch_1024",
+             "tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[16-24-64-8-256-128-64-0]",
+             "tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[128-256-64-8-256-128-64-0]"]
+    report = os.path.join(tempfile.mkdtemp(prefix="rlx_aux_"), "tc_gemms.txt")
+    env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1", RLX_AUX_ENGINE_REPORT=report)
+    try:
+        proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider"] + tests, env=env, cwd=ROOT, capture_output=True,
+                              text=True, timeout=900)
+        count = open(report).read().strip() if os.path.exists(report) else "no report"
+        tail = (proc.stdout + proc.stderr).strip().splitlines()[-1:] or [""]
+        ok = proc.returncode == 0 and count.isdigit() and int(count) > 0 and " passed" in tail[0] and "skipped" not in tail[0]
+        _AUX_VERDICT = {"engine": "tcgen05-3xTF32" if ok else "simt", "check": {"tests": len(tests), "pytest": tail[0], "tensor_gemms_in_check": count,
+                                                                              "returncode": proc.returncode}}
+    except Exception as exc:  # timeout, no pytest, ...
+        _AUX_VERDICT = {"engine": "simt", "check": {"error": f"{type(exc).__name__}: {exc}"}}
+    return _AUX_VERDICT
+
+
+def with_aux_gemm_engine(fn, args):
+    """Run a nested workload with the engine the verdict allows; the record says which engine ran and how many GEMMs the tensor engine took."""
+    from rl_x_b200 import _native as nt
+    lib = nt.load()
+    verdict = aux_gemm_engine_verdict()
+    lib.rlx_set_aux_gemm_engine(1 if verdict["engine"] != "simt" else 0)
+    before = int(lib.rlx_aux_tc_gemm_count())
+    try:
+        line = fn(args)
+    finally:
+        lib.rlx_set_aux_gemm_engine(0)
+    line["gemm_engine"] = dict(verdict, tensor_gemms_in_run=int(lib.rlx_aux_tc_gemm_count()) - before)
+    return line
+
+
 def run_fastsac(args):
     """FastSAC at the reference's default update shape: batch 8192, 4 critic updates per policy update, 2 policy updates per
     environment step (rl_x/algorithms/fastsac/pytorch/default_config.py), 1024 x 4096 ring, synthetic Box(48) / Box(12).  One "step" =
@@ -597,6 +646,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="N=1: skip the bf16-autocast sub-line")
     ap.add_argument("--no-workloads", action="store_true", help="N=1: skip the nested SAC / FastSAC / PPO+LSTM records")
+    ap.add_argument("--no-aux-engine", action="store_true", help="FastSAC / PPO+LSTM workloads: stay on the SIMT GEMM engine without running the tensor-engine check")
     ap.add_argument("--no-parity-check", action="store_true", help="N>1: skip the sharded-vs-single parity run before timing")
     ap.add_argument("--no-strict", action="store_true", help="N>1: skip the second timed region at the contract's GLOBAL minibatch of 32768")
     ap.add_argument("--global-minibatch", type=int, default=0, help="N>1: headline region with this GLOBAL minibatch instead of --minibatch per GPU")
@@ -610,7 +660,8 @@ def main():
 
     if args.workload in ("sac", "fastsac", "ppo_lstm"):
         if rank == 0:
-            print(json.dumps({"sac": run_sac, "fastsac": run_fastsac, "ppo_lstm": run_ppo_lstm}[args.workload](args)))
+            fn = {"sac": run_sac, "fastsac": run_fastsac, "ppo_lstm": run_ppo_lstm}[args.workload]
+            print(json.dumps(fn(args) if args.workload == "sac" or args.no_aux_engine else with_aux_gemm_engine(fn, args)))
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
@@ -829,7 +880,7 @@ def main():
         for name, fn in (("sac", run_sac), ("fastsac", run_fastsac), ("ppo_lstm", run_ppo_lstm)):
             try:
                 torch.cuda.empty_cache()
-                line["workloads"][name] = fn(args)
+                line["workloads"][name] = fn(args) if name == "sac" or args.no_aux_engine else with_aux_gemm_engine(fn, args)
             except Exception as e:
                 line["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:

@@ -51,6 +51,11 @@ const char* rlx_kernel_class_name(int cls);
  * Returns the engine actually in effect (a request for 1 falls back to 0 with an error string if the shape is unsupported). */
 int rlx_set_gemm_engine(int engine);
 int rlx_get_gemm_engine(void);
+/* The same choice for the dense layers of the FastSAC and PPO+LSTM entry points (their own switch: these paths were validated on the SIMT
+ * engine).  1 routes every GEMM whose layout / epilogue / alignment the tcgen05 engine covers to it and leaves the rest on the SIMT
+ * engine (e.g. the 101-column logits of the C51 critics, whose row pitch is not a multiple of 16 bytes).  Default 0.  Returns the value in effect. */
+int rlx_set_aux_gemm_engine(int engine);
+uint64_t rlx_aux_tc_gemm_count(void);     /* GEMMs of those two paths that ran on the tcgen05 engine since load */
 
 /* Test hook: one plain fp32 GEMM through either engine.  layout 0: C[M,N] = A[M,K] B[N,K]^T; 1: C = A[M,K] B[K,N];
  * 2: C = A[K,M]^T B[K,N].  epilogue 0 none, 1 tanh(x + bias[n]) (layout 0), 2 x * (1 - aux[m,n]^2) (layout 1). */

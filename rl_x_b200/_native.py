@@ -153,6 +153,8 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "rlx_version": (C.c_int, []),
     "rlx_last_error_string": (C.c_char_p, []),
+    "rlx_set_aux_gemm_engine": (C.c_int, [C.c_int]),
+    "rlx_aux_tc_gemm_count": (C.c_uint64, []),
     "rlx_launch_count": (C.c_uint64, []),
     "rlx_reset_launch_count": (None, []),
     "rlx_add_launch_count": (None, [C.c_uint64]),
@@ -265,6 +267,10 @@ def load(build_if_missing=True):
         fn.argtypes = args
     if missing:
         raise RuntimeError(f"rl_x_b200: native library lacks symbols: {missing}")
+    # process-wide default of the FastSAC / PPO+LSTM GEMM engine (their configs say gemm_engine="auto" = leave it alone): lets a whole test
+    # run or a bench leg select the tensor engine from outside, e.g. RLX_AUX_GEMM_ENGINE=1 python -m pytest tests/test_gpu_zzzz_fastsac.py
+    if os.environ.get("RLX_AUX_GEMM_ENGINE", "") in ("0", "1"):
+        lib.rlx_set_aux_gemm_engine(int(os.environ["RLX_AUX_GEMM_ENGINE"]))
     _lib = lib
     return lib
 

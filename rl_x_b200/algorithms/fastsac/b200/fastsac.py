@@ -104,6 +104,11 @@ class FastSAC:
         rlx_logger.info(f"Using device: {self.device}")
 
         self.lib = nt.load()
+        engine = a.get("gemm_engine", "auto")   # dense layers: exact-fp32 SIMT, or the tcgen05 3xTF32 engine where it covers the product
+        if engine not in ("auto", "simt", "tcgen05"):
+            raise ValueError("algorithm.gemm_engine must be auto, simt or tcgen05")
+        if engine != "auto":
+            self.lib.rlx_set_aux_gemm_engine(1 if engine == "tcgen05" else 0)
         obs, act = int(self.train_env.single_observation_space.shape[0]), int(np.prod(self.train_env.single_action_space.shape))
         self.dims = nt.FastSacDims(obs, act, int(a.nr_atoms))
         poff, qoff = (C.c_int64 * (nt.RLX_FASTSAC_POLICY_NSEG + 1))(), (C.c_int64 * (nt.RLX_FASTSAC_Q_NSEG + 1))()

@@ -119,6 +119,11 @@ class PPO_LSTM:
         if len(self.os_shape) != 1 or len(self.as_shape) != 1:
             raise ValueError("rl_x_b200 PPO_LSTM supports flat observations and flat continuous actions only.")
         self.lib = nt.load()
+        engine = a.get("gemm_engine", "auto")   # dense layers: exact-fp32 SIMT, or the tcgen05 3xTF32 engine where it covers the product
+        if engine not in ("auto", "simt", "tcgen05"):
+            raise ValueError("algorithm.gemm_engine must be auto, simt or tcgen05")
+        if engine != "auto":
+            self.lib.rlx_set_aux_gemm_engine(1 if engine == "tcgen05" else 0)
         options = (nt.RLX_LSTM_OPT_FILM if a.lstm_obs_combine_method == "film" else 0) | (nt.RLX_LSTM_OPT_SHARED_ENCODER if a.share_lstm_obs_encoder else 0)
         self.dims = nt.LstmDims(int(self.os_shape[0]), int(self.as_shape[0]), int(a.nr_hidden_units), int(a.obs_encoding_dim), int(a.lstm_hidden_dim),
                                 options)

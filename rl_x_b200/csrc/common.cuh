@@ -14,6 +14,8 @@ namespace rlx {
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launch_count;
 extern int g_gemm_engine;
+extern int g_aux_gemm_engine;
+extern std::atomic<uint64_t> g_aux_tc_gemms;
 // bf16-autocast mode of the PPO path (rlx_set_autocast_bf16; the reference's `bf16_mixed_precision_training`, ppo.py:98-107,123,155,208,253):
 // every value torch's autocast would hold in a bf16 tensor is rounded to bf16 (round-to-nearest-even) where torch rounds it, and kept in
 // fp32 storage.  bf16 values are exact TF32 operands, so ONE kind::tf32 MMA per product gives exactly the bf16 x bf16 -> fp32 products of a

@@ -393,7 +393,7 @@ static int lin_fwd(const float* X, int ldx, const float* W, int in, int out, con
   g.A = X; g.B = W; g.C = Y; g.bias = b;
   g.M = (int)n; g.N = out; g.K = in; g.lda = ldx; g.ldb = in; g.ldc = ldy;
   g.splits = 1; g.kchunk = (int)(ceil_div(in, 8) * 8);
-  return launch_sgemm<true, true, EPI_BIAS>(g, 1, st, KC_GEMM_FWD);
+  return aux_gemm<true, true, EPI_BIAS>(g, 1, st, KC_GEMM_FWD, n, out);
 }
 // dX[r, i] = sum_o dY[r, o] W[o, i]
 static int lin_bwd_input(const float* dY, int ldy, const float* W, int in, int out, float* dX, int ldx, long long n, cudaStream_t st) {
@@ -401,7 +401,7 @@ static int lin_bwd_input(const float* dY, int ldy, const float* W, int in, int o
   g.A = dY; g.B = W; g.C = dX;
   g.M = (int)n; g.N = in; g.K = out; g.lda = ldy; g.ldb = in; g.ldc = ldx;
   g.splits = 1; g.kchunk = (int)(ceil_div(out, 8) * 8);
-  return launch_sgemm<true, false, EPI_NONE>(g, 1, st, KC_GEMM_DX);
+  return aux_gemm<true, false, EPI_NONE>(g, 1, st, KC_GEMM_DX, n, out);
 }
 // dW[o, i] = sum_r dY[r, o] X[r, i], split over rows
 static int lin_bwd_weight(const float* dY, int ldy, const float* X, int ldx, int in, int out, long long n, float* part, float* dW, cudaStream_t st) {
@@ -410,7 +410,7 @@ static int lin_bwd_weight(const float* dY, int ldy, const float* X, int ldx, int
   g.A = dY; g.B = X; g.C = part;
   g.M = out; g.N = in; g.K = (int)n; g.lda = ldy; g.ldb = ldx; g.ldc = in;
   g.splits = splits; g.kchunk = kWgradRows; g.sSplitC = (long long)in * out;
-  int rc = launch_sgemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW);
+  int rc = aux_gemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW, n, n);
   if (rc) return rc;
   RLX_FLAT_LAUNCH(reduce_parts_kernel, (long long)in * out, st, part, (long long)splits, (long long)in * out, 1.f, 0.f, dW);
   return RLX_OK;

@@ -7,6 +7,8 @@ namespace rlx {
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launch_count{0};
 int g_gemm_engine = 0;
+int g_aux_gemm_engine = 0;  // FastSAC / PPO+LSTM dense layers (rlx_set_aux_gemm_engine)
+std::atomic<uint64_t> g_aux_tc_gemms{0};
 int g_autocast_bf16 = 0;
 
 void set_error(const char* fmt, ...) {
@@ -57,6 +59,12 @@ extern "C" uint64_t rlx_launch_count(void) { return rlx::g_launch_count.load(); 
 extern "C" void rlx_reset_launch_count(void) { rlx::g_launch_count.store(0); }
 extern "C" void rlx_add_launch_count(uint64_t n) { rlx::g_launch_count.fetch_add(n); }
 extern "C" int rlx_get_gemm_engine(void) { return rlx::g_gemm_engine; }
+extern "C" uint64_t rlx_aux_tc_gemm_count(void) { return rlx::g_aux_tc_gemms.load(); }
+extern "C" int rlx_set_aux_gemm_engine(int engine) {
+  if (engine == 0 || engine == 1) rlx::g_aux_gemm_engine = engine;
+  else rlx::set_error("rlx_set_aux_gemm_engine: unknown engine %d", engine);
+  return rlx::g_aux_gemm_engine;
+}
 extern "C" int rlx_set_autocast_bf16(int on) {
   rlx::g_autocast_bf16 = on ? 1 : 0;
   return rlx::g_autocast_bf16;

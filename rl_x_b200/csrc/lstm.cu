@@ -403,7 +403,7 @@ static int dense_fwd(const float* X, int ldx, const float* W, int in, int out, c
   g.M = (int)R; g.N = out; g.K = in;
   g.lda = ldx; g.ldb = out; g.ldc = ldc;
   g.splits = 1; g.kchunk = (int)(ceil_div(in, 8) * 8);
-  return launch_sgemm<true, false, EPI>(g, 1, st, KC_GEMM_FWD);
+  return aux_gemm<true, false, EPI>(g, 1, st, KC_GEMM_FWD, R, in);
 }
 // backward wrt the input: C[r, i] = (sum_o dY[r, o] W[i, o]) [* (1 - aux[r, i]^2)]
 template <int EPI>
@@ -414,7 +414,7 @@ static int dense_bwd_input(const float* dY, int ldy, const float* W, int in, int
   g.M = (int)R; g.N = in; g.K = out;
   g.lda = ldy; g.ldb = out; g.ldc = ldc; g.ldaux = ldaux;
   g.splits = 1; g.kchunk = (int)(ceil_div(out, 8) * 8);
-  return launch_sgemm<true, true, EPI>(g, 1, st, KC_GEMM_DX);
+  return aux_gemm<true, true, EPI>(g, 1, st, KC_GEMM_DX, R, in);
 }
 // weight gradient: dW[i, o] = sum_r X[r, i] dY[r, o], split over rows in chunks of kWgradRows and summed by reduce_parts_kernel
 static int dense_bwd_weight(const float* X, int ldx, const float* dY, int ldy, int in, int out, long long R, float* part, float* dW, cudaStream_t st) {
@@ -424,7 +424,7 @@ static int dense_bwd_weight(const float* X, int ldx, const float* dY, int ldy, i
   g.M = in; g.N = out; g.K = (int)R;
   g.lda = ldx; g.ldb = ldy; g.ldc = out;
   g.splits = splits; g.kchunk = kWgradRows; g.sSplitC = (long long)in * out;
-  int rc = launch_sgemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW);
+  int rc = aux_gemm<false, false, EPI_NONE>(g, 1, st, KC_GEMM_DW, R, R);
   if (rc) return rc;
   LSTM_LAUNCH(reduce_parts_kernel, (long long)in * out, st, part, (long long)splits, (long long)in * out, 1.f, 0.f, dW);
   return RLX_OK;

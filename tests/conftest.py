@@ -15,6 +15,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """RLX_AUX_ENGINE_REPORT=<file>: leave the number of FastSAC / PPO+LSTM GEMMs that ran on the tcgen05 engine in this process (the
+    subprocess runs of run_suite_on_tensor_engine below read it back: a green suite that never touched the tensor engine proves nothing)."""
+    path = os.environ.get("RLX_AUX_ENGINE_REPORT")
+    if path:
+        try:
+            from rl_x_b200 import _native as nt
+            count = int(nt.load().rlx_aux_tc_gemm_count())
+        except Exception as exc:  # noqa: BLE001 - the report is best effort, the exit status carries the verdict
+            count = f"unavailable: {exc}"
+        with open(path, "w") as fh:
+            fh.write(str(count))
+
+
+def run_suite_on_tensor_engine(test_file, tmp_path, timeout=1500):
+    """Run the GPU parity tests of `test_file` again in a SUBPROCESS with RLX_AUX_GEMM_ENGINE=1 (dense layers on the tcgen05 3xTF32 engine
+    where it covers the product).  A subprocess because a tensor-core kernel that hangs ends in the engine's watchdog trap, which takes
+    the CUDA context with it: here that costs one test, not the rest of the session.  Returns (returncode, output tail, tensor GEMM count)."""
+    import subprocess
+    report = os.path.join(str(tmp_path), "aux_tc_gemms.txt")
+    env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1", RLX_AUX_ENGINE_REPORT=report)
+    proc = subprocess.run([sys.executable, "-m", "pytest", test_file, "-x", "-q", "-m", "gpu", "-k", "not tensor_engine", "-p", "no:cacheprovider"],
+                          env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    count = open(report).read().strip() if os.path.exists(report) else "no report"
+    return proc.returncode, (proc.stdout + proc.stderr)[-3000:], count
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
 

@@ -150,6 +150,17 @@ def test_lstm_plugin_cuda_graph_replay_equals_eager_launches():
     assert keep(log_e) == keep(log_r)
 
 
+@FIRST_RUN
+def test_lstm_suite_passes_with_dense_layers_on_the_tensor_engine(tmp_path):
+    """rlx_set_aux_gemm_engine(1): every dense layer the tcgen05 3xTF32 engine covers (the weight gradients, the input-side gate GEMM, the
+    un-fused input gradients) runs on it, the rest stays on the SIMT engine.  The whole file - oracle parity at the config-5 shape included -
+    must pass that way, and must actually have used the tensor engine."""
+    from conftest import run_suite_on_tensor_engine
+    rc, tail, count = run_suite_on_tensor_engine(__file__, tmp_path)
+    assert rc == 0, tail
+    assert count.isdigit() and int(count) > 0, f"the tensor engine was never used ({count})"
+
+
 def test_lstm_plugin_trains_on_synthetic_env():
     """PPO_LSTM.train() through the plugin surface: two iterations on the synthetic Box env, finite metrics, parameters move, the rollout
     step agrees with the oracle's get_action_and_value on the trained weights."""

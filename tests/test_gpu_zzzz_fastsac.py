@@ -85,6 +85,73 @@ def test_fastsac_updates_match_oracle_on_golden_batches():
             assert float(np.linalg.norm(P.cpu().numpy() - ref) / np.linalg.norm(ref)) <= 3e-5
 
 
+@pytest.mark.skipif(os.environ.get("RLX_AUX_GEMM_ENGINE") != "1", reason="runs inside the tensor-engine subprocess (next test)")
+def test_fastsac_engines_agree_at_batch_1024():
+    """The golden batches above have 16 rows, too few for a tensor-core tile, so they exercise the SIMT engine whatever the switch says.
+    Here: one critic and one policy update at the bench's layer shapes (obs 48, act 12, 101 atoms) on 1024 random rows, once per engine from
+    the same state.  The SIMT engine is the one pinned to the oracle; the 3xTF32 engine is fp32-equivalent (6e-7 + 3.2e-9 K relative per
+    product, tests/test_gpu_tc_engine.py), so gradients must agree to 2e-5 of their norm and the losses to 1e-5."""
+    from rl_x_b200 import _native as nt
+    from test_fastsac_emulation import flat
+    lib = nt.load()
+    obs, act, atoms, n = 48, 12, 101, 1024
+    torch.manual_seed(11)
+    pol, q1, q2 = FS.reference_init(obs, act, atoms, 3)
+    d = nt.FastSacDims(obs, act, atoms)
+    t = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(DEV).contiguous()
+    P0, Q0 = t(flat(pol)), t(np.concatenate([flat(q1), flat(q2)]))
+    batch = dict(states=torch.randn(n, obs), next_states=torch.randn(n, obs), actions=torch.rand(n, act) * 2 - 1, rewards=torch.randn(n),
+                 dones=(torch.rand(n) < 0.05).float(), truncations=(torch.rand(n) < 0.02).float(), effective_n_steps=torch.randint(1, 4, (n,)).float(),
+                 noise=torch.randn(n, act))
+    dev = {k: t(v) for k, v in batch.items()}
+    sc = torch.ones(act, device=DEV)
+    nbytes = lib.rlx_fastsac_workspace_bytes(C.byref(d), n)
+    hp = nt.FastSacHparams(0.99, 0.005, -10.0, 10.0, -float(act), -5.0, 0.0, 0.1, 0.9, 0.95, 1e-8, -1.0, 0.0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    for engine in (0, 1):
+        assert lib.rlx_set_aux_gemm_engine(engine) == engine
+        before = int(lib.rlx_aux_tc_gemm_count())
+        P, Q, QT = P0.clone(), Q0.clone(), Q0.clone()
+        zl = torch.zeros_like
+        gP, mP, vP, gQ, mQ, vQ = zl(P), zl(P), zl(P), zl(Q), zl(Q), zl(Q)
+        la, astate, lr_d = t([np.log(0.001)]), torch.zeros(3, device=DEV), t([3e-4])
+        steps, ws = torch.zeros(3, dtype=torch.int64, device=DEV), torch.zeros(nbytes // 4 + 64, device=DEV)
+        res = {}
+        for fn, names, key in ((lib.rlx_fastsac_critic_update_f32, list(dev), "critic"), (lib.rlx_fastsac_policy_update_f32, ["states", "noise"], "policy")):
+            a = nt.FastSacUpdateArgs()
+            a.dims, a.n = d, n
+            for name in names:
+                setattr(a, name, dev[name].data_ptr())
+            a.action_scale = sc.data_ptr()
+            a.policy_params, a.policy_grads, a.policy_m, a.policy_v = P.data_ptr(), gP.data_ptr(), mP.data_ptr(), vP.data_ptr()
+            a.q_params, a.q_grads, a.q_m, a.q_v, a.q_target_params = Q.data_ptr(), gQ.data_ptr(), mQ.data_ptr(), vQ.data_ptr(), QT.data_ptr()
+            a.log_alpha, a.alpha_state, a.lr, a.steps = la.data_ptr(), astate.data_ptr(), lr_d.data_ptr(), steps.data_ptr()
+            metrics = torch.zeros(8, device=DEV)
+            a.hp, a.metrics, a.workspace, a.workspace_bytes = hp, metrics.data_ptr(), ws.data_ptr(), nbytes
+            nt.check(fn(C.byref(a), st), f"fastsac {key} update, engine {engine}")
+            torch.cuda.synchronize()
+            res[key] = (metrics.cpu().numpy().copy(), (gQ if key == "critic" else gP).cpu().numpy().copy())
+        out[engine] = (res, int(lib.rlx_aux_tc_gemm_count()) - before)
+    lib.rlx_set_aux_gemm_engine(1)   # the subprocess's setting
+    assert out[0][1] == 0 and out[1][1] > 0, "engine 1 must have put GEMMs on the tensor engine, engine 0 none"
+    for key in ("critic", "policy"):
+        (m0, g0), (m1, g1) = out[0][0][key], out[1][0][key]
+        assert np.isfinite(g1).all() and float(np.linalg.norm(g1 - g0) / np.linalg.norm(g0)) <= 2e-5, key
+        assert abs(float(m1[0]) - float(m0[0])) <= 1e-5 * max(1.0, abs(float(m0[0]))), (key, m0[0], m1[0])
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run of this path (written after the round-2 GPU budget was spent)")
+def test_fastsac_suite_passes_with_dense_layers_on_the_tensor_engine(tmp_path):
+    """rlx_set_aux_gemm_engine(1): the torso layers of the policy and of both C51 critics (forward, input and weight gradients) run on the
+    tcgen05 3xTF32 engine; the 101-column logits layer (row pitch not a multiple of 16 bytes) and the skinny heads stay on the SIMT engine.
+    The whole file - the golden-batch parity against the pinned oracle included - must pass that way and must have used the tensor engine."""
+    from conftest import run_suite_on_tensor_engine
+    rc, tail, count = run_suite_on_tensor_engine(__file__, tmp_path)
+    assert rc == 0, tail
+    assert count.isdigit() and int(count) > 0, f"the tensor engine was never used ({count})"
+
+
 def test_fastsac_plugin_runs_on_device_env():
     from rl_x_b200.config_dict import ConfigDict
     from rl_x_b200.algorithms.fastsac.b200.default_config import get_config
