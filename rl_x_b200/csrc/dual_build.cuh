@@ -33,9 +33,11 @@ struct GemmP {
   long long sA, sB, sC, sBias, sAux, sRowsum;
   int splits; int kchunk; long long sSplitC, sSplitRowsum;
 };
-// interpreter of the GemmP contract of gemm_simt.cuh (same fp32 fmaf accumulation in k order within a split)
+// interpreter of the GemmP contract of gemm_simt.cuh (same fp32 fmaf accumulation in k order within a split).
+// a_rows / b_rows >= 0: the operands are read the way the tensor engine reads them, through a descriptor of that many rows in memory with
+// zeros beyond (TMA out-of-bounds fill) - a caller that passes a wrong extent to aux_gemm gets wrong numbers here too.
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
-int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
+int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0, long long a_rows = -1, long long b_rows = -1) {
   for (int z = 0; z < batch * p.splits; ++z) {
     const int b = z / p.splits, sp = z % p.splits;
     const int kbeg = sp * p.kchunk, kend = std::min(p.K, kbeg + p.kchunk);
@@ -45,8 +47,9 @@ int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
       for (int n = 0; n < p.N; ++n) {
         float acc = 0.f;
         for (int k = kbeg; k < kend; ++k) {
-          const float a = A_KMAJ ? A[(long long)m * p.lda + k] : A[(long long)k * p.lda + m];
-          const float w = B_KMAJ ? B[(long long)n * p.ldb + k] : B[(long long)k * p.ldb + n];
+          const bool a_in = a_rows < 0 || (A_KMAJ ? m : k) < a_rows, b_in = b_rows < 0 || (B_KMAJ ? n : k) < b_rows;
+          const float a = !a_in ? 0.f : A_KMAJ ? A[(long long)m * p.lda + k] : A[(long long)k * p.lda + m];
+          const float w = !b_in ? 0.f : B_KMAJ ? B[(long long)n * p.ldb + k] : B[(long long)k * p.ldb + n];
           acc = fmaf(a, w, acc);
         }
         if (EPI == EPI_BIAS) acc += p.bias[b * p.sBias + n];
@@ -61,7 +64,15 @@ int launch_sgemm(const GemmP& p, int batch, cudaStream_t, int = 0) {
 namespace rlx {
 // dense layer of a dual-build source; the host build interprets the GemmP contract (a_rows / b_rows only matter to the tensor engine)
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
-int aux_gemm(const GemmP& p, int batch, cudaStream_t st, int kclass, long long, long long) { return launch_sgemm<A_KMAJ, B_KMAJ, EPI>(p, batch, st, kclass); }
+int aux_gemm(const GemmP& p, int batch, cudaStream_t st, int kclass, long long a_rows, long long b_rows) {
+  if (a_rows <= 0 || b_rows <= 0) return RLX_ERR_INVALID_ARG;
+  // Too small an extent turns operand rows into zeros (wrong numbers in the parity tests); too large a one makes the descriptor cover
+  // memory the operand does not own: touch the last element each descriptor declares, so that an AddressSanitizer build of the
+  // emulation (tests/conftest.py::emu_build_cmd) sees it.
+  volatile float touch = p.A[(a_rows - 1) * p.lda + ((A_KMAJ ? p.K : p.M) - 1)] + p.B[(b_rows - 1) * p.ldb + ((B_KMAJ ? p.K : p.N) - 1)];
+  (void)touch;
+  return launch_sgemm<A_KMAJ, B_KMAJ, EPI>(p, batch, st, kclass, a_rows, b_rows);
+}
 }  // namespace rlx
 extern "C" void rlx_emu_set_thread_order(int reverse) { rlx::g_emu_reverse = reverse; }
 #define __global__
