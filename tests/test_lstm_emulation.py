@@ -470,6 +470,16 @@ def test_emulated_nstep_replay_matches_reference_golden(tmp_path):
         rc = lib.rlx_replay_sample_nstep_f32(idx_t.ctypes.data, idx_e.ctypes.data, n, cap, nr_envs, obs, act, n_steps, disc.ctypes.data, size, pos,
                                              *[ring[k].ctypes.data for k in names[:6]], *[o.ctypes.data for o in outs], scratch.ctypes.data, None)
         assert rc == 0
+        # race check (csrc/dual_build.cuh): descending thread order, same bits
+        outs2 = [np.zeros_like(o) for o in outs]
+        lib.rlx_emu_set_thread_order(1)
+        try:
+            assert lib.rlx_replay_sample_nstep_f32(idx_t.ctypes.data, idx_e.ctypes.data, n, cap, nr_envs, obs, act, n_steps, disc.ctypes.data, size, pos,
+                                                   *[ring[k].ctypes.data for k in names[:6]], *[o.ctypes.data for o in outs2],
+                                                   np.zeros(n, np.int64).ctypes.data, None) == 0
+        finally:
+            lib.rlx_emu_set_thread_order(0)
+        assert all(np.array_equal(x, y) for x, y in zip(outs, outs2)), tag
         want = F.sample(ring, idx_t, idx_e, n_steps, disc, size, pos)
         for name, got, w in zip(names, outs, want):
             assert np.array_equal(got, w), f"{tag}/{name} vs oracle"
