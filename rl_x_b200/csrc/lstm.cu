@@ -52,7 +52,7 @@ static bool dims_ok(const rlx_lstm_dims& d) {
 // workspace carve-up (floats); R = T * n_env rows, time-major (row = t * n_env + e)
 struct Ws {
   size_t Z1, E1, Z2, TI, Gi, Gates, Call, Hall, Hm, Cm, T1, T2, C1, C2, Mean, V, dMean, dV, Terms, dLs, dT2, dT1, dTI, dHall, dG, dE1, dZ1, dZ2,
-      dC2, dC1, Gh, dHn, dCn, Small, Stats1, Stats2, StatsL, Part, Col, WhT, E2, LL, GB, dGB, dOL, dLL, total;
+      dC2, dC1, Gh, dHn, dCn, Small, Stats1, Stats2, StatsL, Part, Col, WhT, E2, LL, GB, dGB, dOL, dLL, TP, TC, total;
 };
 static Ws plan(const rlx_lstm_dims& d, long long T, long long n) {
   const size_t R = (size_t)(T * n), O = d.obs_dim, A = d.act_dim, H = d.hidden, E = d.enc_dim, L = d.lstm_dim;
@@ -79,6 +79,9 @@ static Ws plan(const rlx_lstm_dims& d, long long T, long long n) {
   const size_t film = is_film(d) ? 1 : 0;  // FiLM buffers (policy.py:102-105); zero-sized otherwise
   take(w.E2, film * R * E); take(w.LL, film * R * L); take(w.GB, film * R * 2 * E); take(w.dGB, film * R * 2 * E); take(w.dOL, film * R * E);
   take(w.dLL, film * R * L);
+  // K-major ([out, in]) copies of the dense kernels, at the offsets of the originals (rlx_lstm_ppo_minibatch_fwdbwd_f32 only)
+  const Layout lay = make_layout(d);
+  take(w.TP, (size_t)lay.p[RLX_LSTM_POLICY_NSEG]); take(w.TC, (size_t)lay.c[RLX_LSTM_CRITIC_NSEG]);
   w.total = o * sizeof(float);
   return w;
 }
@@ -416,6 +419,27 @@ static int dense_bwd_input(const float* dY, int ldy, const float* W, int in, int
   g.splits = 1; g.kchunk = (int)(ceil_div(out, 8) * 8);
   return aux_gemm<true, true, EPI>(g, 1, st, KC_GEMM_DX, R, in);
 }
+// The same two products on a K-major copy WT [out, in] of the kernel (torch's Linear layout): these operand layouts are the ones every
+// epilogue of the tensor engine covers (bias, bias + tanh, tanh'), which the Flax layout [in, out] is not (gemm_tc.cu: RLX_TC_DISPATCH).
+template <int EPI>
+static int dense_fwd_t(const float* X, int ldx, const float* WT, int in, int out, const float* bias, float* C, int ldc, long long R, cudaStream_t st) {
+  GemmP g{};
+  g.A = X; g.B = WT; g.C = C; g.bias = bias;
+  g.M = (int)R; g.N = out; g.K = in;
+  g.lda = ldx; g.ldb = in; g.ldc = ldc;
+  g.splits = 1; g.kchunk = (int)(ceil_div(in, 8) * 8);
+  return aux_gemm<true, true, EPI>(g, 1, st, KC_GEMM_FWD, R, out);
+}
+template <int EPI>
+static int dense_bwd_input_t(const float* dY, int ldy, const float* WT, int in, int out, const float* aux, int ldaux, float* C, int ldc, long long R,
+                             cudaStream_t st) {
+  GemmP g{};
+  g.A = dY; g.B = WT; g.C = C; g.aux = aux;
+  g.M = (int)R; g.N = in; g.K = out;
+  g.lda = ldy; g.ldb = in; g.ldc = ldc; g.ldaux = ldaux;
+  g.splits = 1; g.kchunk = (int)(ceil_div(out, 8) * 8);
+  return aux_gemm<true, false, EPI>(g, 1, st, KC_GEMM_DX, R, out);
+}
 // weight gradient: dW[i, o] = sum_r X[r, i] dY[r, o], split over rows in chunks of kWgradRows and summed by reduce_parts_kernel
 static int dense_bwd_weight(const float* X, int ldx, const float* dY, int ldy, int in, int out, long long R, float* part, float* dW, cudaStream_t st) {
   const int splits = (int)ceil_div(R, kWgradRows);
@@ -496,6 +520,16 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   //   torso input TI: [OL | LLp] (concat, width E + L) or OL * gamma + beta (FiLM, width E)
   const bool film = is_film(d), shared = is_shared(d);
   const int TIW = film ? E : EL;
+  // K-major copies of the dense kernels (see dense_fwd_t): PT / CT mirror P / Cp segment by segment
+  float *PT = ws + w.TP, *CT = ws + w.TC;
+  {
+    const struct { int seg, in, out; bool on; } pk[] = {{WE1, O, E, true}, {WE2, O, E, !shared}, {WI, E, 4 * L, true}, {WT1, TIW, H, true}, {WT2, H, H, true},
+                                                        {WM, H, A, true}, {WF, L, 2 * E, film}};
+    for (const auto& k : pk)
+      if (k.on) LSTM_LAUNCH(transpose_kernel, (long long)k.in * k.out, st, P + l.p[k.seg], k.in, k.out, PT + l.p[k.seg]);
+    const struct { int seg, in, out; } ck[] = {{WC1, O, H}, {WC2, H, H}, {WC3, H, 1}};
+    for (const auto& k : ck) LSTM_LAUNCH(transpose_kernel, (long long)k.in * k.out, st, Cp + l.c[k.seg], k.in, k.out, CT + l.c[k.seg]);
+  }
   float* OL = shared ? E1 : (film ? ws + w.E2 : TI);
   const int ldOL = (shared || film) ? E : EL;
   float* LLp = film ? ws + w.LL : TI + E;
@@ -503,16 +537,16 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
 
   // ================================================================ forward
   // encoders (policy.py:79-92): Z = X We + be; E = tanh(LN(Z))
-  LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE1], O, E, P + l.p[BE1], Z1, E, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS>(X, O, PT + l.p[WE1], O, E, P + l.p[BE1], Z1, E, R, st));
   LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z1, E, R, E, P + l.p[G1], P + l.p[N1], E1, E, S1);
   if (!shared) {
-    LSTM_TRY(dense_fwd<EPI_BIAS>(X, O, P + l.p[WE2], O, E, P + l.p[BE2], Z2, E, R, st));
+    LSTM_TRY(dense_fwd_t<EPI_BIAS>(X, O, PT + l.p[WE2], O, E, P + l.p[BE2], Z2, E, R, st));
     LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Z2, E, R, E, P + l.p[G2], P + l.p[N2], OL, ldOL, S2);
   } else if (!film) {
     LSTM_LAUNCH(cols_kernel<false>, R * E, st, E1, E, R, E, TI, EL);
   }
   // input-side gate pre-activations of all steps at once, then the recurrence, one launch per step (policy.py:115-146)
-  LSTM_TRY(dense_fwd<EPI_NONE>(E1, E, P + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_NONE>(E1, E, PT + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, R, st));
   for (long long t = 0; t < T; ++t) {
     const float* hprev = t == 0 ? a->init_h : Hall + (t - 1) * n * L;
     const float* cprev = t == 0 ? a->init_c : Call + (t - 1) * n * L;
@@ -523,16 +557,16 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   // decode (policy.py:95-112): lstm latent = tanh(LN(h)); combination; torso; mean head
   LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Hall, L, R, L, P + l.p[GL], P + l.p[NL], LLp, ldLL, SL);
   if (film) {
-    LSTM_TRY(dense_fwd<EPI_BIAS>(LLp, L, P + l.p[WF], L, 2 * E, P + l.p[BF], ws + w.GB, 2 * E, R, st));
+    LSTM_TRY(dense_fwd_t<EPI_BIAS>(LLp, L, PT + l.p[WF], L, 2 * E, P + l.p[BF], ws + w.GB, 2 * E, R, st));
     LSTM_LAUNCH(film_fwd_kernel, R * E, st, OL, ldOL, ws + w.GB, R, E, TI);
   }
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(TI, TIW, P + l.p[WT1], TIW, H, P + l.p[BT1], T1, H, R, st));
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(T1, H, P + l.p[WT2], H, H, P + l.p[BT2], T2, H, R, st));
-  LSTM_TRY(dense_fwd<EPI_BIAS>(T2, H, P + l.p[WM], H, A, P + l.p[BM], Mean, A, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS_TANH>(TI, TIW, PT + l.p[WT1], TIW, H, P + l.p[BT1], T1, H, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS_TANH>(T1, H, PT + l.p[WT2], H, H, P + l.p[BT2], T2, H, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS>(T2, H, PT + l.p[WM], H, A, P + l.p[BM], Mean, A, R, st));
   // critic (critic.py:22-30)
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(X, O, Cp + l.c[WC1], O, H, Cp + l.c[BC1], C1, H, R, st));
-  LSTM_TRY(dense_fwd<EPI_BIAS_TANH>(C1, H, Cp + l.c[WC2], H, H, Cp + l.c[BC2], C2, H, R, st));
-  LSTM_TRY(dense_fwd<EPI_BIAS>(C2, H, Cp + l.c[WC3], H, 1, Cp + l.c[BC3], V, 1, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS_TANH>(X, O, CT + l.c[WC1], O, H, Cp + l.c[BC1], C1, H, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS_TANH>(C1, H, CT + l.c[WC2], H, H, Cp + l.c[BC2], C2, H, R, st));
+  LSTM_TRY(dense_fwd_t<EPI_BIAS>(C2, H, CT + l.c[WC3], H, 1, Cp + l.c[BC3], V, 1, R, st));
 
   // ================================================================ loss (ppo_lstm.py:146-172) and head gradients
   const float inv_R = 1.f / (float)R;
@@ -546,13 +580,13 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   // ================================================================ backward: policy head and torso
   LSTM_TRY(dense_bwd_weight(T2, H, dMean, A, H, A, R, Part, gP + l.p[WM], st));
   LSTM_TRY(colsum(dMean, A, R, A, Col, 1.f, 0.f, gP + l.p[BM], st));
-  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dMean, A, P + l.p[WM], H, A, T2, H, dT2, H, R, st));          // dL/d(pre-tanh of torso 2)
+  LSTM_TRY(dense_bwd_input_t<EPI_DTANH>(dMean, A, PT + l.p[WM], H, A, T2, H, dT2, H, R, st));          // dL/d(pre-tanh of torso 2)
   LSTM_TRY(dense_bwd_weight(T1, H, dT2, H, H, H, R, Part, gP + l.p[WT2], st));
   LSTM_TRY(colsum(dT2, H, R, H, Col, 1.f, 0.f, gP + l.p[BT2], st));
-  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dT2, H, P + l.p[WT2], H, H, T1, H, dT1, H, R, st));
+  LSTM_TRY(dense_bwd_input_t<EPI_DTANH>(dT2, H, PT + l.p[WT2], H, H, T1, H, dT1, H, R, st));
   LSTM_TRY(dense_bwd_weight(TI, TIW, dT1, H, TIW, H, R, Part, gP + l.p[WT1], st));
   LSTM_TRY(colsum(dT1, H, R, H, Col, 1.f, 0.f, gP + l.p[BT1], st));
-  LSTM_TRY(dense_bwd_input<EPI_NONE>(dT1, H, P + l.p[WT1], TIW, H, nullptr, 0, dTI, TIW, R, st));   // concat: [dOL | dLL]; FiLM: d(OL * gamma + beta)
+  LSTM_TRY(dense_bwd_input_t<EPI_NONE>(dT1, H, PT + l.p[WT1], TIW, H, nullptr, 0, dTI, TIW, R, st));   // concat: [dOL | dLL]; FiLM: d(OL * gamma + beta)
   // gradients wrt the two latents
   const float* dOL = dTI;
   int lddOL = EL;
@@ -563,7 +597,7 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
     LSTM_LAUNCH(film_bwd_kernel, R * E, st, dTI, OL, ldOL, GB, R, E, dGB, ws + w.dOL);
     LSTM_TRY(dense_bwd_weight(LLp, L, dGB, 2 * E, L, 2 * E, R, Part, gP + l.p[WF], st));
     LSTM_TRY(colsum(dGB, 2 * E, R, 2 * E, Col, 1.f, 0.f, gP + l.p[BF], st));
-    LSTM_TRY(dense_bwd_input<EPI_NONE>(dGB, 2 * E, P + l.p[WF], L, 2 * E, nullptr, 0, ws + w.dLL, L, R, st));
+    LSTM_TRY(dense_bwd_input_t<EPI_NONE>(dGB, 2 * E, PT + l.p[WF], L, 2 * E, nullptr, 0, ws + w.dLL, L, R, st));
     dOL = ws + w.dOL; lddOL = E;
     dLL = ws + w.dLL; lddLL = L;
   }
@@ -589,7 +623,7 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   LSTM_TRY(dense_bwd_weight(Hm, L, dG, 4 * L, L, 4 * L, R, Part, gP + l.p[WH], st));
   LSTM_TRY(colsum(dG, 4 * L, R, 4 * L, Col, 1.f, 0.f, gP + l.p[BH], st));
   LSTM_TRY(dense_bwd_weight(E1, E, dG, 4 * L, E, 4 * L, R, Part, gP + l.p[WI], st));
-  LSTM_TRY(dense_bwd_input<EPI_NONE>(dG, 4 * L, P + l.p[WI], E, 4 * L, nullptr, 0, dE1, E, R, st));
+  LSTM_TRY(dense_bwd_input_t<EPI_NONE>(dG, 4 * L, PT + l.p[WI], E, 4 * L, nullptr, 0, dE1, E, R, st));
   if (shared) LSTM_LAUNCH(cols_kernel<true>, R * E, st, dOL, lddOL, R, E, dE1, E);
   // lstm_obs_encoder backward
   LSTM_TRY(ln_param_grads(dE1, E, E1, E, Z1, E, R, E, S1, Col, gP + l.p[G1], gP + l.p[N1], st));
@@ -600,10 +634,10 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   // ================================================================ backward: critic
   LSTM_TRY(dense_bwd_weight(C2, H, dV, 1, H, 1, R, Part, gC + l.c[WC3], st));
   LSTM_TRY(colsum(dV, 1, R, 1, Col, 1.f, 0.f, gC + l.c[BC3], st));
-  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dV, 1, Cp + l.c[WC3], H, 1, C2, H, dC2, H, R, st));
+  LSTM_TRY(dense_bwd_input_t<EPI_DTANH>(dV, 1, CT + l.c[WC3], H, 1, C2, H, dC2, H, R, st));
   LSTM_TRY(dense_bwd_weight(C1, H, dC2, H, H, H, R, Part, gC + l.c[WC2], st));
   LSTM_TRY(colsum(dC2, H, R, H, Col, 1.f, 0.f, gC + l.c[BC2], st));
-  LSTM_TRY(dense_bwd_input<EPI_DTANH>(dC2, H, Cp + l.c[WC2], H, H, C1, H, dC1, H, R, st));
+  LSTM_TRY(dense_bwd_input_t<EPI_DTANH>(dC2, H, CT + l.c[WC2], H, H, C1, H, dC1, H, R, st));
   LSTM_TRY(dense_bwd_weight(X, O, dC1, H, O, H, R, Part, gC + l.c[WC1], st));
   LSTM_TRY(colsum(dC1, H, R, H, Col, 1.f, 0.f, gC + l.c[BC1], st));
   return RLX_OK;
