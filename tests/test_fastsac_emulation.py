@@ -73,7 +73,7 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu, tag):
     lr_a, steps = np.array([lr], np.float32), np.zeros(3, np.int64)
     sc = action_scale.numpy().astype(np.float32)
     nbytes = emu.rlx_fastsac_workspace_bytes(C.byref(d), batch)
-    ws = np.zeros(nbytes // 4 + 64, np.float32)
+    ws = np.full(nbytes // 4, np.nan, np.float32)   # exact size (ASan build) and NaN-filled (a read of workspace nothing wrote in this call poisons the outputs)
     hp = HP(gamma, tau, vmin, vmax, tgt_ent, lsmin, lsmax, wd, b1, b2, 1e-8, max_gn, clipped)
     nmean, nvar, nstd, ncount = np.zeros(obs, np.float32), np.ones(obs, np.float32), np.ones(obs, np.float32), np.zeros(1, np.int64)
     emu.rlx_fastsac_normalize_f32.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
@@ -101,7 +101,7 @@ def test_emulated_fastsac_updates_track_the_pinned_oracle(emu, tag):
             first = {k_: v_.copy() for k_, v_ in state.items()}
             for k_, v_ in state.items():
                 v_[...] = before[k_]
-            ws[:] = 0
+            ws[:] = np.nan
             emu.rlx_emu_set_thread_order(1)
             try:
                 assert fn(C.byref(a), None) == 0

@@ -133,7 +133,9 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
     stats = np.array([float(adv.mean()), float(adv.std(unbiased=False))], dtype=np.float32)
     metrics = np.zeros(8, np.float32)
     nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), T, n)
-    ws = np.zeros(nbytes // 4, np.float32)   # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun
+    # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun; NaN-filled: a kernel that reads workspace before
+    # something wrote it in THIS call (stale data from the previous minibatch on the device) poisons the outputs
+    ws = np.full(nbytes // 4, np.nan, np.float32)
     arrs = dict(states=_np(states), actions=_np(actions), log_probs=_np(log_probs), advantages=_np(adv), returns=_np(ret), dones=_np(dones),
                 init_c=_np(init[0]), init_h=_np(init[1]))
     a = Args()
@@ -160,7 +162,7 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
     # Race check: the same call with the emulated threads of every launch run in DESCENDING order must give the same bits.  A thread that
     # reads what another thread of the same launch writes (a data race on the device) would make the result depend on the order.
     gP2, gC2, metrics2 = np.full_like(P, np.nan), np.full_like(Cc, np.nan), np.zeros(8, np.float32)
-    ws[:] = 0
+    ws[:] = np.nan
     a.policy_grads, a.critic_grads, a.metrics = gP2.ctypes.data, gC2.ctypes.data, metrics2.ctypes.data
     emu.rlx_emu_set_thread_order(1)
     try:
@@ -222,7 +224,9 @@ def test_emulated_rollout_step_matches_oracle(emu, options):
     Cc = np.concatenate([_np(x) for x in flatten_critic(cri)])
     low, high = np.full(act, -2.0, np.float32), np.full(act, 0.5, np.float32)
     nbytes = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, n)
-    ws = np.zeros(nbytes // 4, np.float32)   # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun
+    # exact size: an AddressSanitizer run (conftest.emu_build_cmd) sees any overrun; NaN-filled: a kernel that reads workspace before
+    # something wrote it in THIS call (stale data from the previous minibatch on the device) poisons the outputs
+    ws = np.full(nbytes // 4, np.nan, np.float32)
     c, h = np.zeros((n, lstm), np.float32), np.zeros((n, lstm), np.float32)
     carry = (torch.zeros(n, lstm), torch.zeros(n, lstm))
     emu.rlx_lstm_mask_carry_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
@@ -275,7 +279,7 @@ def test_emulated_rollout_step_matches_oracle(emu, options):
     x = torch.randn(rows, obs_d)
     xv, outv = _np(x), np.zeros(rows, np.float32)
     nb = emu.rlx_lstm_minibatch_workspace_bytes(C.byref(d), 1, rows)
-    ws2 = np.zeros(nb // 4, np.float32)
+    ws2 = np.full(nb // 4, np.nan, np.float32)
     emu.rlx_lstm_critic_forward_f32.argtypes = [C.POINTER(Dims), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     assert emu.rlx_lstm_critic_forward_f32(C.byref(d), Cc.ctypes.data, xv.ctypes.data, rows, outv.ctypes.data, ws2.ctypes.data, nb, None) == 0
     with torch.no_grad():
