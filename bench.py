@@ -409,7 +409,7 @@ def aux_gemm_engine_verdict():
     env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1", RLX_AUX_ENGINE_REPORT=report)
     try:
         proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider"] + tests, env=env, cwd=ROOT, capture_output=True,
-                              text=True, timeout=900)
+                              text=True, timeout=420)
         count = open(report).read().strip() if os.path.exists(report) else "no report"
         tail = (proc.stdout + proc.stderr).strip().splitlines()[-1:] or [""]
         ok = proc.returncode == 0 and count.isdigit() and int(count) > 0 and " passed" in tail[0] and "skipped" not in tail[0]

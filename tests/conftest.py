@@ -29,7 +29,7 @@ def pytest_sessionfinish(session, exitstatus):
             fh.write(str(count))
 
 
-def run_suite_on_tensor_engine(test_file, tmp_path, timeout=1500):
+def run_suite_on_tensor_engine(test_file, tmp_path, timeout=900):
     """Run the GPU parity tests of `test_file` again in a SUBPROCESS with RLX_AUX_GEMM_ENGINE=1 (dense layers on the tcgen05 3xTF32 engine
     where it covers the product).  A subprocess because a tensor-core kernel that hangs ends in the engine's watchdog trap, which takes
     the CUDA context with it: here that costs one test, not the rest of the session.  Returns (returncode, output tail, tensor GEMM count)."""
