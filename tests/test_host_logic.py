@@ -468,3 +468,37 @@ def test_build_digest_does_not_depend_on_the_checkout_path(tmp_path, monkeypatch
     with open(other / "csrc" / "gae.cu", "a") as fh:
         fh.write("\n// changed\n")
     assert b._digest() != here
+
+
+def _last_json_line(path):
+    import json
+    with open(path) as fh:
+        lines = [ln for ln in fh.read().splitlines() if ln.startswith("{")]
+    return json.loads(lines[-1])
+
+
+def test_committed_bench_records_carry_the_contract_keys():
+    """The bench lines committed under profiles/ (the last hardware runs of `python bench.py` and `bench.py --impl reference`) against the
+    key list of the measurement contract: a renamed or dropped key would otherwise only be noticed by the driver."""
+    import os
+    prof = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
+    line = _last_json_line(os.path.join(prof, "r02_bench_1gpu.json"))
+    for key in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "gpu_launches", "clocks", "roofline", "cpu_baseline", "e2e"]:
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["warmup"] >= 3 and line["higher_is_better"] is True and line["vs_baseline"] is None
+    assert line["dtype"] == "f32" and line["data"] == "synthetic" and "workload" in line["config"] and "model" not in line["config"]
+    assert abs(line["value"] - 4096 * 128 / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]       # value and ms_per_step tell one story
+    roof = line["roofline"]
+    assert set(["bound", "achieved", "peak", "unit", "frac", "traffic"]) <= set(roof) and roof["bound"] in ("hbm", "tensor")
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) <= 1e-9
+    assert set(["value", "unit", "cores", "kind", "sample"]) <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] in ("reference", "port")
+    e2e = line["e2e"]
+    assert set(["value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"]) <= set(e2e) and e2e["h2d_bytes_per_step"] > 0 < e2e["d2h_bytes_per_step"]
+    assert e2e["value"] < line["value"]                              # host copies inside the timed region cannot be free
+    assert set(["sm_mhz", "sm_max_mhz", "reasons"]) <= set(line["clocks"]) and line["gpu_launches"] > 0
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    ref = _last_json_line(os.path.join(prof, "r02_reference_arm.json"))
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"] and ref["config"]["workload"] == line["config"]["workload"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 == ref["e2e"]["d2h_bytes_per_step"] and ref["e2e"]["value"] == ref["value"]
+    assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["value"] == ref["value"]
