@@ -389,57 +389,78 @@ def run_sac(args):
 _AUX_VERDICT = None
 
 
-def aux_gemm_engine_verdict():
-    """May the FastSAC / PPO+LSTM workloads run their dense layers on the tcgen05 3xTF32 engine (rlx_set_aux_gemm_engine(1))?  That switch was
-    written after the round's GPU budget was spent, so it has to prove itself ON THIS BOX before a timed run may use it: a subprocess (a
-    tensor-core kernel that hangs ends in the watchdog trap and takes its CUDA context along - not this process's) runs, with the engine on,
-    the FastSAC golden-batch parity test, the SIMT-vs-tensor gradient agreement at batch 1024, and the PPO+LSTM oracle parity tests at the
-    config-5 shape (T=128, 256 envs) and a smaller one.  All green AND tensor GEMMs actually counted -> engine 1; anything else -> SIMT, with
-    the reason in the record.  No CPU oracle is timed here: the tests use it as the checker only."""
+def aux_paths_verdict():
+    """May the FastSAC / PPO+LSTM workloads use (1) the tcgen05 3xTF32 engine for their dense layers (rlx_set_aux_gemm_engine) and (2) the
+    one-launch-per-direction LSTM recurrence (rlx_set_lstm_persistent)?  Both switches were written after the round's GPU budget was spent,
+    so they have to prove themselves ON THIS BOX before a timed run may use them: a subprocess (a kernel that traps or faults takes its CUDA
+    context along - not this process's) runs, with the switches on, the FastSAC golden-batch parity test, the SIMT-vs-tensor gradient
+    agreement at batch 1024, the PPO+LSTM oracle parity tests at the config-5 shape (T=128, 256 envs) and a smaller one, and the bit-for-bit
+    comparison of the two recurrence paths.  Green AND the paths actually counted -> on.  If both together fail, each is tried alone.  The
+    record carries every attempt.  No CPU oracle is timed here: the tests use it as the checker only."""
     global _AUX_VERDICT
     if _AUX_VERDICT is not None:
         return _AUX_VERDICT
     import subprocess
     import tempfile
-    tests = ["tests/test_gpu_zzzz_fastsac.py::test_fastsac_updates_match_oracle_on_golden_batches",
-             "tests/test_gpu_zzzz_fastsac.py::test_fastsac_engines_agree_at_batch_1024",
-             "tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[16-24-64-8-256-128-64-0]",
-             "tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[128-256-64-8-256-128-64-0]"]
-    report = os.path.join(tempfile.mkdtemp(prefix="rlx_aux_"), "tc_gemms.txt")
-    env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1", RLX_AUX_ENGINE_REPORT=report)
-    try:
-        proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider"] + tests, env=env, cwd=ROOT, capture_output=True,
-                              text=True, timeout=420)
-        count = open(report).read().strip() if os.path.exists(report) else "no report"
-        tail = (proc.stdout + proc.stderr).strip().splitlines()[-1:] or [""]
-        ok = proc.returncode == 0 and count.isdigit() and int(count) > 0 and " passed" in tail[0] and "skipped" not in tail[0]
-        _AUX_VERDICT = {"engine": "tcgen05-3xTF32" if ok else "simt", "check": {"tests": len(tests), "pytest": tail[0], "tensor_gemms_in_check": count,
-                                                                              "returncode": proc.returncode}}
-    except Exception as exc:  # timeout, no pytest, ...
-        _AUX_VERDICT = {"engine": "simt", "check": {"error": f"{type(exc).__name__}: {exc}"}}
+    fastsac = ["tests/test_gpu_zzzz_fastsac.py::test_fastsac_updates_match_oracle_on_golden_batches",
+               "tests/test_gpu_zzzz_fastsac.py::test_fastsac_engines_agree_at_batch_1024"]
+    lstm = ["tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[16-24-64-8-256-128-64-0]",
+            "tests/test_gpu_zzz_ppo_lstm.py::test_lstm_fwdbwd_matches_oracle_autograd[128-256-64-8-256-128-64-0]"]
+    bitwise = ["tests/test_gpu_zzz_ppo_lstm.py::test_lstm_one_launch_recurrence_equals_per_step_recurrence_bit_for_bit"]
+
+    def attempt(tensor, persistent):
+        tests = (fastsac if tensor else []) + lstm + (bitwise if persistent else [])
+        report = os.path.join(tempfile.mkdtemp(prefix="rlx_aux_"), "paths.txt")
+        env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1" if tensor else "0", RLX_LSTM_PERSISTENT="1" if persistent else "0", RLX_AUX_ENGINE_REPORT=report)
+        rec = {"tensor_engine": tensor, "persistent_recurrence": persistent, "tests": len(tests)}
+        try:
+            proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider"] + tests, env=env, cwd=ROOT, capture_output=True,
+                                  text=True, timeout=420)
+            counts = open(report).read().split() if os.path.exists(report) else []
+            tail = ((proc.stdout + proc.stderr).strip().splitlines() or [""])[-1]
+            used = len(counts) == 2 and all(x.isdigit() for x in counts) and (not tensor or int(counts[0]) > 0) and (not persistent or int(counts[1]) > 0)
+            rec.update(pytest=tail, returncode=proc.returncode, tensor_gemms=counts[0] if counts else None, persistent_launches=counts[1] if len(counts) > 1 else None)
+            rec["green"] = bool(proc.returncode == 0 and used and f"{len(tests)} passed" in tail)
+        except Exception as exc:  # timeout, no pytest, ...
+            rec.update(error=f"{type(exc).__name__}: {exc}", green=False)
+        return rec
+
+    attempts = [attempt(True, True)]
+    tensor = persistent = attempts[0]["green"]
+    if not attempts[0]["green"]:
+        attempts.append(attempt(True, False))
+        tensor = attempts[-1]["green"]
+        attempts.append(attempt(False, True))
+        persistent = attempts[-1]["green"]
+    _AUX_VERDICT = {"tensor_engine": bool(tensor), "persistent_recurrence": bool(persistent), "attempts": attempts}
     return _AUX_VERDICT
 
 
-def with_aux_gemm_engine(fn, args):
-    """Run a nested workload with the engine the verdict allows; the record says which engine ran and how many GEMMs the tensor engine took."""
+def with_aux_paths(fn, args):
+    """Run a nested workload with the opt-in paths the verdict allows; the record says which ran and carries the counters as evidence."""
     from rl_x_b200 import _native as nt
     lib = nt.load()
-    verdict = dict(aux_gemm_engine_verdict())
-    lib.rlx_set_aux_gemm_engine(1 if verdict["engine"] != "simt" else 0)
-    before = int(lib.rlx_aux_tc_gemm_count())
+    verdict = dict(aux_paths_verdict())
+
+    def switches(tensor, persistent):
+        lib.rlx_set_aux_gemm_engine(1 if tensor else 0)
+        lib.rlx_set_lstm_persistent(1 if persistent else 0)
+        return int(lib.rlx_aux_tc_gemm_count()), int(lib.rlx_lstm_persistent_launch_count())
+
+    before = switches(verdict["tensor_engine"], verdict["persistent_recurrence"])
     try:
         line = fn(args)
     except Exception as exc:
-        if verdict["engine"] == "simt":
+        if not (verdict["tensor_engine"] or verdict["persistent_recurrence"]):
             raise
-        # green check, failing workload: the number must not be lost to an opt-in - time it on the SIMT engine and say so
-        verdict = {"engine": "simt", "check": verdict["check"], "fell_back_after": f"{type(exc).__name__}: {exc}"}
-        lib.rlx_set_aux_gemm_engine(0)
-        before = int(lib.rlx_aux_tc_gemm_count())
+        # green check, failing workload: the number must not be lost to an opt-in - time it on the default paths and say so
+        verdict.update(tensor_engine=False, persistent_recurrence=False, fell_back_after=f"{type(exc).__name__}: {exc}")
+        before = switches(False, False)
         line = fn(args)
     finally:
-        lib.rlx_set_aux_gemm_engine(0)
-    line["gemm_engine"] = dict(verdict, tensor_gemms_in_run=int(lib.rlx_aux_tc_gemm_count()) - before)
+        after = switches(False, False)
+    line["gemm_engine"] = dict(verdict, engine="tcgen05-3xTF32" if verdict["tensor_engine"] else "simt", tensor_gemms_in_run=after[0] - before[0],
+                               persistent_launches_in_run=after[1] - before[1])
     return line
 
 
@@ -669,7 +690,7 @@ def main():
     if args.workload in ("sac", "fastsac", "ppo_lstm"):
         if rank == 0:
             fn = {"sac": run_sac, "fastsac": run_fastsac, "ppo_lstm": run_ppo_lstm}[args.workload]
-            print(json.dumps(fn(args) if args.workload == "sac" or args.no_aux_engine else with_aux_gemm_engine(fn, args)))
+            print(json.dumps(fn(args) if args.workload == "sac" or args.no_aux_engine else with_aux_paths(fn, args)))
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU oracle)")
@@ -888,7 +909,7 @@ def main():
         for name, fn in (("sac", run_sac), ("fastsac", run_fastsac), ("ppo_lstm", run_ppo_lstm)):
             try:
                 torch.cuda.empty_cache()
-                line["workloads"][name] = fn(args) if name == "sac" or args.no_aux_engine else with_aux_gemm_engine(fn, args)
+                line["workloads"][name] = fn(args) if name == "sac" or args.no_aux_engine else with_aux_paths(fn, args)
             except Exception as e:
                 line["workloads"][name] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:

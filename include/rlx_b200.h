@@ -331,6 +331,13 @@ typedef struct rlx_lstm_dims { int32_t obs_dim, act_dim, hidden, enc_dim, lstm_d
 int rlx_lstm_param_layout(const rlx_lstm_dims* d, int64_t* policy_offsets /*[NSEG+1]*/, int64_t* critic_offsets /*[NSEG+1]*/);
 size_t rlx_lstm_minibatch_workspace_bytes(const rlx_lstm_dims* d, int64_t T, int64_t n_env);
 
+/* Recurrence of rlx_lstm_ppo_minibatch_fwdbwd_f32: 0 (default) one launch per time step and direction; 1 ONE launch per direction - a block
+ * owns a few envs for all T steps, recurrent kernel (Wh / Wh^T) resident in shared memory, hidden state / gate gradients exchanged through
+ * shared memory with one barrier per step, cell state in a register.  Used when the kernel fits (lstm_dim <= 100 or so: 64 KB at 64), else
+ * the per-step path runs.  Bit-identical results.  Returns the value in effect; the counter says how many such launches have run. */
+int rlx_set_lstm_persistent(int on);
+uint64_t rlx_lstm_persistent_launch_count(void);
+
 typedef struct rlx_lstm_minibatch_args {
   rlx_lstm_dims dims;
   int64_t T, n_env;             /* sequence length, envs in this minibatch (ppo_lstm.py:58: minibatch_size // nr_steps) */

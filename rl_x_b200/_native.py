@@ -179,6 +179,8 @@ _SIGNATURES = {
                                               C.c_int64, C.c_int64] + [C.c_void_p] * 15),
     "rlx_lstm_param_layout": (C.c_int, [C.POINTER(LstmDims), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rlx_lstm_minibatch_workspace_bytes": (C.c_size_t, [C.POINTER(LstmDims), C.c_int64, C.c_int64]),
+    "rlx_set_lstm_persistent": (C.c_int, [C.c_int]),
+    "rlx_lstm_persistent_launch_count": (C.c_uint64, []),
     "rlx_lstm_ppo_minibatch_fwdbwd_f32": (C.c_int, [C.POINTER(LstmMinibatchArgs), C.c_void_p]),
     "rlx_lstm_step_f32": (C.c_int, [C.POINTER(LstmStepArgs), C.c_void_p]),
     "rlx_lstm_mask_carry_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
@@ -271,6 +273,8 @@ def load(build_if_missing=True):
     # run or a bench leg select the tensor engine from outside, e.g. RLX_AUX_GEMM_ENGINE=1 python -m pytest tests/test_gpu_zzzz_fastsac.py
     if os.environ.get("RLX_AUX_GEMM_ENGINE", "") in ("0", "1"):
         lib.rlx_set_aux_gemm_engine(int(os.environ["RLX_AUX_GEMM_ENGINE"]))
+    if os.environ.get("RLX_LSTM_PERSISTENT", "") in ("0", "1"):   # same idea for the one-launch-per-direction LSTM recurrence
+        lib.rlx_set_lstm_persistent(int(os.environ["RLX_LSTM_PERSISTENT"]))
     _lib = lib
     return lib
 

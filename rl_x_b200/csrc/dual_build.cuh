@@ -1,7 +1,10 @@
 // Dual-build support for the "one thread = one row / element" sources (lstm.cu, replay_nstep.cu): the same file compiles with nvcc into
 // the product library, and with  g++ -x c++ -DRLX_EMU  into a host library for the CPU tests, where a kernel launch is a loop over
-// (block, thread) and a GEMM is an interpreter of the GemmP contract of gemm_simt.cuh.  Kernels written against this header must not
-// use shared memory, warp primitives or barriers.  The emulation build is test scaffolding; nothing in the product loads it.
+// (block, thread) and a GEMM is an interpreter of the GemmP contract of gemm_simt.cuh.  Kernels launched with RLX_FLAT_LAUNCH must not
+// use shared memory, warp primitives or barriers.  Block-cooperative kernels (dynamic shared memory + __syncthreads, no warp
+// primitives) go through RLX_BLOCK_LAUNCH: the emulation runs one block at a time with one OS thread per CUDA thread and a real
+// barrier, so a missing __syncthreads is a real data race there too (and ThreadSanitizer sees it: tests/emu_tsan_lstm.cpp).
+// The emulation build is test scaffolding; nothing in the product loads it.
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
@@ -13,9 +16,27 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
 namespace rlx {
 struct EmuDim { unsigned x, y, z; };
-static EmuDim threadIdx, blockIdx, blockDim, gridDim;
+static thread_local EmuDim threadIdx, blockIdx, blockDim, gridDim;
+// one block of a block-cooperative launch: its dynamic shared memory and its barrier
+struct EmuBlock {
+  std::vector<float> smem;
+  std::mutex m;
+  std::condition_variable cv;
+  unsigned nthreads = 0, waiting = 0, generation = 0;
+  void sync() {
+    std::unique_lock<std::mutex> lk(m);
+    const unsigned gen = generation;
+    if (++waiting == nthreads) { waiting = 0; ++generation; cv.notify_all(); }
+    else cv.wait(lk, [&] { return generation != gen; });
+  }
+};
+static thread_local EmuBlock* g_emu_block = nullptr;
 // Order in which the emulated threads of a launch run: 0 = ascending (block, thread), 1 = descending.  A kernel whose threads only
 // touch their own outputs gives bit-identical results either way; one thread reading what another thread of the SAME launch writes
 // (a data race on the device) does not.  tests/test_*_emulation.py run every entry point both ways.
@@ -75,6 +96,29 @@ int aux_gemm(const GemmP& p, int batch, cudaStream_t st, int kclass, long long a
 }
 }  // namespace rlx
 extern "C" void rlx_emu_set_thread_order(int reverse) { rlx::g_emu_reverse = reverse; }
+#define __syncthreads() rlx::g_emu_block->sync()
+#define RLX_DYN_SMEM(name) float* name = rlx::g_emu_block->smem.data()
+// block-cooperative launch: blocks one after the other, the threads of a block concurrently (they meet at __syncthreads)
+#define RLX_BLOCK_LAUNCH(kernel, nb_, nt_, smem_, stream, ...)                            \
+  do {                                                                                            \
+    const unsigned _nb = (unsigned)(nb_), _nt = (unsigned)(nt_);                         \
+    for (unsigned _b = 0; _b < _nb; ++_b) {                                                       \
+      rlx::EmuBlock _blk;                                                                         \
+      _blk.smem.assign(((size_t)(smem_) + 3) / 4, nanf(""));                                 \
+      _blk.nthreads = _nt;                                                                        \
+      std::vector<std::thread> _ths;                                                              \
+      for (unsigned _t = 0; _t < _nt; ++_t)                                                       \
+        _ths.emplace_back([=, &_blk] {                                                            \
+          rlx::g_emu_block = &_blk;                                                               \
+          rlx::blockDim = {_nt, 1, 1};                                                            \
+          rlx::gridDim = {_nb, 1, 1};                                                             \
+          rlx::blockIdx = {_b, 0, 0};                                                             \
+          rlx::threadIdx = {_t, 0, 0};                                                            \
+          kernel(__VA_ARGS__);                                                                    \
+        });                                                                                       \
+      for (auto& _th : _ths) _th.join();                                                          \
+    }                                                                                             \
+  } while (0)
 #define __global__
 #define __device__
 #define __forceinline__ inline
@@ -117,6 +161,17 @@ static int aux_gemm(const GemmP& p, int batch, cudaStream_t st, int kclass, long
   do {                                                                                                                         \
     const long long _n = (nthreads_total);                                                                                     \
     if (_n > 0) RLX_LAUNCH_C(rlx::KC_OTHER, 0, 0, kernel, (unsigned)rlx::ceil_div(_n, 256), 256, 0, (cudaStream_t)(stream), __VA_ARGS__); \
+  } while (0)
+#define RLX_DYN_SMEM(name) extern __shared__ float name[]
+// block-cooperative launch with dynamic shared memory (opted in above the 48 KB default once per kernel)
+#define RLX_BLOCK_LAUNCH(kernel, nb_, nt_, smem_, stream, ...)                                                                   \
+  do {                                                                                                                         \
+    static size_t _smem_set = 0;                                                                                               \
+    if ((size_t)(smem_) > _smem_set) {                                                                                    \
+      RLX_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_)));            \
+      _smem_set = (size_t)(smem_);                                                                                        \
+    }                                                                                                                          \
+    RLX_LAUNCH_C(rlx::KC_OTHER, 0, 0, kernel, (unsigned)(nb_), (unsigned)(nt_), (size_t)(smem_), (cudaStream_t)(stream), __VA_ARGS__); \
   } while (0)
 #endif
 

@@ -251,6 +251,102 @@ __global__ void lstm_step_bwd_kernel(const float* __restrict__ dHall, const floa
   dCprev[id] = dC * f * keep;
 }
 
+// ---- the whole recurrence in ONE launch per direction (rlx_set_lstm_persistent): a block owns EPB envs for all T steps, thread = (env, unit).
+// The recurrent kernel lives in shared memory for the life of the block (Wh: [L, 4L], 64 KB at L = 64), the hidden state / the gate
+// gradients of the block's envs are exchanged through shared memory (double-buffered: ONE barrier per step) and the cell state / its
+// gradient stay in a register.  Every thread performs exactly the arithmetic of lstm_step_fwd_kernel / lstm_step_bwd_kernel in the same
+// order, so the results are bit-identical to the one-launch-per-step path.
+// shared: sWh [L * 4L] | sH [2][EPB * L]
+__global__ void lstm_seq_fwd_kernel(const float* __restrict__ Gi, const float* __restrict__ Wh, const float* __restrict__ bh,
+                                    const float* __restrict__ init_h, const float* __restrict__ init_c, const float* __restrict__ dones,
+                                    long long T, long long n, int L, int EPB, float* __restrict__ Hm, float* __restrict__ Cm,
+                                    float* __restrict__ gates, float* __restrict__ Call, float* __restrict__ Hall) {
+  RLX_DYN_SMEM(sm);
+  float* sWh = sm;
+  float* sH = sm + (long long)L * 4 * L;
+  const int tid = (int)threadIdx.x, el = tid / L, j = tid % L;
+  const long long e = (long long)blockIdx.x * EPB + el;
+  const bool active = e < n;
+  for (int i = tid; i < L * 4 * L; i += (int)blockDim.x) sWh[i] = Wh[i];
+  float c = active ? init_c[e * L + j] : 0.f;
+  sH[el * L + j] = active ? init_h[e * L + j] : 0.f;
+  __syncthreads();
+  for (long long t = 0; t < T; ++t) {
+    const float* hcur = sH + (t & 1) * EPB * L + el * L;
+    float* hnext = sH + ((t + 1) & 1) * EPB * L + el * L;
+    if (active) {
+      const long long row = t * n + e, base = row * 4 * L, id = row * L + j;
+      const float keep = t > 0 ? 1.f - dones[(t - 1) * n + e] : 1.f;
+      float zi = Gi[base + j] + bh[j], zf = Gi[base + L + j] + bh[L + j], zg = Gi[base + 2 * L + j] + bh[2 * L + j], zo = Gi[base + 3 * L + j] + bh[3 * L + j];
+      for (int k = 0; k < L; ++k) {
+        const float hk = hcur[k] * keep;
+        const float* w = sWh + (long long)k * 4 * L + j;
+        zi = fmaf(hk, w[0], zi);
+        zf = fmaf(hk, w[L], zf);
+        zg = fmaf(hk, w[2 * L], zg);
+        zo = fmaf(hk, w[3 * L], zo);
+      }
+      const float cm = c * keep;
+      Hm[id] = hcur[j] * keep;
+      Cm[id] = cm;
+      const float i = sigmoidf_(zi), f = sigmoidf_(zf), g = tanhf(zg), o = sigmoidf_(zo);
+      c = f * cm + i * g;
+      gates[base + j] = i;
+      gates[base + L + j] = f;
+      gates[base + 2 * L + j] = g;
+      gates[base + 3 * L + j] = o;
+      Call[id] = c;
+      const float h = o * tanhf(c);
+      Hall[id] = h;
+      hnext[j] = h;
+    }
+    __syncthreads();
+  }
+}
+// shared: sWhT [4L * L] | sdG [2][EPB * 4L]
+__global__ void lstm_seq_bwd_kernel(const float* __restrict__ dHall, const float* __restrict__ WhT, const float* __restrict__ dones,
+                                    const float* __restrict__ gates, const float* __restrict__ Call, const float* __restrict__ Cm,
+                                    long long T, long long n, int L, int EPB, float* __restrict__ dG) {
+  RLX_DYN_SMEM(sm);
+  float* sWhT = sm;
+  float* sdG = sm + (long long)4 * L * L;
+  const int tid = (int)threadIdx.x, el = tid / L, j = tid % L;
+  const long long e = (long long)blockIdx.x * EPB + el;
+  const bool active = e < n;
+  for (int i = tid; i < 4 * L * L; i += (int)blockDim.x) sWhT[i] = WhT[i];
+  float dCn = 0.f;
+  __syncthreads();
+  for (long long t = T - 1; t >= 0; --t) {
+    const int cur = (int)((T - 1 - t) & 1);                    // slot holding dG_{t+1} of this block's envs; this step writes the other one
+    const float* dgn = sdG + cur * EPB * 4 * L + el * 4 * L;
+    float* dgo = sdG + (cur ^ 1) * EPB * 4 * L + el * 4 * L;
+    if (active) {
+      const long long row = t * n + e, base = row * 4 * L, id = row * L + j;
+      float dH = dHall[id];
+      if (t < T - 1) {
+        float acc = 0.f;
+        for (int q = 0; q < 4 * L; ++q) acc = fmaf(dgn[q], sWhT[(long long)q * L + j], acc);
+        dH += acc * (1.f - dones[t * n + e]);
+      }
+      const float i = gates[base + j], f = gates[base + L + j], g = gates[base + 2 * L + j], o = gates[base + 3 * L + j];
+      const float tc = tanhf(Call[id]);
+      const float dC = (t < T - 1 ? dCn : 0.f) + dH * o * (1.f - tc * tc);
+      const float gi = dC * g * i * (1.f - i), gf = dC * Cm[id] * f * (1.f - f), gg = dC * i * (1.f - g * g), go = dH * tc * o * (1.f - o);
+      dG[base + j] = gi;
+      dG[base + L + j] = gf;
+      dG[base + 2 * L + j] = gg;
+      dG[base + 3 * L + j] = go;
+      dgo[j] = gi;
+      dgo[L + j] = gf;
+      dgo[2 * L + j] = gg;
+      dgo[3 * L + j] = go;
+      const float keep = t > 0 ? 1.f - dones[(t - 1) * n + e] : 1.f;
+      dCn = dC * f * keep;
+    }
+    __syncthreads();
+  }
+}
+
 // FiLM combination (policy.py:102-105): GB = [gamma | beta] ([R, 2W]); out = OL * gamma + beta.  thread = element
 __global__ void film_fwd_kernel(const float* __restrict__ OL, int ldo, const float* __restrict__ GB, long long R, int W, float* __restrict__ out) {
   const long long id = gtid();
@@ -473,6 +569,25 @@ using namespace rlx::lstm;
 
 #define LSTM_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
+// recurrence: one launch per direction when asked for and when the recurrent kernel fits in shared memory, else one launch per step
+static int g_lstm_persistent = 0;
+static unsigned long long g_lstm_persistent_launches = 0;  // evidence for tests / bench records that the one-launch path really ran
+extern "C" int rlx_set_lstm_persistent(int on) {
+  g_lstm_persistent = on ? 1 : 0;
+  return g_lstm_persistent;
+}
+extern "C" uint64_t rlx_lstm_persistent_launch_count(void) { return g_lstm_persistent_launches; }
+struct SeqCfg { int epb, threads; size_t smem_fwd, smem_bwd; bool ok; };
+static SeqCfg seq_cfg(int L) {
+  SeqCfg c;
+  c.epb = std::max(1, 128 / L);
+  c.threads = c.epb * L;
+  c.smem_fwd = ((size_t)L * 4 * L + 2 * (size_t)c.epb * L) * sizeof(float);
+  c.smem_bwd = ((size_t)4 * L * L + 2 * (size_t)c.epb * 4 * L) * sizeof(float);
+  c.ok = g_lstm_persistent == 1 && c.threads <= 1024 && std::max(c.smem_fwd, c.smem_bwd) <= 200 * 1024;
+  return c;
+}
+
 extern "C" int rlx_lstm_param_layout(const rlx_lstm_dims* d, int64_t* policy_offsets, int64_t* critic_offsets) {
   RLX_CHECK_ARG(d != nullptr && dims_ok(*d), "unsupported dims");
   const Layout l = make_layout(*d);
@@ -547,12 +662,19 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
   }
   // input-side gate pre-activations of all steps at once, then the recurrence, one launch per step (policy.py:115-146)
   LSTM_TRY(dense_fwd_t<EPI_NONE>(E1, E, PT + l.p[WI], E, 4 * L, nullptr, Gi, 4 * L, R, st));
-  for (long long t = 0; t < T; ++t) {
-    const float* hprev = t == 0 ? a->init_h : Hall + (t - 1) * n * L;
-    const float* cprev = t == 0 ? a->init_c : Call + (t - 1) * n * L;
-    const float* done_prev = t == 0 ? nullptr : a->dones + (t - 1) * n;
-    LSTM_LAUNCH(lstm_step_fwd_kernel, n * L, st, Gi + t * n * 4 * L, P + l.p[WH], P + l.p[BH], hprev, cprev, done_prev, n, L, Hm + t * n * L,
-                Cm + t * n * L, Gates + t * n * 4 * L, Call + t * n * L, Hall + t * n * L);
+  const SeqCfg seq = seq_cfg(L);
+  if (seq.ok) {
+    RLX_BLOCK_LAUNCH(lstm_seq_fwd_kernel, ceil_div(n, seq.epb), seq.threads, seq.smem_fwd, st, Gi, P + l.p[WH], P + l.p[BH], a->init_h, a->init_c, a->dones,
+                     T, n, L, seq.epb, Hm, Cm, Gates, Call, Hall);
+    ++g_lstm_persistent_launches;
+  } else {
+    for (long long t = 0; t < T; ++t) {
+      const float* hprev = t == 0 ? a->init_h : Hall + (t - 1) * n * L;
+      const float* cprev = t == 0 ? a->init_c : Call + (t - 1) * n * L;
+      const float* done_prev = t == 0 ? nullptr : a->dones + (t - 1) * n;
+      LSTM_LAUNCH(lstm_step_fwd_kernel, n * L, st, Gi + t * n * 4 * L, P + l.p[WH], P + l.p[BH], hprev, cprev, done_prev, n, L, Hm + t * n * L,
+                  Cm + t * n * L, Gates + t * n * 4 * L, Call + t * n * L, Hall + t * n * L);
+    }
   }
   // decode (policy.py:95-112): lstm latent = tanh(LN(h)); combination; torso; mean head
   LSTM_LAUNCH(ln_tanh_fwd_kernel, R, st, Hall, L, R, L, P + l.p[GL], P + l.p[NL], LLp, ldLL, SL);
@@ -614,11 +736,16 @@ extern "C" int rlx_lstm_ppo_minibatch_fwdbwd_f32(const rlx_lstm_minibatch_args* 
 
   // ================================================================ back-propagation through time, one launch per step
   LSTM_LAUNCH(transpose_kernel, (long long)L * 4 * L, st, P + l.p[WH], L, 4 * L, WhT);
-  for (long long t = T - 1; t >= 0; --t) {
-    const bool last = (t == T - 1);
-    LSTM_LAUNCH(lstm_step_bwd_kernel, n * L, st, dHall + t * n * L, last ? nullptr : dG + (t + 1) * n * 4 * L, WhT, last ? nullptr : a->dones + t * n,
-                last ? nullptr : dCn, Gates + t * n * 4 * L, Call + t * n * L, Cm + t * n * L, t == 0 ? nullptr : a->dones + (t - 1) * n, n, L,
-                dG + t * n * 4 * L, dCn);
+  if (seq.ok) {
+    RLX_BLOCK_LAUNCH(lstm_seq_bwd_kernel, ceil_div(n, seq.epb), seq.threads, seq.smem_bwd, st, dHall, WhT, a->dones, Gates, Call, Cm, T, n, L, seq.epb, dG);
+    ++g_lstm_persistent_launches;
+  } else {
+    for (long long t = T - 1; t >= 0; --t) {
+      const bool last = (t == T - 1);
+      LSTM_LAUNCH(lstm_step_bwd_kernel, n * L, st, dHall + t * n * L, last ? nullptr : dG + (t + 1) * n * 4 * L, WhT, last ? nullptr : a->dones + t * n,
+                  last ? nullptr : dCn, Gates + t * n * 4 * L, Call + t * n * L, Cm + t * n * L, t == 0 ? nullptr : a->dones + (t - 1) * n, n, L,
+                  dG + t * n * 4 * L, dCn);
+    }
   }
   LSTM_TRY(dense_bwd_weight(Hm, L, dG, 4 * L, L, 4 * L, R, Part, gP + l.p[WH], st));
   LSTM_TRY(colsum(dG, 4 * L, R, 4 * L, Col, 1.f, 0.f, gP + l.p[BH], st));

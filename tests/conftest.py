@@ -16,30 +16,34 @@ def pytest_configure(config):
 
 
 def pytest_sessionfinish(session, exitstatus):
-    """RLX_AUX_ENGINE_REPORT=<file>: leave the number of FastSAC / PPO+LSTM GEMMs that ran on the tcgen05 engine in this process (the
-    subprocess runs of run_suite_on_tensor_engine below read it back: a green suite that never touched the tensor engine proves nothing)."""
+    """RLX_AUX_ENGINE_REPORT=<file>: leave "<tensor GEMMs> <persistent recurrence launches>" of this process - the FastSAC / PPO+LSTM GEMMs
+    that ran on the tcgen05 engine and the one-launch-per-direction LSTM recurrences (the subprocess runs of run_suite_with_switches below read
+    it back: a green suite that never took the path it was asked to take proves nothing)."""
     path = os.environ.get("RLX_AUX_ENGINE_REPORT")
     if path:
         try:
             from rl_x_b200 import _native as nt
-            count = int(nt.load().rlx_aux_tc_gemm_count())
+            lib = nt.load()
+            text = f"{int(lib.rlx_aux_tc_gemm_count())} {int(lib.rlx_lstm_persistent_launch_count())}"
         except Exception as exc:  # noqa: BLE001 - the report is best effort, the exit status carries the verdict
-            count = f"unavailable: {exc}"
+            text = f"unavailable: {exc}"
         with open(path, "w") as fh:
-            fh.write(str(count))
+            fh.write(text)
 
 
-def run_suite_on_tensor_engine(test_file, tmp_path, timeout=900):
-    """Run the GPU parity tests of `test_file` again in a SUBPROCESS with RLX_AUX_GEMM_ENGINE=1 (dense layers on the tcgen05 3xTF32 engine
-    where it covers the product).  A subprocess because a tensor-core kernel that hangs ends in the engine's watchdog trap, which takes
-    the CUDA context with it: here that costs one test, not the rest of the session.  Returns (returncode, output tail, tensor GEMM count)."""
+def run_suite_with_switches(test_file, tmp_path, tensor_engine=False, persistent=False, timeout=900):
+    """Run the GPU parity tests of `test_file` again in a SUBPROCESS with the opt-in paths on: RLX_AUX_GEMM_ENGINE=1 (dense layers on the tcgen05
+    3xTF32 engine where it covers the product) and / or RLX_LSTM_PERSISTENT=1 (LSTM recurrence as one block-cooperative launch per direction).
+    A subprocess because a kernel that traps or faults takes the CUDA context with it: here that costs one test, not the rest of the
+    session.  Returns (returncode, output tail, tensor GEMM count, persistent launch count); the counts are -1 when no report came back."""
     import subprocess
-    report = os.path.join(str(tmp_path), "aux_tc_gemms.txt")
-    env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1", RLX_AUX_ENGINE_REPORT=report)
-    proc = subprocess.run([sys.executable, "-m", "pytest", test_file, "-x", "-q", "-m", "gpu", "-k", "not tensor_engine", "-p", "no:cacheprovider"],
+    report = os.path.join(str(tmp_path), "aux_paths.txt")
+    env = dict(os.environ, RLX_AUX_GEMM_ENGINE="1" if tensor_engine else "0", RLX_LSTM_PERSISTENT="1" if persistent else "0", RLX_AUX_ENGINE_REPORT=report)
+    proc = subprocess.run([sys.executable, "-m", "pytest", test_file, "-x", "-q", "-m", "gpu", "-k", "not subprocess", "-p", "no:cacheprovider"],
                           env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
-    count = open(report).read().strip() if os.path.exists(report) else "no report"
-    return proc.returncode, (proc.stdout + proc.stderr)[-3000:], count
+    counts = open(report).read().split() if os.path.exists(report) else []
+    tc, pers = (int(counts[0]), int(counts[1])) if len(counts) == 2 and all(x.isdigit() for x in counts) else (-1, -1)
+    return proc.returncode, (proc.stdout + proc.stderr)[-3000:], tc, pers
 
 
 def pytest_collection_modifyitems(config, items):
@@ -128,5 +132,5 @@ def emu_build_cmd(out, src):
     ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_lstm_emulation.py tests/test_fastsac_emulation.py"""
     import os
     import shlex
-    return (["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-DRLX_EMU"] + shlex.split(os.environ.get("RLX_EMU_CXXFLAGS", ""))
+    return (["g++", "-x", "c++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-DRLX_EMU"] + shlex.split(os.environ.get("RLX_EMU_CXXFLAGS", ""))
             + ["-o", str(out), str(src)])

@@ -4,6 +4,7 @@ The same sources are validated in host emulation (tests/test_lstm_emulation.py).
 strict since round 2.  The FiLM / shared-encoder cases and the one-launch-per-step recurrence were written after the round-2 GPU budget
 was spent: they passed the emulation suite, their first hardware run is the driver's."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -151,14 +152,64 @@ def test_lstm_plugin_cuda_graph_replay_equals_eager_launches():
 
 
 @FIRST_RUN
-def test_lstm_suite_passes_with_dense_layers_on_the_tensor_engine(tmp_path):
-    """rlx_set_aux_gemm_engine(1): every dense layer the tcgen05 3xTF32 engine covers (the weight gradients, the input-side gate GEMM, the
-    un-fused input gradients) runs on it, the rest stays on the SIMT engine.  The whole file - oracle parity at the config-5 shape included -
-    must pass that way, and must actually have used the tensor engine."""
-    from conftest import run_suite_on_tensor_engine
-    rc, tail, count = run_suite_on_tensor_engine(__file__, tmp_path)
+def test_lstm_suite_in_a_subprocess_with_dense_layers_on_the_tensor_engine(tmp_path):
+    """rlx_set_aux_gemm_engine(1): every dense layer of the update with at least half a tile per output dimension runs on the tcgen05 3xTF32
+    engine (forward and input-gradient products on K-major copies of the kernels), the heads stay on the SIMT engine.  The whole file -
+    oracle parity at the config-5 shape included - must pass that way, and must actually have used the tensor engine."""
+    from conftest import run_suite_with_switches
+    rc, tail, tc, _ = run_suite_with_switches(__file__, tmp_path, tensor_engine=True)
     assert rc == 0, tail
-    assert count.isdigit() and int(count) > 0, f"the tensor engine was never used ({count})"
+    assert tc > 0, f"the tensor engine was never used ({tc})"
+
+
+@FIRST_RUN
+def test_lstm_suite_in_a_subprocess_with_the_one_launch_recurrence(tmp_path):
+    """rlx_set_lstm_persistent(1): the recurrence of every update as ONE block-cooperative launch per direction (recurrent kernel in shared
+    memory, a barrier per step).  Bit-identical to the per-step path in emulation (and race-free under ThreadSanitizer); on the device the
+    whole file must pass that way and the path must have run."""
+    from conftest import run_suite_with_switches
+    rc, tail, _, pers = run_suite_with_switches(__file__, tmp_path, persistent=True)
+    assert rc == 0, tail
+    assert pers > 0, f"the one-launch recurrence never ran ({pers})"
+
+
+@pytest.mark.skipif(os.environ.get("RLX_LSTM_PERSISTENT") != "1", reason="runs inside the one-launch-recurrence subprocess (previous test)")
+def test_lstm_one_launch_recurrence_equals_per_step_recurrence_bit_for_bit():
+    """Same arithmetic in the same order: gradients and metrics of one update at the config-5 widths (lstm 64: the recurrent kernel takes
+    64 KB of shared memory) must not differ in a single bit between the two recurrence paths."""
+    from rl_x_b200 import _native as nt
+    lib = nt.load()
+    T, n, obs, act, hid, enc, lstm = 32, 50, 64, 8, 256, 128, 64     # 50 envs: the last block has inactive threads
+    torch.manual_seed(3)
+    pol, cri = _perturbed(obs, act, hid, enc, lstm, 5)
+    d = nt.LstmDims(obs, act, hid, enc, lstm, 0)
+    P, Cc = torch.cat(flatten_policy(pol)).to(DEV), torch.cat(flatten_critic(cri)).to(DEV)
+    adv = torch.randn(T, n)
+    dev = {k: v.contiguous().to(DEV) for k, v in dict(
+        states=torch.randn(T, n, obs), actions=torch.randn(T, n, act), log_probs=torch.randn(T, n) * 0.1 - 2.5, advantages=adv, returns=torch.randn(T, n),
+        dones=(torch.rand(T, n) < 0.2).float(), init_c=torch.randn(n, lstm) * 0.5, init_h=torch.randn(n, lstm) * 0.5).items()}
+    stats = torch.tensor([float(adv.mean()), float(adv.std(unbiased=False))], device=DEV)
+    nbytes = lib.rlx_lstm_minibatch_workspace_bytes(C.byref(d), T, n)
+    out = {}
+    for persistent in (0, 1):
+        assert lib.rlx_set_lstm_persistent(persistent) == persistent
+        before = int(lib.rlx_lstm_persistent_launch_count())
+        gP, gC, metrics = torch.full_like(P, float("nan")), torch.full_like(Cc, float("nan")), torch.zeros(8, device=DEV)
+        ws = torch.full((nbytes // 4 + 64,), float("nan"), device=DEV)
+        a = nt.LstmMinibatchArgs()
+        a.dims, a.T, a.n_env = d, T, n
+        for k, v in dev.items():
+            setattr(a, k, v.data_ptr())
+        a.adv_stats, a.policy_params, a.critic_params = stats.data_ptr(), P.data_ptr(), Cc.data_ptr()
+        a.policy_grads, a.critic_grads, a.metrics = gP.data_ptr(), gC.data_ptr(), metrics.data_ptr()
+        a.clip_range, a.entropy_coef, a.critic_coef = 0.2, 0.01, 0.5
+        a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+        nt.check(lib.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fwdbwd")
+        torch.cuda.synchronize()
+        out[persistent] = (gP.cpu(), gC.cpu(), metrics.cpu(), int(lib.rlx_lstm_persistent_launch_count()) - before)
+    lib.rlx_set_lstm_persistent(1)   # the subprocess's setting
+    assert out[0][3] == 0 and out[1][3] == 2
+    assert torch.isfinite(out[1][0]).all() and all(torch.equal(x, y) for x, y in zip(out[0][:3], out[1][:3]))
 
 
 def test_lstm_plugin_trains_on_synthetic_env():

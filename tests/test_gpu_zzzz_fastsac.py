@@ -144,14 +144,14 @@ def test_fastsac_engines_agree_at_batch_1024():
 
 
 @pytest.mark.xfail(strict=False, reason="first hardware run of this path (written after the round-2 GPU budget was spent)")
-def test_fastsac_suite_passes_with_dense_layers_on_the_tensor_engine(tmp_path):
+def test_fastsac_suite_in_a_subprocess_with_dense_layers_on_the_tensor_engine(tmp_path):
     """rlx_set_aux_gemm_engine(1): the torso layers of the policy and of both C51 critics (forward, input and weight gradients) run on the
     tcgen05 3xTF32 engine; the 101-column logits layer (row pitch not a multiple of 16 bytes) and the skinny heads stay on the SIMT engine.
     The whole file - the golden-batch parity against the pinned oracle included - must pass that way and must have used the tensor engine."""
-    from conftest import run_suite_on_tensor_engine
-    rc, tail, count = run_suite_on_tensor_engine(__file__, tmp_path)
+    from conftest import run_suite_with_switches
+    rc, tail, tc, _ = run_suite_with_switches(__file__, tmp_path, tensor_engine=True)
     assert rc == 0, tail
-    assert count.isdigit() and int(count) > 0, f"the tensor engine was never used ({count})"
+    assert tc > 0, f"the tensor engine was never used ({tc})"
 
 
 def test_fastsac_plugin_runs_on_device_env():

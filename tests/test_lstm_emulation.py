@@ -174,6 +174,20 @@ def test_emulated_lstm_fwdbwd_matches_oracle_autograd(emu, T, n, obs, act, hid, 
     finally:
         emu.rlx_emu_set_thread_order(0)
     assert np.array_equal(gP, gP2) and np.array_equal(gC, gC2) and np.array_equal(metrics, metrics2)
+    # The recurrence as ONE block-cooperative launch per direction (rlx_set_lstm_persistent: recurrent kernel and the envs' hidden state in
+    # shared memory, a barrier per step; emulated with one OS thread per CUDA thread): same arithmetic in the same order, so the same bits.
+    gP3, gC3, metrics3 = np.full_like(P, np.nan), np.full_like(Cc, np.nan), np.zeros(8, np.float32)
+    ws[:] = np.nan
+    a.policy_grads, a.critic_grads, a.metrics = gP3.ctypes.data, gC3.ctypes.data, metrics3.ctypes.data
+    emu.rlx_lstm_persistent_launch_count.restype = C.c_uint64
+    launches = emu.rlx_lstm_persistent_launch_count()
+    assert emu.rlx_set_lstm_persistent(1) == 1
+    try:
+        assert emu.rlx_lstm_ppo_minibatch_fwdbwd_f32(C.byref(a), None) == 0
+    finally:
+        emu.rlx_set_lstm_persistent(0)
+    assert emu.rlx_lstm_persistent_launch_count() == launches + 2   # forward and backward
+    assert np.array_equal(gP, gP3) and np.array_equal(gC, gC3) and np.array_equal(metrics, metrics3)
 
 
 def test_emulated_optax_step_and_env_gather(emu):
@@ -551,3 +565,19 @@ def test_emulated_ppo_head_gemm_path(tmp_path, m, hid, act, rd):
     sums = [float(t.detach()) for t in (pg.sum(), vl.sum(), ((ratio - 1) - logratio).sum(), cf)]
     np.testing.assert_allclose(part[2 * act + 1:2 * act + 5], sums, rtol=2e-4, atol=1e-4)
     np.testing.assert_allclose(part[2 * act + 5:], f(Z2.grad).sum(0), rtol=2e-4, atol=2e-6)
+
+
+def test_persistent_recurrence_is_race_free_under_tsan(tmp_path):
+    """The one-launch-per-direction recurrence kernels (lstm_seq_fwd_kernel / lstm_seq_bwd_kernel: shared memory + one barrier per step) under
+    ThreadSanitizer: the emulation runs each CUDA thread of a block as an OS thread and __syncthreads as a real barrier, so a barrier missing
+    between a shared-memory write and another thread's read is a reported data race (dropping the per-step barrier of the forward kernel
+    was tried: TSan flags it at the shared-memory read).  The driver also demands bit-identity with the per-step path."""
+    exe = tmp_path / "emu_tsan_lstm"
+    build = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-DRLX_EMU", "-x", "c++",
+                            os.path.join(ROOT, "rl_x_b200", "csrc", "lstm.cu"), os.path.join(ROOT, "tests", "emu_tsan_lstm.cpp"), "-o", str(exe)],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "tsan" in (build.stderr or "").lower():
+        pytest.skip("this toolchain has no ThreadSanitizer runtime")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([str(exe)], env=dict(os.environ, TSAN_OPTIONS="exitcode=66"), capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and run.stdout.strip().endswith("ok"), (run.returncode, (run.stdout + run.stderr)[-3000:])
