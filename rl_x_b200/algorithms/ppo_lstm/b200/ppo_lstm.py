@@ -281,6 +281,7 @@ class PPO_LSTM:
 
             # Acting (ppo_lstm.py:274-304)
             dones_this_rollout = 0
+            dones_on_device = torch.zeros((), dtype=torch.float32, device=dev)  # TORCH envs: counted on the device, read back once per rollout
             step_info_collection = {}
             init_c.copy_(carry_c)
             init_h.copy_(carry_h)
@@ -303,13 +304,14 @@ class PPO_LSTM:
                         saving_return_buffer.append(env.get_final_info_value_at_index(info, "episode_return", int(i)))
                         dones_this_rollout += 1
                 else:
-                    dones_this_rollout += int(done_dev.sum().item())
+                    dones_on_device += done_dev.sum()   # no per-step host synchronisation
                 for key, info_value in env.get_logging_info_dict(info).items():
                     step_info_collection.setdefault(key, []).extend(info_value)
                 rewards[step].copy_(self._to_dev(reward))
                 terminations[step].copy_(self._to_dev(terminated))
                 dones[step].copy_(done_dev)
                 global_step += N
+            dones_this_rollout += int(dones_on_device.item())
             nr_episodes += dones_this_rollout
             acting_end_time = time.time()
             time_metrics["time/acting_time"] = acting_end_time - start_time

@@ -455,7 +455,7 @@ def test_plugin_class_runs_under_emulation(emu, tmp_path):
         np.testing.assert_allclose([v for nme, v in logged if nme == "lr/learning_rate"], [1e-3, 1e-3 * 2 / 3, 1e-3 / 3], rtol=1e-6)
         assert [v for nme, v in logged if nme == "steps/nr_updates"] == [4.0, 8.0, 12.0]
         assert float((model.policy_params - before).abs().max()) > 1e-4
-        results[(iface, combine, share, graph)] = ([(nme, v) for nme, v in logged if nme.split("/")[0] in ("loss", "gradients", "policy_ratio", "lr")],
+        results[(iface, combine, share, graph)] = ([(nme, v) for nme, v in logged if nme.split("/")[0] in ("loss", "gradients", "policy_ratio", "lr", "steps")],
                                                    model.policy_params.clone(), model.critic_params.clone())
         assert (model._graph is not None) == graph and (not graph or len(model._graph.calls) == 12)   # 8 gathers, stats, fwd+bwd, 2 x Adam
         pol_named, _ = model.named_parameters()
