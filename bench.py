@@ -415,7 +415,7 @@ def aux_paths_verdict():
         rec = {"tensor_engine": tensor, "persistent_recurrence": persistent, "tests": len(tests)}
         try:
             proc = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider"] + tests, env=env, cwd=ROOT, capture_output=True,
-                                  text=True, timeout=420)
+                                  text=True, timeout=240)
             counts = open(report).read().split() if os.path.exists(report) else []
             tail = ((proc.stdout + proc.stderr).strip().splitlines() or [""])[-1]
             used = len(counts) == 2 and all(x.isdigit() for x in counts) and (not tensor or int(counts[0]) > 0) and (not persistent or int(counts[1]) > 0)
