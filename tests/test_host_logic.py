@@ -502,3 +502,65 @@ def test_committed_bench_records_carry_the_contract_keys():
     assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"] and ref["config"]["workload"] == line["config"]["workload"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 == ref["e2e"]["d2h_bytes_per_step"] and ref["e2e"]["value"] == ref["value"]
     assert ref["cpu_baseline"]["kind"] == "reference" and ref["cpu_baseline"]["value"] == ref["value"]
+
+
+def test_sac_checkpoint_written_by_the_reference_maps_onto_the_flat_layout():
+    """tests/golden/sac_ref_checkpoint.model was written by the executed reference's own SAC.save() (make_golden_sac_ckpt.py).  Module keys,
+    the parameter numbering inside the three Adam state dicts (policy; q1 then q2; log_alpha - sac.py:75-77) and the param_group keys
+    must be what rl_x_b200's SAC.load() / save() assume: every tensor lands on its segment of the flat buffers, and the dicts save()
+    builds from those buffers equal the reference's entry for entry."""
+    from rl_x_b200.algorithms.sac.b200 import sac as S
+    ck = torch.load(os.path.join(ROOT, "tests", "golden", "sac_ref_checkpoint.model"), weights_only=False)
+    ex = np.load(os.path.join(ROOT, "tests", "golden", "sac_ref_checkpoint_expect.npz"))
+    N, obs, act, hid, batch = (int(x) for x in ex["meta"])
+    k = S.SacKernels(obs, act, hid, -5.0, 2.0)
+    strip = lambda d: {key.replace("_orig_mod.", ""): v for key, v in d.items()}
+    assert list(strip(ck["policy_state_dict"])) == list(S.POLICY_PARAM_ORDER)
+    for net in ("q1", "q2", "q1_target", "q2_target"):
+        assert list(strip(ck[f"{net}_state_dict"])) == list(S.Q_PARAM_ORDER)
+    # parameters: what load_named() does, on CPU flats
+    policy, q = torch.zeros(k.Pp), torch.zeros(4 * k.Pq)
+    pv, qv = k.policy_views(policy), k.q_views(q)
+    for key, v in strip(ck["policy_state_dict"]).items():
+        pv[key].copy_(v.detach().reshape(pv[key].shape))
+        assert np.array_equal(pv[key].numpy(), ex[f"policy/{key}/param"]), key
+    for net in S.Q_NETS:
+        for key, v in strip(ck[f"{net}_state_dict"]).items():
+            qv[net][key].copy_(v.detach().reshape(qv[net][key].shape))
+            assert np.array_equal(qv[net][key].numpy(), ex[f"{net}/{key}/param"]), (net, key)
+    assert np.array_equal(torch.as_tensor(ck["log_alpha"]).detach().numpy().reshape(-1), ex["log_alpha/param"].reshape(-1))
+    # optimizer states: the views SAC._optimizer_views() hands to _load_adam_state, rebuilt here on CPU flats
+    m_p, v_p, m_q, v_q, m_a, v_a = torch.zeros(k.Pp), torch.zeros(k.Pp), torch.zeros(2 * k.Pq), torch.zeros(2 * k.Pq), torch.zeros(1), torch.zeros(1)
+    pol_views = lambda flat: [k.policy_views(flat)[name] for name in S.POLICY_PARAM_ORDER]
+
+    def q_views(flat):  # q1's six tensors, then q2's
+        both = k.q_views(torch.cat([flat, torch.zeros(2 * k.Pq)]))   # q_views expects the four-net buffer; only q1 / q2 are looked at
+        return [both[net][name] for net in ("q1", "q2") for name in S.Q_PARAM_ORDER]
+
+    steps = S._load_adam_state(ck["policy_optimizer_state_dict"], pol_views(m_p), pol_views(v_p), "policy")
+    for name, m, v in zip(S.POLICY_PARAM_ORDER, pol_views(m_p), pol_views(v_p)):
+        assert np.array_equal(m.numpy(), ex[f"policy/{name}/exp_avg"]) and np.array_equal(v.numpy(), ex[f"policy/{name}/exp_avg_sq"]), name
+        assert float(ex[f"policy/{name}/step"]) == steps
+    qm, qvv = [torch.zeros_like(t) for t in q_views(m_q)], [torch.zeros_like(t) for t in q_views(v_q)]
+    q_steps = S._load_adam_state(ck["q_optimizer_state_dict"], qm, qvv, "q")
+    names = [(net, name) for net in ("q1", "q2") for name in S.Q_PARAM_ORDER]
+    for (net, name), m, v in zip(names, qm, qvv):
+        assert np.array_equal(m.numpy(), ex[f"{net}/{name}/exp_avg"]) and np.array_equal(v.numpy(), ex[f"{net}/{name}/exp_avg_sq"]), (net, name)
+        assert float(ex[f"{net}/{name}/step"]) == q_steps
+    a_steps = S._load_adam_state(ck["entropy_optimizer_state_dict"], [m_a], [v_a], "entropy")
+    assert np.array_equal(m_a.numpy(), ex["log_alpha/exp_avg"].reshape(-1)) and float(ex["log_alpha/step"]) == a_steps
+    # and back: the state dicts save() builds are, key for key and tensor for tensor, what the reference wrote
+    for key, (ms, vs, st) in (("policy_optimizer_state_dict", (pol_views(m_p), pol_views(v_p), steps)), ("q_optimizer_state_dict", (qm, qvv, q_steps)),
+                             ("entropy_optimizer_state_dict", ([m_a], [v_a], a_steps))):
+        ours, ref = S._adam_state_dict(ms, vs, st, ck[key]["param_groups"][0]["lr"]), ck[key]
+        assert ours["param_groups"][0]["params"] == ref["param_groups"][0]["params"]
+        assert set(ours["param_groups"][0]) == set(ref["param_groups"][0]), set(ours["param_groups"][0]) ^ set(ref["param_groups"][0])
+        assert set(ours["state"]) == set(ref["state"])
+        for i in ref["state"]:
+            for f in ("exp_avg", "exp_avg_sq"):
+                assert torch.equal(ours["state"][i][f].reshape(ref["state"][i][f].shape), ref["state"][i][f]), (key, i, f)
+            assert float(ours["state"][i]["step"]) == float(ref["state"][i]["step"])
+    # a state of the wrong shape (e.g. a permuted numbering) is refused, not mis-assigned
+    bad = {"state": {0: ck["policy_optimizer_state_dict"]["state"][1]}}
+    with pytest.raises(ValueError, match="expected"):
+        S._load_adam_state(bad, pol_views(m_p), pol_views(v_p), "policy")
