@@ -564,3 +564,62 @@ def test_sac_checkpoint_written_by_the_reference_maps_onto_the_flat_layout():
     bad = {"state": {0: ck["policy_optimizer_state_dict"]["state"][1]}}
     with pytest.raises(ValueError, match="expected"):
         S._load_adam_state(bad, pol_views(m_p), pol_views(v_p), "policy")
+
+
+def test_sac_checkpoint_written_here_loads_into_the_reference_modules():
+    """The other direction for SAC, with the reference's own classes (staged copy oracle/_ref): the state dicts SAC.save() builds from the flat
+    buffers go through strict load_state_dict / optimizer.load_state_dict exactly as the reference's load() does (sac.py:398-416), and every
+    parameter / Adam moment ends up where its name says."""
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+    from oracle import ref_arm
+    from rl_x_b200.algorithms.sac.b200 import sac as S
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    ref_arm.import_reference()
+    import rl_x.algorithms.sac.pytorch.sac as refsac
+    from rl_x.algorithms.sac.pytorch.default_config import get_config
+    from rl_x.environments.action_space_type import ActionSpaceType
+    from rl_x.environments.data_interface_type import DataInterfaceType
+    from rl_x.environments.observation_space_type import ObservationSpaceType
+    N, obs, act, hid = 2, 5, 3, 16
+
+    class Props:
+        observation_space_type, action_space_type, data_interface_type = ObservationSpaceType.FLAT_VALUES, ActionSpaceType.CONTINUOUS, DataInterfaceType.NUMPY
+
+    class Env:
+        general_properties = Props
+        single_observation_space = ref_arm._Space((obs,))
+        single_action_space = ref_arm._Space((act,), np.full(act, -1.0, np.float32), np.full(act, 1.0, np.float32))
+
+    a = get_config("sac.pytorch")
+    a.device, a.bf16_mixed_precision_training, a.nr_hidden_units = "cpu", False, hid
+    cfg = ref_arm._ConfigDict(algorithm=a, environment=ref_arm._ConfigDict(seed=0, nr_envs=N),
+                              runner=ref_arm._ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False))
+    model = refsac.SAC(cfg, Env(), Env(), "/tmp/rlx_sac_ckpt_interop", None)
+    k = S.SacKernels(obs, act, hid, float(a.log_std_min), float(a.log_std_max))
+    g = torch.Generator().manual_seed(1)
+    policy, q = torch.randn(k.Pp, generator=g), torch.randn(4 * k.Pq, generator=g)
+    m_p, v_p, m_q, v_q = torch.randn(k.Pp, generator=g), torch.rand(k.Pp, generator=g), torch.randn(4 * k.Pq, generator=g), torch.rand(4 * k.Pq, generator=g)
+    pv, qv = k.policy_views(policy), k.q_views(q)
+    model.policy.load_state_dict({name: pv[name] for name in S.POLICY_PARAM_ORDER})
+    for net, mod in (("q1", model.critic.q1), ("q2", model.critic.q2), ("q1_target", model.critic.q1_target), ("q2_target", model.critic.q2_target)):
+        mod.load_state_dict(qv[net])
+    pm, pvv = k.policy_views(m_p), k.policy_views(v_p)
+    qm, qvv = k.q_views(m_q), k.q_views(v_q)
+    model.policy_optimizer.load_state_dict(S._adam_state_dict([pm[n] for n in S.POLICY_PARAM_ORDER], [pvv[n] for n in S.POLICY_PARAM_ORDER], 7, 3e-4))
+    model.q_optimizer.load_state_dict(S._adam_state_dict([qm[net][n] for net in ("q1", "q2") for n in S.Q_PARAM_ORDER],
+                                                         [qvv[net][n] for net in ("q1", "q2") for n in S.Q_PARAM_ORDER], 7, 3e-4))
+    model.entropy_optimizer.load_state_dict(S._adam_state_dict([torch.tensor([0.25])], [torch.tensor([0.5])], 7, 3e-4))
+    for name, p in model.policy.named_parameters():
+        name = name.replace("_orig_mod.", "")
+        st = model.policy_optimizer.state[p]
+        assert torch.equal(p.detach(), pv[name]) and torch.equal(st["exp_avg"], pm[name]) and torch.equal(st["exp_avg_sq"], pvv[name]), name
+        assert float(st["step"]) == 7.0
+    for net, mod in (("q1", model.critic.q1), ("q2", model.critic.q2)):
+        for name, p in mod.named_parameters():
+            name = name.replace("_orig_mod.", "")
+            st = model.q_optimizer.state[p]
+            assert torch.equal(p.detach(), qv[net][name]) and torch.equal(st["exp_avg"], qm[net][name]) and torch.equal(st["exp_avg_sq"], qvv[net][name]), (net, name)
+    st = model.entropy_optimizer.state[model.entropy_coefficient.log_alpha]
+    assert float(st["exp_avg"]) == 0.25 and float(st["exp_avg_sq"]) == 0.5 and float(st["step"]) == 7.0
