@@ -47,6 +47,18 @@ FILES = [
     "rl_x/algorithms/sac/pytorch/q_network.py",
     "rl_x/algorithms/sac/pytorch/replay_buffer.py",
     "rl_x/algorithms/sac/pytorch/sac.py",
+    # FastSAC: staged for the checkpoint interop test (tests/test_fastsac_emulation.py), not timed anywhere
+    "rl_x/algorithms/fastsac/__init__.py",
+    "rl_x/algorithms/fastsac/pytorch/__init__.py",
+    "rl_x/algorithms/fastsac/pytorch/critic.py",
+    "rl_x/algorithms/fastsac/pytorch/default_config.py",
+    "rl_x/algorithms/fastsac/pytorch/entropy_coefficient.py",
+    "rl_x/algorithms/fastsac/pytorch/fastsac.py",
+    "rl_x/algorithms/fastsac/pytorch/general_properties.py",
+    "rl_x/algorithms/fastsac/pytorch/observation_normalizer.py",
+    "rl_x/algorithms/fastsac/pytorch/policy.py",
+    "rl_x/algorithms/fastsac/pytorch/q_network.py",
+    "rl_x/algorithms/fastsac/pytorch/replay_buffer.py",
     "rl_x/environments/__init__.py",
     "rl_x/environments/action_space_type.py",
     "rl_x/environments/data_interface_type.py",

@@ -386,7 +386,8 @@ class FastSAC:
             "policy_state_dict": cpu(pol),
             "q1_state_dict": cpu(q1), "q2_state_dict": cpu(q2),
             "q1_target_state_dict": cpu(self._named(self.q_target_params[:nq], "q")), "q2_target_state_dict": cpu(self._named(self.q_target_params[nq:], "q")),
-            "log_alpha": self.log_alpha.detach().cpu().clone(),
+            # an nn.Parameter like the reference's own entry: its load() assigns it to a registered parameter (fastsac.py:494), which refuses plain tensors
+            "log_alpha": torch.nn.Parameter(self.log_alpha.detach().cpu().clone().reshape(1)),
             "policy_optimizer_state_dict": self._adamw_state(self.policy_m, self.policy_v, steps[2], pol),
             "q_optimizer_state_dict": self._adamw_state(self.q_m, self.q_v, steps[0], q_both),
             "entropy_optimizer_state_dict": self._adamw_state(self.alpha_state[1:2], self.alpha_state[2:3], steps[1], {"log_alpha": self.log_alpha}),

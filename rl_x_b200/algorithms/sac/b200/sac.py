@@ -42,6 +42,20 @@ def _adam_state_dict(views_m, views_v, step, lr):
     return {"state": state, "param_groups": [group]}
 
 
+def checkpoint_dict(config_algorithm, pol, qs, log_alpha, optimizer_views, steps, lr):
+    """The reference's `best.model` dictionary (sac.py:381-396) from named tensors: `pol` {key: tensor}, `qs` {net: {key: tensor}} for the four
+    Q networks, `optimizer_views` {"policy" | "q" | "entropy": (exp_avg views, exp_avg_sq views)} in the reference's parameter numbering,
+    `steps` (policy, q, entropy).  Module state_dicts in parameters() order, the three torch.optim.Adam state dicts, and log_alpha as an
+    nn.Parameter like the reference's own entry: its load() assigns it to a registered parameter (sac.py:410), which refuses plain tensors."""
+    ov = optimizer_views
+    return {"config_algorithm": config_algorithm, "policy_state_dict": {k: pol[k] for k in POLICY_PARAM_ORDER}, "q1_state_dict": qs["q1"],
+            "q2_state_dict": qs["q2"], "q1_target_state_dict": qs["q1_target"], "q2_target_state_dict": qs["q2_target"],
+            "log_alpha": torch.nn.Parameter(torch.as_tensor(log_alpha).detach().cpu().clone().reshape(1)),
+            "policy_optimizer_state_dict": _adam_state_dict(*ov["policy"], steps[0], lr),
+            "q_optimizer_state_dict": _adam_state_dict(*ov["q"], steps[1], lr),
+            "entropy_optimizer_state_dict": _adam_state_dict(*ov["entropy"], steps[2], lr)}
+
+
 def _load_adam_state(osd, views_m, views_v, what):
     step = 0
     for i, (m, v) in enumerate(zip(views_m, views_v)):
@@ -456,16 +470,9 @@ class SAC:
         """Checkpoint with the reference's keys and optimizer layout (sac.py:381-396): module state_dicts in parameters() order, log_alpha,
         and the three torch.optim.Adam state dicts, so that either side's load() accepts the other's file."""
         pol, qs = self.state_dicts()
-        pol = {k: pol[k] for k in POLICY_PARAM_ORDER}
         steps = [int(x) for x in self.steps.cpu().tolist()]  # policy, q, entropy
-        ov = self._optimizer_views()
-        lr = float(self.lr_dev.item())
-        file_path = self.save_path + "/best.model"
-        torch.save({"config_algorithm": self.config.algorithm, "policy_state_dict": pol, "q1_state_dict": qs["q1"], "q2_state_dict": qs["q2"],
-                    "q1_target_state_dict": qs["q1_target"], "q2_target_state_dict": qs["q2_target"], "log_alpha": self.log_alpha.detach().cpu().clone(),
-                    "policy_optimizer_state_dict": _adam_state_dict(*ov["policy"], steps[0], lr),
-                    "q_optimizer_state_dict": _adam_state_dict(*ov["q"], steps[1], lr),
-                    "entropy_optimizer_state_dict": _adam_state_dict(*ov["entropy"], steps[2], lr)}, file_path)
+        torch.save(checkpoint_dict(self.config.algorithm, pol, qs, self.log_alpha, self._optimizer_views(), steps, float(self.lr_dev.item())),
+                   self.save_path + "/best.model")
 
     def load(config, train_env, eval_env, run_path, writer, explicitly_set_algorithm_params):
         ck = torch.load(config.runner.load_model, weights_only=False)

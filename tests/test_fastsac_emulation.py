@@ -378,3 +378,120 @@ def test_plugin_checkpoint_has_the_reference_layout(tmp_path):
         if name == "alpha_state":
             a_, b_ = a_[1:], b_[1:]   # element 0 is the transient gradient
         assert torch.equal(a_, b_), name
+
+
+def test_checkpoints_move_between_the_plugin_and_the_reference_classes(tmp_path):
+    """f2 for FastSAC with the reference's OWN classes (staged copy oracle/_ref, rl_x/algorithms/fastsac/pytorch): (1) a `latest.model`
+    written by the reference's FastSAC.save() (fastsac.py:463-478) after AdamW steps on every parameter is read by the plugin's load() and
+    every tensor - parameters, targets, both AdamW moments, step counts, log_alpha, normaliser statistics - lands on the segment its name
+    says; (2) the file the plugin's save() writes goes through the reference's FastSAC.load() (strict load_state_dict + optimizer
+    load_state_dict, :481-500) and arrives tensor for tensor.  The plugin runs on CPU with the source rewrites of the tests above."""
+    import types
+    from oracle import make_ref
+    if not make_ref.available() or not os.path.exists(os.path.join(make_ref.DST, "rl_x", "algorithms", "fastsac", "pytorch", "fastsac.py")):
+        pytest.skip("oracle/_ref (with the FastSAC modules) not staged: python oracle/make_ref.py")
+    from oracle import ref_arm
+    os.environ["TORCHDYNAMO_DISABLE"] = "1"
+    ref_arm.import_reference()
+    import rl_x.algorithms.fastsac.pytorch.fastsac as reffs
+    from rl_x.algorithms.fastsac.pytorch.default_config import get_config as ref_config
+    from rl_x.environments.action_space_type import ActionSpaceType as RA
+    from rl_x.environments.data_interface_type import DataInterfaceType as RD
+    from rl_x.environments.observation_space_type import ObservationSpaceType as RO
+    from rl_x_b200.config_dict import ConfigDict
+    from rl_x_b200.algorithms.fastsac.b200.default_config import get_config
+    obs, act, atoms, N = 9, 4, 21, 4
+
+    class Sp:
+        def __init__(self, shape, **kw):
+            self.shape = shape
+            self.__dict__.update(kw)
+
+    class Props:
+        observation_space_type, action_space_type, data_interface_type = RO.FLAT_VALUES, RA.CONTINUOUS, RD.TORCH
+
+    class Env:
+        general_properties, horizon = Props, 3
+        single_observation_space = Sp((obs,))
+        single_action_space = Sp((act,), low=np.full(act, -1.0, np.float32), high=np.full(act, 1.0, np.float32), center=np.zeros(act, np.float32),
+                                 scale=np.ones(act, np.float32))
+
+    # ---- the reference model, with optimiser state on every parameter
+    ra = ref_config("fastsac.pytorch")
+    ra.device, ra.bf16_mixed_precision_training, ra.compile_mode, ra.nr_atoms = "cpu", False, "default", atoms
+    rcfg = ref_arm._ConfigDict(algorithm=ra, environment=ref_arm._ConfigDict(seed=8, nr_envs=N),
+                               runner=ref_arm._ConfigDict(save_model=True, track_console=False, track_tb=False, track_wandb=False))
+    ref_run = tmp_path / "ref_run"
+    ref = reffs.FastSAC(rcfg, Env(), Env(), str(ref_run), None)
+    g = torch.Generator().manual_seed(0)
+    for opt in (ref.policy_optimizer, ref.q_optimizer, ref.entropy_optimizer):
+        for _ in range(3):
+            for group in opt.param_groups:
+                for p in group["params"]:
+                    p.grad = torch.randn(p.shape, generator=g) * 0.1
+            opt.step()
+    with torch.no_grad():
+        for tgt in (ref.critic.q1_target, ref.critic.q2_target):
+            for p in tgt.parameters():
+                p.add_(torch.randn(p.shape, generator=g) * 0.01)
+    ref.observation_normalizer.train()
+    ref.observation_normalizer.normalize(torch.randn(32, obs, generator=g) * 2 + 1, update=True)   # non-trivial running statistics
+    os.makedirs(os.path.join(str(ref_run), "models"), exist_ok=True)
+    ref.save()
+    ref_file = os.path.join(str(ref_run), "models", "latest.model")
+
+    # ---- the plugin class on CPU (device hooks rewritten; only host functions of the library are used)
+    src = open(os.path.join(ROOT, "rl_x_b200", "algorithms", "fastsac", "b200", "fastsac.py")).read()
+    src = src.replace("from rl_x_b200.algorithms.fastsac.b200.replay_buffer import ReplayBuffer", "ReplayBuffer = None")
+    for old, new in [('torch.device("cuda", torch.cuda.current_device())', 'torch.device("cpu")'),
+                     ('if a.device != "gpu" or not torch.cuda.is_available():', 'if False:')]:
+        assert old in src
+        src = src.replace(old, new)
+    mod = types.ModuleType("fastsac_interop")
+    exec(compile(src, "fastsac_interop", "exec"), mod.__dict__)
+    a = get_config("fastsac.b200")
+    cfg = ConfigDict(algorithm=a, environment=ConfigDict(seed=8, nr_envs=N),
+                     runner=ConfigDict(save_model=True, track_console=False, track_tb=False, track_wandb=False, load_model=ref_file))
+    ours = mod.FastSAC.load(cfg, Env(), Env(), str(tmp_path / "our_run"), None, [])
+    assert int(ours.dims.nr_atoms) == atoms     # taken from the file's config_algorithm
+    nq = ours.q_offsets[-1]
+    strip = lambda name: name.replace("_orig_mod.", "")
+
+    def check(module, opt, flat, m, v, net, step_index):
+        named, nm, nv = ours._named(flat, net), ours._named(m, net) if m is not None else None, ours._named(v, net) if v is not None else None
+        for name, p in module.named_parameters():
+            name = strip(name)
+            assert torch.equal(named[name], p.detach()), (net, name)
+            if opt is not None:
+                st = opt.state[p]
+                assert torch.equal(nm[name], st["exp_avg"]) and torch.equal(nv[name], st["exp_avg_sq"]), (net, name)
+                assert int(ours.steps[step_index]) == int(float(st["step"])) == 3
+
+    check(ref.policy, ref.policy_optimizer, ours.policy_params, ours.policy_m, ours.policy_v, "policy", 2)
+    check(ref.critic.q1, ref.q_optimizer, ours.q_params[:nq], ours.q_m[:nq], ours.q_v[:nq], "q", 0)
+    check(ref.critic.q2, ref.q_optimizer, ours.q_params[nq:], ours.q_m[nq:], ours.q_v[nq:], "q", 0)
+    check(ref.critic.q1_target, None, ours.q_target_params[:nq], None, None, "q", 0)
+    check(ref.critic.q2_target, None, ours.q_target_params[nq:], None, None, "q", 0)
+    la = ref.entropy_coefficient.log_alpha
+    assert torch.equal(ours.log_alpha.reshape(-1), la.detach().reshape(-1))
+    st = ref.entropy_optimizer.state[la]
+    assert float(ours.alpha_state[1]) == float(st["exp_avg"]) and float(ours.alpha_state[2]) == float(st["exp_avg_sq"]) and int(ours.steps[1]) == 3
+    nsd = ref.observation_normalizer.state_dict()
+    assert torch.equal(ours.norm_mean.reshape(-1), nsd["running_mean"].reshape(-1)) and torch.equal(ours.norm_var.reshape(-1), nsd["running_var"].reshape(-1))
+    assert int(ours.norm_count[0]) == int(nsd["count"])
+
+    # ---- and back: what the plugin writes, through the reference's own load()
+    for t in (ours.policy_params, ours.q_params, ours.q_target_params, ours.policy_m, ours.q_m):
+        t.add_(torch.randn(t.shape, generator=g) * 0.01)          # not the tensors that came in
+    ours.save()
+    rcfg2 = ref_arm._ConfigDict(algorithm=ref_config("fastsac.pytorch"), environment=ref_arm._ConfigDict(seed=8, nr_envs=N),
+                                runner=ref_arm._ConfigDict(save_model=False, track_console=False, track_tb=False, track_wandb=False,
+                                                           load_model=os.path.join(str(tmp_path / "our_run"), "models", "latest.model")))
+    rcfg2.algorithm.device, rcfg2.algorithm.bf16_mixed_precision_training, rcfg2.algorithm.compile_mode = "cpu", False, "default"
+    back = reffs.FastSAC.load(rcfg2, Env(), Env(), str(tmp_path / "ref_run2"), None, ["algorithm.device", "algorithm.bf16_mixed_precision_training",
+                                                                                     "algorithm.compile_mode"])
+    ref = back
+    check(ref.policy, ref.policy_optimizer, ours.policy_params, ours.policy_m, ours.policy_v, "policy", 2)
+    check(ref.critic.q1, ref.q_optimizer, ours.q_params[:nq], ours.q_m[:nq], ours.q_v[:nq], "q", 0)
+    check(ref.critic.q2, ref.q_optimizer, ours.q_params[nq:], ours.q_m[nq:], ours.q_v[nq:], "q", 0)
+    check(ref.critic.q1_target, None, ours.q_target_params[:nq], None, None, "q", 0)

@@ -623,3 +623,22 @@ def test_sac_checkpoint_written_here_loads_into_the_reference_modules():
             assert torch.equal(p.detach(), qv[net][name]) and torch.equal(st["exp_avg"], qm[net][name]) and torch.equal(st["exp_avg_sq"], qvv[net][name]), (net, name)
     st = model.entropy_optimizer.state[model.entropy_coefficient.log_alpha]
     assert float(st["exp_avg"]) == 0.25 and float(st["exp_avg_sq"]) == 0.5 and float(st["step"]) == 7.0
+    # the whole file, as save() assembles it (checkpoint_dict), through the reference's own load() (sac.py:398-416): its assignment of
+    # checkpoint["log_alpha"] to a registered parameter only accepts an nn.Parameter
+    import tempfile
+    views = {"policy": ([pm[n] for n in S.POLICY_PARAM_ORDER], [pvv[n] for n in S.POLICY_PARAM_ORDER]),
+             "q": ([qm[net][n] for net in ("q1", "q2") for n in S.Q_PARAM_ORDER], [qvv[net][n] for net in ("q1", "q2") for n in S.Q_PARAM_ORDER]),
+             "entropy": ([torch.tensor([0.25])], [torch.tensor([0.5])])}
+    path = os.path.join(tempfile.mkdtemp(prefix="rlx_sac_ck_"), "best.model")
+    torch.save(S.checkpoint_dict(a, {n: pv[n].clone() for n in pv}, {net: {n: t.clone() for n, t in d.items()} for net, d in qv.items()},
+                                 torch.tensor([-0.7]), views, [7, 7, 7], 3e-4), path)
+    cfg.runner.load_model = path
+    back = refsac.SAC.load(cfg, Env(), Env(), "/tmp/rlx_sac_ckpt_interop2", None, ["algorithm.device", "algorithm.bf16_mixed_precision_training"])
+    assert isinstance(back.entropy_coefficient.log_alpha, torch.nn.Parameter) and float(back.entropy_coefficient.log_alpha.detach()) == pytest.approx(-0.7)
+    for name, p in back.policy.named_parameters():
+        assert torch.equal(p.detach(), pv[name.replace("_orig_mod.", "")]), name
+    for net, mod in (("q1", back.critic.q1), ("q2", back.critic.q2), ("q1_target", back.critic.q1_target), ("q2_target", back.critic.q2_target)):
+        for name, p in mod.named_parameters():
+            assert torch.equal(p.detach(), qv[net][name.replace("_orig_mod.", "")]), (net, name)
+    for name, p in back.critic.q2.named_parameters():
+        assert torch.equal(back.q_optimizer.state[p]["exp_avg_sq"], qvv["q2"][name.replace("_orig_mod.", "")]), name
