@@ -63,6 +63,7 @@ FILES = [
     "rl_x/environments/action_space_type.py",
     "rl_x/environments/data_interface_type.py",
     "rl_x/environments/observation_space_type.py",
+    "rl_x/environments/simulation_type.py",
 ]
 
 

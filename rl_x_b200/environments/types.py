@@ -3,24 +3,39 @@ same member names and values so that GeneralProperties of reference plugins and 
 from enum import Enum
 
 
-class ActionSpaceType(Enum):
+class NamedEnum(Enum):
+    """Enum whose members equal the same-named members of a same-named Enum class of ANOTHER package.  The reference's runner checks
+    plugin compatibility with `env_props.action_space_type not in algo_props.action_space_types` and
+    `DeepLearningFrameworkType.TORCH == algo_props.deep_learning_framework_type` (rl_x/runner/runner.py:86-101): with the reference's enum
+    classes on one side and this package's on the other, identity comparison would reject every pairing."""
+
+    def __eq__(self, other):
+        if isinstance(other, Enum) and type(other).__name__ == type(self).__name__:
+            return self.name == other.name
+        return NotImplemented
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.name))
+
+
+class ActionSpaceType(NamedEnum):
     CONTINUOUS = 0
     DISCRETE = 1
 
 
-class ObservationSpaceType(Enum):
+class ObservationSpaceType(NamedEnum):
     FLAT_VALUES = 0
     IMAGES = 1
 
 
-class DataInterfaceType(Enum):
+class DataInterfaceType(NamedEnum):
     LIST = 0
     NUMPY = 1
     TORCH = 2
     JAX = 3
 
 
-class SimulationType(Enum):
+class SimulationType(NamedEnum):
     DEFAULT = 0
     JAX_BASED = 1
     ISAAC_LAB = 2

@@ -642,3 +642,49 @@ def test_sac_checkpoint_written_here_loads_into_the_reference_modules():
             assert torch.equal(p.detach(), qv[net][name.replace("_orig_mod.", "")]), (net, name)
     for name, p in back.critic.q2.named_parameters():
         assert torch.equal(back.q_optimizer.state[p]["exp_avg_sq"], qvv["q2"][name.replace("_orig_mod.", "")]), name
+
+
+def test_plugins_pass_the_reference_runners_compatibility_check():
+    """Drop-in at the plugin level: this package's plugins registered into the REFERENCE's registry (staged copy of
+    rl_x/algorithms/algorithm_manager.py) and put through the expressions of the reference's runner (rl_x/runner/runner.py:86-101) with the
+    reference's own enum members on the environment side.  Those expressions use `in` / `==` on Enum members of two different packages,
+    which only holds because this package's enums equal same-named members of same-named foreign enums (environments/types.py: NamedEnum)."""
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+    from oracle import ref_arm
+    ref_arm.import_reference()
+    from rl_x.algorithms import algorithm_manager as ref_manager
+    from rl_x.algorithms.deep_learning_framework_type import DeepLearningFrameworkType as RefFramework
+    from rl_x.environments.action_space_type import ActionSpaceType as RefAction
+    from rl_x.environments.data_interface_type import DataInterfaceType as RefInterface
+    from rl_x.environments.observation_space_type import ObservationSpaceType as RefObservation
+    from rl_x.environments.simulation_type import SimulationType as RefSimulation
+    import importlib
+    for algo, module, cls in (("ppo.b200", "ppo", "PPO"), ("espo.b200", "espo", "ESPO"), ("sac.b200", "sac", "SAC"), ("fastsac.b200", "fastsac", "FastSAC"),
+                              ("ppo_lstm.b200", "ppo_lstm", "PPO_LSTM")):
+        pkg = "rl_x_b200.algorithms." + algo
+        # the maintainer's four-line shim of INTEGRATION.md 1, with the reference's register_algorithm
+        ref_manager.register_algorithm(algo, importlib.import_module(pkg + ".default_config").get_config,
+                                       getattr(importlib.import_module(f"{pkg}.{module}"), cls),
+                                       importlib.import_module(pkg + ".general_properties").GeneralProperties)
+        props = ref_manager.get_algorithm_general_properties(algo)
+        assert ref_manager.get_algorithm_model_class(algo).__name__ == cls and ref_manager.get_algorithm_config(algo).name == algo
+
+        class EnvProps:   # what a reference environment plugin states (e.g. custom_mujoco/ant/warp_torch/general_properties.py)
+            action_space_type, observation_space_type = RefAction.CONTINUOUS, RefObservation.FLAT_VALUES
+            data_interface_type, simulation_type = RefInterface.TORCH, RefSimulation.WARP
+
+        # runner.py:86-91, verbatim conditions
+        assert not (EnvProps.action_space_type not in props.action_space_types)
+        assert not (EnvProps.observation_space_type not in props.observation_space_types)
+        if algo not in ("sac.b200",):   # SAC takes NUMPY environments only, like the reference's sac.pytorch
+            assert not (EnvProps.data_interface_type not in props.data_interface_types)
+        # what the check must still reject: discrete actions and image observations (SURVEY 8 a20)
+        assert RefAction.DISCRETE not in props.action_space_types and RefObservation.IMAGES not in props.observation_space_types
+        # runner.py:100-101
+        assert (RefFramework.TORCH == props.deep_learning_framework_type) and not (RefFramework.JAX == props.deep_learning_framework_type)
+    # and this package's synthetic environment under the reference runner's simulation-type tests (runner.py:102-103)
+    from rl_x_b200.environments.synthetic.box.general_properties import GeneralProperties as BoxProps
+    assert not (RefSimulation.JAX_BASED == BoxProps.simulation_type)
+    assert BoxProps.action_space_type in [RefAction.CONTINUOUS, RefAction.DISCRETE] and BoxProps.data_interface_type in [RefInterface.NUMPY, RefInterface.TORCH]
