@@ -23,9 +23,21 @@ class ConfigDict(dict):
         return ConfigDict({k: (v.copy_and_resolve_references() if isinstance(v, ConfigDict) else v) for k, v in self.items()})
 
 
+def config_tree_class():
+    """The class default configs are built from: `ml_collections.config_dict.ConfigDict` where ml_collections is installed - the reference's
+    runner hands the plugins' defaults to `config_flags.DEFINE_config_dict` (runner.py:179-181), which only accepts that class - and the
+    stand-in above where it is not (this image)."""
+    try:
+        from ml_collections import config_dict as _mlc
+        return _mlc.ConfigDict
+    except ImportError:
+        return ConfigDict
+
+
 def config_from_defaults(name, defaults):
     """A plugin's default config tree from its (key, value) table; `name` is the registered plugin name."""
-    config = ConfigDict(name=name)
+    config = config_tree_class()()
+    config["name"] = name
     for key, value in defaults:
         config[key] = value
     return config

@@ -1,10 +1,10 @@
-from rl_x_b200.config_dict import ConfigDict
+from rl_x_b200.config_dict import config_tree_class
 
 
 def get_config(environment_name):
     """Keys follow the reference's torch-interface env (custom_mujoco/ant/warp_torch/default_config.py:4-17) plus the
     synthetic-stream parameters of BASELINE config 2 (SURVEY.md §8 d)."""
-    config = ConfigDict()
+    config = config_tree_class()()   # ml_collections.ConfigDict where installed (the reference runner requires it)
 
     config.name = environment_name
 

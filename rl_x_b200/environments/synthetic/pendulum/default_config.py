@@ -1,10 +1,10 @@
-from rl_x_b200.config_dict import ConfigDict
+from rl_x_b200.config_dict import config_tree_class
 
 
 def get_config(environment_name):
     """Keys of the reference's gym environments (gym/mujoco/humanoid_v4/default_config.py:4-15); `type` is fixed: gymnasium is not in
     this image, so Pendulum-v1 is restated in NumPy (BASELINE.json configs[0]: nr_envs=4, CPU-side env, plumbing check)."""
-    config = ConfigDict()
+    config = config_tree_class()()   # ml_collections.ConfigDict where installed (the reference runner requires it)
 
     config.name = environment_name
 

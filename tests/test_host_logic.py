@@ -688,3 +688,33 @@ def test_plugins_pass_the_reference_runners_compatibility_check():
     from rl_x_b200.environments.synthetic.box.general_properties import GeneralProperties as BoxProps
     assert not (RefSimulation.JAX_BASED == BoxProps.simulation_type)
     assert BoxProps.action_space_type in [RefAction.CONTINUOUS, RefAction.DISCRETE] and BoxProps.data_interface_type in [RefInterface.NUMPY, RefInterface.TORCH]
+
+
+def test_default_configs_are_ml_collections_config_dicts_where_available(monkeypatch):
+    """The reference's runner passes every plugin's default config to ml_collections' config_flags.DEFINE_config_dict (runner.py:179-181), which
+    accepts ml_collections.config_dict.ConfigDict instances only.  ml_collections is absent from this image, so a stand-in module proves the
+    selection: with it importable, every get_config() of this package returns an instance of ITS ConfigDict; without it, the local class."""
+    import sys
+    import types
+    from rl_x_b200 import config_dict as local
+
+    class FakeMlConfigDict(dict):   # the part of the real class's surface the default_config modules use
+        __getattr__, __setattr__ = dict.__getitem__, dict.__setitem__
+
+    fake, fake_cd = types.ModuleType("ml_collections"), types.ModuleType("ml_collections.config_dict")
+    fake_cd.ConfigDict, fake.config_dict = FakeMlConfigDict, fake_cd
+    getters = []
+    for algo in ("ppo", "espo", "sac", "fastsac", "ppo_lstm"):
+        mod = __import__(f"rl_x_b200.algorithms.{algo}.b200.default_config", fromlist=["get_config"])
+        getters.append((mod.get_config, f"{algo}.b200"))
+    for env in ("box", "pendulum"):
+        mod = __import__(f"rl_x_b200.environments.synthetic.{env}.default_config", fromlist=["get_config"])
+        getters.append((mod.get_config, f"synthetic.{env}"))
+    from rl_x_b200.runner.default_config import get_config as runner_config
+    assert all(type(get(name)) is local.ConfigDict for get, name in getters)
+    monkeypatch.setitem(sys.modules, "ml_collections", fake)
+    monkeypatch.setitem(sys.modules, "ml_collections.config_dict", fake_cd)
+    for get, name in getters:
+        cfg = get(name)
+        assert type(cfg) is FakeMlConfigDict and cfg.name == name, name
+    assert type(runner_config("train")) is FakeMlConfigDict
