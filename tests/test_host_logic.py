@@ -711,6 +711,8 @@ def test_default_configs_are_ml_collections_config_dicts_where_available(monkeyp
         mod = __import__(f"rl_x_b200.environments.synthetic.{env}.default_config", fromlist=["get_config"])
         getters.append((mod.get_config, f"synthetic.{env}"))
     from rl_x_b200.runner.default_config import get_config as runner_config
+    monkeypatch.setitem(sys.modules, "ml_collections", None)             # "not installed" (other tests of this session stage a stub of their own)
+    monkeypatch.setitem(sys.modules, "ml_collections.config_dict", None)
     assert all(type(get(name)) is local.ConfigDict for get, name in getters)
     monkeypatch.setitem(sys.modules, "ml_collections", fake)
     monkeypatch.setitem(sys.modules, "ml_collections.config_dict", fake_cd)
