@@ -64,6 +64,8 @@ FILES = [
     "rl_x/environments/data_interface_type.py",
     "rl_x/environments/observation_space_type.py",
     "rl_x/environments/simulation_type.py",
+    "rl_x/environments/environment.py",
+    "rl_x/environments/environment_manager.py",
 ]
 
 

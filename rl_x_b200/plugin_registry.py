@@ -19,6 +19,20 @@ class PluginRegistry:
 
     def register(self, name, *objects):
         self.entries[name] = self.Entry(name, *objects)
+        self._mirror_into_reference(name, objects)
+
+    def _mirror_into_reference(self, name, objects):
+        """Where the reference package is importable, the plugin also goes into ITS registry.  The reference's runner imports
+        `<package>.<kind>.<name>` for every implementation package it is given and then looks the plugin up in rl_x's own manager
+        (rl_x/runner/runner.py:232-247, 86-96), so `Runner(implementation_package_names=["rl_x", "rl_x_b200"])` finds `ppo.b200` without
+        any bridge package.  Same argument order on both sides (rl_x/algorithms/algorithm_manager.py:12, environment_manager.py:12)."""
+        import importlib
+        singular = self.kind[:-1]
+        try:
+            manager = importlib.import_module(f"rl_x.{self.kind}.{singular}_manager")
+        except ImportError:
+            return
+        getattr(manager, f"register_{singular}")(name, *objects)
 
     def lookup(self, name):
         try:

@@ -720,3 +720,29 @@ def test_default_configs_are_ml_collections_config_dicts_where_available(monkeyp
         cfg = get(name)
         assert type(cfg) is FakeMlConfigDict and cfg.name == name, name
     assert type(runner_config("train")) is FakeMlConfigDict
+
+
+def test_importing_a_plugin_package_registers_it_with_the_reference_too():
+    """No bridge package: the reference's runner does importlib.import_module(f"{package}.algorithms.{name}") for each implementation
+    package and then asks rl_x's OWN managers for the plugin (runner.py:232-247, 86-96).  With rl_x importable (here: the staged copy),
+    importing rl_x_b200's plugin packages must therefore leave them in rl_x's registries as well as in this package's."""
+    import importlib
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+    from oracle import ref_arm
+    ref_arm.import_reference()
+    from rl_x.algorithms import algorithm_manager as ref_algorithms
+    from rl_x.environments import environment_manager as ref_environments
+    for name in ("ppo.b200", "espo.b200", "sac.b200", "fastsac.b200", "ppo_lstm.b200"):
+        ref_algorithms._algorithms.pop(name, None)
+        importlib.reload(importlib.import_module(f"rl_x_b200.algorithms.{name}"))       # what runner.import_algorithm does, from a clean slate
+        assert ref_algorithms.get_algorithm_model_class(name).__module__.startswith("rl_x_b200.algorithms." + name)
+        assert ref_algorithms.get_algorithm_config(name).name == name
+        assert ref_algorithms.get_algorithm_general_properties(name).deep_learning_framework_type.name == "TORCH"
+    for name in ("synthetic.box", "synthetic.pendulum"):
+        ref_environments._environments.pop(name, None)
+        importlib.reload(importlib.import_module(f"rl_x_b200.environments.{name}"))
+        assert callable(ref_environments.get_environment_create_train_and_eval_env(name))
+        assert ref_environments.get_environment_config(name).name == name
+        assert ref_environments.get_environment_general_properties(name).action_space_type.name == "CONTINUOUS"
