@@ -4,7 +4,7 @@ from rl_x_b200.config_dict import config_from_defaults
 
 _DEFAULTS = (
     ('device', "gpu"),  # a CUDA device is mandatory: there is no CPU fallback
-    ('compile_mode', "default"),
+    ('compile_mode', "reduce-overhead"),
     ('bf16_mixed_precision_training', False),
     ('total_timesteps', 1e9),
     ('learning_rate', 3e-4),

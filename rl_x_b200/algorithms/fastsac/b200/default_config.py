@@ -5,7 +5,7 @@ from rl_x_b200.config_dict import config_from_defaults
 
 _DEFAULTS = (
     ('device', "gpu"),
-    ('compile_mode', "default"),
+    ('compile_mode', "reduce-overhead"),
     ('bf16_mixed_precision_training', False),
     ('total_timesteps', 2000158720),
     ('learning_rate', 3e-4),

@@ -746,3 +746,31 @@ def test_importing_a_plugin_package_registers_it_with_the_reference_too():
         assert callable(ref_environments.get_environment_create_train_and_eval_env(name))
         assert ref_environments.get_environment_config(name).name == name
         assert ref_environments.get_environment_general_properties(name).action_space_type.name == "CONTINUOUS"
+
+
+def test_default_configs_carry_every_reference_key_with_the_reference_value():
+    """Every key of the reference's default_config.py of the five algorithms is present with the SAME default, except the one documented
+    difference (bf16_mixed_precision_training: this build's default is the fp32 parity path); keys this build adds are not reference keys.
+    Reference modules: the staged copies (ppo, sac, fastsac) and, in the build container only, /root/reference for espo and ppo_lstm."""
+    import importlib
+    import runpy
+    from oracle import make_ref, ref_arm
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+    ref_arm._install_stub()
+    sources = {"ppo": os.path.join(make_ref.DST, "rl_x/algorithms/ppo/pytorch/default_config.py"),
+               "sac": os.path.join(make_ref.DST, "rl_x/algorithms/sac/pytorch/default_config.py"),
+               "fastsac": os.path.join(make_ref.DST, "rl_x/algorithms/fastsac/pytorch/default_config.py"),
+               "espo": "/root/reference/rl_x/algorithms/espo/pytorch/default_config.py",
+               "ppo_lstm": "/root/reference/rl_x/algorithms/ppo_lstm/flax/default_config.py"}
+    checked = 0
+    for algo, path in sources.items():
+        if not os.path.exists(path):
+            continue
+        ref = runpy.run_path(path)["get_config"]("x")
+        ours = importlib.import_module(f"rl_x_b200.algorithms.{algo}.b200.default_config").get_config("x")
+        assert [k for k in ref if k not in ours] == [], algo
+        different = {k: (ref[k], ours[k]) for k in ref if k != "name" and ref[k] != ours[k]}
+        assert set(different) <= {"bf16_mixed_precision_training"}, (algo, different)
+        checked += 1
+    assert checked >= 3
