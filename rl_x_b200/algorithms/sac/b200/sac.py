@@ -304,11 +304,14 @@ class SAC:
         self.time_metrics_collection, self.step_info_collection = {}, {}
         self.updates_since_log = 0
         self.prev_saving_end_time = None
+        self.logging_time_prev = None
 
     def _train_step(self):
         """One pass of the reference's while-loop body (sac.py:180-348): act, env.step, replay add, sample, update, eval/save/log."""
         env, replay_buffer, state = self.train_env, self.replay_buffer, self.state
         start_time = time.time()
+        if self.logging_time_prev:  # sac.py:183-184
+            self.time_metrics_collection.setdefault("time/logging_time_prev", []).append(self.logging_time_prev)
         dones_this_rollout = 0
         # Acting (sac.py:187-196)
         if self.global_step < self.learning_starts:
@@ -390,6 +393,7 @@ class SAC:
                 self.log(f"{key}", value, global_step)
             self.time_metrics_collection, self.step_info_collection = {}, {}
             self.end_logging()
+        self.logging_time_prev = time.time() - saving_end_time  # sac.py:347-348
 
     def _evaluate(self):
         """ref: sac.py:264-283."""
