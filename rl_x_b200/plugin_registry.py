@@ -31,6 +31,10 @@ class PluginRegistry:
         try:
             manager = importlib.import_module(f"rl_x.{self.kind}.{singular}_manager")
         except ImportError:
+            return                       # no reference here: this package's own runner and registry are all there is
+        except Exception as exc:         # a reference install that does not import must not take this package's plugins down with it
+            import logging
+            logging.getLogger("rl_x").warning(f"rl_x_b200: {name!r} not mirrored into rl_x's {singular} registry ({type(exc).__name__}: {exc})")
             return
         getattr(manager, f"register_{singular}")(name, *objects)
 
