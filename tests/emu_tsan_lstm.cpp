@@ -12,9 +12,8 @@
 
 #include "../include/rlx_b200.h"
 
-int main() {
-  rlx_lstm_dims d{6, 2, 12, 8, 4, 0};
-  const long long T = 9, n = 7, R = T * n;   // 7 envs: the last block has inactive threads
+static int run_case(rlx_lstm_dims d, long long T, long long n, unsigned long long expect_launches) {
+  const long long R = T * n;
   int64_t poff[RLX_LSTM_POLICY_NSEG + 1], coff[RLX_LSTM_CRITIC_NSEG + 1];
   if (rlx_lstm_param_layout(&d, poff, coff)) return 2;
   std::mt19937 gen(5);
@@ -42,11 +41,19 @@ int main() {
     if (rlx_lstm_ppo_minibatch_fwdbwd_f32(&a, nullptr)) return 3;
     out[persistent][0] = gP; out[persistent][1] = gC; out[persistent][2] = metrics;
   }
-  if (rlx_lstm_persistent_launch_count() != 2) { printf("the persistent path did not run\n"); return 4; }
+  if (rlx_lstm_persistent_launch_count() != expect_launches) { printf("the persistent path did not run\n"); return 4; }
   for (int k = 0; k < 3; ++k) {
     for (float x : out[1][k]) if (!std::isfinite(x)) { printf("non-finite output\n"); return 5; }
     if (memcmp(out[0][k].data(), out[1][k].data(), out[0][k].size() * sizeof(float))) { printf("persistent and per-step paths differ\n"); return 6; }
   }
-  printf("ok\n");
   return 0;
+}
+
+int main() {
+  // lstm_dim 4: 32 envs per block, 7 envs -> one block, most of its env slots inactive;  lstm_dim 64 (the reference width): 2 envs per
+  // block of 128 threads, the recurrent kernel takes 64 KB of (emulated) shared memory, 3 envs -> the second block has an inactive slot
+  int rc = run_case(rlx_lstm_dims{6, 2, 12, 8, 4, 0}, 9, 7, 2);
+  if (!rc) rc = run_case(rlx_lstm_dims{6, 2, 16, 16, 64, 0}, 5, 3, 4);
+  if (!rc) printf("ok\n");
+  return rc;
 }
