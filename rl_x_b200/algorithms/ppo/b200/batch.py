@@ -6,7 +6,12 @@ class Batch:
 
     __slots__ = ("states", "next_states", "actions", "rewards", "values", "terminations", "log_probs", "advantages", "returns")
 
-    def __init__(self, **tensors):
+    def __init__(self, *positional, **tensors):
+        # the reference's signature: Batch(states, next_states, actions, rewards, values, terminations, log_probs, advantages, returns),
+        # positionally or by keyword (ppo.py:171-181 uses keywords)
+        if len(positional) > len(self.__slots__) or set(self.__slots__[:len(positional)]) & set(tensors):
+            raise TypeError(f"Batch takes the fields {self.__slots__} once each")
+        tensors.update(zip(self.__slots__, positional))
         missing = set(self.__slots__) - set(tensors)
         if missing or len(tensors) != len(self.__slots__):
             raise TypeError(f"Batch needs exactly the fields {self.__slots__}; missing {sorted(missing)}, got {sorted(tensors)}")
