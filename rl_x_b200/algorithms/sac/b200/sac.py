@@ -432,7 +432,11 @@ class SAC:
         if self.track_tb:
             self.writer.add_scalar(name, value, step)
         if self.track_console:
-            rlx_logger.info(f"│ {name.ljust(30)}│ {str(np.format_float_positional(value, trim='-')).ljust(14)[:14]} │")
+            self.log_console(name, value)
+
+    def log_console(self, name, value):
+        value = np.format_float_positional(value, trim="-")
+        rlx_logger.info(f"│ {name.ljust(30)}│ {str(value).ljust(14)[:14]} │")
 
     def start_logging(self, step):
         if self.track_wandb:
