@@ -774,3 +774,36 @@ def test_default_configs_carry_every_reference_key_with_the_reference_value():
         assert set(different) <= {"bf16_mixed_precision_training"}, (algo, different)
         checked += 1
     assert checked >= 3
+
+
+def test_model_classes_have_the_reference_classes_methods_and_signatures():
+    """Duck typing is the boundary (SURVEY 8 b): every method of the reference's model class exists on this package's class with the same
+    parameter names (`load` may be a classmethod: the runner calls it on the class either way, runner.py:334-337).  Read from the sources."""
+    import ast
+    from oracle import make_ref
+    if not make_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py)")
+
+    def methods(path, cls):
+        for node in ast.walk(ast.parse(open(path).read())):
+            if isinstance(node, ast.ClassDef) and node.name == cls:
+                return {f.name: [a.arg for a in f.args.args if a.arg != "cls"] for f in node.body if isinstance(f, ast.FunctionDef)}
+        raise AssertionError(f"no class {cls} in {path}")
+
+    pkg = os.path.join(ROOT, "rl_x_b200", "algorithms")
+    cases = [("PPO", os.path.join(make_ref.DST, "rl_x/algorithms/ppo/pytorch/ppo.py"), [f"{pkg}/ppo/b200/ppo.py"]),
+             ("SAC", os.path.join(make_ref.DST, "rl_x/algorithms/sac/pytorch/sac.py"), [f"{pkg}/sac/b200/sac.py"]),
+             ("FastSAC", os.path.join(make_ref.DST, "rl_x/algorithms/fastsac/pytorch/fastsac.py"), [f"{pkg}/fastsac/b200/fastsac.py"]),
+             ("ESPO", "/root/reference/rl_x/algorithms/espo/pytorch/espo.py", [f"{pkg}/ppo/b200/ppo.py", f"{pkg}/espo/b200/espo.py"]),
+             ("PPO_LSTM", "/root/reference/rl_x/algorithms/ppo_lstm/flax/ppo_lstm.py", [f"{pkg}/ppo_lstm/b200/ppo_lstm.py"])]
+    checked = 0
+    for cls, ref_path, our_paths in cases:
+        if not os.path.exists(ref_path):
+            continue
+        ref, ours = methods(ref_path, cls), {}
+        for p, c in zip(our_paths, ["PPO", cls] if len(our_paths) == 2 else [cls]):   # ESPO inherits PPO here
+            ours.update(methods(p, c))
+        assert [m for m in ref if m not in ours] == [], cls
+        assert {m: (ref[m], ours[m]) for m in ref if ref[m] != ours[m]} == {}, cls
+        checked += 1
+    assert checked >= 3
